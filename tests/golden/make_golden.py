@@ -1,0 +1,158 @@
+"""
+Generates the committed golden fixtures tests/golden/*.npz by running the UNMODIFIED NuRadioMC Python reference
+(scratch copy baseline/_ref, see oracle/pyref/ref_harness.py) in the build container.
+
+    python tests/golden/make_golden.py [case ...]
+
+Every fixture holds the inputs (X1, X2, frequencies, configuration) and the reference's outputs through its public
+scalar API (find_solutions / get_solution_type / get_launch_vector / get_receive_vector / get_path_length /
+get_travel_time / get_reflection_angle / get_attenuation), plus
+  * `attenuation_tight`: same reference integrand integrated with quad(epsrel=1e-11), and
+  * `arbiter_C0`: for pairs where the reference's count differs from the oracle's, the roots found by a dense
+    scan of the reference's *own* objective (SURVEY.md F6 protocol).
+The reference's golden pickles of T05/T06 are copied as plain arrays too (they are data, 1000x2 and 1000x10 f64).
+"""
+import os
+import pickle
+import sys
+import time
+from multiprocessing import Pool
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, os.path.join(REPO, "oracle", "pyref"))
+sys.path.insert(0, REPO)
+
+RNOG = np.array([[0, 20, -97], [0, 20, -96], [0, 20, -95], [0, 20, -94], [0, 20, -93], [0, 20, -92], [0, 20, -80],
+                 [0, 20, -60], [0, 20, -40], [-17.3, -10, -96], [-17.3, -10, -95], [-17.3, -10, -94], [1.5, 11, -2],
+                 [0, 11, -2], [-1.5, 11, -2], [-10.276, -4.2, -2], [-9.526, -5.5, -2], [-8.776, -6.8, -2],
+                 [8.776, -6.8, -2], [9.526, -5.5, -2], [10.276, -4.2, -2], [17.3, -10, -96], [17.3, -10, -95],
+                 [17.3, -10, -94]], float)
+
+
+def cylinder(seed, n, rmax, zmin, rmin=0.0):
+    """uniform-in-cylinder vertices, NuRadioMC/EvtGen/generator.py:613-618"""
+    rng = np.random.default_rng(seed)
+    r = np.sqrt(rng.uniform(rmin ** 2, rmax ** 2, n))
+    phi = rng.uniform(0, 2 * np.pi, n)
+    z = rng.uniform(zmin, 0, n)
+    return np.array([r * np.cos(phi), r * np.sin(phi), z]).T
+
+
+def t05_points(seed, zmax, n=1000):
+    """T05/T06/T01 vertex distribution (legacy numpy RNG), T05unit_test_C0_SP.py:15-26"""
+    np.random.seed(seed)
+    rr = np.random.triangular(50., 3000., 3000., n)
+    ph = np.random.uniform(0, 2 * np.pi, n)
+    xx, yy = rr * np.cos(ph), rr * np.sin(ph)
+    zz = np.random.uniform(0., zmax, n)
+    return np.array([xx, yy, zz]).T
+
+
+def pairs(vertices, antennas):
+    V = np.repeat(vertices, len(antennas), axis=0)
+    A = np.tile(antennas, (len(vertices), 1))
+    return V, A
+
+
+def cases():
+    c = {}
+    X1 = t05_points(10, -3000.)[:300]
+    c["sp_simple_T05"] = dict(ice="southpole_simple", att=None, n_refl=0, n_freq=100, X1=X1,
+                              X2=np.repeat([[0, 0, -5.]], len(X1), 0))
+    V, A = pairs(cylinder(2, 150, 4000., -2700.), np.array([[10, 10, -190.], [-10, 10, -190.]]))
+    c["sp2015_cfg2"] = dict(ice="southpole_2015", att=None, n_refl=0, n_freq=100, X1=V, X2=A)
+    X1 = t05_points(0, -3000.)[:36]
+    c["sp1_cfg1"] = dict(ice="southpole_simple", att="SP1", n_refl=0, n_freq=100, X1=X1,
+                         X2=np.repeat([[0, 0, -100.]], len(X1), 0), freqs=np.linspace(0, 0.5, 129), fmax=None)
+    V, A = pairs(cylinder(3, 24, 4000., -2700.), RNOG[[0, 8, 13]])
+    c["greenland_cfg3"] = dict(ice="greenland_simple", att="GL1", n_refl=0, n_freq=25, X1=V, X2=A,
+                               freqs=np.fft.rfftfreq(1022, 0.2), fmax=1.2)
+    V, A = pairs(cylinder(4, 60, 1000., -500.), np.array([[3, 3, -5.], [-3, 0, -1.]]))
+    c["mooresbay_cfg4"] = dict(ice="mooresbay_simple", att=None, n_refl=1, n_freq=25, X1=V, X2=A)
+    V, A = pairs(cylinder(14, 12, 1000., -500.), np.array([[3, 3, -5.]]))
+    c["mooresbay_cfg4_MB1"] = dict(ice="mooresbay_simple", att="MB1", n_refl=1, n_freq=25, X1=V, X2=A,
+                                   freqs=np.fft.rfftfreq(256, 0.5), fmax=None)
+    X1 = t05_points(10, -500.)[:80]
+    c["mooresbay_T06"] = dict(ice="mooresbay_simple", att=None, n_refl=2, n_freq=100, X1=X1,
+                              X2=np.repeat([[0, 0, -5.]], len(X1), 0))
+    V, A = pairs(cylinder(5, 20, 6000., -2700.), np.array([[0, 0, -150.], [1500, -1500, -160.]]))
+    c["sp2015_cfg5_SP1"] = dict(ice="southpole_2015", att="SP1", n_refl=0, n_freq=25, X1=V, X2=A,
+                                freqs=np.fft.rfftfreq(1022, 0.2), fmax=1.2)
+    V, A = pairs(cylinder(6, 16, 3000., -2500.), np.array([[0, 0, -100.]]))
+    c["greenland_GL2"] = dict(ice="greenland_simple", att="GL2", n_refl=0, n_freq=20, X1=V, X2=A,
+                              freqs=np.fft.rfftfreq(256, 0.5), fmax=None)
+    return c
+
+
+def _work(args):
+    name, cfg, lo, hi = args
+    import ref_harness as rh
+    r = rh.make_tracer(cfg["ice"], attenuation_model=cfg["att"] or "SP1", n_freq=cfg["n_freq"], n_reflections=cfg["n_refl"])
+    with_att = cfg["att"] is not None
+    t = time.time()
+    out = rh.trace_pairs(r, cfg["X1"][lo:hi], cfg["X2"][lo:hi], freqs=cfg.get("freqs"), max_detector_freq=cfg.get("fmax"),
+                         with_attenuation=with_att, tight_attenuation=with_att)
+    out["_seconds"] = time.time() - t
+    return name, lo, out
+
+
+def _arbiter(args):
+    cfg, i = args
+    import ref_harness as rh
+    r = rh.make_tracer(cfg["ice"], n_reflections=cfg["n_refl"])
+    res = []
+    for md in range(1 + 2 * cfg["n_refl"]):
+        refl = 0 if md == 0 else (md - 1) // 2 + 1
+        case = 1 if md == 0 else (md - 1) % 2 + 1
+        res.extend(list(rh.arbiter_roots(r, cfg["X1"][i], cfg["X2"][i], refl, case, n_scan=28001, lo=-12.0, hi=16.0)))
+    return i, res
+
+
+def main(names):
+    all_cases = cases()
+    names = names or list(all_cases)
+    pool = Pool(8)
+    for name in names:
+        cfg = all_cases[name]
+        N = len(cfg["X1"])
+        chunk = max(1, N // 32)
+        jobs = [(name, cfg, lo, min(N, lo + chunk)) for lo in range(0, N, chunk)]
+        t0 = time.time()
+        parts = sorted(pool.map(_work, jobs), key=lambda p: p[1])
+        out = {}
+        for k in parts[0][2]:
+            if k == "_seconds":
+                out["ref_cpu_seconds"] = np.array(sum(p[2][k] for p in parts))
+            else:
+                out[k] = np.concatenate([p[2][k] for p in parts], axis=0)
+        # F6 arbiter where the oracle disagrees on the count
+        from oracle.oracle import Oracle
+        o = Oracle(cfg["ice"], n_reflections=cfg["n_refl"])
+        oo = o.trace(cfg["X1"], cfg["X2"])
+        bad = np.nonzero(oo["n_sol"] != out["n_sol"])[0]
+        arb = np.full((N, out["C0"].shape[1]), np.nan)
+        arb_n = np.full(N, -1, np.int32)
+        for i, roots in pool.map(_arbiter, [(cfg, int(i)) for i in bad]):
+            arb_n[i] = len(roots)
+            arb[i, :min(len(roots), arb.shape[1])] = roots[:arb.shape[1]]
+        out["arbiter_C0"], out["arbiter_n"] = arb, arb_n
+        meta = dict(ice=cfg["ice"], attenuation_model=cfg["att"] or "", n_reflections=cfg["n_refl"], n_freq=cfg["n_freq"],
+                    max_detector_freq=np.nan if cfg.get("fmax") is None else cfg["fmax"])
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), X1=cfg["X1"], X2=cfg["X2"],
+                            frequencies=cfg.get("freqs", np.zeros(0)), **meta, **out)
+        print(f"{name}: N={N} solutions={int(out['n_sol'].sum())} count-mismatch-vs-oracle={len(bad)} "
+              f"ref_cpu={float(out['ref_cpu_seconds']):.1f}s wall={time.time() - t0:.1f}s", flush=True)
+    # the reference's own goldens (data): T05 / T06
+    for fn in ("reference_C0.pkl", "reference_C0_MooresBay.pkl"):
+        src = os.path.join("/root/reference/NuRadioMC/test/SignalProp", fn)
+        if os.path.exists(src):
+            with open(src, "rb") as f:
+                arr = pickle.load(f, encoding="latin1")
+            np.save(os.path.join(HERE, fn.replace(".pkl", ".npy")), np.asarray(arr, float))
+
+
+if __name__ == "__main__":
+    main(sys.argv[1:])
