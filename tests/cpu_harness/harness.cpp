@@ -1,0 +1,19 @@
+// TEST-ONLY: host build of the kernels' scalar maths (nuradiomc_b200/csrc/nrmc_math.cuh) so that the algorithm can be
+// compared with the oracle on machines without a GPU (`pytest -m "not gpu"`).  Never loaded by the product.
+#include "../../nuradiomc_b200/csrc/nrmc_math.cuh"
+#include <vector>
+using namespace nrmc;
+extern "C" int harness_trace(double n_ice, double dn, double z0, double zr, int n_refl, int64_t N, const double *X1,
+                             const double *X2, int32_t *n_sol, int32_t *status, int8_t *type, int8_t *reflection,
+                             int8_t *reflection_case, double *C0, double *C1, double *path_length, double *travel_time,
+                             double *launch, double *receive, double *reflection_angle)
+{
+    IceParams ice;
+    ice.n_ice = n_ice; ice.dn = dn; ice.z0 = z0; ice.inv_z0 = 1.0 / z0; ice.ns = n_ice - dn;
+    ice.n_refl = n_refl; ice.zr = n_refl > 0 ? zr : -1e30;
+    ice.gr = n_refl > 0 ? dn * exp(zr / z0) : 0.0; ice.nr = n_ice - ice.gr; ice.att_model = 0;
+    TraceOutputs o = {n_sol, status, type, reflection, reflection_case, C0, C1, path_length, travel_time, launch, receive, reflection_angle};
+    for (int64_t i = 0; i < N; ++i)
+        trace_pair(ice, X1[3 * i], X1[3 * i + 1], X1[3 * i + 2], X2[3 * i], X2[3 * i + 1], X2[3 * i + 2], i, o, nullptr);
+    return 0;
+}
