@@ -1,0 +1,139 @@
+/*
+ * nrmc_rt.h -- C ABI of the B200-native batched analytic ray tracer (libnrmc_rt.so).
+ *
+ * Drop-in boundary.  The reference's only native FFI for this path is the Cython shim
+ *   NuRadioMC/SignalProp/CPPAnalyticRayTracing/wrapper.pyx:8-33
+ *     find_solutions(x1, x2, n_ice, delta_n, z_0, reflection, reflection_case, ice_reflection) -> list[dict]
+ *     get_attenuation_along_path(x1, x2, C0, frequency, n_ice, delta_n, z_0, model) -> float
+ *     get_attenuation_length(z, frequency, model) -> float
+ * over analytic_raytracing.cpp:877-896 (find_solutions2) / :365 (get_attenuation_along_path): scalar, one pair and
+ * one frequency per call.  This header replaces that surface with a batched one: one call traces N (vertex, antenna)
+ * pairs through everything the Python class needs for
+ *   ray_tracing.set_start_and_end_point / find_solutions / get_solution_type / get_launch_vector /
+ *   get_receive_vector / get_reflection_angle / get_path_length / get_travel_time / get_attenuation
+ *   (NuRadioMC/SignalProp/analyticraytracing.py:2057-2146, 2560-2776).
+ * Plain pointers and sizes only; the caller owns every buffer; status codes instead of exceptions.
+ * Units are NuRadioMC's (NuRadioReco/utilities/units.py): metre, nanosecond, GHz, radian.
+ */
+#ifndef NRMC_RT_H
+#define NRMC_RT_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NRMC_OK 0
+#define NRMC_ERR_INVALID_ARGUMENT (-1)
+#define NRMC_ERR_CUDA (-2)
+#define NRMC_ERR_NO_DEVICE (-3)
+#define NRMC_ERR_UNSUPPORTED (-4)
+#define NRMC_ERR_NO_FREQUENCIES (-5)
+
+/* attenuation model integers: NuRadioMC/utilities/attenuation.py:14 */
+#define NRMC_ATT_NONE 0
+#define NRMC_ATT_SP1 1
+#define NRMC_ATT_GL1 2
+#define NRMC_ATT_MB1 3
+#define NRMC_ATT_GL2 4
+#define NRMC_ATT_GL3 5
+
+/* per-pair status bits (nrmc_rt_output.status) */
+#define NRMC_PAIR_IN_AIR 1           /* a point lies above the surface: the reference finds no solution (py:1445-1448) */
+#define NRMC_PAIR_BELOW_REFLECTOR 2  /* a point lies below the reflective layer: the reference raises AttributeError
+                                        (propagation_base_class.py:156-161) */
+#define NRMC_PAIR_NONFINITE 4        /* NaN / inf coordinate */
+
+#define NRMC_MEMORY_HOST 0
+#define NRMC_MEMORY_DEVICE 1
+
+typedef struct nrmc_rt_s *nrmc_rt_t;
+
+/* Replaces the (medium, attenuation_model, n_frequencies_integration, n_reflections) constructor arguments of
+ * ray_tracing (analyticraytracing.py:1938-1941) and the IceModelSimple parameters (medium_base.py:206-252). */
+typedef struct {
+    double n_ice, delta_n, z_0;
+    double reflection_z;               /* depth of the reflective bottom layer [m] (medium_base.py:47-66); NaN if none */
+    int32_t attenuation_model;         /* NRMC_ATT_* */
+    int32_t n_reflections;             /* 0..4 */
+    int32_t n_frequencies_integration; /* propagation_base_class.py:118 default 100 */
+    int32_t device;                    /* CUDA device ordinal */
+    const double *gl3_table;           /* GL3 only: rows of (depth, slope, offset), attenuation.py:16-33 */
+    int32_t gl3_rows;
+    int32_t reserved;
+} nrmc_rt_config;
+
+/* N pairs.  outer == 0: pair i = (vertex i, antenna i), n_antennas == n_vertices.
+ *           outer == 1: pair i = (vertex i / n_antennas, antenna i % n_antennas), N = n_vertices * n_antennas. */
+typedef struct {
+    int64_t n_vertices;
+    const double *vx, *vy, *vz;        /* SoA start points (the reference's x1), metres */
+    int64_t n_antennas;
+    const double *ax, *ay, *az;        /* SoA end points (the reference's x2) */
+    int32_t outer;
+    int32_t memory;                    /* NRMC_MEMORY_HOST or NRMC_MEMORY_DEVICE: where ALL input and output pointers live */
+} nrmc_rt_input;
+
+/* SoA outputs, pair-major, S = nrmc_rt_max_solutions() slots per pair ordered as the reference orders
+ * ray_tracing._results (mode (reflection, case) first, then C0 ascending; py:2122-2125, :1547).  Unused slots hold
+ * 0 / NaN.  Any pointer may be NULL (that output is skipped). */
+typedef struct {
+    int32_t *n_sol;            /* [N]      get_number_of_solutions()                                  */
+    int32_t *status;           /* [N]      NRMC_PAIR_* bits                                            */
+    int8_t *solution_type;     /* [N,S]    get_solution_type(iS): 1 direct, 2 refracted, 3 reflected   */
+    int8_t *reflection;        /* [N,S]    get_results()[iS]['reflection']                             */
+    int8_t *reflection_case;   /* [N,S]    get_results()[iS]['reflection_case']                        */
+    double *C0, *C1;           /* [N,S]    get_results()[iS]['C0'|'C1']                                */
+    double *path_length;       /* [N,S]    get_path_length(iS)   (analytic)                            */
+    double *travel_time;       /* [N,S]    get_travel_time(iS)   (analytic)                            */
+    double *launch_vector;     /* [N,S,3]  get_launch_vector(iS)                                       */
+    double *receive_vector;    /* [N,S,3]  get_receive_vector(iS)                                      */
+    double *reflection_angle;  /* [N,S,n_reflections+1]  get_reflection_angle(iS), NaN = None          */
+    double *attenuation_sparse;/* [N,S,Fs] attenuation factors at the Fs integration frequencies       */
+    double *attenuation;       /* [N,S,F]  get_attenuation(iS, frequency, max_detector_freq)           */
+} nrmc_rt_output;
+
+typedef struct {
+    int64_t n_pairs, n_solutions;
+    float ms_solve;            /* device time of the root-finding + properties kernel(s), CUDA events   */
+    float ms_attenuation;      /* device time of the attenuation kernel(s)                              */
+    float ms_total;            /* device time of the whole call on the library's stream (incl. copies)  */
+    int32_t n_launches;        /* kernels launched by this call                                         */
+    int32_t n_chunks;
+    int64_t h2d_bytes, d2h_bytes;
+} nrmc_rt_stats;
+
+int nrmc_rt_create(const nrmc_rt_config *cfg, nrmc_rt_t *out);
+void nrmc_rt_destroy(nrmc_rt_t h);
+const char *nrmc_rt_last_error(nrmc_rt_t h);
+int nrmc_rt_max_solutions(nrmc_rt_t h);       /* 2 + 4 n_reflections, propagation_base_class.py:424-429 */
+
+/* The frequency vector of get_attenuation(iS, frequency, max_detector_freq) (max_detector_freq = NaN for None).
+ * Builds the sparse integration frequencies exactly as __get_frequencies_for_attenuation (py:885-931) and the
+ * np.interp tables (py:1075-1078).  Returns Fs (>0) or an error code. */
+int nrmc_rt_set_frequencies(nrmc_rt_t h, const double *frequency, int32_t n, double max_detector_freq);
+int nrmc_rt_get_sparse_frequencies(nrmc_rt_t h, double *out, int32_t capacity);
+
+/* Traces all pairs.  With NRMC_MEMORY_HOST the call is synchronous and copies inputs/outputs itself (chunked and
+ * overlapped on two streams); with NRMC_MEMORY_DEVICE the work is enqueued on `stream` (a cudaStream_t, may be 0)
+ * and the call returns after enqueueing unless `stats` is non-NULL (then it synchronises to fill it). */
+int nrmc_rt_trace(nrmc_rt_t h, const nrmc_rt_input *in, const nrmc_rt_output *out, void *stream, nrmc_rt_stats *stats);
+
+/* pinned host memory for fast NRMC_MEMORY_HOST transfers */
+int nrmc_rt_host_alloc(void **ptr, uint64_t bytes);
+int nrmc_rt_host_free(void *ptr);
+
+/* attenuation length L(z, f) [m] on the device for n points (replaces wrapper.pyx:32-33 get_attenuation_length) */
+int nrmc_rt_attenuation_length(nrmc_rt_t h, const double *z, const double *frequency, int64_t n, double *out_host);
+
+/* measured FP64 FMA peak of the device [TFLOP/s] (independent DFMA chains on all SMs for >= `seconds`) */
+int nrmc_rt_measure_fp64_peak(int32_t device, double seconds, double *tflops, double *sm_clock_mhz);
+
+int nrmc_rt_device_count(void);
+const char *nrmc_rt_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NRMC_RT_H */

@@ -1,0 +1,484 @@
+"""
+Analytic ray tracer -- the reference's `ray_tracing` class (NuRadioMC/SignalProp/analyticraytracing.py:1932-3052)
+re-implemented on top of the batched sm_100a library (include/nrmc_rt.h).
+
+* Same constructor, same stateful scalar API (set_start_and_end_point / find_solutions / get_* ...), same exceptions.
+  A scalar call is a batch of one pair on the GPU (or a lookup in a batch traced ahead with `prepare_batch`).
+* New: `trace_batch` / `trace_batch_device` -- every (vertex, antenna) pair in one device pass, SoA results.
+
+There is no CPU implementation behind this class: without libnrmc_rt.so and a CUDA device every compute call raises.
+"""
+import ctypes as C
+import logging
+
+import numpy as np
+
+from nuradiomc_b200 import _lib
+from nuradiomc_b200.SignalProp.propagation import solution_types, solution_types_revert  # noqa: F401 (re-export, as the reference)
+from nuradiomc_b200.SignalProp.propagation_base_class import ray_tracing_base
+from nuradiomc_b200.utilities import attenuation as attenuation_util
+from nuradiomc_b200.utilities import units
+
+logger = logging.getLogger("NuRadioMC.analytic_ray_tracing")
+
+speed_of_light = units.speed_of_light
+cpp_available = False     # kept for source compatibility with the reference module; the native path here is CUDA
+numba_available = False
+cuda_available = True     # resolved lazily: the library is loaded on first use
+
+
+class _Handle:
+    """owns one nrmc_rt_t"""
+
+    def __init__(self, ptr):
+        self.ptr = ptr
+        self.freq_key = None
+        self.sparse = None
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                _lib.load().nrmc_rt_destroy(self.ptr)
+                self.ptr = None
+        except Exception:
+            pass
+
+
+def _make_handle(n_ice, delta_n, z_0, reflection_z, att_model_int, n_reflections, n_freq, device):
+    lib = _lib.load()
+    cfg = _lib.Config()
+    cfg.n_ice, cfg.delta_n, cfg.z_0 = float(n_ice), float(delta_n), float(z_0)
+    cfg.reflection_z = float("nan") if reflection_z is None else float(reflection_z)
+    cfg.attenuation_model = int(att_model_int)
+    cfg.n_reflections = int(n_reflections)
+    cfg.n_frequencies_integration = int(n_freq)
+    cfg.device = int(device)
+    keep = None
+    if att_model_int == attenuation_util.model_to_int["GL3"]:
+        keep = attenuation_util.gl3_parameters()
+        cfg.gl3_table = keep.ctypes.data
+        cfg.gl3_rows = keep.shape[0]
+    ptr = C.c_void_p()
+    _lib.check(lib.nrmc_rt_create(C.byref(cfg), C.byref(ptr)), None, "create")
+    return _Handle(ptr)
+
+
+class PinnedArray:
+    """numpy view of page-locked host memory (nrmc_rt_host_alloc) for fast host<->device copies"""
+
+    def __init__(self, shape, dtype):
+        self.shape = tuple(int(s) for s in np.atleast_1d(shape))
+        self.dtype = np.dtype(dtype)
+        nbytes = max(int(np.prod(self.shape)) * self.dtype.itemsize, 1)
+        self._ptr = C.c_void_p()
+        _lib.check(_lib.load().nrmc_rt_host_alloc(C.byref(self._ptr), nbytes), None, "host_alloc")
+        buf = (C.c_char * nbytes).from_address(self._ptr.value)
+        self.array = np.frombuffer(buf, dtype=self.dtype, count=int(np.prod(self.shape))).reshape(self.shape)
+
+    def __del__(self):
+        try:
+            if self._ptr:
+                self.array = None
+                _lib.load().nrmc_rt_host_free(self._ptr)
+                self._ptr = None
+        except Exception:
+            pass
+
+
+_OUT_SPECS = {  # name -> (dtype, trailing shape as function of (S, K1, Fs, F))
+    "n_sol": (np.int32, lambda S, K1, Fs, F: ()),
+    "status": (np.int32, lambda S, K1, Fs, F: ()),
+    "solution_type": (np.int8, lambda S, K1, Fs, F: (S,)),
+    "reflection": (np.int8, lambda S, K1, Fs, F: (S,)),
+    "reflection_case": (np.int8, lambda S, K1, Fs, F: (S,)),
+    "C0": (np.float64, lambda S, K1, Fs, F: (S,)),
+    "C1": (np.float64, lambda S, K1, Fs, F: (S,)),
+    "path_length": (np.float64, lambda S, K1, Fs, F: (S,)),
+    "travel_time": (np.float64, lambda S, K1, Fs, F: (S,)),
+    "launch_vector": (np.float64, lambda S, K1, Fs, F: (S, 3)),
+    "receive_vector": (np.float64, lambda S, K1, Fs, F: (S, 3)),
+    "reflection_angle": (np.float64, lambda S, K1, Fs, F: (S, K1)),
+    "attenuation_sparse": (np.float64, lambda S, K1, Fs, F: (S, Fs)),
+    "attenuation": (np.float64, lambda S, K1, Fs, F: (S, F)),
+}
+DEFAULT_OUTPUTS = ("n_sol", "status", "solution_type", "reflection", "reflection_case", "C0", "C1", "path_length",
+                   "travel_time", "launch_vector", "receive_vector", "reflection_angle")
+
+
+class BatchResult(dict):
+    """SoA results of `trace_batch`: arrays keyed by the field names of nrmc_rt_output, plus `.stats`,
+    `.frequencies_sparse`."""
+    stats = None
+    frequencies_sparse = None
+    _keep = None
+
+    def solutions(self, i):
+        """results of pair i in the reference's `get_results()` format"""
+        return [{'type': int(self["solution_type"][i, s]), 'C0': float(self["C0"][i, s]), 'C1': float(self["C1"][i, s]),
+                 'reflection': int(self["reflection"][i, s]), 'reflection_case': int(self["reflection_case"][i, s])}
+                for s in range(int(self["n_sol"][i]))]
+
+
+class ray_tracing(ray_tracing_base):
+    """
+    utility class to get ray tracing solutions in 3D for two arbitrary points x1 and x2
+    (drop-in for NuRadioMC.SignalProp.analyticraytracing.ray_tracing, :1932)
+    """
+
+    def __init__(self, medium, attenuation_model=None, log_level=logging.NOTSET,
+                 n_frequencies_integration=None, n_reflections=None, config=None,
+                 detector=None, ray_tracing_2D_kwards={},
+                 use_cpp=None, compile_numba=None, device=0):
+        """
+        Same parameters as the reference (:1938-1998).  `use_cpp` / `compile_numba` select between the reference's CPU
+        back ends and are accepted for call compatibility; the computation always runs on CUDA device `device`.
+        """
+        self.__logger = logging.getLogger('NuRadioMC.ray_tracing')
+        self.__logger.setLevel(log_level)
+
+        if not all(hasattr(medium, a) for a in ("n_ice", "delta_n", "z_0")) or getattr(medium, "z_shift", 0) != 0:
+            # the reference checks isinstance(medium, IceModelSimple) (:2002-2005); any object exposing the
+            # exponential-profile parameters (this package's or the reference's IceModelSimple) is accepted here
+            self.__logger.error("The analytic raytracer can only handle ice model of the type 'IceModelSimple'")
+            raise TypeError("The analytic raytracer can only handle ice model of the type 'IceModelSimple'")
+
+        super().__init__(medium=medium, attenuation_model=attenuation_model, log_level=log_level,
+                         n_frequencies_integration=n_frequencies_integration, n_reflections=n_reflections,
+                         config=config, detector=detector)
+        self.set_config(config=config)
+
+        if medium.delta_n == 0:   # uniform_ice (:433-437)
+            msg = ('Analytic raytracer does not work with a uniform ice model. '
+                   'Abort.... ! Use direct raytracing or a non-uniform ice model instead.')
+            self.__logger.error(msg)
+            raise RuntimeError(msg)
+        if not hasattr(self._medium, "reflection"):
+            self._medium.reflection = None
+        if self._attenuation_model not in attenuation_util.model_to_int:   # (:449-450)
+            raise NotImplementedError("attenuation model {} is not implemented".format(self._attenuation_model))
+        if use_cpp:
+            self.__logger.warning("use_cpp=True requests the reference's C++/GSL extension; this implementation runs "
+                                  "the CUDA library instead")
+        self.use_cpp = False
+        self._device = device
+        self._handle = None
+        self._swap = None
+        self._x1 = None
+        self._x2 = None
+        self._cache = None          # results of the current pair (arrays with leading dimension S)
+        self._att_cache = {}
+        self._batch = None          # (lookup dict, BatchResult) from prepare_batch
+        self._batch_index = None
+
+    # ------------------------------------------------------------------------------------------------------
+    # native handle
+    # ------------------------------------------------------------------------------------------------------
+    def _h(self):
+        if self._handle is None:
+            m = self._medium
+            self._handle = _make_handle(m.n_ice, m.delta_n, m.z_0, getattr(m, "reflection", None),
+                                        attenuation_util.model_to_int[self._attenuation_model], self._n_reflections,
+                                        self._n_frequencies_integration, self._device)
+        return self._handle
+
+    def _set_frequencies(self, frequency, max_detector_freq):
+        h = self._h()
+        frequency = np.ascontiguousarray(frequency, dtype=np.float64)
+        key = (frequency.tobytes(), None if max_detector_freq is None else float(max_detector_freq))
+        if h.freq_key != key:
+            lib = _lib.load()
+            fmax = float("nan") if max_detector_freq is None else float(max_detector_freq)
+            Fs = _lib.check(lib.nrmc_rt_set_frequencies(h.ptr, frequency.ctypes.data, len(frequency), fmax), h.ptr,
+                            "set_frequencies")
+            sp = np.empty(Fs)
+            lib.nrmc_rt_get_sparse_frequencies(h.ptr, sp.ctypes.data, Fs)
+            h.freq_key, h.sparse, h.n_out = key, sp, len(frequency)
+        return h.sparse
+
+    # ------------------------------------------------------------------------------------------------------
+    # batched entry points (new)
+    # ------------------------------------------------------------------------------------------------------
+    def trace_batch(self, X1, X2, frequency=None, max_detector_freq=None, outer=False, outputs=None,
+                    attenuation="dense", pinned=False, out=None):
+        """
+        Trace all pairs in one device pass (host arrays in, host arrays out).
+
+        X1: (Nv, 3) start points (vertices); X2: (Na, 3) end points (antennas).
+        outer=False: Na == Nv (or Na == 1), pair i = (X1[i], X2[i]);  outer=True: all Nv x Na pairs, vertex-major.
+        frequency / max_detector_freq: as in `get_attenuation`; if given, attenuation factors are computed
+        (`attenuation` = "dense": on `frequency`; "sparse": at the integration frequencies; "both").
+        outputs: iterable of field names (default: everything but attenuation).  pinned=True allocates page-locked
+        result arrays; `out` may pass a previous BatchResult of the same shape to reuse its buffers.
+        """
+        X1 = np.asarray(X1, dtype=np.float64).reshape(-1, 3)
+        X2 = np.asarray(X2, dtype=np.float64).reshape(-1, 3)
+        if not outer and X2.shape[0] == 1 and X1.shape[0] != 1:
+            X2 = np.repeat(X2, X1.shape[0], axis=0)
+        if not outer and X1.shape[0] != X2.shape[0]:
+            raise ValueError("X1 and X2 must have the same number of points unless outer=True")
+        v = np.ascontiguousarray(X1.T)
+        a = np.ascontiguousarray(X2.T)
+        N = X1.shape[0] * X2.shape[0] if outer else X1.shape[0]
+        h = self._h()
+        names = list(outputs) if outputs is not None else list(DEFAULT_OUTPUTS)
+        Fs = F = 0
+        if frequency is not None:
+            sp = self._set_frequencies(frequency, max_detector_freq)
+            Fs, F = len(sp), len(frequency)
+            if attenuation in ("dense", "both") and "attenuation" not in names:
+                names.append("attenuation")
+            if attenuation in ("sparse", "both") and "attenuation_sparse" not in names:
+                names.append("attenuation_sparse")
+        elif any(n in ("attenuation", "attenuation_sparse") for n in names):
+            raise ValueError("attenuation outputs need `frequency`")
+        S, K1 = self.get_number_of_raytracing_solutions(), self._n_reflections + 1
+        res = out if out is not None else BatchResult()
+        keep = []
+        o = _lib.Output()
+        for name in names:
+            dtype, trail = _OUT_SPECS[name]
+            shape = (N,) + trail(S, K1, Fs, F)
+            if name in res and res[name].shape == shape:
+                arr = res[name]
+            elif pinned:
+                pa = PinnedArray(shape, dtype)
+                keep.append(pa)
+                arr = pa.array
+            else:
+                arr = np.empty(shape, dtype=dtype)
+            res[name] = arr
+            setattr(o, name, arr.ctypes.data)
+        if keep:
+            res._keep = (res._keep or []) + keep
+        inp = _lib.Input()
+        inp.n_vertices, inp.vx, inp.vy, inp.vz = X1.shape[0], v[0].ctypes.data, v[1].ctypes.data, v[2].ctypes.data
+        inp.n_antennas, inp.ax, inp.ay, inp.az = X2.shape[0], a[0].ctypes.data, a[1].ctypes.data, a[2].ctypes.data
+        inp.outer, inp.memory = int(bool(outer)), _lib.MEMORY_HOST
+        st = _lib.Stats()
+        _lib.check(_lib.load().nrmc_rt_trace(h.ptr, C.byref(inp), C.byref(o), None, C.byref(st)), h.ptr, "trace")
+        res.stats = {k: getattr(st, k) for k, _ in _lib.Stats._fields_}
+        res.frequencies_sparse = h.sparse if frequency is not None else None
+        return res
+
+    def trace_batch_device(self, v, a, frequency=None, max_detector_freq=None, outer=False, outputs=None,
+                           attenuation="sparse", out=None, sync_stats=False):
+        """
+        Device-resident variant: `v` (3, Nv) and `a` (3, Na) are contiguous float64 CUDA torch tensors (SoA); the results
+        are CUDA torch tensors, the kernels are enqueued on torch's current stream.  Used by bench.py for the
+        HBM-resident number and by callers that keep the next stage on the GPU.
+        """
+        import torch
+        assert v.is_cuda and a.is_cuda and v.dtype == torch.float64 and a.dtype == torch.float64
+        assert v.dim() == 2 and v.shape[0] == 3 and a.dim() == 2 and a.shape[0] == 3 and v.is_contiguous() and a.is_contiguous()
+        Nv, Na = v.shape[1], a.shape[1]
+        N = Nv * Na if outer else Nv
+        h = self._h()
+        names = list(outputs) if outputs is not None else list(DEFAULT_OUTPUTS)
+        Fs = F = 0
+        if frequency is not None:
+            sp = self._set_frequencies(frequency, max_detector_freq)
+            Fs, F = len(sp), len(frequency)
+            if attenuation in ("dense", "both") and "attenuation" not in names:
+                names.append("attenuation")
+            if attenuation in ("sparse", "both") and "attenuation_sparse" not in names:
+                names.append("attenuation_sparse")
+        S, K1 = self.get_number_of_raytracing_solutions(), self._n_reflections + 1
+        res = out if out is not None else BatchResult()
+        o = _lib.Output()
+        tdt = {np.int32: torch.int32, np.int8: torch.int8, np.float64: torch.float64}
+        for name in names:
+            dtype, trail = _OUT_SPECS[name]
+            shape = (N,) + trail(S, K1, Fs, F)
+            if not (name in res and tuple(res[name].shape) == shape):
+                res[name] = torch.empty(shape, dtype=tdt[dtype], device=v.device)
+            setattr(o, name, res[name].data_ptr())
+        inp = _lib.Input()
+        inp.n_vertices, inp.vx, inp.vy, inp.vz = Nv, v[0].data_ptr(), v[1].data_ptr(), v[2].data_ptr()
+        inp.n_antennas, inp.ax, inp.ay, inp.az = Na, a[0].data_ptr(), a[1].data_ptr(), a[2].data_ptr()
+        inp.outer, inp.memory = int(bool(outer)), _lib.MEMORY_DEVICE
+        stream = torch.cuda.current_stream(v.device).cuda_stream
+        st = _lib.Stats()
+        _lib.check(_lib.load().nrmc_rt_trace(h.ptr, C.byref(inp), C.byref(o), C.c_void_p(stream),
+                                             C.byref(st) if sync_stats else None), h.ptr, "trace")
+        res.stats = {k: getattr(st, k) for k, _ in _lib.Stats._fields_} if sync_stats else None
+        res.frequencies_sparse = h.sparse if frequency is not None else None
+        return res
+
+    def prepare_batch(self, X1, X2, outer=False, **kwargs):
+        """
+        Trace many pairs ahead of a scalar loop (e.g. all (shower, channel) pairs of an event group in
+        NuRadioMC/simulation/simulation.py:155-210).  Afterwards `set_start_and_end_point(x1, x2)` +
+        `find_solutions()` on one of these pairs is a cache lookup instead of a kernel launch.
+        """
+        X1 = np.asarray(X1, dtype=np.float64).reshape(-1, 3)
+        X2 = np.asarray(X2, dtype=np.float64).reshape(-1, 3)
+        res = self.trace_batch(X1, X2, outer=outer, **kwargs)
+        lookup = {}
+        if outer:
+            na = X2.shape[0]
+            for i in range(X1.shape[0]):
+                for j in range(na):
+                    lookup[X1[i].tobytes() + X2[j].tobytes()] = i * na + j
+        else:
+            X2b = X2 if X2.shape[0] == X1.shape[0] else np.repeat(X2, X1.shape[0], axis=0)
+            for i in range(X1.shape[0]):
+                lookup[X1[i].tobytes() + X2b[i].tobytes()] = i
+        self._batch = (lookup, res)
+        return res
+
+    # ------------------------------------------------------------------------------------------------------
+    # the reference's scalar API
+    # ------------------------------------------------------------------------------------------------------
+    def reset_solutions(self):
+        super().reset_solutions()
+        self._x1 = None
+        self._x2 = None
+        self._swap = None
+        self._cache = None
+        self._att_cache = {}
+        self._batch_index = None
+
+    def set_start_and_end_point(self, x1, x2):
+        super().set_start_and_end_point(x1, x2)
+        # 2-D frame as exposed by the reference (:2072-2089): deeper point first, rho along +x
+        self._swap = bool(self._X2[2] < self._X1[2])
+        A, B = (self._X2, self._X1) if self._swap else (self._X1, self._X2)
+        self._x1 = np.array([A[0], A[2]])
+        self._x2 = np.array([A[0] + np.hypot(B[0] - A[0], B[1] - A[1]), B[2]])
+
+    def set_solution(self, raytracing_results):
+        """Read an already calculated raytracing solution from the input array (:2092-2116)"""
+        results = []
+        C0s = raytracing_results['ray_tracing_C0']
+        for i in range(len(C0s)):
+            if not np.isnan(C0s[i]):
+                if 'ray_tracing_reflection' in raytracing_results.keys():
+                    reflection = raytracing_results['ray_tracing_reflection'][i]
+                    reflection_case = raytracing_results['ray_tracing_reflection_case'][i]
+                else:
+                    reflection = 0
+                    reflection_case = 0
+                results.append({'type': raytracing_results['ray_tracing_solution_type'][i], 'C0': C0s[i],
+                                'C1': raytracing_results['ray_tracing_C1'][i], 'reflection': reflection,
+                                'reflection_case': reflection_case})
+        self._results = results
+
+    def find_solutions(self):
+        """find all solutions between x1 and x2 (:2118-2130)"""
+        if self._X1 is None:
+            raise AttributeError("set_start_and_end_point has to be called before find_solutions")
+        src, idx = None, None
+        if self._batch is not None:
+            idx = self._batch[0].get(self._X1.tobytes() + self._X2.tobytes())
+            if idx is not None:
+                src = self._batch[1]
+        if src is None:
+            src, idx = self.trace_batch(self._X1[None, :], self._X2[None, :]), 0
+        self._batch_index = idx if (self._batch is not None and src is self._batch[1]) else None
+        n = int(src["n_sol"][idx])
+        self._cache = {k: np.array(src[k][idx]) for k in DEFAULT_OUTPUTS if k in src}
+        self._results = [{'type': int(self._cache["solution_type"][s]), 'C0': float(self._cache["C0"][s]),
+                          'C1': float(self._cache["C1"][s]), 'reflection': int(self._cache["reflection"][s]),
+                          'reflection_case': int(self._cache["reflection_case"][s])} for s in range(n)]
+
+    def _check(self, iS):
+        n = self.get_number_of_solutions()
+        if iS >= n:
+            self.__logger.error("solution number {:d} requested but only {:d} solutions exist".format(iS + 1, n))
+            raise IndexError
+
+    def _need_cache(self):
+        if self._cache is None:
+            raise AttributeError("find_solutions has to be called first (solutions injected with set_solution carry no "
+                                 "geometry; call set_start_and_end_point + find_solutions)")
+
+    def get_solution_type(self, iS):
+        self._check(iS)
+        if self._cache is None:
+            return self._results[iS]['type']
+        return int(self._cache["solution_type"][iS])
+
+    def get_launch_vector(self, iS):
+        self._check(iS)
+        self._need_cache()
+        return np.array(self._cache["launch_vector"][iS])
+
+    def get_receive_vector(self, iS):
+        self._check(iS)
+        self._need_cache()
+        return np.array(self._cache["receive_vector"][iS])
+
+    def get_reflection_angle(self, iS):
+        """angle of reflection at the surface: None for direct/refracted rays; array (one entry per path segment)
+        when bottom reflections are simulated (:2626-2648, np.squeeze of a per-segment list :1237)"""
+        self._check(iS)
+        self._need_cache()
+        k = self._results[iS]['reflection']
+        ang = self._cache["reflection_angle"][iS][:k + 1]
+        vals = [None if np.isnan(a) else float(a) for a in ang]
+        return np.squeeze(vals)
+
+    def get_path_length(self, iS, analytic=True):
+        self._check(iS)
+        self._need_cache()
+        return float(self._cache["path_length"][iS])
+
+    def get_travel_time(self, iS, analytic=True):
+        self._check(iS)
+        self._need_cache()
+        return float(self._cache["travel_time"][iS])
+
+    def get_attenuation(self, iS, frequency, max_detector_freq=None):
+        """fraction of the signal that reaches the observer per frequency (:2744-2776)"""
+        self._check(iS)
+        frequency = np.asarray(frequency, dtype=np.float64)
+        key = (frequency.tobytes(), max_detector_freq)
+        if key not in self._att_cache:
+            res = self.trace_batch(self._X1[None, :], self._X2[None, :], frequency=frequency,
+                                   max_detector_freq=max_detector_freq, outputs=("n_sol",), attenuation="dense")
+            self._att_cache[key] = res["attenuation"][0]
+        return np.array(self._att_cache[key][iS])
+
+    def get_path(self, iS, n_points=1000):
+        """not on the hot path (path sampling is plotting support) -- not provided"""
+        raise NotImplementedError("get_path (path sampling for plotting) is outside the scope of nuradiomc_b200")
+
+    def get_output_parameters(self):
+        return [
+            {'name': 'ray_tracing_C0', 'ndim': 1},
+            {'name': 'ray_tracing_C1', 'ndim': 1},
+            {'name': 'focusing_factor', 'ndim': 1},
+            {'name': 'ray_tracing_reflection', 'ndim': 1},
+            {'name': 'ray_tracing_reflection_case', 'ndim': 1},
+            {'name': 'ray_tracing_solution_type', 'ndim': 1}
+        ]
+
+    def get_raytracing_output(self, i_solution):
+        if self._config['propagation']['focusing']:
+            raise NotImplementedError("focusing is outside the scope of nuradiomc_b200 (SURVEY.md section 8a)")
+        return {
+            'ray_tracing_C0': self.get_results()[i_solution]['C0'],
+            'ray_tracing_C1': self.get_results()[i_solution]['C1'],
+            'ray_tracing_reflection': self.get_results()[i_solution]['reflection'],
+            'ray_tracing_reflection_case': self.get_results()[i_solution]['reflection_case'],
+            'ray_tracing_solution_type': self.get_solution_type(i_solution),
+            'focusing_factor': 1
+        }
+
+    def set_config(self, config):
+        """default config as the reference (:3035-3052)"""
+        if config is None:
+            self._config = {'propagation': {}}
+            self._config['propagation']['attenuate_ice'] = True
+            self._config['propagation']['focusing_limit'] = 2
+            self._config['propagation']['focusing'] = False
+            self._config['propagation']['birefringence'] = False
+        else:
+            self._config = config
+
+
+def measure_fp64_peak(device=0, seconds=1.0):
+    """measured FP64 FMA peak [TFLOP/s] of the device (roofline denominator), and the nominal SM clock [MHz]"""
+    t, clk = C.c_double(), C.c_double()
+    _lib.check(_lib.load().nrmc_rt_measure_fp64_peak(device, seconds, C.byref(t), C.byref(clk)), None, "fp64_peak")
+    return t.value, clk.value

@@ -1,0 +1,780 @@
+// nrmc_rt.cu -- sm_100a kernels and the C ABI (include/nrmc_rt.h) of the batched analytic ray tracer.
+//
+//   K_solve        one thread per (vertex, antenna) pair: 2-D frame, all (reflection, case) modes, bracketed FP64 root
+//                  finding on Snell's invariant, closed-form properties, SoA stores; warp-aggregated (ballot/shuffle)
+//                  compaction of the found solutions into a work list for K_att.
+//   K_att          one warp per solution: 2 x 16 Gauss-Legendre nodes per pass (half-warp per u-panel), per-frequency
+//                  constants staged in shared memory with a TMA bulk copy (cp.async.bulk + mbarrier), half-warp shuffle
+//                  reduction of the path integral, exp, np.interp-equivalent expansion to the output frequency grid.
+//   K_fp64_peak    independent DFMA chains: measures the FP64 roofline denominator.
+//
+// No tensor cores: nothing here is a contraction.  There is no CPU fallback: every entry point
+// fails with NRMC_ERR_NO_DEVICE / NRMC_ERR_CUDA if the device path is unavailable.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <cmath>
+#include <string>
+#include <vector>
+
+#include "../../include/nrmc_rt.h"
+#include "nrmc_att.cuh"
+
+using namespace nrmc;
+
+// ---------------------------------------------------------------------------------------------------------------
+// device side
+// ---------------------------------------------------------------------------------------------------------------
+struct KInput {
+    const double *vx, *vy, *vz, *ax, *ay, *az;
+    int64_t n_pairs;       // pairs in this launch
+    int64_t n_antennas;    // outer-product divisor (1 pair = vertex p / n_antennas, antenna p % n_antennas) if outer
+    int32_t outer;
+};
+
+__device__ __forceinline__ void load_pair(const KInput &in, int64_t p, double &x1, double &y1, double &z1, double &x2,
+                                          double &y2, double &z2)
+{
+    int64_t iv = p, ia = p;
+    if (in.outer) { iv = p / in.n_antennas; ia = p - iv * in.n_antennas; }
+    x1 = __ldg(in.vx + iv); y1 = __ldg(in.vy + iv); z1 = __ldg(in.vz + iv);
+    x2 = __ldg(in.ax + ia); y2 = __ldg(in.ay + ia); z2 = __ldg(in.az + ia);
+}
+
+#define SOLVE_THREADS 128
+#define MAX_S (2 + 4 * NRMC_MAX_REFLECTIONS)
+
+__global__ void __launch_bounds__(SOLVE_THREADS)
+K_solve(IceParams ice, KInput in, TraceOutputs out, SolRec *worklist, unsigned long long *work_count)
+{
+    const int64_t p = (int64_t)blockIdx.x * SOLVE_THREADS + threadIdx.x;
+    const unsigned lane = threadIdx.x & 31u;
+    SolRec recs[MAX_S];
+    int n = 0;
+    if (p < in.n_pairs) {
+        double x1, y1, z1, x2, y2, z2;
+        load_pair(in, p, x1, y1, z1, x2, y2, z2);
+        n = trace_pair(ice, x1, y1, z1, x2, y2, z2, p, out, worklist ? recs : nullptr);
+    }
+    if (worklist) {
+        // warp-aggregated append: inclusive scan of the per-lane counts, one atomic per warp
+        int incl = n;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= (unsigned)d) incl += t;
+        }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        unsigned long long base = 0;
+        if (lane == 31 && total > 0) base = atomicAdd(work_count, (unsigned long long)total);
+        base = __shfl_sync(0xffffffffu, base, 31);
+        if (total > 0) {
+            SolRec *dst = worklist + base + (unsigned long long)(incl - n);
+            for (int j = 0; j < n; ++j) dst[j] = recs[j];
+        }
+    }
+}
+
+// ---- TMA bulk copy helpers (1-D, global -> shared, completion on an mbarrier) --------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    }
+}
+__device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+struct AttTables {            // device pointers, every array padded to a multiple of 16 bytes
+    const double *fa, *fb;    // [Fs_pad] per integration frequency constants (att_freq_consts)
+    const double *it;         // [F_pad]  interpolation weight t of every output bin
+    const int32_t *ii;        // [F_pad]  left sparse index of every output bin; -1: bin <= 0 Hz (factor 1)
+    int32_t Fs, Fs_pad, F, F_pad;
+    Gl3Table gl3;
+};
+
+#define ATT_WARPS 4
+#define ATT_THREADS (ATT_WARPS * 32)
+
+// dynamic shared memory layout (doubles): fa[Fs_pad] fb[Fs_pad] it[F_pad] | ii[F_pad] (int32) | per warp: H[4][Fs_pad] fac[nseg][Fs_pad]
+__global__ void __launch_bounds__(ATT_THREADS)
+K_att(IceParams ice, KInput in, AttTables tb, const SolRec *worklist, const unsigned long long *work_count, int nseg_max,
+      double *att_sparse, double *att_dense)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t bar;
+    double *s_fa = reinterpret_cast<double *>(smem_raw);
+    double *s_fb = s_fa + tb.Fs_pad;
+    double *s_it = s_fb + tb.Fs_pad;
+    int32_t *s_ii = reinterpret_cast<int32_t *>(s_it + tb.F_pad);
+    double *s_warp = reinterpret_cast<double *>(s_ii + tb.F_pad + (tb.F_pad & 1));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int per_warp = (NRMC_MAX_SLOTS + nseg_max) * tb.Fs_pad;
+    double *H = s_warp + warp * per_warp;            // [4][Fs_pad] slot sums
+    double *fac = H + NRMC_MAX_SLOTS * tb.Fs_pad;    // [nseg][Fs_pad] exp(-I_seg)
+
+    // stage the per-frequency tables with TMA bulk copies (one elected thread issues, everybody waits on the mbarrier)
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t b_fs = (uint32_t)tb.Fs_pad * 8u, b_it = (uint32_t)tb.F_pad * 8u, b_ii = (uint32_t)tb.F_pad * 4u;
+        mbar_expect_tx(&bar, 2u * b_fs + b_it + b_ii);
+        tma_bulk_g2s(s_fa, tb.fa, b_fs, &bar);
+        tma_bulk_g2s(s_fb, tb.fb, b_fs, &bar);
+        if (b_it) { tma_bulk_g2s(s_it, tb.it, b_it, &bar); tma_bulk_g2s(s_ii, tb.ii, b_ii, &bar); }
+    }
+    mbar_wait(&bar, 0);
+
+    const double glx[8] = NRMC_GL16_X, glw[8] = NRMC_GL16_W;
+    const int q = lane & 15, half = lane >> 4;
+    const double xq = (q < 8) ? -glx[7 - q] : glx[q - 8];
+    const double wq = (q < 8) ? glw[7 - q] : glw[q - 8];
+
+    const unsigned long long n_work = *work_count;
+    const int S = 2 + 4 * ice.n_refl;
+    for (unsigned long long w = (unsigned long long)blockIdx.x * ATT_WARPS + warp; w < n_work;
+         w += (unsigned long long)gridDim.x * ATT_WARPS) {
+        const SolRec rec = worklist[w];
+        // rebuild the ray (warp-uniform)
+        double x1, y1, z1, x2, y2, z2;
+        load_pair(in, rec.pair, x1, y1, z1, x2, y2, z2);
+        Frame2D f;
+        make_frame(x1, y1, z1, x2, y2, z2, f);
+        PairGeom g;
+        make_pair_geom(ice, f.z1, f.z2, fmax(f.rho, 1e-12), g);
+        RayState rs;
+        ray_state(ice, g, (rec.piece == 1 || rec.piece == 2), rec.v, rs);
+        AttPlan plan;
+        att_plan(ice, g, rec.piece, rec.k, rec.rcase, rs, plan);
+
+        // quadrature: each half-warp integrates one 16-node slot per pass
+        for (int pass = 0; pass * 2 < plan.n_slots; ++pass) {
+            const int slot = pass * 2 + half;
+            double z, wds;
+            att_node_geometry(ice, plan, slot, xq, wq, z, wds);
+            AttNode nd;
+            att_node(ice.att_model, z, tb.gl3, nd);
+            for (int j = 0; j < tb.Fs; ++j) {
+                double term = wds * att_inv_length(ice.att_model, nd, s_fa[j], s_fb[j]);
+                term += __shfl_xor_sync(0xffffffffu, term, 8);
+                term += __shfl_xor_sync(0xffffffffu, term, 4);
+                term += __shfl_xor_sync(0xffffffffu, term, 2);
+                term += __shfl_xor_sync(0xffffffffu, term, 1);
+                if (q == 0) H[slot * tb.Fs_pad + j] = term;
+            }
+        }
+        __syncwarp();
+        // per segment: I_seg = sum_slot mult[seg][panel(slot)] * H[slot];  factor = exp(-I_seg)   (py:1075)
+        const int64_t slot_index = rec.pair * S + rec.slot;
+        for (int j = lane; j < tb.Fs; j += 32) {
+            double prod = 1.0;
+            for (int s = 0; s < plan.nseg; ++s) {
+                double I = 0.0;
+                for (int t = 0; t < plan.n_slots; ++t) I += (double)plan.mult[s][plan.panel[t]] * H[t * tb.Fs_pad + j];
+                const double e = exp(-I);
+                fac[s * tb.Fs_pad + j] = e;
+                prod *= e;
+            }
+            if (att_sparse) att_sparse[slot_index * tb.Fs + j] = prod;
+        }
+        __syncwarp();
+        if (att_dense) {
+            // np.interp of every segment's factors onto the output grid, product over segments (py:1077-1078,1086)
+            double *dst = att_dense + slot_index * tb.F;
+            for (int b = lane; b < tb.F; b += 32) {
+                const int i0 = s_ii[b];
+                double val = 1.0;
+                if (i0 >= 0) {
+                    const double t = s_it[b];
+                    for (int s = 0; s < plan.nseg; ++s) {
+                        const double f0 = fac[s * tb.Fs_pad + i0], f1 = fac[s * tb.Fs_pad + i0 + 1];
+                        val *= (f1 - f0) * t + f0;
+                    }
+                }
+                dst[b] = val;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// fills the attenuation slots of pairs that have fewer than S solutions with NaN
+__global__ void K_att_fill(const int32_t *n_sol, int64_t n_pairs, int S, int Fs, int F, double *att_sparse, double *att_dense)
+{
+    const int64_t total = n_pairs * S;
+    for (int64_t q = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); q < total;
+         q += (int64_t)gridDim.x * (blockDim.x >> 5)) {
+        const int64_t p = q / S;
+        const int s = (int)(q - p * S);
+        if (s < n_sol[p]) continue;
+        const int lane = threadIdx.x & 31;
+        if (att_sparse) for (int j = lane; j < Fs; j += 32) att_sparse[q * Fs + j] = NAN;
+        if (att_dense) for (int j = lane; j < F; j += 32) att_dense[q * F + j] = NAN;
+    }
+}
+
+__global__ void K_att_length(IceParams ice, Gl3Table gl3, const double *z, const double *f, int64_t n, double *out)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    AttNode nd;
+    att_node(ice.att_model, z[i], gl3, nd);
+    double fa, fb;
+    att_freq_consts(ice.att_model, f[i], fa, fb);
+    const double inv = att_inv_length(ice.att_model, nd, fa, fb);
+    out[i] = (z[i] > 0.0) ? INFINITY : 1.0 / inv;   // attenuation.py:256-257
+}
+
+// FP64 roofline denominator: 8 independent FMA chains per thread
+__global__ void K_fp64_peak(double *out, int iters)
+{
+    double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double m = 1.0000001, c = 1e-7;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+            a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+        }
+    }
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------------
+#define CK(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess) {                                                                         \
+            h->err = std::string(#call) + ": " + cudaGetErrorString(e_);                                 \
+            return NRMC_ERR_CUDA;                                                                        \
+        }                                                                                                \
+    } while (0)
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct Lane {               // one pipeline lane (stream + scratch) for host-memory calls
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    DevBuf in, out, work;
+    bool timed = false;
+};
+
+struct nrmc_rt_s {
+    nrmc_rt_config cfg;
+    IceParams ice;
+    int S = 2, K1 = 1, n_sm = 148;
+    std::string err;
+    // frequencies
+    std::vector<double> freq_out, freq_sparse;
+    AttTables tb;
+    DevBuf d_tables, d_gl3;
+    bool have_freq = false;
+    Lane lanes[2];
+    DevBuf d_count;       // work-list counters (one per lane)
+    DevBuf d_ant;         // antenna table for outer-product host calls
+};
+
+static void numpy_linspace(double a, double b, int n, std::vector<double> &out)
+{
+    if (n <= 0) return;
+    if (n == 1) { out.push_back(a); return; }
+    const double step = (b - a) / (n - 1);
+    for (int i = 0; i < n - 1; ++i) out.push_back(a + i * step);
+    out.push_back(b);
+}
+
+extern "C" {
+
+const char *nrmc_rt_version(void) { return "nrmc_rt 0.1 (sm_100a)"; }
+
+int nrmc_rt_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+int nrmc_rt_create(const nrmc_rt_config *cfg, nrmc_rt_t *out)
+{
+    if (!cfg || !out) return NRMC_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    if (!(cfg->n_ice > 1.0) || !(cfg->delta_n > 0.0) || !(cfg->delta_n < cfg->n_ice) || !(cfg->z_0 > 0.0)) return NRMC_ERR_INVALID_ARGUMENT;
+    if (cfg->n_reflections < 0 || cfg->n_reflections > NRMC_MAX_REFLECTIONS) return NRMC_ERR_UNSUPPORTED;
+    if (cfg->attenuation_model < 0 || cfg->attenuation_model > 5) return NRMC_ERR_UNSUPPORTED;
+    if (cfg->attenuation_model == NRMC_ATT_GL3 && (!cfg->gl3_table || cfg->gl3_rows < 2)) return NRMC_ERR_INVALID_ARGUMENT;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || cfg->device < 0 || cfg->device >= ndev) return NRMC_ERR_NO_DEVICE;
+    nrmc_rt_s *h = new nrmc_rt_s();
+    h->cfg = *cfg;
+    IceParams &ice = h->ice;
+    ice.n_ice = cfg->n_ice; ice.dn = cfg->delta_n; ice.z0 = cfg->z_0; ice.inv_z0 = 1.0 / cfg->z_0;
+    ice.ns = cfg->n_ice - cfg->delta_n;
+    int n_refl = cfg->n_reflections;
+    if (n_refl > 0 && !(cfg->reflection_z == cfg->reflection_z)) n_refl = 0;   // propagation_base_class.py:128-133
+    ice.n_refl = n_refl;
+    ice.zr = n_refl > 0 ? cfg->reflection_z : -1e30;
+    ice.gr = n_refl > 0 ? ice.dn * exp(ice.zr * ice.inv_z0) : 0.0;
+    ice.nr = ice.n_ice - ice.gr;
+    ice.att_model = cfg->attenuation_model;
+    h->S = 2 + 4 * n_refl;
+    h->K1 = n_refl + 1;
+    memset(&h->tb, 0, sizeof(h->tb));
+    if (cudaSetDevice(cfg->device) != cudaSuccess) { delete h; return NRMC_ERR_NO_DEVICE; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess) { delete h; return NRMC_ERR_NO_DEVICE; }
+    h->n_sm = prop.multiProcessorCount;
+    for (int l = 0; l < 2; ++l) {
+        if (cudaStreamCreateWithFlags(&h->lanes[l].stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return NRMC_ERR_CUDA; }
+        for (int e = 0; e < 6; ++e) cudaEventCreate(&h->lanes[l].ev[e]);
+    }
+    if (h->d_count.reserve(64) != cudaSuccess) { delete h; return NRMC_ERR_CUDA; }
+    if (cfg->attenuation_model == NRMC_ATT_GL3) {
+        const size_t bytes = (size_t)cfg->gl3_rows * 3 * sizeof(double);
+        if (h->d_gl3.reserve(bytes) != cudaSuccess ||
+            cudaMemcpy(h->d_gl3.p, cfg->gl3_table, bytes, cudaMemcpyHostToDevice) != cudaSuccess) { delete h; return NRMC_ERR_CUDA; }
+        h->tb.gl3.rows = (const double *)h->d_gl3.p;
+        h->tb.gl3.n = cfg->gl3_rows;
+    }
+    *out = h;
+    return NRMC_OK;
+}
+
+void nrmc_rt_destroy(nrmc_rt_t h)
+{
+    if (!h) return;
+    cudaSetDevice(h->cfg.device);
+    for (int l = 0; l < 2; ++l) {
+        if (h->lanes[l].stream) { cudaStreamSynchronize(h->lanes[l].stream); cudaStreamDestroy(h->lanes[l].stream); }
+        for (int e = 0; e < 6; ++e) if (h->lanes[l].ev[e]) cudaEventDestroy(h->lanes[l].ev[e]);
+        h->lanes[l].in.release(); h->lanes[l].out.release(); h->lanes[l].work.release();
+    }
+    h->d_tables.release(); h->d_gl3.release(); h->d_count.release(); h->d_ant.release();
+    delete h;
+}
+
+const char *nrmc_rt_last_error(nrmc_rt_t h) { return h ? h->err.c_str() : "null handle"; }
+int nrmc_rt_max_solutions(nrmc_rt_t h) { return h ? h->S : NRMC_ERR_INVALID_ARGUMENT; }
+
+int nrmc_rt_set_frequencies(nrmc_rt_t h, const double *frequency, int32_t n, double max_detector_freq)
+{
+    if (!h || !frequency || n <= 0) return NRMC_ERR_INVALID_ARGUMENT;
+    if (h->ice.att_model == 0) { h->err = "no attenuation model configured"; return NRMC_ERR_UNSUPPORTED; }
+    cudaSetDevice(h->cfg.device);
+    // --- __get_frequencies_for_attenuation, analyticraytracing.py:885-931 ---
+    const int n_int = h->cfg.n_frequencies_integration > 0 ? h->cfg.n_frequencies_integration : 100;
+    int n_nonnull = 0;
+    double flo = INFINITY, fhi = -INFINITY;
+    for (int i = 0; i < n; ++i) if (frequency[i] > 0) { ++n_nonnull; flo = std::min(flo, frequency[i]); fhi = std::max(fhi, frequency[i]); }
+    if (n_nonnull == 0) { h->err = "no frequency above 0"; return NRMC_ERR_NO_FREQUENCIES; }
+    std::vector<double> sp;
+    int nf = std::min(n_int, n_nonnull);
+    numpy_linspace(flo, fhi, nf, sp);
+    if (nf < n_nonnull && max_detector_freq == max_detector_freq) {
+        int n_tot = 0, n_above = 0;
+        double tlo = INFINITY, thi = -INFINITY, alo = INFINITY, ahi = -INFINITY;
+        for (int i = 0; i < n; ++i) {
+            const bool det = frequency[i] <= max_detector_freq;
+            if (det && frequency[i] > 0) { ++n_tot; tlo = std::min(tlo, frequency[i]); thi = std::max(thi, frequency[i]); }
+            if (!det) { ++n_above; alo = std::min(alo, frequency[i]); ahi = std::max(ahi, frequency[i]); }
+        }
+        if (n_tot == 0) { h->err = "no frequency in (0, max_detector_freq]"; return NRMC_ERR_NO_FREQUENCIES; }
+        nf = std::min(n_int, n_tot);
+        sp.clear();
+        numpy_linspace(tlo, thi, nf, sp);
+        if (n_above > 1) numpy_linspace(alo, ahi, nf / 2, sp);
+    }
+    const int Fs = (int)sp.size();
+    const int Fs_pad = (Fs + 1) & ~1, F_pad = (n + 3) & ~3;
+    // --- np.interp tables (py:1077-1078): left index + weight per output bin; bins <= 0 Hz keep factor 1 ---
+    std::vector<double> fa(Fs_pad, 0.0), fb(Fs_pad, 0.0), it(F_pad, 0.0);
+    std::vector<int32_t> ii(F_pad, -1);
+    for (int j = 0; j < Fs; ++j) att_freq_consts(h->ice.att_model, sp[j], fa[j], fb[j]);
+    for (int b = 0; b < n; ++b) {
+        const double x = frequency[b];
+        if (!(x > 0)) { ii[b] = -1; continue; }
+        if (Fs == 1) { ii[b] = 0; it[b] = 0.0; continue; }   // handled below: i0+1 must stay in range
+        if (x <= sp[0]) { ii[b] = 0; it[b] = 0.0; }
+        else if (x >= sp[Fs - 1]) { ii[b] = Fs - 2; it[b] = 1.0; }
+        else {
+            int lo = 0, hi = Fs - 1;
+            while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (sp[mid] <= x) lo = mid; else hi = mid; }
+            ii[b] = lo;
+            it[b] = (x - sp[lo]) / (sp[hi] - sp[lo]);
+        }
+    }
+    if (Fs == 1) { fa.resize(2, fa[0]); fb.resize(2, fb[0]); }   // Fs_pad == 2: duplicate so that i0+1 is valid
+    const size_t bytes = (size_t)Fs_pad * 16 + (size_t)F_pad * 12 + 64;
+    CK(h->d_tables.reserve(bytes));
+    unsigned char *base = (unsigned char *)h->d_tables.p;
+    double *d_fa = (double *)base, *d_fb = d_fa + Fs_pad, *d_it = d_fb + Fs_pad;
+    int32_t *d_ii = (int32_t *)(d_it + F_pad);
+    CK(cudaMemcpy(d_fa, fa.data(), Fs_pad * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_fb, fb.data(), Fs_pad * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_it, it.data(), F_pad * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_ii, ii.data(), F_pad * 4, cudaMemcpyHostToDevice));
+    h->tb.fa = d_fa; h->tb.fb = d_fb; h->tb.it = d_it; h->tb.ii = d_ii;
+    h->tb.Fs = Fs; h->tb.Fs_pad = Fs_pad; h->tb.F = n; h->tb.F_pad = F_pad;
+    h->freq_out.assign(frequency, frequency + n);
+    h->freq_sparse = sp;
+    h->have_freq = true;
+    return Fs;
+}
+
+int nrmc_rt_get_sparse_frequencies(nrmc_rt_t h, double *out, int32_t capacity)
+{
+    if (!h || !h->have_freq) return NRMC_ERR_NO_FREQUENCIES;
+    const int n = (int)h->freq_sparse.size();
+    if (out) for (int i = 0; i < n && i < capacity; ++i) out[i] = h->freq_sparse[i];
+    return n;
+}
+
+int nrmc_rt_host_alloc(void **ptr, uint64_t bytes)
+{
+    if (!ptr) return NRMC_ERR_INVALID_ARGUMENT;
+    return cudaHostAlloc(ptr, bytes, cudaHostAllocDefault) == cudaSuccess ? NRMC_OK : NRMC_ERR_CUDA;
+}
+int nrmc_rt_host_free(void *ptr) { return cudaFreeHost(ptr) == cudaSuccess ? NRMC_OK : NRMC_ERR_CUDA; }
+
+}  // extern "C"
+
+// enqueue the kernels for one chunk of pairs whose inputs/outputs are device resident
+static int launch_chunk(nrmc_rt_s *h, Lane &ln, int lane_id, const KInput &kin, const TraceOutputs &to, double *att_sparse,
+                        double *att_dense, int *n_launches)
+{
+    const bool want_att = (att_sparse || att_dense);
+    unsigned long long *d_count = (unsigned long long *)h->d_count.p + lane_id;
+    SolRec *wl = nullptr;
+    if (want_att) {
+        CK(ln.work.reserve((size_t)kin.n_pairs * h->S * sizeof(SolRec)));
+        wl = (SolRec *)ln.work.p;
+        CK(cudaMemsetAsync(d_count, 0, sizeof(unsigned long long), ln.stream));
+    }
+    if (ln.timed) cudaEventRecord(ln.ev[0], ln.stream);
+    const int64_t blocks = (kin.n_pairs + SOLVE_THREADS - 1) / SOLVE_THREADS;
+    K_solve<<<(unsigned)blocks, SOLVE_THREADS, 0, ln.stream>>>(h->ice, kin, to, wl, d_count);
+    ++*n_launches;
+    if (ln.timed) cudaEventRecord(ln.ev[1], ln.stream);
+    if (want_att) {
+        const AttTables &tb = h->tb;
+        const int nseg_max = h->ice.n_refl + 1;
+        const size_t smem = (size_t)tb.Fs_pad * 16 + (size_t)tb.F_pad * 8 + (size_t)(tb.F_pad + (tb.F_pad & 1)) * 4 +
+                            (size_t)ATT_WARPS * (NRMC_MAX_SLOTS + nseg_max) * tb.Fs_pad * 8;
+        if (smem > 48 * 1024) CK(cudaFuncSetAttribute(K_att, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        K_att_fill<<<h->n_sm * 8, 256, 0, ln.stream>>>(to.n_sol, kin.n_pairs, h->S, tb.Fs, tb.F, att_sparse, att_dense);
+        K_att<<<h->n_sm * 8, ATT_THREADS, smem, ln.stream>>>(h->ice, kin, tb, wl, d_count, nseg_max, att_sparse, att_dense);
+        *n_launches += 2;
+    }
+    if (ln.timed) cudaEventRecord(ln.ev[2], ln.stream);
+    CK(cudaGetLastError());
+    return NRMC_OK;
+}
+
+struct OutLayout {           // byte offsets of every output inside one contiguous per-chunk device block
+    size_t off[14];
+    size_t elem[14];         // bytes per pair
+    size_t total;
+};
+
+static void *out_ptr(const nrmc_rt_output *o, int i)
+{
+    switch (i) {
+    case 0: return o->n_sol; case 1: return o->status; case 2: return o->solution_type; case 3: return o->reflection;
+    case 4: return o->reflection_case; case 5: return o->C0; case 6: return o->C1; case 7: return o->path_length;
+    case 8: return o->travel_time; case 9: return o->launch_vector; case 10: return o->receive_vector;
+    case 11: return o->reflection_angle; case 12: return o->attenuation_sparse; case 13: return o->attenuation;
+    }
+    return nullptr;
+}
+
+extern "C" int nrmc_rt_trace(nrmc_rt_t h, const nrmc_rt_input *in, const nrmc_rt_output *out, void *stream, nrmc_rt_stats *stats)
+{
+    if (!h || !in || !out) return NRMC_ERR_INVALID_ARGUMENT;
+    if (in->n_vertices < 0 || in->n_antennas < 0) return NRMC_ERR_INVALID_ARGUMENT;
+    if (!in->outer && in->n_antennas != in->n_vertices) { h->err = "pair mode needs n_antennas == n_vertices"; return NRMC_ERR_INVALID_ARGUMENT; }
+    const int64_t N = in->outer ? in->n_vertices * in->n_antennas : in->n_vertices;
+    if (stats) memset(stats, 0, sizeof(*stats));
+    if (N == 0) return NRMC_OK;
+    if (!in->vx || !in->vy || !in->vz || !in->ax || !in->ay || !in->az) return NRMC_ERR_INVALID_ARGUMENT;
+    const bool want_att = out->attenuation_sparse || out->attenuation;
+    if (want_att && h->ice.att_model == 0) { h->err = "attenuation requested but no attenuation model configured"; return NRMC_ERR_UNSUPPORTED; }
+    if (want_att && !h->have_freq) { h->err = "attenuation requested before nrmc_rt_set_frequencies"; return NRMC_ERR_NO_FREQUENCIES; }
+    CK(cudaSetDevice(h->cfg.device));
+    const int S = h->S, K1 = h->K1, Fs = h->tb.Fs, F = h->tb.F;
+    const size_t elem[14] = {4, 4, (size_t)S, (size_t)S, (size_t)S, 8u * S, 8u * S, 8u * S, 8u * S, 24u * S, 24u * S,
+                             8u * S * K1, 8u * (size_t)S * Fs, 8u * (size_t)S * F};
+    int n_launches = 0;
+
+    if (in->memory == NRMC_MEMORY_DEVICE) {
+        // device-resident: the caller's pointers are used directly; chunked only to bound the work-list scratch
+        Lane &ln = h->lanes[0];
+        cudaStream_t user = (cudaStream_t)stream;
+        cudaStream_t saved = ln.stream;
+        ln.stream = user;
+        ln.timed = false;
+        cudaEvent_t e0 = ln.ev[3], e1 = ln.ev[4];
+        if (stats) cudaEventRecord(e0, user);
+        int64_t chunk = want_att ? (int64_t)1 << 24 : N;
+        if (in->outer && chunk < N) chunk = std::max<int64_t>(in->n_antennas, (chunk / in->n_antennas) * in->n_antennas);
+        float ms_solve = 0, ms_att = 0;
+        int rc = NRMC_OK, n_chunks = 0;
+        for (int64_t p0 = 0; p0 < N && rc == NRMC_OK; p0 += chunk, ++n_chunks) {
+            const int64_t np = std::min(chunk, N - p0);
+            KInput kin;
+            kin.outer = in->outer; kin.n_antennas = in->n_antennas; kin.n_pairs = np;
+            if (in->outer) {
+                // chunk boundaries must fall on whole vertices
+                if (p0 % in->n_antennas != 0) { rc = NRMC_ERR_INVALID_ARGUMENT; break; }
+                const int64_t v0 = p0 / in->n_antennas;
+                kin.vx = in->vx + v0; kin.vy = in->vy + v0; kin.vz = in->vz + v0;
+                kin.ax = in->ax; kin.ay = in->ay; kin.az = in->az;
+            } else {
+                kin.vx = in->vx + p0; kin.vy = in->vy + p0; kin.vz = in->vz + p0;
+                kin.ax = in->ax + p0; kin.ay = in->ay + p0; kin.az = in->az + p0;
+            }
+            TraceOutputs to;
+            to.n_sol = out->n_sol ? out->n_sol + p0 : nullptr;
+            to.status = out->status ? out->status + p0 : nullptr;
+            to.type = out->solution_type ? out->solution_type + p0 * S : nullptr;
+            to.reflection = out->reflection ? out->reflection + p0 * S : nullptr;
+            to.reflection_case = out->reflection_case ? out->reflection_case + p0 * S : nullptr;
+            to.C0 = out->C0 ? out->C0 + p0 * S : nullptr;
+            to.C1 = out->C1 ? out->C1 + p0 * S : nullptr;
+            to.path_length = out->path_length ? out->path_length + p0 * S : nullptr;
+            to.travel_time = out->travel_time ? out->travel_time + p0 * S : nullptr;
+            to.launch = out->launch_vector ? out->launch_vector + p0 * S * 3 : nullptr;
+            to.receive = out->receive_vector ? out->receive_vector + p0 * S * 3 : nullptr;
+            to.reflection_angle = out->reflection_angle ? out->reflection_angle + p0 * S * K1 : nullptr;
+            if (want_att && !to.n_sol) {   // the fill kernel needs n_sol
+                CK(ln.out.reserve((size_t)np * 4));
+                to.n_sol = (int32_t *)ln.out.p;
+            }
+            ln.timed = (stats != nullptr);
+            rc = launch_chunk(h, ln, 0, kin, to, out->attenuation_sparse ? out->attenuation_sparse + p0 * S * Fs : nullptr,
+                              out->attenuation ? out->attenuation + p0 * S * F : nullptr, &n_launches);
+            if (rc == NRMC_OK && stats) {
+                cudaEventSynchronize(ln.ev[2]);
+                if (want_att) {
+                    unsigned long long cnt = 0;
+                    cudaMemcpy(&cnt, h->d_count.p, sizeof(cnt), cudaMemcpyDeviceToHost);
+                    stats->n_solutions += (int64_t)cnt;
+                }
+                float a = 0, b = 0;
+                cudaEventElapsedTime(&a, ln.ev[0], ln.ev[1]);
+                cudaEventElapsedTime(&b, ln.ev[1], ln.ev[2]);
+                ms_solve += a; ms_att += b;
+            }
+        }
+        if (stats && rc == NRMC_OK) {
+            cudaEventRecord(e1, user);
+            CK(cudaEventSynchronize(e1));
+            cudaEventElapsedTime(&stats->ms_total, e0, e1);
+            stats->ms_solve = ms_solve; stats->ms_attenuation = ms_att;
+            stats->n_pairs = N; stats->n_launches = n_launches; stats->n_chunks = n_chunks;
+        }
+        ln.stream = saved;
+        ln.timed = false;
+        return rc;
+    }
+
+    // ---------------- host memory: chunked, two lanes (streams) so copies of one chunk overlap kernels of the other --------
+    const int64_t na = in->n_antennas;
+    size_t per_pair = 0;
+    bool want[14];
+    for (int i = 0; i < 14; ++i) { want[i] = out_ptr(out, i) != nullptr; }
+    const bool need_nsol_dev = want_att || want[0];
+    for (int i = 0; i < 14; ++i) if (want[i] || (i == 0 && need_nsol_dev)) per_pair += elem[i] + 16;
+    per_pair += h->S * sizeof(SolRec) + 48;
+    int64_t chunk = (int64_t)((size_t)1536 * 1024 * 1024 / per_pair);   // ~1.5 GB of device scratch per lane
+    chunk = std::max<int64_t>(chunk, 1024);
+    if (in->outer) chunk = std::max<int64_t>(na, (chunk / na) * na);
+    chunk = std::min(chunk, N);
+    if (N > chunk && N < 2 * chunk) { chunk = (N + 1) / 2; if (in->outer) chunk = ((chunk + na - 1) / na) * na; }
+    const double *d_ax = nullptr, *d_ay = nullptr, *d_az = nullptr;
+    int64_t h2d = 0, d2h = 0;
+    if (in->outer) {
+        CK(h->d_ant.reserve((size_t)na * 24));
+        double *a = (double *)h->d_ant.p;
+        CK(cudaMemcpyAsync(a, in->ax, na * 8, cudaMemcpyHostToDevice, h->lanes[0].stream));
+        CK(cudaMemcpyAsync(a + na, in->ay, na * 8, cudaMemcpyHostToDevice, h->lanes[0].stream));
+        CK(cudaMemcpyAsync(a + 2 * na, in->az, na * 8, cudaMemcpyHostToDevice, h->lanes[0].stream));
+        CK(cudaStreamSynchronize(h->lanes[0].stream));
+        d_ax = a; d_ay = a + na; d_az = a + 2 * na;
+        h2d += na * 24;
+    }
+    cudaEvent_t e0 = h->lanes[0].ev[3], e1 = h->lanes[0].ev[4];
+    cudaEventRecord(e0, h->lanes[0].stream);
+    float ms_solve = 0, ms_att = 0;
+    int n_chunks = 0;
+    int64_t n_solutions = 0;
+    for (int64_t p0 = 0; p0 < N; p0 += chunk, ++n_chunks) {
+        const int lid = n_chunks & 1;
+        Lane &ln = h->lanes[lid];
+        const int64_t np = std::min(chunk, N - p0);
+        if (n_chunks >= 2 && stats && ln.timed) {   // collect the timing of the chunk that used this lane before
+            cudaEventSynchronize(ln.ev[2]);
+            float a = 0, b = 0;
+            cudaEventElapsedTime(&a, ln.ev[0], ln.ev[1]); cudaEventElapsedTime(&b, ln.ev[1], ln.ev[2]);
+            ms_solve += a; ms_att += b;
+        }
+        // inputs
+        KInput kin;
+        kin.outer = in->outer; kin.n_antennas = na; kin.n_pairs = np;
+        const int64_t nv = in->outer ? np / na : np, v0 = in->outer ? p0 / na : p0;
+        const size_t in_bytes = (size_t)nv * 24 + (in->outer ? 0 : (size_t)np * 24);
+        CK(ln.in.reserve(in_bytes));
+        double *din = (double *)ln.in.p;
+        CK(cudaMemcpyAsync(din, in->vx + v0, nv * 8, cudaMemcpyHostToDevice, ln.stream));
+        CK(cudaMemcpyAsync(din + nv, in->vy + v0, nv * 8, cudaMemcpyHostToDevice, ln.stream));
+        CK(cudaMemcpyAsync(din + 2 * nv, in->vz + v0, nv * 8, cudaMemcpyHostToDevice, ln.stream));
+        kin.vx = din; kin.vy = din + nv; kin.vz = din + 2 * nv;
+        h2d += nv * 24;
+        if (in->outer) { kin.ax = d_ax; kin.ay = d_ay; kin.az = d_az; }
+        else {
+            double *da = din + 3 * nv;
+            CK(cudaMemcpyAsync(da, in->ax + p0, np * 8, cudaMemcpyHostToDevice, ln.stream));
+            CK(cudaMemcpyAsync(da + np, in->ay + p0, np * 8, cudaMemcpyHostToDevice, ln.stream));
+            CK(cudaMemcpyAsync(da + 2 * np, in->az + p0, np * 8, cudaMemcpyHostToDevice, ln.stream));
+            kin.ax = da; kin.ay = da + np; kin.az = da + 2 * np;
+            h2d += np * 24;
+        }
+        // outputs: one device block per lane, every array 16-byte aligned
+        size_t off[14], total = 0;
+        for (int i = 0; i < 14; ++i) {
+            off[i] = total;
+            if (want[i] || (i == 0 && need_nsol_dev)) total += ((size_t)np * elem[i] + 15) & ~(size_t)15;
+        }
+        CK(ln.out.reserve(total));
+        unsigned char *dout = (unsigned char *)ln.out.p;
+        auto dp = [&](int i) -> void * { return (want[i] || (i == 0 && need_nsol_dev)) ? (void *)(dout + off[i]) : nullptr; };
+        TraceOutputs to;
+        to.n_sol = (int32_t *)dp(0); to.status = (int32_t *)dp(1); to.type = (int8_t *)dp(2); to.reflection = (int8_t *)dp(3);
+        to.reflection_case = (int8_t *)dp(4); to.C0 = (double *)dp(5); to.C1 = (double *)dp(6); to.path_length = (double *)dp(7);
+        to.travel_time = (double *)dp(8); to.launch = (double *)dp(9); to.receive = (double *)dp(10);
+        to.reflection_angle = (double *)dp(11);
+        ln.timed = (stats != nullptr);
+        int rc = launch_chunk(h, ln, lid, kin, to, (double *)dp(12), (double *)dp(13), &n_launches);
+        if (rc != NRMC_OK) return rc;
+        for (int i = 0; i < 14; ++i) {
+            if (!want[i]) continue;
+            const size_t bytes = (size_t)np * elem[i];
+            CK(cudaMemcpyAsync((unsigned char *)out_ptr(out, i) + (size_t)p0 * elem[i], dout + off[i], bytes, cudaMemcpyDeviceToHost, ln.stream));
+            d2h += bytes;
+        }
+    }
+    for (int l = 0; l < 2; ++l) {
+        Lane &ln = h->lanes[l];
+        CK(cudaStreamSynchronize(ln.stream));
+        if (stats && ln.timed && l < n_chunks) {
+            float a = 0, b = 0;
+            cudaEventElapsedTime(&a, ln.ev[0], ln.ev[1]); cudaEventElapsedTime(&b, ln.ev[1], ln.ev[2]);
+            ms_solve += a; ms_att += b;
+        }
+        ln.timed = false;
+    }
+    cudaEventRecord(e1, h->lanes[0].stream);
+    CK(cudaEventSynchronize(e1));
+    if (stats) {
+        cudaEventElapsedTime(&stats->ms_total, e0, e1);
+        stats->ms_solve = ms_solve; stats->ms_attenuation = ms_att;
+        stats->n_pairs = N; stats->n_launches = n_launches; stats->n_chunks = n_chunks;
+        stats->h2d_bytes = h2d; stats->d2h_bytes = d2h;
+        if (out->n_sol) { for (int64_t i = 0; i < N; ++i) n_solutions += out->n_sol[i]; stats->n_solutions = n_solutions; }
+    }
+    return NRMC_OK;
+}
+
+extern "C" int nrmc_rt_attenuation_length(nrmc_rt_t h, const double *z, const double *frequency, int64_t n, double *out_host)
+{
+    if (!h || !z || !frequency || !out_host || n < 0) return NRMC_ERR_INVALID_ARGUMENT;
+    if (h->ice.att_model == 0) return NRMC_ERR_UNSUPPORTED;
+    if (n == 0) return NRMC_OK;
+    CK(cudaSetDevice(h->cfg.device));
+    DevBuf b;
+    CK(b.reserve((size_t)n * 24));
+    double *dz = (double *)b.p, *df = dz + n, *dout = df + n;
+    cudaStream_t st = h->lanes[0].stream;
+    CK(cudaMemcpyAsync(dz, z, n * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(df, frequency, n * 8, cudaMemcpyHostToDevice, st));
+    K_att_length<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(h->ice, h->tb.gl3, dz, df, n, dout);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out_host, dout, n * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    b.release();
+    return NRMC_OK;
+}
+
+extern "C" int nrmc_rt_measure_fp64_peak(int32_t device, double seconds, double *tflops, double *sm_clock_mhz)
+{
+    if (!tflops) return NRMC_ERR_INVALID_ARGUMENT;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return NRMC_ERR_NO_DEVICE;
+    if (cudaSetDevice(device) != cudaSuccess) return NRMC_ERR_NO_DEVICE;
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, device);
+    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 4096;
+    double *d = nullptr;
+    if (cudaMalloc(&d, (size_t)blocks * threads * 8) != cudaSuccess) return NRMC_ERR_CUDA;
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    K_fp64_peak<<<blocks, threads>>>(d, 64);
+    cudaDeviceSynchronize();
+    double best = 0, elapsed = 0;
+    while (elapsed < seconds * 1e3) {
+        cudaEventRecord(a);
+        K_fp64_peak<<<blocks, threads>>>(d, iters);
+        cudaEventRecord(b);
+        if (cudaEventSynchronize(b) != cudaSuccess) { cudaFree(d); return NRMC_ERR_CUDA; }
+        float ms = 0;
+        cudaEventElapsedTime(&ms, a, b);
+        elapsed += ms;
+        const double flops = 2.0 * 64.0 * iters * (double)blocks * threads;
+        best = std::max(best, flops / (ms * 1e-3) / 1e12);
+    }
+    *tflops = best;
+    if (sm_clock_mhz) *sm_clock_mhz = prop.clockRate / 1e3;
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    cudaFree(d);
+    return NRMC_OK;
+}
