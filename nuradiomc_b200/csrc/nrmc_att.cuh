@@ -17,12 +17,12 @@
 namespace nrmc {
 
 #define NRMC_NQ 16            // Gauss-Legendre points per half-warp slot
-#define NRMC_MAX_SLOTS 4
+#define NRMC_MAX_SLOTS 24
 #define NRMC_MAX_SEG (NRMC_MAX_REFLECTIONS + 1)
 
 struct AttPlan {
     double beta, delta, zv;               // ray invariant, n_ice - beta, apex height (may be > 0: virtual)
-    int n_slots;                          // 16-node slots in use (2 or 4)
+    int n_slots;                          // 16-node slots in use (<= NRMC_MAX_SLOTS)
     double lo[NRMC_MAX_SLOTS], hi[NRMC_MAX_SLOTS];
     int panel[NRMC_MAX_SLOTS];            // 0: [u_T,u_2]  1: [u_2,u_1]  2: [u_1,u_r]
     int nseg;
@@ -58,27 +58,23 @@ NRMC_HD void att_plan(const IceParams &ice, const PairGeom &g, int piece, int k,
     for (int s = 0; s < p.nseg; ++s) for (int q = 0; q < 3; ++q) tot[q] += p.mult[s][q];
     int act[3], na = 0;
     for (int q = 0; q < 3; ++q) if (tot[q] > 0 && phi[q] > plo[q]) act[na++] = q;
+    // every active panel is cut into `spp` equal sub-panels of 16 nodes: 1 for the entire-function models (SP1, GL2,
+    // MB1: <= 2e-7 measured), 8 for the rational GL1 (1/max(A(z) - s_f, 1) has poles close to the path and kinks at
+    // the 1 m / 100 m floors: on bins above 1e-3 two sub-panels already leave 4e-6, but the absolute error of the
+    // strongly attenuated bins only falls to 1e-7 with 4 and 9e-9 with 8).  A path with a single panel gets twice as
+    // many so that no half-warp idles.
+    int spp = (ice.att_model == 2 || ice.att_model == 5) ? 8 : 1;
+    if (na == 1) spp *= 2;
     p.n_slots = 0;
-    if (na == 1) {
-        const int q = act[0]; const double mid = 0.5 * (plo[q] + phi[q]);
-        p.lo[0] = plo[q]; p.hi[0] = mid; p.panel[0] = q;
-        p.lo[1] = mid; p.hi[1] = phi[q]; p.panel[1] = q;
-        p.n_slots = 2;
-    } else if (na == 2) {
-        for (int i = 0; i < 2; ++i) { p.lo[i] = plo[act[i]]; p.hi[i] = phi[act[i]]; p.panel[i] = act[i]; }
-        p.n_slots = 2;
-    } else if (na == 3) {
-        int longest = 0;
-        for (int q = 1; q < 3; ++q) if (phi[q] - plo[q] > phi[longest] - plo[longest]) longest = q;
-        int n = 0;
-        for (int q = 0; q < 3; ++q) {
-            if (q == longest) {
-                const double mid = 0.5 * (plo[q] + phi[q]);
-                p.lo[n] = plo[q]; p.hi[n] = mid; p.panel[n] = q; ++n;
-                p.lo[n] = mid; p.hi[n] = phi[q]; p.panel[n] = q; ++n;
-            } else { p.lo[n] = plo[q]; p.hi[n] = phi[q]; p.panel[n] = q; ++n; }
+    for (int i = 0; i < na; ++i) {
+        const int q = act[i];
+        const double w = (phi[q] - plo[q]) / spp;
+        for (int j = 0; j < spp; ++j) {
+            p.lo[p.n_slots] = plo[q] + j * w;
+            p.hi[p.n_slots] = (j == spp - 1) ? phi[q] : plo[q] + (j + 1) * w;
+            p.panel[p.n_slots] = q;
+            ++p.n_slots;
         }
-        p.n_slots = 4;
     }
 }
 

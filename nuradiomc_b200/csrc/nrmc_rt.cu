@@ -134,7 +134,7 @@ K_att(IceParams ice, KInput in, AttTables tb, const SolRec *worklist, const unsi
     double *s_warp = reinterpret_cast<double *>(s_ii + tb.F_pad + (tb.F_pad & 1));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int per_warp = (NRMC_MAX_SLOTS + nseg_max) * tb.Fs_pad;
-    double *H = s_warp + warp * per_warp;            // [4][Fs_pad] slot sums
+    double *H = s_warp + warp * per_warp;            // [NRMC_MAX_SLOTS][Fs_pad] slot sums
     double *fac = H + NRMC_MAX_SLOTS * tb.Fs_pad;    // [nseg][Fs_pad] exp(-I_seg)
 
     // stage the per-frequency tables with TMA bulk copies (one elected thread issues, everybody waits on the mbarrier)
@@ -177,8 +177,9 @@ K_att(IceParams ice, KInput in, AttTables tb, const SolRec *worklist, const unsi
         // quadrature: each half-warp integrates one 16-node slot per pass
         for (int pass = 0; pass * 2 < plan.n_slots; ++pass) {
             const int slot = pass * 2 + half;
-            double z, wds;
-            att_node_geometry(ice, plan, slot, xq, wq, z, wds);
+            const bool live = slot < plan.n_slots;
+            double z = 0.0, wds = 0.0;
+            if (live) att_node_geometry(ice, plan, slot, xq, wq, z, wds);
             AttNode nd;
             att_node(ice.att_model, z, tb.gl3, nd);
             for (int j = 0; j < tb.Fs; ++j) {
@@ -187,7 +188,7 @@ K_att(IceParams ice, KInput in, AttTables tb, const SolRec *worklist, const unsi
                 term += __shfl_xor_sync(0xffffffffu, term, 4);
                 term += __shfl_xor_sync(0xffffffffu, term, 2);
                 term += __shfl_xor_sync(0xffffffffu, term, 1);
-                if (q == 0) H[slot * tb.Fs_pad + j] = term;
+                if (q == 0 && live) H[slot * tb.Fs_pad + j] = term;
             }
         }
         __syncwarp();
@@ -539,6 +540,13 @@ extern "C" int nrmc_rt_trace(nrmc_rt_t h, const nrmc_rt_input *in, const nrmc_rt
     if (!in->vx || !in->vy || !in->vz || !in->ax || !in->ay || !in->az) return NRMC_ERR_INVALID_ARGUMENT;
     const bool want_att = out->attenuation_sparse || out->attenuation;
     if (want_att && h->ice.att_model == 0) { h->err = "attenuation requested but no attenuation model configured"; return NRMC_ERR_UNSUPPORTED; }
+    if (want_att && h->ice.att_model == NRMC_ATT_GL3) {
+        // GL3 is a 300-row table of rough measured data: the smooth Gauss-Legendre panels used for the other models
+        // do not integrate it to the stated tolerance, and the reference itself switches to a 10 m midpoint sum for it
+        // (analyticraytracing.py:998-1064).  Not built in this round -- refuse instead of returning inaccurate numbers.
+        h->err = "attenuation along the path is not available for the GL3 model in this version";
+        return NRMC_ERR_UNSUPPORTED;
+    }
     if (want_att && !h->have_freq) { h->err = "attenuation requested before nrmc_rt_set_frequencies"; return NRMC_ERR_NO_FREQUENCIES; }
     CK(cudaSetDevice(h->cfg.device));
     const int S = h->S, K1 = h->K1, Fs = h->tb.Fs, F = h->tb.F;

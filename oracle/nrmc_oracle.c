@@ -662,6 +662,11 @@ int ora_find_roots_2d(const ora_cfg *m, const double x1[2], const double x2[2], 
                 if (fmx > 0) {
                     roots[nr++] = brentq(obj_delta_y, &ctx, l - 2 * h, xm, fm2, fmx);
                     roots[nr++] = brentq(obj_delta_y, &ctx, xm, l, fmx, f);
+                } else if (fmx >= -1e-9) {
+                    /* tangency: the objective touches zero without changing sign.  Happens systematically for a
+                     * receiver exactly at the surface (z2 = 0: both branches of py:255-272 give -|rho - y_turn|);
+                     * the reference's hybr on f^2 (py:1479-1483) reports this single root. */
+                    roots[nr++] = xm;
                 }
             }
         }

@@ -1,0 +1,355 @@
+"""
+GPU parity tests (run on the B200 box with `-m gpu`): the CUDA path, called through the C ABI (include/nrmc_rt.h) via
+the Python `ray_tracing` class, against the oracle on seeded inputs, against the committed golden fixtures, and -- at the
+BASELINE sizes -- through size-independent properties.  Tolerances are BASELINE.json's: solution count and type
+bit-exact; angles 1e-6 rad; path length / travel time 1e-6 relative; attenuation 1e-4 relative.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, assert_attenuation_parity, assert_parity, cylinder, golden_config, load_golden, t05_points
+
+pytestmark = pytest.mark.gpu
+
+RNOG = np.array([[0, 20, -97], [0, 20, -96], [0, 20, -95], [0, 20, -94], [0, 20, -93], [0, 20, -92], [0, 20, -80],
+                 [0, 20, -60], [0, 20, -40], [-17.3, -10, -96], [-17.3, -10, -95], [-17.3, -10, -94], [1.5, 11, -2],
+                 [0, 11, -2], [-1.5, 11, -2], [-10.276, -4.2, -2], [-9.526, -5.5, -2], [-8.776, -6.8, -2],
+                 [8.776, -6.8, -2], [9.526, -5.5, -2], [10.276, -4.2, -2], [17.3, -10, -96], [17.3, -10, -95],
+                 [17.3, -10, -94]], float)
+
+
+@pytest.fixture(scope="module")
+def make():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from nuradiomc_b200.SignalProp import propagation
+    from nuradiomc_b200.utilities import medium
+    prop = propagation.get_propagation_module("analytic")
+
+    def _make(ice, **kw):
+        return prop(medium.get_ice_model(ice), **kw)
+    return _make
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# reference goldens through the kernels
+# ---------------------------------------------------------------------------------------------------------------
+def test_T05_golden_through_kernel(make):
+    """T05unit_test_C0_SP.py: reference_C0.pkl, identical counts and slot order"""
+    ref = np.load(os.path.join(GOLDEN, "reference_C0.npy"))
+    res = make("southpole_simple").trace_batch(t05_points(10, -3000.), np.array([[0, 0, -5.]]))
+    assert np.array_equal(res["n_sol"], np.count_nonzero(ref, axis=1))
+    np.testing.assert_allclose(np.nan_to_num(res["C0"]), ref, rtol=1e-6)
+
+
+def test_T06_golden_through_kernel(make):
+    """T06unit_test_C0_mooresbay.py: reference_C0_MooresBay.pkl (n_reflections=2, up to 10 solutions)"""
+    ref = np.load(os.path.join(GOLDEN, "reference_C0_MooresBay.npy"))
+    res = make("mooresbay_simple", n_reflections=2).trace_batch(t05_points(10, -500.), np.array([[0, 0, -5.]]))
+    assert np.array_equal(res["n_sol"], np.count_nonzero(ref, axis=1))
+    np.testing.assert_allclose(np.nan_to_num(res["C0"]), ref, rtol=1e-6)
+
+
+@pytest.mark.parametrize("name", ["sp_simple_T05", "sp2015_cfg2", "mooresbay_cfg4", "mooresbay_T06", "sp1_cfg1",
+                                  "greenland_cfg3", "mooresbay_cfg4_MB1", "sp2015_cfg5_SP1", "greenland_GL2"])
+def test_python_reference_fixtures(make, name):
+    """fixtures produced by the reference's own Python path (tests/golden/make_golden.py)"""
+    g = load_golden(name)
+    c = golden_config(g)
+    rt = make(c["ice"], attenuation_model=c["attenuation_model"], n_reflections=c["n_reflections"],
+              n_frequencies_integration=c["n_freq"])
+    res = rt.trace_batch(g["X1"], g["X2"], frequency=c["frequencies"], max_detector_freq=c["max_detector_freq"])
+    same = res["n_sol"] == g["n_sol"]
+    assert np.array_equal(res["n_sol"][~same], g["arbiter_n"][~same])   # the arbiter decides
+    assert_parity(res, g, exact_count=False)
+    if c["attenuation_model"]:
+        # types 1,3 and 2 alike against the reference integrand at quad(epsrel=1e-11) ...
+        assert_attenuation_parity(res["attenuation"][same], g["attenuation_tight"][same])
+        # ... and within the reference's own tolerance of its stock epsrel=1e-2 result (T01test_python_vs_cpp.py:86-90)
+        np.testing.assert_allclose(res["attenuation"][same], g["attenuation"][same], rtol=1e-2, atol=1e-3, equal_nan=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# oracle on seeded inputs, one case per BASELINE config
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("ice,n_refl,rmax,zmin,antennas", [
+    ("southpole_2015", 0, 4000, -2700, [[10, 10, -190.], [10, -10, -190.], [-10, -10, -190.], [-10, 10, -190.]]),   # cfg2
+    ("southpole_simple", 0, 3000, -3000, [[0, 0, -100.]]),                                                          # cfg1
+    ("greenland_simple", 0, 4000, -2700, RNOG[[0, 6, 8, 9, 12, 17, 22]].tolist()),                                  # cfg3
+    ("mooresbay_simple", 1, 1000, -500, [[-3, 0, -1.], [3, 3, -5.]]),                                               # cfg4
+    ("mooresbay_simple", 2, 1000, -570, [[0, 0, -5.]]),
+    ("southpole_2015", 0, 6000, -2700, [[0, 0, -145.], [1500, -3000, -160.]]),                                      # cfg5
+    ("ARA_2022", 0, 3000, -1500, [[0, 0, -50.]]),
+])
+def test_solutions_vs_oracle(make, oracle_mod, ice, n_refl, rmax, zmin, antennas):
+    V = cylinder(100 + n_refl, 4000 // len(antennas), rmax, zmin)
+    A = np.array(antennas, float)
+    res = make(ice, n_reflections=n_refl).trace_batch(V, A, outer=True)
+    X1, X2 = np.repeat(V, len(A), axis=0), np.tile(A, (len(V), 1))
+    ora = oracle_mod.Oracle(ice, n_reflections=n_refl).trace(X1, X2)
+    assert (ora["status"] == 0).all()
+    assert_parity(res, ora)
+    assert (res["status"] == 0).all()
+
+
+@pytest.mark.parametrize("ice,model,n_refl,rmax,zmin,ant,freqs,fmax,n_freq", [
+    ("southpole_simple", "SP1", 0, 3000, -3000, [0, 0, -100.], np.linspace(0, 0.5, 129), None, 100),               # cfg1
+    ("greenland_simple", "GL1", 0, 4000, -2700, [0, 20, -97.], np.fft.rfftfreq(1022, 0.2), 1.2, 25),                # cfg3 deep
+    ("greenland_simple", "GL1", 0, 4000, -2700, [1.5, 11, -2.], np.fft.rfftfreq(1022, 0.2), 1.2, 25),               # cfg3 LPDA
+    ("mooresbay_simple", "MB1", 1, 1000, -500, [3, 3, -5.], np.fft.rfftfreq(256, 0.5), None, 25),                   # cfg4
+    ("southpole_2015", "SP1", 0, 6000, -2700, [1500, 1500, -150.], np.fft.rfftfreq(1022, 0.2), 1.2, 25),            # cfg5
+    ("greenland_simple", "GL2", 0, 3000, -2500, [0, 0, -100.], np.fft.rfftfreq(256, 0.5), None, 20),
+    ("mooresbay_simple", "MB1", 2, 800, -570, [0, 0, -5.], np.fft.rfftfreq(256, 0.5), 0.6, 10),
+])
+def test_attenuation_vs_tight_oracle(make, oracle_mod, ice, model, n_refl, rmax, zmin, ant, freqs, fmax, n_freq):
+    from nuradiomc_b200.utilities import attenuation
+    X1 = cylinder(200 + n_refl, 500, rmax, zmin)
+    X2 = np.repeat([ant], len(X1), axis=0)
+    rt = make(ice, attenuation_model=model, n_reflections=n_refl, n_frequencies_integration=n_freq)
+    res = rt.trace_batch(X1, X2, frequency=freqs, max_detector_freq=fmax, attenuation="both")
+    gl3 = attenuation.gl3_parameters() if model == "GL3" else None
+    ora = oracle_mod.Oracle(ice, attenuation_model=model, n_reflections=n_refl, n_freq=n_freq, tight=True,
+                            gl3_table=gl3).trace(X1, X2, freqs, fmax)
+    assert_parity(res, ora)
+    np.testing.assert_allclose(res.frequencies_sparse, ora["frequencies_sparse"], rtol=1e-15)
+    assert_attenuation_parity(res["attenuation_sparse"], ora["attenuation_sparse"])
+    assert_attenuation_parity(res["attenuation"], ora["attenuation"])
+    assert (res["attenuation"][:, :, freqs <= 0][res["n_sol"] > 0][:, 0] == 1.0).all()   # the 0 Hz bin is 1 (py:1077)
+
+
+def test_gl3_path_attenuation_is_refused_not_approximated(make):
+    rt = make("greenland_simple", attenuation_model="GL3")
+    with pytest.raises(RuntimeError, match="GL3"):
+        rt.trace_batch(np.array([[100., 0, -500.]]), np.array([[0, 0, -100.]]), frequency=np.linspace(0, 1, 33))
+
+
+def test_attenuation_length_models(make, oracle_mod):
+    """get_attenuation_length(z, f, model) on the device vs the oracle's restatement of attenuation.py:145-262"""
+    from nuradiomc_b200.utilities import attenuation
+    rng = np.random.default_rng(0)
+    z = rng.uniform(-3000, 0, 2000)
+    f = rng.uniform(0.01, 2.5, 2000)
+    for model in ("SP1", "GL1", "MB1", "GL2", "GL3"):
+        if model == "MB1":
+            z = np.maximum(z, -576.)   # the MB1 depth factor is only defined inside the 576 m thick shelf (attenuation.py:239-240)
+        o = oracle_mod.Oracle("southpole_2015", attenuation_model=model,
+                              gl3_table=attenuation.gl3_parameters() if model == "GL3" else None)
+        ref = np.array([o.attenuation_length(a, b) for a, b in zip(z, f)])
+        got = attenuation.get_attenuation_length(z, f, model)
+        np.testing.assert_allclose(got, ref, rtol=1e-12, err_msg=model)
+    assert attenuation.get_attenuation_length(1.0, 0.3, "SP1") == np.inf          # air (attenuation.py:256-257)
+    assert attenuation.get_attenuation_length(-2900., 2.4, "GL1") == 1.0          # 1 m floor (:252-255)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the reference's scalar API
+# ---------------------------------------------------------------------------------------------------------------
+def test_scalar_api_matches_batch_and_reference_semantics(make, oracle_mod):
+    rt = make("southpole_2015", attenuation_model="SP1", n_frequencies_integration=25)
+    ff = np.fft.rfftfreq(256, 0.5)
+    X1 = cylinder(5, 40, 3000, -2000)
+    x2 = np.array([10., 10., -190.])
+    batch = rt.trace_batch(X1, x2[None, :], frequency=ff, max_detector_freq=0.8)
+    ora = oracle_mod.Oracle("southpole_2015", attenuation_model="SP1", n_freq=25).trace(X1, x2, ff, 0.8)
+    for i, x1 in enumerate(X1):
+        rt.set_start_and_end_point(x1, x2)
+        rt.find_solutions()
+        n = rt.get_number_of_solutions()
+        assert n == ora["n_sol"][i] == batch["n_sol"][i]
+        assert rt.has_solution() == (n > 0)
+        assert rt.get_results() == batch.solutions(i)
+        for iS in range(n):
+            assert rt.get_solution_type(iS) == ora["type"][i, iS]
+            assert rt.get_results()[iS]["reflection"] == 0
+            np.testing.assert_allclose(rt.get_launch_vector(iS), ora["launch"][i, iS], atol=1e-6)
+            np.testing.assert_allclose(rt.get_receive_vector(iS), ora["receive"][i, iS], atol=1e-6)
+            np.testing.assert_allclose(rt.get_path_length(iS), ora["path_length"][i, iS], rtol=1e-6)
+            np.testing.assert_allclose(rt.get_travel_time(iS), ora["travel_time"][i, iS], rtol=1e-6)
+            ra = rt.get_reflection_angle(iS)
+            if ora["type"][i, iS] == 3:
+                np.testing.assert_allclose(float(ra), ora["reflection_angle"][i, iS, 0], atol=1e-6)
+            else:
+                assert ra[()] is None
+            att = rt.get_attenuation(iS, ff, 0.8)
+            np.testing.assert_array_equal(att, batch["attenuation"][i, iS])
+            assert att.shape == ff.shape and att[0] == 1.0 and (att[1:] > 0).all() and (att <= 1).all()
+            out = rt.get_raytracing_output(iS)
+            assert out["ray_tracing_solution_type"] == ora["type"][i, iS] and out["focusing_factor"] == 1
+        with pytest.raises(IndexError):
+            rt.get_launch_vector(n)
+        with pytest.raises(IndexError):
+            rt.get_attenuation(n, ff)
+
+
+def test_scalar_api_with_bottom_reflections(make, oracle_mod):
+    rt = make("mooresbay_simple", n_reflections=1)
+    o = oracle_mod.Oracle("mooresbay_simple", n_reflections=1)
+    for x1 in cylinder(9, 25, 800, -500):
+        x2 = np.array([3., 3., -5.])
+        rt.set_start_and_end_point(x1, x2)
+        rt.find_solutions()
+        ora = o.trace(x1[None, :], x2)
+        assert rt.get_number_of_solutions() == ora["n_sol"][0]
+        for iS, r in enumerate(rt.get_results()):
+            assert (r["reflection"], r["reflection_case"]) == (ora["reflection"][0, iS], ora["reflection_case"][0, iS])
+            ra = np.atleast_1d(rt.get_reflection_angle(iS))
+            assert len(ra) == r["reflection"] + 1
+            ref = ora["reflection_angle"][0, iS, :len(ra)]
+            for a, b in zip(ra, ref):
+                assert (a is None and np.isnan(b)) or abs(a - b) < 1e-6
+    with pytest.raises(AttributeError):
+        rt.set_start_and_end_point([0, 0, -580.], [0, 0, -5.])
+
+
+def test_prepare_batch_serves_scalar_loop(make):
+    """the simulation-loop hook: pre-trace all (shower, channel) pairs, then the scalar calls are lookups"""
+    rt = make("greenland_simple")
+    V, A = cylinder(3, 30, 2000, -1500), RNOG[[0, 12]]
+    res = rt.prepare_batch(V, A, outer=True)
+    launches_before = res.stats["n_launches"]
+    assert launches_before >= 1
+    for i, v in enumerate(V):
+        for j, a in enumerate(A):
+            rt.set_start_and_end_point(v, a)
+            rt.find_solutions()
+            assert rt._batch_index == i * len(A) + j
+            assert rt.get_number_of_solutions() == res["n_sol"][i * len(A) + j]
+            for iS in range(rt.get_number_of_solutions()):
+                assert rt.get_travel_time(iS) == res["travel_time"][i * len(A) + j, iS]
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# edge cases
+# ---------------------------------------------------------------------------------------------------------------
+def test_edge_cases(make, oracle_mod):
+    rt = make("southpole_2015")
+    # empty batch
+    res = rt.trace_batch(np.zeros((0, 3)), np.zeros((0, 3)))
+    assert res["n_sol"].shape == (0,) and res["C0"].shape == (0, 2)
+    # swapped points, equal depths, receiver at the surface, receiver in air, tiny horizontal offset, deep horizontal, NaN
+    X1 = np.array([[0, 0, -50.], [100, 50, -300.], [0, 0, -100.], [0, 0, -100.], [5, 5, -20.], [0, 0, -1000.], [np.nan, 0, -10.]])
+    X2 = np.array([[200, 0, -300.], [0, 0, -300.], [100, 0, 0.], [50, 0, 1.], [5.001, 5, -10.], [3000, 0, -1000.], [1, 1, -1.]])
+    res = rt.trace_batch(X1, X2)
+    assert list(res["n_sol"]) == [2, 2, 1, 0, 2, 2, 0]
+    assert list(res["status"]) == [0, 0, 0, 1, 0, 0, 4]
+    assert np.isnan(res["C0"][3]).all() and (res["solution_type"][3] == 0).all()
+    ora = oracle_mod.Oracle("southpole_2015").trace(X1[[0, 1, 4, 5]], X2[[0, 1, 4, 5]])
+    assert_parity({k: v[[0, 1, 4, 5]] for k, v in res.items()}, ora)
+    # physical bound where the reference's closed form breaks down: path >= straight line (reference: 2998.04 m)
+    assert (res["path_length"][5] >= 3000.0).all() and (res["path_length"][5] < 3001.0).any()
+    # single pair / ragged tail (N not a multiple of the block size)
+    for n in (1, 31, 129, 1000):
+        V = cylinder(n, n, 3000, -2000)
+        r1 = rt.trace_batch(V, np.array([[0, 0, -100.]]))
+        r2 = rt.trace_batch(V[::-1].copy(), np.array([[0, 0, -100.]]))
+        assert np.array_equal(r1["n_sol"], r2["n_sol"][::-1])
+        np.testing.assert_array_equal(r1["C0"], r2["C0"][::-1])
+    # points below the reflective layer
+    rtm = make("mooresbay_simple", n_reflections=1)
+    res = rtm.trace_batch(np.array([[0, 0, -600.], [0, 0, -100.]]), np.array([[10, 0, -5.], [10, 0, -5.]]))
+    assert list(res["status"]) == [2, 0] and res["n_sol"][0] == 0 and res["n_sol"][1] > 0
+
+
+def test_pair_mode_equals_outer_mode_and_pinned_buffers(make):
+    rt = make("southpole_2015", attenuation_model="SP1", n_frequencies_integration=10)
+    ff = np.fft.rfftfreq(128, 0.5)
+    V, A = cylinder(8, 300, 4000, -2700), np.array([[0, 0, -150.], [1500, 0, -160.], [0, -1500, -145.]])
+    r_outer = rt.trace_batch(V, A, outer=True, frequency=ff, attenuation="both", pinned=True)
+    r_pairs = rt.trace_batch(np.repeat(V, 3, axis=0), np.tile(A, (300, 1)), frequency=ff, attenuation="both")
+    for k in r_pairs:
+        np.testing.assert_array_equal(r_outer[k], r_pairs[k], err_msg=k)
+    assert r_outer.stats["h2d_bytes"] < r_pairs.stats["h2d_bytes"]
+
+
+def test_device_resident_path_equals_host_path(make):
+    import torch
+    rt = make("southpole_2015", attenuation_model="SP1", n_frequencies_integration=25)
+    ff = np.fft.rfftfreq(1022, 0.2)
+    V, A = cylinder(12, 5000, 6000, -2700), np.array([[0, 0, -150.], [1500, 0, -160.]])
+    host = rt.trace_batch(V, A, outer=True, frequency=ff, max_detector_freq=1.2, attenuation="both")
+    dv = torch.tensor(np.ascontiguousarray(V.T), device="cuda:0")
+    da = torch.tensor(np.ascontiguousarray(A.T), device="cuda:0")
+    dev = rt.trace_batch_device(dv, da, outer=True, frequency=ff, max_detector_freq=1.2, attenuation="both", sync_stats=True)
+    for k in host:
+        np.testing.assert_array_equal(host[k], dev[k].cpu().numpy(), err_msg=k)
+    assert dev.stats["n_solutions"] == int(host["n_sol"].sum())
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# BASELINE sizes: size-independent properties
+# ---------------------------------------------------------------------------------------------------------------
+def test_full_size_properties_cfg2(make):
+    """cfg2: 1e6 vertices x 4 antennas, southpole_2015, no attenuation -- invariants instead of the (too slow) oracle"""
+    import torch
+    rt = make("southpole_2015")
+    V = cylinder(2, 1_000_000, 4000, -2700)
+    A = np.array([[10, 10, -190.], [10, -10, -190.], [-10, -10, -190.], [-10, 10, -190.]])
+    dv = torch.tensor(np.ascontiguousarray(V.T), device="cuda:0")
+    da = torch.tensor(np.ascontiguousarray(A.T), device="cuda:0")
+    res = rt.trace_batch_device(dv, da, outer=True)
+    torch.cuda.synchronize()
+    n_sol = res["n_sol"].cpu().numpy()
+    assert set(np.unique(n_sol)) <= {0, 2}                     # 0 or 2 solutions per pair (unimodal range curve)
+    frac2 = (n_sol == 2).mean()
+    assert 0.6 < frac2 < 0.95                                   # ~81 % of cfg2 pairs have two solutions
+    C0 = res["C0"].cpu().numpy()
+    typ = res["solution_type"].cpu().numpy()
+    has = n_sol == 2
+    assert (C0[has, 0] < C0[has, 1]).all() and (C0[has] > 1 / 1.78).all()      # sorted by C0 (py:1547), C0 > 1/n_ice
+    assert np.isnan(C0[~has]).all() and (typ[~has] == 0).all() and np.isin(typ[has], (1, 2, 3)).all()
+    # path >= straight line; n_min * path <= c * t <= n_ice * path
+    X1, X2 = np.repeat(V, 4, axis=0), np.tile(A, (len(V), 1))
+    dist = np.linalg.norm(X1 - X2, axis=1)
+    path, time = res["path_length"].cpu().numpy(), res["travel_time"].cpu().numpy()
+    assert (path[has] >= dist[has, None] * (1 - 1e-12)).all()
+    ct = time[has] * 0.299792458
+    assert (ct <= 1.78 * path[has] * (1 + 1e-12)).all() and (ct >= (1.78 - 0.423) * path[has]).all()
+    # launch / receive vectors are unit vectors; direct rays arrive from below, reflected / refracted from above
+    lv, rv = res["launch_vector"].cpu().numpy(), res["receive_vector"].cpu().numpy()
+    np.testing.assert_allclose(np.linalg.norm(lv[has], axis=-1), 1.0, atol=1e-12)
+    np.testing.assert_allclose(np.linalg.norm(rv[has], axis=-1), 1.0, atol=1e-12)
+    # determinism: a second pass is bit-identical
+    res2 = rt.trace_batch_device(dv, da, outer=True)
+    torch.cuda.synchronize()
+    assert torch.equal(res["C0"].nan_to_num(), res2["C0"].nan_to_num()) and torch.equal(res["n_sol"], res2["n_sol"])
+    # reciprocity on a slice: exchanging start and end point exchanges the vectors, keeps C0 / path / time
+    sl = slice(0, 200_000)
+    fwd = rt.trace_batch(X1[sl], X2[sl])
+    bwd = rt.trace_batch(X2[sl], X1[sl])
+    assert np.array_equal(fwd["n_sol"], bwd["n_sol"])
+    np.testing.assert_allclose(fwd["C0"], bwd["C0"], rtol=1e-12, equal_nan=True)
+    np.testing.assert_allclose(fwd["travel_time"], bwd["travel_time"], rtol=1e-12, equal_nan=True)
+    np.testing.assert_allclose(fwd["launch_vector"], bwd["receive_vector"], atol=1e-12, equal_nan=True)
+
+
+def test_full_size_properties_attenuation_cfg5_slice(make, oracle_mod):
+    """cfg5 set-up (southpole_2015, SP1, 37 integration frequencies, sparse output) on 1e5 vertices x 20 channels:
+    invariants at size + oracle parity on a random subsample"""
+    import torch
+    rt = make("southpole_2015", attenuation_model="SP1", n_frequencies_integration=25)
+    ff = np.fft.rfftfreq(1022, 0.2)
+    V = cylinder(5, 100_000, 6000, -2700)
+    A = np.array([[x, y, z] for x in (-1500., 1500.) for y in (-3000., 0.) for z in (-145., -150., -155., -160., -100.)])
+    dv = torch.tensor(np.ascontiguousarray(V.T), device="cuda:0")
+    da = torch.tensor(np.ascontiguousarray(A.T), device="cuda:0")
+    res = rt.trace_batch_device(dv, da, outer=True, frequency=ff, max_detector_freq=1.2, attenuation="sparse")
+    torch.cuda.synchronize()
+    att = res["attenuation_sparse"].cpu().numpy()
+    n_sol = res["n_sol"].cpu().numpy()
+    assert att.shape == (2_000_000, 2, 37)
+    has = n_sol == 2
+    assert np.isnan(att[~has]).all()
+    a = att[has]
+    assert (a > 0).all() and (a <= 1).all()
+    assert (np.diff(a[..., :25], axis=-1) <= 1e-15).all()       # SP1: attenuation grows with frequency
+    path = res["path_length"].cpu().numpy()[has]
+    # exp(-path / L_min) <= factor: SP1 attenuation lengths stay above 200 m below 1.2 GHz
+    assert (a[..., :25] >= np.exp(-path / 200.)[..., None]).all()
+    idx = np.random.default_rng(1).choice(len(n_sol), 300, replace=False)
+    X1, X2 = V[idx // len(A)], A[idx % len(A)]
+    ora = oracle_mod.Oracle("southpole_2015", attenuation_model="SP1", n_freq=25).trace(X1, X2, ff, 1.2, dense=False)
+    sub = {k: v.cpu().numpy()[idx] for k, v in res.items()}
+    assert_parity(sub, ora)
+    assert_attenuation_parity(sub["attenuation_sparse"], ora["attenuation_sparse"])
