@@ -17,65 +17,72 @@
 namespace nrmc {
 
 #define NRMC_NQ 16            // Gauss-Legendre points per half-warp slot
-#define NRMC_MAX_SLOTS 24
 #define NRMC_MAX_SEG (NRMC_MAX_REFLECTIONS + 1)
 
-struct AttPlan {
+struct AttPlan {                          // all scalars: nothing here is indexed dynamically (no local memory)
     double beta, delta, zv;               // ray invariant, n_ice - beta, apex height (may be > 0: virtual)
-    int n_slots;                          // 16-node slots in use (<= NRMC_MAX_SLOTS)
-    double lo[NRMC_MAX_SLOTS], hi[NRMC_MAX_SLOTS];
-    int panel[NRMC_MAX_SLOTS];            // 0: [u_T,u_2]  1: [u_2,u_1]  2: [u_1,u_r]
-    int nseg;
-    int mult[NRMC_MAX_SEG][3];            // times segment s runs through panel p
+    double uT, u2, u1, ur;                // panel boundaries in u = sqrt(zv - z): 0: [uT,u2]  1: [u2,u1]  2: [u1,ur]
+    int act0, act1, act2, na;             // active panels (multiplicity > 0 and non-empty)
+    int spp, n_slots;                     // sub-panels per active panel, 16-node slots in total
+    int nseg, k, rcase;
+    bool turned;
 };
 
-// Segment / panel bookkeeping equivalent to get_path_segments (py:1091-1159) + the first-segment mirroring for
-// downward starts (py:943-950).
+// times path segment s runs through panel p -- equivalent to get_path_segments (py:1091-1159) plus the
+// first-segment mirroring for downward starts (py:943-950)
+NRMC_HD int plan_mult(const AttPlan &p, int s, int panel)
+{
+    if (p.k == 0) return panel == 0 ? (p.turned ? 2 : 0) : (panel == 1 ? 1 : 0);
+    if (s == 0) return p.rcase == 1 ? (panel == 2 ? 1 : 2) : (panel == 2 ? 1 : 0);
+    if (s < p.k) return 2;
+    return panel == 0 ? (p.turned ? 2 : 0) : 1;
+}
+
+NRMC_HD int plan_total_mult(const AttPlan &p, int panel)
+{
+    int t = 0;
+    for (int s = 0; s < p.nseg; ++s) t += plan_mult(p, s, panel);
+    return t;
+}
+
+NRMC_HD void plan_slot(const AttPlan &p, int slot, double &lo, double &hi, int &panel)
+{
+    const int ai = slot / p.spp, sub = slot - ai * p.spp;
+    panel = ai == 0 ? p.act0 : (ai == 1 ? p.act1 : p.act2);
+    const double plo = panel == 0 ? p.uT : (panel == 1 ? p.u2 : p.u1);
+    const double phi = panel == 0 ? p.u2 : (panel == 1 ? p.u1 : p.ur);
+    const double w = (phi - plo) / p.spp;
+    lo = plo + sub * w;
+    hi = (sub == p.spp - 1) ? phi : plo + (sub + 1) * w;
+}
+
 NRMC_HD void att_plan(const IceParams &ice, const PairGeom &g, int piece, int k, int rcase, const RayState &r, AttPlan &p)
 {
-    const bool turned = piece >= 2;
+    p.turned = piece >= 2;
+    p.k = k; p.rcase = rcase; p.nseg = k + 1;
     p.beta = r.beta;
     p.delta = (r.rc * r.rc) / (ice.n_ice + r.beta);      // n_ice - beta without cancellation
     p.zv = ice.z0 * log(p.delta / ice.dn);
-    const double uT = r.reflected ? sqrt(fmax(p.zv, 0.0)) : 0.0;
-    const double u2 = sqrt(fmax(p.zv - g.z2, 0.0));
-    const double u1 = sqrt(fmax(p.zv - g.z1, 0.0));
-    const double ur = (k > 0) ? sqrt(fmax(p.zv - ice.zr, 0.0)) : u1;
-    const double plo[3] = {uT, u2, u1}, phi[3] = {u2, u1, ur};
-    p.nseg = k + 1;
-    for (int s = 0; s < NRMC_MAX_SEG; ++s) { p.mult[s][0] = 0; p.mult[s][1] = 0; p.mult[s][2] = 0; }
-    if (k == 0) {
-        p.mult[0][1] = 1;
-        if (turned) p.mult[0][0] = 2;
-    } else {
-        if (rcase == 1) { p.mult[0][0] = 2; p.mult[0][1] = 2; p.mult[0][2] = 1; } else p.mult[0][2] = 1;
-        for (int s = 1; s < k; ++s) { p.mult[s][0] = 2; p.mult[s][1] = 2; p.mult[s][2] = 2; }
-        p.mult[k][1] += 1; p.mult[k][2] += 1;
-        if (turned) p.mult[k][0] += 2;
+    p.uT = r.reflected ? sqrt(fmax(p.zv, 0.0)) : 0.0;
+    p.u2 = sqrt(fmax(p.zv - g.z2, 0.0));
+    p.u1 = sqrt(fmax(p.zv - g.z1, 0.0));
+    p.ur = (k > 0) ? sqrt(fmax(p.zv - ice.zr, 0.0)) : p.u1;
+    p.na = 0; p.act0 = p.act1 = p.act2 = 0;
+    for (int q = 0; q < 3; ++q) {
+        const double plo = q == 0 ? p.uT : (q == 1 ? p.u2 : p.u1), phi = q == 0 ? p.u2 : (q == 1 ? p.u1 : p.ur);
+        if (plan_total_mult(p, q) > 0 && phi > plo) {
+            if (p.na == 0) p.act0 = q; else if (p.na == 1) p.act1 = q; else p.act2 = q;
+            ++p.na;
+        }
     }
-    // k > 0 and the first segment is also the last one cannot happen (k+1 >= 2 segments)
-    int tot[3] = {0, 0, 0};
-    for (int s = 0; s < p.nseg; ++s) for (int q = 0; q < 3; ++q) tot[q] += p.mult[s][q];
-    int act[3], na = 0;
-    for (int q = 0; q < 3; ++q) if (tot[q] > 0 && phi[q] > plo[q]) act[na++] = q;
     // every active panel is cut into `spp` equal sub-panels of 16 nodes: 1 for the entire-function models (SP1, GL2,
     // MB1: <= 2e-7 measured), 8 for the rational GL1 (1/max(A(z) - s_f, 1) has poles close to the path and kinks at
     // the 1 m / 100 m floors: on bins above 1e-3 two sub-panels already leave 4e-6, but the absolute error of the
     // strongly attenuated bins only falls to 1e-7 with 4 and 9e-9 with 8).  A path with a single panel gets twice as
     // many so that no half-warp idles.
-    int spp = (ice.att_model == 2 || ice.att_model == 5) ? 8 : 1;
-    if (na == 1) spp *= 2;
-    p.n_slots = 0;
-    for (int i = 0; i < na; ++i) {
-        const int q = act[i];
-        const double w = (phi[q] - plo[q]) / spp;
-        for (int j = 0; j < spp; ++j) {
-            p.lo[p.n_slots] = plo[q] + j * w;
-            p.hi[p.n_slots] = (j == spp - 1) ? phi[q] : plo[q] + (j + 1) * w;
-            p.panel[p.n_slots] = q;
-            ++p.n_slots;
-        }
-    }
+    p.spp = (ice.att_model == 2 || ice.att_model == 5) ? 8 : 1;
+    if (p.na == 1) p.spp *= 2;
+    p.n_slots = p.na * p.spp;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -158,11 +165,11 @@ NRMC_HD double att_inv_length(int model, const AttNode &nd, double fa, double fb
     return 1.0 / fmax(L, 1.0);
 }
 
-// one quadrature node of slot `slot`: abscissa x in [-1,1] with weight w -> depth z and ds-weight (without 1/L)
-NRMC_HD void att_node_geometry(const IceParams &ice, const AttPlan &p, int slot, double x, double w, double &z, double &wds)
+// one quadrature node of the u-interval [lo, hi]: abscissa x in [-1,1] with weight w -> depth z and ds-weight (without 1/L)
+NRMC_HD void att_node_geometry(const IceParams &ice, const AttPlan &p, double lo, double hi, double x, double w, double &z, double &wds)
 {
-    const double half = 0.5 * (p.hi[slot] - p.lo[slot]);
-    const double u = 0.5 * (p.hi[slot] + p.lo[slot]) + half * x;
+    const double half = 0.5 * (hi - lo);
+    const double u = 0.5 * (hi + lo) + half * x;
     const double uu = u * u;
     z = fmin(p.zv - uu, 0.0);
     const double em = -expm1(-uu * ice.inv_z0);

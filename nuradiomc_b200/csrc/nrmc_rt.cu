@@ -109,6 +109,19 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gme
                  : "memory");
 }
 
+__constant__ double c_glx[16] = {-0.9894009349916499325961541734503326, -0.9445750230732325760779884155346083,
+    -0.8656312023878317438804678977123931, -0.7554044083550030338951011948474422, -0.6178762444026437484466717640487910,
+    -0.4580167776572273863424194429835775, -0.2816035507792589132304605014604961, -0.0950125098376374401853193354249581,
+    0.0950125098376374401853193354249581, 0.2816035507792589132304605014604961, 0.4580167776572273863424194429835775,
+    0.6178762444026437484466717640487910, 0.7554044083550030338951011948474422, 0.8656312023878317438804678977123931,
+    0.9445750230732325760779884155346083, 0.9894009349916499325961541734503326};
+__constant__ double c_glw[16] = {0.0271524594117540948517805724560181, 0.0622535239386478928628438369943776,
+    0.0951585116824927848099251076022462, 0.1246289712555338720524762821920164, 0.1495959888165767320815017305474785,
+    0.1691565193950025381893120790303599, 0.1826034150449235888667636679692199, 0.1894506104550684962853967232082831,
+    0.1894506104550684962853967232082831, 0.1826034150449235888667636679692199, 0.1691565193950025381893120790303599,
+    0.1495959888165767320815017305474785, 0.1246289712555338720524762821920164, 0.0951585116824927848099251076022462,
+    0.0622535239386478928628438369943776, 0.0271524594117540948517805724560181};
+
 struct AttTables {            // device pointers, every array padded to a multiple of 16 bytes
     const double *fa, *fb;    // [Fs_pad] per integration frequency constants (att_freq_consts)
     const double *it;         // [F_pad]  interpolation weight t of every output bin
@@ -120,85 +133,107 @@ struct AttTables {            // device pointers, every array padded to a multip
 #define ATT_WARPS 4
 #define ATT_THREADS (ATT_WARPS * 32)
 
-// dynamic shared memory layout (doubles): fa[Fs_pad] fb[Fs_pad] it[F_pad] | ii[F_pad] (int32) | per warp: H[4][Fs_pad] fac[nseg][Fs_pad]
+__device__ __forceinline__ void stage_tables(uint64_t *bar, void *dst0, const void *src0, uint32_t b0, void *dst1, const void *src1,
+                                             uint32_t b1, void *dst2, const void *src2, uint32_t b2, void *dst3, const void *src3,
+                                             uint32_t b3)
+{
+    // per-frequency tables -> shared memory with TMA bulk copies: one elected thread issues, everybody waits on the mbarrier
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(bar, b0 + b1 + b2 + b3);
+        if (b0) tma_bulk_g2s(dst0, src0, b0, bar);
+        if (b1) tma_bulk_g2s(dst1, src1, b1, bar);
+        if (b2) tma_bulk_g2s(dst2, src2, b2, bar);
+        if (b3) tma_bulk_g2s(dst3, src3, b3, bar);
+    }
+    mbar_wait(bar, 0);
+}
+
+// rebuild the ray of a work-list record (uniform per warp in K_att, per thread in K_att_sp1)
+__device__ __forceinline__ void rebuild_ray(const IceParams &ice, const KInput &in, const SolRec &rec, PairGeom &g, AttPlan &plan)
+{
+    double x1, y1, z1, x2, y2, z2;
+    load_pair(in, rec.pair, x1, y1, z1, x2, y2, z2);
+    Frame2D f;
+    make_frame(x1, y1, z1, x2, y2, z2, f);
+    make_pair_geom(ice, f.z1, f.z2, fmax(f.rho, 1e-12), g);
+    RayState rs;
+    ray_state(ice, g, (rec.piece == 1 || rec.piece == 2), rec.v, rs);
+    att_plan(ice, g, rec.piece, rec.k, rec.rcase, rs, plan);
+}
+
+// Generic attenuation kernel (all models, any number of bottom reflections): one warp per solution.
+// dynamic shared memory (doubles): fa[Fs_pad] fb[Fs_pad] it[F_pad] | ii[F_pad] (int32) | per warp: H[3][Fs_pad] fac[nseg][Fs_pad]
 __global__ void __launch_bounds__(ATT_THREADS)
 K_att(IceParams ice, KInput in, AttTables tb, const SolRec *worklist, const unsigned long long *work_count, int nseg_max,
       double *att_sparse, double *att_dense)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t bar;
+    const bool dense = att_dense != nullptr;
+    const int Fd_pad = dense ? tb.F_pad : 0;
     double *s_fa = reinterpret_cast<double *>(smem_raw);
     double *s_fb = s_fa + tb.Fs_pad;
     double *s_it = s_fb + tb.Fs_pad;
-    int32_t *s_ii = reinterpret_cast<int32_t *>(s_it + tb.F_pad);
-    double *s_warp = reinterpret_cast<double *>(s_ii + tb.F_pad + (tb.F_pad & 1));
+    int32_t *s_ii = reinterpret_cast<int32_t *>(s_it + Fd_pad);
+    double *s_warp = reinterpret_cast<double *>(s_ii + Fd_pad);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int per_warp = (NRMC_MAX_SLOTS + nseg_max) * tb.Fs_pad;
-    double *H = s_warp + warp * per_warp;            // [NRMC_MAX_SLOTS][Fs_pad] slot sums
-    double *fac = H + NRMC_MAX_SLOTS * tb.Fs_pad;    // [nseg][Fs_pad] exp(-I_seg)
+    const int per_warp = (3 + nseg_max) * tb.Fs_pad;
+    double *H = s_warp + warp * per_warp;            // [3][Fs_pad] panel integrals
+    double *fac = H + 3 * tb.Fs_pad;                 // [nseg][Fs_pad] exp(-I_seg)
+    stage_tables(&bar, s_fa, tb.fa, (uint32_t)tb.Fs_pad * 8u, s_fb, tb.fb, (uint32_t)tb.Fs_pad * 8u, s_it, tb.it,
+                 (uint32_t)Fd_pad * 8u, s_ii, tb.ii, (uint32_t)Fd_pad * 4u);
 
-    // stage the per-frequency tables with TMA bulk copies (one elected thread issues, everybody waits on the mbarrier)
-    if (threadIdx.x == 0) {
-        mbar_init(&bar, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const uint32_t b_fs = (uint32_t)tb.Fs_pad * 8u, b_it = (uint32_t)tb.F_pad * 8u, b_ii = (uint32_t)tb.F_pad * 4u;
-        mbar_expect_tx(&bar, 2u * b_fs + b_it + b_ii);
-        tma_bulk_g2s(s_fa, tb.fa, b_fs, &bar);
-        tma_bulk_g2s(s_fb, tb.fb, b_fs, &bar);
-        if (b_it) { tma_bulk_g2s(s_it, tb.it, b_it, &bar); tma_bulk_g2s(s_ii, tb.ii, b_ii, &bar); }
-    }
-    mbar_wait(&bar, 0);
-
-    const double glx[8] = NRMC_GL16_X, glw[8] = NRMC_GL16_W;
     const int q = lane & 15, half = lane >> 4;
-    const double xq = (q < 8) ? -glx[7 - q] : glx[q - 8];
-    const double wq = (q < 8) ? glw[7 - q] : glw[q - 8];
-
+    const double xq = c_glx[q], wq = c_glw[q];
     const unsigned long long n_work = *work_count;
     const int S = 2 + 4 * ice.n_refl;
     for (unsigned long long w = (unsigned long long)blockIdx.x * ATT_WARPS + warp; w < n_work;
          w += (unsigned long long)gridDim.x * ATT_WARPS) {
         const SolRec rec = worklist[w];
-        // rebuild the ray (warp-uniform)
-        double x1, y1, z1, x2, y2, z2;
-        load_pair(in, rec.pair, x1, y1, z1, x2, y2, z2);
-        Frame2D f;
-        make_frame(x1, y1, z1, x2, y2, z2, f);
         PairGeom g;
-        make_pair_geom(ice, f.z1, f.z2, fmax(f.rho, 1e-12), g);
-        RayState rs;
-        ray_state(ice, g, (rec.piece == 1 || rec.piece == 2), rec.v, rs);
         AttPlan plan;
-        att_plan(ice, g, rec.piece, rec.k, rec.rcase, rs, plan);
-
-        // quadrature: each half-warp integrates one 16-node slot per pass
+        rebuild_ray(ice, in, rec, g, plan);
+        for (int j = lane; j < 3 * tb.Fs_pad; j += 32) H[j] = 0.0;
+        __syncwarp();
+        // quadrature: each half-warp integrates one 16-node slot per pass; slot sums are added to their panel
         for (int pass = 0; pass * 2 < plan.n_slots; ++pass) {
             const int slot = pass * 2 + half;
             const bool live = slot < plan.n_slots;
-            double z = 0.0, wds = 0.0;
-            if (live) att_node_geometry(ice, plan, slot, xq, wq, z, wds);
+            double lo = 0.0, hi = 0.0, z = 0.0, wds = 0.0;
+            int panel = 0;
             AttNode nd;
-            att_node(ice.att_model, z, tb.gl3, nd);
+            nd.p0 = nd.p1 = nd.p2 = 0.0;
+            if (live) {
+                plan_slot(plan, slot, lo, hi, panel);
+                att_node_geometry(ice, plan, lo, hi, xq, wq, z, wds);
+                att_node(ice.att_model, z, tb.gl3, nd);
+            }
+            const int panel_other = __shfl_xor_sync(0xffffffffu, live ? panel : -1, 16);
+            const bool merge = (panel_other == panel);       // both half-warps work on the same panel
             for (int j = 0; j < tb.Fs; ++j) {
-                double term = wds * att_inv_length(ice.att_model, nd, s_fa[j], s_fb[j]);
+                double term = live ? wds * att_inv_length(ice.att_model, nd, s_fa[j], s_fb[j]) : 0.0;
                 term += __shfl_xor_sync(0xffffffffu, term, 8);
                 term += __shfl_xor_sync(0xffffffffu, term, 4);
                 term += __shfl_xor_sync(0xffffffffu, term, 2);
                 term += __shfl_xor_sync(0xffffffffu, term, 1);
-                if (q == 0 && live) H[slot * tb.Fs_pad + j] = term;
+                const double other = __shfl_xor_sync(0xffffffffu, term, 16);
+                if (merge) { if (lane == 0) H[panel * tb.Fs_pad + j] += term + other; }
+                else if (q == 0 && live) H[panel * tb.Fs_pad + j] += term;
             }
+            __syncwarp();
         }
-        __syncwarp();
-        // per segment: I_seg = sum_slot mult[seg][panel(slot)] * H[slot];  factor = exp(-I_seg)   (py:1075)
+        // per segment: I_seg = sum_panel mult[seg][panel] * H[panel];  factor = exp(-I_seg)   (py:1075)
         const int64_t slot_index = rec.pair * S + rec.slot;
         for (int j = lane; j < tb.Fs; j += 32) {
+            const double h0 = H[j], h1 = H[tb.Fs_pad + j], h2 = H[2 * tb.Fs_pad + j];
             double prod = 1.0;
             for (int s = 0; s < plan.nseg; ++s) {
-                double I = 0.0;
-                for (int t = 0; t < plan.n_slots; ++t) I += (double)plan.mult[s][plan.panel[t]] * H[t * tb.Fs_pad + j];
+                const double I = plan_mult(plan, s, 0) * h0 + plan_mult(plan, s, 1) * h1 + plan_mult(plan, s, 2) * h2;
                 const double e = exp(-I);
                 fac[s * tb.Fs_pad + j] = e;
                 prod *= e;
@@ -206,7 +241,7 @@ K_att(IceParams ice, KInput in, AttTables tb, const SolRec *worklist, const unsi
             if (att_sparse) att_sparse[slot_index * tb.Fs + j] = prod;
         }
         __syncwarp();
-        if (att_dense) {
+        if (dense) {
             // np.interp of every segment's factors onto the output grid, product over segments (py:1077-1078,1086)
             double *dst = att_dense + slot_index * tb.F;
             for (int b = lane; b < tb.F; b += 32) {
@@ -223,6 +258,120 @@ K_att(IceParams ice, KInput in, AttTables tb, const SolRec *worklist, const unsi
             }
         }
         __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// SP1 fast path (no bottom reflections): 1/L = exp(b1(z) + p(z) ln f) with the slope p(z) confined to a narrow band
+// around a constant p_ref, so  sum_q c_q exp(p_q w) = exp(p_ref w) sum_k (w^k / k!) M_k,  M_k = sum_q c_q (p_q - p_ref)^k:
+// the per-(node, frequency) exponential disappears.  One THREAD per solution: 32 nodes accumulate 2 x SP1_K moments in
+// registers (no reduction at all), then every integration frequency is a SP1_K-term dot product with a table staged in
+// shared memory by TMA.  Solutions whose slopes leave the band where the SP1_K-term series is accurate to 1e-9, or that
+// could touch the 1 m floor of attenuation.py:252-255, are handed to the generic kernel (fallback list).
+// ---------------------------------------------------------------------------------------------------------------
+#define SP1_K 12
+struct Sp1Tables {
+    const double *wk;         // [Fs_pad][SP1_K]  w_j^k / k!
+    const double *E;          // [Fs_pad]         exp(p_ref(band_j) * w_j)
+    const int32_t *band;      // [Fs_pad]         0: f < 1 GHz, 1: f >= 1 GHz (attenuation.py:180-185)
+    double pref_lo, pref_hi;
+    double wabs_lo, wabs_hi;  // max |ln f| per band (series radius)
+    double wmin_lo, wmax_lo, wmin_hi, wmax_hi;
+    int32_t n_lo, n_hi;
+};
+#define SP1_THREADS 128
+
+__global__ void __launch_bounds__(SP1_THREADS)
+K_att_sp1(IceParams ice, KInput in, AttTables tb, Sp1Tables sp, const SolRec *worklist, const unsigned long long *work_count,
+          double *att_sparse, SolRec *fallback, unsigned long long *fallback_count)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t bar;
+    double *s_wk = reinterpret_cast<double *>(smem_raw);
+    double *s_E = s_wk + tb.Fs_pad * SP1_K;
+    int32_t *s_band = reinterpret_cast<int32_t *>(s_E + tb.Fs_pad);
+    stage_tables(&bar, s_wk, sp.wk, (uint32_t)tb.Fs_pad * SP1_K * 8u, s_E, sp.E, (uint32_t)tb.Fs_pad * 8u, s_band, sp.band,
+                 (uint32_t)((tb.Fs_pad + 3) & ~3) * 4u, nullptr, nullptr, 0u);
+    const unsigned long long n_work = *work_count;
+    const double xlim = 0.9;     // 0.9^12 / 12! = 5.9e-10
+    for (unsigned long long w = (unsigned long long)blockIdx.x * SP1_THREADS + threadIdx.x; w < n_work;
+         w += (unsigned long long)gridDim.x * SP1_THREADS) {
+        const SolRec rec = worklist[w];
+        PairGeom g;
+        AttPlan plan;
+        rebuild_ray(ice, in, rec, g, plan);
+        double Mlo[SP1_K], Mhi[SP1_K];
+#pragma unroll
+        for (int k = 0; k < SP1_K; ++k) { Mlo[k] = 0.0; Mhi[k] = 0.0; }
+        bool ok = true;
+        for (int slot = 0; slot < plan.n_slots; ++slot) {
+            double lo, hi;
+            int panel;
+            plan_slot(plan, slot, lo, hi, panel);
+            const double mult = (double)plan_mult(plan, 0, panel);
+#pragma unroll 1
+            for (int i = 0; i < 16; ++i) {
+                const double x = c_glx[i], wgt = c_glw[i];
+                double z, wds;
+                att_node_geometry(ice, plan, lo, hi, x, wgt, z, wds);
+                AttNode nd;
+                att_node(1, z, tb.gl3, nd);
+                const double c = mult * wds * exp(nd.p0);
+                const double dlo = nd.p1 - sp.pref_lo, dhi = nd.p2 - sp.pref_hi;
+                // series radius and the 1 m floor (1/L <= 1 <=> exponent <= 0 at the band edges)
+                ok = ok && (fabs(dlo) * sp.wabs_lo <= xlim) && (fabs(dhi) * sp.wabs_hi <= xlim);
+                if (sp.n_lo) ok = ok && (nd.p0 + fmax(nd.p1 * sp.wmin_lo, nd.p1 * sp.wmax_lo) < 0.0);
+                if (sp.n_hi) ok = ok && (nd.p0 + fmax(nd.p2 * sp.wmin_hi, nd.p2 * sp.wmax_hi) < 0.0);
+                double t = c;
+#pragma unroll
+                for (int k = 0; k < SP1_K; ++k) { Mlo[k] += t; t *= dlo; }
+                if (sp.n_hi) {
+                    t = c;
+#pragma unroll
+                    for (int k = 0; k < SP1_K; ++k) { Mhi[k] += t; t *= dhi; }
+                }
+            }
+        }
+        if (!ok) {
+            const unsigned long long idx = atomicAdd(fallback_count, 1ull);
+            fallback[idx] = rec;
+            continue;
+        }
+        const int S = 2;
+        double *dst = att_sparse + (rec.pair * S + rec.slot) * (int64_t)tb.Fs;
+        for (int j = 0; j < tb.Fs; ++j) {
+            const double *wk = s_wk + j * SP1_K;
+            double acc = 0.0;
+            if (s_band[j] == 0) {
+#pragma unroll
+                for (int k = 0; k < SP1_K; ++k) acc = fma(Mlo[k], wk[k], acc);
+            } else {
+#pragma unroll
+                for (int k = 0; k < SP1_K; ++k) acc = fma(Mhi[k], wk[k], acc);
+            }
+            dst[j] = exp(-acc * s_E[j]);
+        }
+    }
+}
+
+// dense expansion for single-segment paths: np.interp of the sparse factors onto the output grid (py:1077-1078)
+__global__ void __launch_bounds__(256)
+K_att_expand(AttTables tb, const int32_t *n_sol, int64_t n_pairs, int S, const double *att_sparse, double *att_dense)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t total = n_pairs * S;
+    for (int64_t qi = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); qi < total;
+         qi += (int64_t)gridDim.x * (blockDim.x >> 5)) {
+        const int64_t p = qi / S;
+        if ((int)(qi - p * S) >= n_sol[p]) continue;
+        const double *src = att_sparse + qi * tb.Fs;
+        double *dst = att_dense + qi * tb.F;
+        for (int b = lane; b < tb.F; b += 32) {
+            const int i0 = __ldg(tb.ii + b);
+            double val = 1.0;
+            if (i0 >= 0) { const double f0 = src[i0], f1 = src[i0 + 1]; val = (f1 - f0) * __ldg(tb.it + b) + f0; }
+            dst[b] = val;
+        }
     }
 }
 
@@ -298,7 +447,7 @@ struct DevBuf {
 struct Lane {               // one pipeline lane (stream + scratch) for host-memory calls
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    DevBuf in, out, work;
+    DevBuf in, out, work, fallback, sparse_tmp;
     bool timed = false;
 };
 
@@ -310,7 +459,11 @@ struct nrmc_rt_s {
     // frequencies
     std::vector<double> freq_out, freq_sparse;
     AttTables tb;
-    DevBuf d_tables, d_gl3;
+    Sp1Tables sp1;
+    bool have_sp1 = false;
+    int grid_att = 0, grid_sp1 = 0;      // resident blocks (occupancy x SMs) of the persistent attenuation kernels
+    size_t smem_att = 0, smem_sp1 = 0;
+    DevBuf d_tables, d_gl3, d_sp1;
     bool have_freq = false;
     Lane lanes[2];
     DevBuf d_count;       // work-list counters (one per lane)
@@ -390,8 +543,9 @@ void nrmc_rt_destroy(nrmc_rt_t h)
         if (h->lanes[l].stream) { cudaStreamSynchronize(h->lanes[l].stream); cudaStreamDestroy(h->lanes[l].stream); }
         for (int e = 0; e < 6; ++e) if (h->lanes[l].ev[e]) cudaEventDestroy(h->lanes[l].ev[e]);
         h->lanes[l].in.release(); h->lanes[l].out.release(); h->lanes[l].work.release();
+        h->lanes[l].fallback.release(); h->lanes[l].sparse_tmp.release();
     }
-    h->d_tables.release(); h->d_gl3.release(); h->d_count.release(); h->d_ant.release();
+    h->d_tables.release(); h->d_gl3.release(); h->d_sp1.release(); h->d_count.release(); h->d_ant.release();
     delete h;
 }
 
@@ -460,6 +614,51 @@ int nrmc_rt_set_frequencies(nrmc_rt_t h, const double *frequency, int32_t n, dou
     h->freq_out.assign(frequency, frequency + n);
     h->freq_sparse = sp;
     h->have_freq = true;
+    // persistent-grid sizes: exactly the resident blocks, so that no partial second wave forms
+    {
+        const int nseg_max = h->ice.n_refl + 1;
+        h->smem_att = (size_t)Fs_pad * 16 + (size_t)F_pad * 12 + (size_t)ATT_WARPS * (3 + nseg_max) * Fs_pad * 8;
+        if (h->smem_att > 48 * 1024) CK(cudaFuncSetAttribute(K_att, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_att));
+        int nb = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, K_att, ATT_THREADS, h->smem_att));
+        h->grid_att = std::max(1, nb) * h->n_sm;
+    }
+    h->have_sp1 = false;
+    if (h->ice.att_model == NRMC_ATT_SP1 && h->ice.n_refl == 0) {
+        // tables of the SP1 moment kernel: w_j^k / k!, exp(p_ref w_j), band flag (attenuation.py:170-192)
+        Sp1Tables &t = h->sp1;
+        t.pref_lo = 0.24; t.pref_hi = 1.75;
+        t.wabs_lo = t.wabs_hi = 0.0; t.n_lo = t.n_hi = 0;
+        t.wmin_lo = t.wmin_hi = INFINITY; t.wmax_lo = t.wmax_hi = -INFINITY;
+        const int band_pad = (Fs_pad + 3) & ~3;
+        std::vector<double> wk((size_t)Fs_pad * SP1_K, 0.0), E(Fs_pad, 0.0);
+        std::vector<int32_t> band(band_pad, 0);
+        for (int j = 0; j < Fs; ++j) {
+            const double w = log(sp[j]);
+            const int b = sp[j] < 1.0 ? 0 : 1;
+            band[j] = b;
+            E[j] = exp((b ? t.pref_hi : t.pref_lo) * w);
+            double term = 1.0;
+            for (int k = 0; k < SP1_K; ++k) { wk[(size_t)j * SP1_K + k] = term; term *= w / (k + 1); }
+            if (b) { ++t.n_hi; t.wabs_hi = std::max(t.wabs_hi, fabs(w)); t.wmin_hi = std::min(t.wmin_hi, w); t.wmax_hi = std::max(t.wmax_hi, w); }
+            else { ++t.n_lo; t.wabs_lo = std::max(t.wabs_lo, fabs(w)); t.wmin_lo = std::min(t.wmin_lo, w); t.wmax_lo = std::max(t.wmax_lo, w); }
+        }
+        const size_t b_wk = wk.size() * 8, b_E = E.size() * 8, b_band = band.size() * 4;
+        CK(h->d_sp1.reserve(b_wk + b_E + b_band + 64));
+        unsigned char *q = (unsigned char *)h->d_sp1.p;
+        CK(cudaMemcpy(q, wk.data(), b_wk, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(q + b_wk, E.data(), b_E, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(q + b_wk + b_E, band.data(), b_band, cudaMemcpyHostToDevice));
+        t.wk = (const double *)q; t.E = (const double *)(q + b_wk); t.band = (const int32_t *)(q + b_wk + b_E);
+        h->smem_sp1 = b_wk + b_E + b_band;
+        if (h->smem_sp1 <= 200 * 1024) {
+            if (h->smem_sp1 > 48 * 1024) CK(cudaFuncSetAttribute(K_att_sp1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_sp1));
+            int nb = 0;
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, K_att_sp1, SP1_THREADS, h->smem_sp1));
+            h->grid_sp1 = std::max(1, nb) * h->n_sm;
+            h->have_sp1 = true;
+        }
+    }
     return Fs;
 }
 
@@ -500,12 +699,31 @@ static int launch_chunk(nrmc_rt_s *h, Lane &ln, int lane_id, const KInput &kin, 
     if (want_att) {
         const AttTables &tb = h->tb;
         const int nseg_max = h->ice.n_refl + 1;
-        const size_t smem = (size_t)tb.Fs_pad * 16 + (size_t)tb.F_pad * 8 + (size_t)(tb.F_pad + (tb.F_pad & 1)) * 4 +
-                            (size_t)ATT_WARPS * (NRMC_MAX_SLOTS + nseg_max) * tb.Fs_pad * 8;
-        if (smem > 48 * 1024) CK(cudaFuncSetAttribute(K_att, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         K_att_fill<<<h->n_sm * 8, 256, 0, ln.stream>>>(to.n_sol, kin.n_pairs, h->S, tb.Fs, tb.F, att_sparse, att_dense);
-        K_att<<<h->n_sm * 8, ATT_THREADS, smem, ln.stream>>>(h->ice, kin, tb, wl, d_count, nseg_max, att_sparse, att_dense);
-        *n_launches += 2;
+        ++*n_launches;
+        if (h->have_sp1) {
+            // SP1 moment kernel -> sparse factors; rare out-of-band solutions -> generic kernel; dense = interp(sparse)
+            unsigned long long *d_fb = (unsigned long long *)h->d_count.p + 2 + lane_id;
+            CK(ln.fallback.reserve((size_t)kin.n_pairs * h->S * sizeof(SolRec)));
+            double *sparse = att_sparse;
+            if (!sparse) {
+                CK(ln.sparse_tmp.reserve((size_t)kin.n_pairs * h->S * tb.Fs * sizeof(double)));
+                sparse = (double *)ln.sparse_tmp.p;
+            }
+            CK(cudaMemsetAsync(d_fb, 0, sizeof(unsigned long long), ln.stream));
+            K_att_sp1<<<h->grid_sp1, SP1_THREADS, h->smem_sp1, ln.stream>>>(h->ice, kin, tb, h->sp1, wl, d_count, sparse,
+                                                                            (SolRec *)ln.fallback.p, d_fb);
+            K_att<<<h->grid_att, ATT_THREADS, h->smem_att, ln.stream>>>(h->ice, kin, tb, (const SolRec *)ln.fallback.p, d_fb,
+                                                                        nseg_max, sparse, nullptr);
+            *n_launches += 2;
+            if (att_dense) {
+                K_att_expand<<<h->n_sm * 8, 256, 0, ln.stream>>>(tb, to.n_sol, kin.n_pairs, h->S, sparse, att_dense);
+                ++*n_launches;
+            }
+        } else {
+            K_att<<<h->grid_att, ATT_THREADS, h->smem_att, ln.stream>>>(h->ice, kin, tb, wl, d_count, nseg_max, att_sparse, att_dense);
+            ++*n_launches;
+        }
     }
     if (ln.timed) cudaEventRecord(ln.ev[2], ln.stream);
     CK(cudaGetLastError());
