@@ -3,7 +3,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libnrmc_rt.so")
+LIB_PATH = os.environ.get("NRMC_RT_LIB", os.path.join(HERE, "libnrmc_rt.so"))   # override: A/B builds of the same source
 
 NRMC_OK = 0
 ERRORS = {-1: "invalid argument", -2: "CUDA error", -3: "no CUDA device", -4: "unsupported configuration",

@@ -110,7 +110,7 @@ NRMC_HD void ray_state(const IceParams &ice, const PairGeom &g, bool band, doubl
         c = g.c0_sub + sg2;
         r.s1 = sqrt(g.A1 + sg2);
         r.s2 = sqrt(g.A2 + sg2);
-        r.sr = sqrt(g.Ar + sg2);
+        r.sr = ice.n_refl > 0 ? sqrt(g.Ar + sg2) : 0.0;
         r.reflected = true;
     } else {
         double sg2 = v * v;
@@ -119,13 +119,13 @@ NRMC_HD void ray_state(const IceParams &ice, const PairGeom &g, bool band, doubl
         c = g.c0_band + sg2;
         r.s1 = sqrt(g.B1 + sg2);
         r.s2 = v;
-        r.sr = sqrt(g.Br + sg2);
+        r.sr = ice.n_refl > 0 ? sqrt(g.Br + sg2) : 0.0;
         r.reflected = false;
     }
     r.rc = sqrt(c);
     r.k1_1 = r.rc * r.s1 + (c - ice.n_ice * g.g1);
     r.k1_2 = r.rc * r.s2 + (c - ice.n_ice * g.g2);
-    r.k1_r = r.rc * r.sr + (c - ice.n_ice * ice.gr);
+    r.k1_r = ice.n_refl > 0 ? r.rc * r.sr + (c - ice.n_ice * ice.gr) : 1.0;
     r.KT = r.reflected ? r.rc * r.ss + (c - ice.n_ice * ice.dn) : ice.dn * r.beta;
 }
 
@@ -151,6 +151,9 @@ struct Curve {                // one (reflection, case) mode of one pair
 // piece p in {0,1,2,3}; value of R - rho at parameter v of that piece
 NRMC_HD double curve_g(const Curve &cv, int p, double v)
 {
+#ifdef NRMC_COUNT_EVALS
+    ++g_evals;
+#endif
     RayState r;
     ray_state(*cv.ice, *cv.g, (p == 1 || p == 2), v, r);
     double R = range_of(*cv.ice, *cv.g, (p >= 2) ? cv.m_trn : cv.m_dir, r);
@@ -158,9 +161,57 @@ NRMC_HD double curve_g(const Curve &cv, int p, double v)
     return R - cv.g->rho;
 }
 
+// g = R - rho and its derivative with respect to the piece parameter v (closed form; used to locate the maximum of R
+// when the whole curve was sampled below rho).
+NRMC_HD double curve_gd(const Curve &cv, int p, double v, double &dg)
+{
+#ifdef NRMC_COUNT_EVALS
+    ++g_evals;
+#endif
+    const IceParams &ice = *cv.ice;
+    const PairGeom &g = *cv.g;
+    const bool band = (p == 1 || p == 2);
+    const ModeCoeffs &m = (p >= 2) ? cv.m_trn : cv.m_dir;
+    RayState r;
+    ray_state(ice, g, band, v, r);
+    double db, dc, ds1, ds2, dsr, dKT;     // derivatives of beta, c, s1, s2, sr, KT with respect to v
+    if (!band) {
+        const double q = 1.0 / (1.0 + v * v);
+        db = 2.0 * r.ss * q;
+        const double dss = -2.0 * r.beta * q;
+        const double h = r.ss * dss;        // d(ss^2)/dv / 2
+        dc = 2.0 * h;
+        ds1 = r.s1 > 0 ? h / r.s1 : 0.0; ds2 = r.s2 > 0 ? h / r.s2 : 0.0; dsr = r.sr > 0 ? h / r.sr : 0.0;
+        const double drc = h / r.rc;
+        dKT = drc * r.ss + r.rc * dss + dc;
+    } else {
+        db = -v / r.beta;
+        dc = 2.0 * v;
+        ds1 = r.s1 > 0 ? v / r.s1 : 0.0; ds2 = 1.0; dsr = r.sr > 0 ? v / r.sr : 0.0;
+        dKT = ice.dn * db;
+    }
+    const double drc = 0.5 * dc / r.rc;
+    const double dk1 = drc * r.s1 + r.rc * ds1 + dc, dk2 = drc * r.s2 + r.rc * ds2 + dc;
+    double dlnP = m.a1 * dk1 / r.k1_1 + m.a2 * dk2 / r.k1_2 + (m.aT ? m.aT * dKT / r.KT : 0.0);
+    if (m.ar != 0) dlnP += m.ar * (drc * r.sr + r.rc * dsr + dc) / r.k1_r;
+    const double A = r.beta / r.rc;
+    const double dA = (db - A * drc) / r.rc;
+    double num = 1.0, den = 1.0;
+    if (m.a1 > 0) num *= r.k1_1; else den *= r.k1_1;
+    if (m.a2 > 0) num *= r.k1_2; else den *= r.k1_2;
+    num *= ipow(r.KT, m.aT);
+    double lin = m.a1 * g.z1 + m.a2 * g.z2;
+    if (m.ar != 0) { den *= ipow(r.k1_r, -m.ar); lin += m.ar * ice.zr; }
+    const double Bk = lin - ice.z0 * log(num / den);
+    double R = A * Bk;
+    dg = dA * Bk - A * ice.z0 * dlnP;
+    if (!(R == R)) { R = 1e300; dg = 0.0; }
+    return R - g.rho;
+}
+
 // Bracketed root of g on piece p between a and b (ga, gb of opposite strict sign): regula falsi with the Illinois
 // modification, bisection safeguard; converges superlinearly on the smooth pieces.
-NRMC_HDN double solve_piece(const Curve &cv, int p, double a, double ga, double b, double gb)
+NRMC_HD double solve_piece(const Curve &cv, int p, double a, double ga, double b, double gb)
 {
     const double gtol = 1e-10;
     int side = 0;
@@ -179,56 +230,43 @@ NRMC_HDN double solve_piece(const Curve &cv, int p, double a, double ga, double 
     return x;
 }
 
-// Maximise g on piece p over [a,b] (g(a), g(b) <= 0).  Brent's golden-section / parabolic search; returns as soon as
-// a point with g > 0 is found (xm, gm); otherwise the converged maximum.  Returns true if g(xm) > 0.
-NRMC_HDN bool maximise_piece(const Curve &cv, int p, double a, double b, double &xm, double &gm)
+// Look for an interior maximum of g on piece p (end values <= 0): bracket the sign change of dg/dv and close it
+// with Illinois steps on the derivative.  Returns true as soon as a point with g > 0 is found (xm, gm); false if the
+// maximum is at an end point or stays <= 0.  `interior` tells the caller whether this piece holds the curve's maximum.
+NRMC_HD bool maximise_piece(const Curve &cv, int p, double a, double b, double &xm, double &gm, bool &interior)
 {
-    const double cg = 0.3819660112501051;
     double lo = fmin(a, b), hi = fmax(a, b);
-    double x = lo + cg * (hi - lo), w = x, v = x;
-    double fx = -curve_g(cv, p, x), fw = fx, fv = fx;   // minimise -g
-    double d = 0.0, e = 0.0;
-    const double tol_rel = 1e-9, tol_abs = 1e-12 * (hi - lo) + 1e-300;
+    double dlo, dhi;
+    double glo = curve_gd(cv, p, lo, dlo);
+    double ghi = curve_gd(cv, p, hi, dhi);
+    interior = (dlo > 0.0) && (dhi < 0.0);
+    xm = lo; gm = glo;
+    if (!interior) return false;
+    int side = 0;
     for (int it = 0; it < 60; ++it) {
-        if (fx < 0) break;  // g > 0 found
-        double xmid = 0.5 * (lo + hi);
-        double tol1 = tol_rel * fabs(x) + tol_abs, tol2 = 2.0 * tol1;
-        if (fabs(x - xmid) <= tol2 - 0.5 * (hi - lo)) break;
-        bool golden = true;
-        if (fabs(e) > tol1) {
-            double r = (x - w) * (fx - fv), q = (x - v) * (fx - fw), pp = (x - v) * q - (x - w) * r;
-            q = 2.0 * (q - r);
-            if (q > 0) pp = -pp;
-            q = fabs(q);
-            double etemp = e;
-            e = d;
-            if (!(fabs(pp) >= fabs(0.5 * q * etemp) || pp <= q * (lo - x) || pp >= q * (hi - x))) {
-                d = pp / q;
-                double u = x + d;
-                if (u - lo < tol2 || hi - u < tol2) d = (xmid - x >= 0) ? tol1 : -tol1;
-                golden = false;
-            }
-        }
-        if (golden) { e = (x >= xmid) ? lo - x : hi - x; d = cg * e; }
-        double u = (fabs(d) >= tol1) ? x + d : x + ((d >= 0) ? tol1 : -tol1);
-        double fu = -curve_g(cv, p, u);
-        if (fu <= fx) {
-            if (u >= x) lo = x; else hi = x;
-            v = w; fv = fw; w = x; fw = fx; x = u; fx = fu;
-        } else {
-            if (u < x) lo = u; else hi = u;
-            if (fu <= fw || w == x) { v = w; fv = fw; w = u; fw = fu; }
-            else if (fu <= fv || v == x || v == w) { v = u; fv = fu; }
-        }
+        double x = (lo * dhi - hi * dlo) / (dhi - dlo);
+        if (!(x > lo && x < hi)) x = 0.5 * (lo + hi);
+        double dx;
+        const double gx = curve_gd(cv, p, x, dx);
+        if (gx > gm || it == 0) { xm = x; gm = gx; }
+        if (gx > 0.0) return true;
+        if (dx > 0.0) { lo = x; dlo = dx; if (side == 1) dhi *= 0.5; side = 1; }
+        else if (dx < 0.0) { hi = x; dhi = dx; if (side == -1) dlo *= 0.5; side = -1; }
+        else break;
+        // the remaining gain is bounded by |slope| x bracket once the bracket lies in the concave cap around the maximum
+        const double gain = fmax(fabs(dlo), fabs(dhi)) * (hi - lo);
+        if (gain < 1e-11 || (hi - lo) <= 4e-16 * (fabs(lo) + fabs(hi))) break;
+        if (it >= 2 && gm + 4.0 * gain < 0.0) break;     // deep in the shadow zone: cannot reach rho any more
     }
-    xm = x; gm = -fx;
-    return gm > 0;
+    return gm > 0.0;
 }
 
 struct Root { double v; int piece; double beta; };
 
 // All roots (0 or 2; 1 only on a tangency) of one mode, ordered by increasing C0 = 1/beta.
-NRMC_HDN int find_roots_mode(const IceParams &ice, const PairGeom &g, int k, int rcase, Root out[2])
+// Written so that the solver and the maximum search each have ONE call site: everything inlines into the kernel and
+// the pair geometry stays in registers.
+NRMC_HD int find_roots_mode(const IceParams &ice, const PairGeom &g, int k, int rcase, Root out[2])
 {
     Curve cv;
     cv.ice = &ice; cv.g = &g;
@@ -236,48 +274,59 @@ NRMC_HDN int find_roots_mode(const IceParams &ice, const PairGeom &g, int k, int
     cv.m_trn = mode_coeffs(k, rcase, true);
     const bool has_band = g.s2max > 0.0;
     // piece end points (parameter values) in curve order: P0 t:0->1, P1 s2:s2max->0, P2 s2:0->s2max, P3 t:1->0
-    const double pa[4] = {0.0, g.s2max, 0.0, 1.0};
-    const double pb[4] = {1.0, 0.0, g.s2max, 0.0};
-    double J[5];
-    J[0] = -g.rho; J[4] = -g.rho;
-    J[1] = curve_g(cv, 0, 1.0);
-    J[3] = curve_g(cv, 3, 1.0);
-    J[2] = has_band ? curve_g(cv, 1, 0.0) : J[1];
-    int n = 0;
-    Root r[4];
-    for (int p = 0; p < 4; ++p) {
-        if (!has_band && (p == 1 || p == 2)) continue;
-        if (!has_band && p == 0) continue;            // receiver exactly at the surface: P0 and P3 coincide (py: one 'reflected' solution)
-        double ga = J[p], gb = J[p + 1];
-        if ((ga > 0) != (gb > 0)) {
-            if (n < 4) { r[n].piece = p; r[n].v = solve_piece(cv, p, pa[p], ga, pb[p], gb); ++n; }
-        }
-    }
-    if (n == 0 && J[1] <= 0 && J[2] <= 0 && J[3] <= 0) {
+    const double J0 = -g.rho, J4 = -g.rho;
+    const double J1 = curve_g(cv, 0, 1.0);
+    const double J3 = curve_g(cv, 3, 1.0);
+    const double J2 = has_band ? curve_g(cv, 1, 0.0) : J1;
+    // brackets: (piece, a, g(a), b, g(b)), at most two
+    int bp0 = 0, bp1 = 0, nb = 0;
+    double ba0 = 0, bga0 = 0, bb0 = 0, bgb0 = 0, ba1 = 0, bga1 = 0, bb1 = 0, bgb1 = 0;
+#define NRMC_PUSH_BRACKET(P, A, GA, B, GB)                                               \
+    do {                                                                                  \
+        if (nb == 0) { bp0 = (P); ba0 = (A); bga0 = (GA); bb0 = (B); bgb0 = (GB); }       \
+        else if (nb == 1) { bp1 = (P); ba1 = (A); bga1 = (GA); bb1 = (B); bgb1 = (GB); }  \
+        ++nb;                                                                             \
+    } while (0)
+    // receiver exactly at the surface (no band): P0 and P3 coincide (py: one 'reflected' solution) -> only P3
+    if (has_band && ((J0 > 0) != (J1 > 0))) NRMC_PUSH_BRACKET(0, 0.0, J0, 1.0, J1);
+    if (has_band && ((J1 > 0) != (J2 > 0))) NRMC_PUSH_BRACKET(1, g.s2max, J1, 0.0, J2);
+    if (has_band && ((J2 > 0) != (J3 > 0))) NRMC_PUSH_BRACKET(2, 0.0, J2, g.s2max, J3);
+    if ((J3 > 0) != (J4 > 0)) NRMC_PUSH_BRACKET(3, 1.0, J3, 0.0, J4);
+    if (nb == 0 && J1 <= 0 && J2 <= 0 && J3 <= 0) {
         // whole curve sampled below rho: look for a hump inside the pieces adjacent to the largest junction
         int jm = 1;
-        if (J[2] > J[jm]) jm = 2;
-        if (J[3] > J[jm]) jm = 3;
-        for (int side = 0; side < 2 && n == 0; ++side) {
-            int p = jm - 1 + side;
+        double Jm = J1;
+        if (J2 > Jm) { jm = 2; Jm = J2; }
+        if (J3 > Jm) { jm = 3; Jm = J3; }
+        bool interior = false;
+        for (int side = 0; side < 2 && nb == 0 && !interior; ++side) {
+            const int p = jm - 1 + side;
             if (!has_band && p != 3) continue;
+            const double pa = (p == 1) ? g.s2max : ((p == 3) ? 1.0 : 0.0);
+            const double pb = (p == 0) ? 1.0 : ((p == 2) ? g.s2max : 0.0);
+            const double ja = (p == 0) ? J0 : (p == 1 ? J1 : (p == 2 ? J2 : J3));
+            const double jb = (p == 0) ? J1 : (p == 1 ? J2 : (p == 2 ? J3 : J4));
             double xm, gm;
-            if (maximise_piece(cv, p, pa[p], pb[p], xm, gm)) {
-                r[0].piece = p; r[0].v = solve_piece(cv, p, pa[p], J[p], xm, gm);
-                r[1].piece = p; r[1].v = solve_piece(cv, p, xm, gm, pb[p], J[p + 1]);
-                n = 2;
+            if (maximise_piece(cv, p, pa, pb, xm, gm, interior)) {
+                NRMC_PUSH_BRACKET(p, pa, ja, xm, gm);
+                NRMC_PUSH_BRACKET(p, xm, gm, pb, jb);
             }
         }
     }
-    if (n > 2) n = 2;
-    for (int i = 0; i < n; ++i) {
+#undef NRMC_PUSH_BRACKET
+    if (nb > 2) nb = 2;
+    Root r0, r1;
+    r0.v = r1.v = 0; r0.piece = r1.piece = 0; r0.beta = r1.beta = 0;
+    for (int i = 0; i < nb; ++i) {
+        const int p = i == 0 ? bp0 : bp1;
+        const double v = solve_piece(cv, p, i == 0 ? ba0 : ba1, i == 0 ? bga0 : bga1, i == 0 ? bb0 : bb1, i == 0 ? bgb0 : bgb1);
         RayState rs;
-        ray_state(ice, g, (r[i].piece == 1 || r[i].piece == 2), r[i].v, rs);
-        r[i].beta = rs.beta;
+        ray_state(ice, g, (p == 1 || p == 2), v, rs);
+        if (i == 0) { r0.v = v; r0.piece = p; r0.beta = rs.beta; } else { r1.v = v; r1.piece = p; r1.beta = rs.beta; }
     }
-    if (n == 2 && r[0].beta < r[1].beta) { Root t = r[0]; r[0] = r[1]; r[1] = t; }  // ascending C0 (py:1547)
-    for (int i = 0; i < n; ++i) out[i] = r[i];
-    return n;
+    if (nb == 2 && r0.beta < r1.beta) { Root t = r0; r0 = r1; r1 = t; }  // ascending C0 (py:1547)
+    out[0] = r0; out[1] = r1;
+    return nb;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -294,7 +343,7 @@ struct SolutionProps {
     int n_segments;
 };
 
-NRMC_HDN void solution_props(const IceParams &ice, const PairGeom &g, double x1y, int k, int rcase, const Root &root,
+NRMC_HD void solution_props(const IceParams &ice, const PairGeom &g, double x1y, int k, int rcase, const Root &root,
                              SolutionProps &o)
 {
     const bool band = (root.piece == 1 || root.piece == 2);
@@ -388,7 +437,7 @@ NRMC_HD void make_frame(double ax, double ay, double az, double bx, double by, d
 }
 
 // Returns the number of solutions; fills the SoA slots of pair i and (if recs != null) one SolRec per solution.
-NRMC_HDN int trace_pair(const IceParams &ice, double ax, double ay, double az, double bx, double by, double bz,
+NRMC_HD int trace_pair(const IceParams &ice, double ax, double ay, double az, double bx, double by, double bz,
                         int64_t i, const TraceOutputs &o, SolRec *recs)
 {
     const int S = 2 + 4 * ice.n_refl, K1 = ice.n_refl + 1;

@@ -46,7 +46,10 @@ __device__ __forceinline__ void load_pair(const KInput &in, int64_t p, double &x
 #define SOLVE_THREADS 128
 #define MAX_S (2 + 4 * NRMC_MAX_REFLECTIONS)
 
-__global__ void __launch_bounds__(SOLVE_THREADS)
+#ifndef SOLVE_MIN_BLOCKS
+#define SOLVE_MIN_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(SOLVE_THREADS, SOLVE_MIN_BLOCKS)
 K_solve(IceParams ice, KInput in, TraceOutputs out, SolRec *worklist, unsigned long long *work_count)
 {
     const int64_t p = (int64_t)blockIdx.x * SOLVE_THREADS + threadIdx.x;
