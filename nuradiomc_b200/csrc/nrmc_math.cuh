@@ -16,14 +16,17 @@
 //
 // so the horizontal range of every path family (n bottom bounces, launch up/down, arrival before/after the turning
 // point) is one logarithm:  R(beta) = beta/sqrt(c) * [a1 z1 + a2 z2 + ar zr - z0 ln(k1(z1)^a1 k1(z2)^a2 k1(zr)^ar K_T^aT)]
-// with small integer exponents (mode_coeffs).  R is traced along a closed curve of four smooth pieces
-//   P0: arrival up-going,   beta in (0, n_s]   (t-parametrised:  beta = n_s 2t/(1+t^2), s(0) = n_s (1-t^2)/(1+t^2))
-//   P1: arrival up-going,   beta in [n_s, n2]  (parametrised by s2 = s(z2) in [0, s2max])
-//   P2: arrival down-going, beta in [n_s, n2]  (refracted: apex inside the ice)
-//   P3: arrival down-going, beta in (0, n_s]   (reflected off the surface)
+// with small integer exponents (mode_coeffs).  R is traced along a closed curve of four smooth pieces, all of them
+// parametrised by the rational parameter t of a circle beta^2 + sigma^2 = nX^2 (beta = nX 2t/(1+t^2), sigma = nX (1-t^2)/(1+t^2)):
+//   P0: arrival up-going,   beta in (0, n_s]   nX = n_s, sigma = s(0),  t: 0 -> 1
+//   P1: arrival up-going,   beta in [n_s, n2]  nX = n2,  sigma = s(z2), t: tmin -> 1
+//   P2: arrival down-going, beta in [n_s, n2]  (refracted: apex inside the ice), t: 1 -> tmin
+//   P3: arrival down-going, beta in (0, n_s]   (reflected off the surface),      t: 1 -> 0
 // R starts and ends at 0 and is unimodal along the curve, so R = rho has 0 or 2 roots per mode: the three junction
 // values bracket them; when all junctions are below rho the maximum is searched in the two pieces next to the
-// largest junction.  All radicands are assembled from differences of gamma's (no cancellation against n_ice).
+// largest junction.  All radicands are an offset assembled from differences of gamma's plus sigma^2 (no cancellation
+// against n_ice), so ONE code path evaluates every piece, and dR/dt comes out of the same pass for ~25 % more
+// arithmetic: roots are closed with safeguarded Newton steps (3-4 evaluations from straight-line starting points).
 #pragma once
 #include <math.h>
 #include <stdint.h>
@@ -53,11 +56,12 @@ struct IceParams {            // medium_base.py:206-252 (+ add_reflective_bottom
 struct PairGeom {             // 2-D problem after set_start_and_end_point (py:2057-2090): z1 <= z2
     double z1, z2, rho;
     double g1, g2, n1, n2;    // gamma and n at z1, z2
-    // radicand offsets (see eval_range)
-    double A1, A2, Ar;        // (dn - gamma_i)(n_i + ns):  s_i^2 = A_i + sigma_s^2   ("sub" pieces)
-    double B1, Br;            // (g2 - gamma_i)(n_i + n2):  s_i^2 = B_i + s2^2        ("band" pieces)
+    // radicand offsets (see ray_state)
+    double A1, A2, Ar;        // (dn - gamma_i)(n_i + ns):  s_i^2 = A_i + sigma^2   ("sub" pieces,  sigma = s(0))
+    double B1, Br;            // (g2 - gamma_i)(n_i + n2):  s_i^2 = B_i + sigma^2   ("band" pieces, sigma = s(z2))
     double c0_sub, c0_band;   // c = c0 + sigma^2
     double s2max;             // sqrt(n2^2 - ns^2)
+    double tmin;              // band pieces: t in [tmin, 1]  <->  beta in [ns, n2]
 };
 
 struct ModeCoeffs { int aT, a1, a2, ar; };
@@ -74,11 +78,11 @@ NRMC_HD ModeCoeffs mode_coeffs(int k, int rcase, bool turned)
 
 NRMC_HD double ipow(double x, int n) { double r = 1.0; for (int i = 0; i < n; ++i) r *= x; return r; }
 
-NRMC_HD void make_pair_geom(const IceParams &ice, double z1, double z2, double rho, PairGeom &g)
+// pair geometry from the depths and the two gammas (gamma = dn exp(z/z0) is the only transcendental in it)
+NRMC_HD void make_pair_geom_g(const IceParams &ice, double z1, double z2, double rho, double g1, double g2, PairGeom &g)
 {
     g.z1 = z1; g.z2 = z2; g.rho = rho;
-    g.g1 = ice.dn * exp(z1 * ice.inv_z0);
-    g.g2 = ice.dn * exp(z2 * ice.inv_z0);
+    g.g1 = g1; g.g2 = g2;
     g.n1 = ice.n_ice - g.g1; g.n2 = ice.n_ice - g.g2;
     g.A1 = (ice.dn - g.g1) * (g.n1 + ice.ns);
     g.A2 = (ice.dn - g.g2) * (g.n2 + ice.ns);
@@ -88,6 +92,30 @@ NRMC_HD void make_pair_geom(const IceParams &ice, double z1, double z2, double r
     g.c0_sub = ice.dn * (ice.n_ice + ice.ns);
     g.c0_band = g.g2 * (ice.n_ice + g.n2);
     g.s2max = sqrt(fmax(g.A2, 0.0));
+    g.tmin = ice.ns / (g.n2 + g.s2max);
+}
+
+NRMC_HD void make_pair_geom(const IceParams &ice, double z1, double z2, double rho, PairGeom &g)
+{
+    make_pair_geom_g(ice, z1, z2, rho, ice.dn * exp(z1 * ice.inv_z0), ice.dn * exp(z2 * ice.inv_z0), g);
+}
+
+// Both piece classes use the rational parametrisation of the circle beta^2 + sigma^2 = nX^2:
+//   beta = nX 2t/(1+t^2),  sigma = nX (1-t^2)/(1+t^2),  t in (0, 1],
+// "sub" (P0, P3): nX = n_s, sigma = s(0);  "band" (P1, P2): nX = n2, sigma = s(z2), t in [tmin, 1].
+// Every other radicand is an offset plus sigma^2, so one code path evaluates both classes (no divergence).
+struct PieceConsts { double nX, c0, O1, O2, Or; bool band; };
+
+NRMC_HD PieceConsts piece_consts(const IceParams &ice, const PairGeom &g, bool band)
+{
+    PieceConsts pc;
+    pc.band = band;
+    pc.nX = band ? g.n2 : ice.ns;
+    pc.c0 = band ? g.c0_band : g.c0_sub;
+    pc.O1 = band ? g.B1 : g.A1;
+    pc.O2 = band ? 0.0 : g.A2;
+    pc.Or = band ? g.Br : g.Ar;
+    return pc;
 }
 
 // Quantities of one ray (one value of beta) that the property formulas need.
@@ -98,30 +126,20 @@ struct RayState {
     bool reflected;           // turning point is the surface (beta <= n_s)
 };
 
-// Evaluate the ray state for a point of the curve.  sub: v = t in [0,1]; band: v = s2 in [0, s2max].
-NRMC_HD void ray_state(const IceParams &ice, const PairGeom &g, bool band, double v, RayState &r)
+// Evaluate the ray state for the point t of a piece of class `band`.
+NRMC_HD void ray_state(const IceParams &ice, const PairGeom &g, bool band, double t, RayState &r)
 {
-    double c;
-    if (!band) {
-        double q = 1.0 / (1.0 + v * v);
-        r.beta = ice.ns * (2.0 * v) * q;
-        r.ss = ice.ns * ((1.0 - v) * (1.0 + v)) * q;
-        double sg2 = r.ss * r.ss;
-        c = g.c0_sub + sg2;
-        r.s1 = sqrt(g.A1 + sg2);
-        r.s2 = sqrt(g.A2 + sg2);
-        r.sr = ice.n_refl > 0 ? sqrt(g.Ar + sg2) : 0.0;
-        r.reflected = true;
-    } else {
-        double sg2 = v * v;
-        r.beta = sqrt(fmax(g.n2 * g.n2 - sg2, 0.0));
-        r.ss = 0.0;
-        c = g.c0_band + sg2;
-        r.s1 = sqrt(g.B1 + sg2);
-        r.s2 = v;
-        r.sr = ice.n_refl > 0 ? sqrt(g.Br + sg2) : 0.0;
-        r.reflected = false;
-    }
+    const PieceConsts pc = piece_consts(ice, g, band);
+    const double q = 1.0 / (1.0 + t * t);
+    r.beta = pc.nX * (2.0 * t) * q;
+    const double sig = pc.nX * ((1.0 - t) * (1.0 + t)) * q;
+    const double sg2 = sig * sig;
+    const double c = pc.c0 + sg2;
+    r.ss = band ? 0.0 : sig;
+    r.s1 = sqrt(pc.O1 + sg2);
+    r.s2 = band ? sig : sqrt(pc.O2 + sg2);
+    r.sr = ice.n_refl > 0 ? sqrt(pc.Or + sg2) : 0.0;
+    r.reflected = !band;
     r.rc = sqrt(c);
     r.k1_1 = r.rc * r.s1 + (c - ice.n_ice * g.g1);
     r.k1_2 = r.rc * r.s2 + (c - ice.n_ice * g.g2);
@@ -129,108 +147,132 @@ NRMC_HD void ray_state(const IceParams &ice, const PairGeom &g, bool band, doubl
     r.KT = r.reflected ? r.rc * r.ss + (c - ice.n_ice * ice.dn) : ice.dn * r.beta;
 }
 
-// horizontal range of the path family m for the ray r
-NRMC_HD double range_of(const IceParams &ice, const PairGeom &g, const ModeCoeffs &m, const RayState &r)
-{
-    double num = 1.0, den = 1.0;
-    if (m.a1 > 0) num *= r.k1_1; else den *= r.k1_1;            // |a1| == 1
-    if (m.a2 > 0) num *= r.k1_2; else den *= r.k1_2;            // |a2| == 1
-    num *= ipow(r.KT, m.aT);
-    double lin = m.a1 * g.z1 + m.a2 * g.z2;
-    if (m.ar != 0) { den *= ipow(r.k1_r, -m.ar); lin += m.ar * ice.zr; }
-    double R = (r.beta / r.rc) * (lin - ice.z0 * log(num / den));
-    return R;
-}
+// parameter t of the ray with invariant beta inside a class with radius nX (beta < nX)
+NRMC_HD double t_of_beta(double nX, double beta) { return beta / (nX + sqrt(fmax((nX - beta) * (nX + beta), 0.0))); }
 
 struct Curve {                // one (reflection, case) mode of one pair
     const IceParams *ice;
     const PairGeom *g;
-    ModeCoeffs m_dir, m_trn;
+    int k, rcase;
 };
 
-// piece p in {0,1,2,3}; value of R - rho at parameter v of that piece
-NRMC_HD double curve_g(const Curve &cv, int p, double v)
-{
-#ifdef NRMC_COUNT_EVALS
-    ++g_evals;
+#ifndef NRMC_RSQRT
+#if defined(__CUDA_ARCH__)
+#define NRMC_RSQRT(x) rsqrt(x)
+#else
+#define NRMC_RSQRT(x) (1.0 / sqrt(x))
 #endif
-    RayState r;
-    ray_state(*cv.ice, *cv.g, (p == 1 || p == 2), v, r);
-    double R = range_of(*cv.ice, *cv.g, (p >= 2) ? cv.m_trn : cv.m_dir, r);
-    if (!(R == R)) R = 1e300;  // horizontal ray in (numerically) homogeneous ice: infinite range
-    return R - cv.g->rho;
-}
+#endif
 
-// g = R - rho and its derivative with respect to the piece parameter v (closed form; used to locate the maximum of R
-// when the whole curve was sampled below rho).
-NRMC_HD double curve_gd(const Curve &cv, int p, double v, double &dg)
+// g = R - rho on piece p in {0,1,2,3} at parameter t and (WITH_D) dg/dt, in ONE pass.  With h = sigma sigma',
+//   d k1_i = h (s_i/rc + rc/s_i + 2),  d ln P = sum a_i d k_i / k_i  (one shared reciprocal for k = 0),
+//   R = A B,  A = beta/rc,  B = lin - z0 ln P.
+template <bool WITH_D>
+NRMC_HD double curve_eval(const Curve &cv, int p, double t, double &dg)
 {
 #ifdef NRMC_COUNT_EVALS
     ++g_evals;
 #endif
     const IceParams &ice = *cv.ice;
     const PairGeom &g = *cv.g;
-    const bool band = (p == 1 || p == 2);
-    const ModeCoeffs &m = (p >= 2) ? cv.m_trn : cv.m_dir;
-    RayState r;
-    ray_state(ice, g, band, v, r);
-    double db, dc, ds1, ds2, dsr, dKT;     // derivatives of beta, c, s1, s2, sr, KT with respect to v
-    if (!band) {
-        const double q = 1.0 / (1.0 + v * v);
-        db = 2.0 * r.ss * q;
-        const double dss = -2.0 * r.beta * q;
-        const double h = r.ss * dss;        // d(ss^2)/dv / 2
-        dc = 2.0 * h;
-        ds1 = r.s1 > 0 ? h / r.s1 : 0.0; ds2 = r.s2 > 0 ? h / r.s2 : 0.0; dsr = r.sr > 0 ? h / r.sr : 0.0;
-        const double drc = h / r.rc;
-        dKT = drc * r.ss + r.rc * dss + dc;
-    } else {
-        db = -v / r.beta;
-        dc = 2.0 * v;
-        ds1 = r.s1 > 0 ? v / r.s1 : 0.0; ds2 = 1.0; dsr = r.sr > 0 ? v / r.sr : 0.0;
-        dKT = ice.dn * db;
+    const bool band = (p == 1 || p == 2), turned = (p >= 2);
+    const PieceConsts pc = piece_consts(ice, g, band);
+    const double q = 1.0 / (1.0 + t * t);
+    const double beta = pc.nX * (2.0 * t) * q;
+    const double sig = pc.nX * ((1.0 - t) * (1.0 + t)) * q;
+    const double sg2 = sig * sig;
+    const double c = pc.c0 + sg2;
+    const double irc = NRMC_RSQRT(c), rc = c * irc;
+    const double x1 = pc.O1 + sg2, x2 = pc.O2 + sg2;
+    const double is1 = NRMC_RSQRT(fmax(x1, 1e-300)), is2 = NRMC_RSQRT(fmax(x2, 1e-300));
+    const double s1 = x1 * is1, s2 = band ? sig : x2 * is2;
+    const double k1 = rc * s1 + (c - ice.n_ice * g.g1), k2 = rc * s2 + (c - ice.n_ice * g.g2);
+    const double KT = band ? ice.dn * beta : rc * sig + (c - ice.n_ice * ice.dn);
+    const double A = beta * irc;
+    // derivatives with respect to t
+    double bp = 0, sp = 0, h = 0, drc = 0, dc = 0, dk1 = 0, dk2 = 0, dKT = 0;
+    if (WITH_D) {
+        bp = 2.0 * sig * q; sp = -2.0 * beta * q; h = sig * sp;
+        drc = h * irc; dc = 2.0 * h;
+        dk1 = drc * s1 + rc * (sp * (sig * is1)) + dc;
+        dk2 = drc * s2 + rc * (band ? sp : sp * (sig * is2)) + dc;
+        dKT = band ? ice.dn * bp : drc * sig + rc * sp + dc;
     }
-    const double drc = 0.5 * dc / r.rc;
-    const double dk1 = drc * r.s1 + r.rc * ds1 + dc, dk2 = drc * r.s2 + r.rc * ds2 + dc;
-    double dlnP = m.a1 * dk1 / r.k1_1 + m.a2 * dk2 / r.k1_2 + (m.aT ? m.aT * dKT / r.KT : 0.0);
-    if (m.ar != 0) dlnP += m.ar * (drc * r.sr + r.rc * dsr + dc) / r.k1_r;
-    const double A = r.beta / r.rc;
-    const double dA = (db - A * drc) / r.rc;
-    double num = 1.0, den = 1.0;
-    if (m.a1 > 0) num *= r.k1_1; else den *= r.k1_1;
-    if (m.a2 > 0) num *= r.k1_2; else den *= r.k1_2;
-    num *= ipow(r.KT, m.aT);
-    double lin = m.a1 * g.z1 + m.a2 * g.z2;
-    if (m.ar != 0) { den *= ipow(r.k1_r, -m.ar); lin += m.ar * ice.zr; }
-    const double Bk = lin - ice.z0 * log(num / den);
+    double P, lin, dlnP = 0.0;
+    if (cv.k == 0) {
+        const double Kx = turned ? KT : 1.0;
+        const double iv = 1.0 / (k1 * k2 * Kx);
+        P = (turned ? KT * KT * KT : k2 * k2) * iv;
+        lin = turned ? -g.z1 - g.z2 : g.z2 - g.z1;
+        if (WITH_D) dlnP = ((turned ? 2.0 * dKT * k1 * k2 - dk2 * k1 * KT : dk2 * k1) - dk1 * k2 * Kx) * iv;
+    } else {
+        const ModeCoeffs m = mode_coeffs(cv.k, cv.rcase, turned);
+        const double xr = pc.Or + sg2, isr = NRMC_RSQRT(fmax(xr, 1e-300)), sr = xr * isr;
+        const double kr = rc * sr + (c - ice.n_ice * ice.gr);
+        double num = 1.0, den = 1.0;
+        if (m.a1 > 0) num *= k1; else den *= k1;            // |a1| == 1
+        if (m.a2 > 0) num *= k2; else den *= k2;            // |a2| == 1
+        num *= ipow(KT, m.aT);
+        den *= ipow(kr, -m.ar);
+        P = num / den;
+        lin = m.a1 * g.z1 + m.a2 * g.z2 + m.ar * ice.zr;
+        if (WITH_D) {
+            const double dkr = drc * sr + rc * (sp * (sig * isr)) + dc;
+            dlnP = m.a1 * dk1 / k1 + m.a2 * dk2 / k2 + m.ar * dkr / kr + (m.aT ? m.aT * dKT / KT : 0.0);
+        }
+    }
+    const double Bk = lin - ice.z0 * log(P);
     double R = A * Bk;
-    dg = dA * Bk - A * ice.z0 * dlnP;
-    if (!(R == R)) { R = 1e300; dg = 0.0; }
+    if (WITH_D) dg = (bp - A * drc) * irc * Bk - A * ice.z0 * dlnP;
+    if (!(R == R)) { R = 1e300; if (WITH_D) dg = 0.0; }   // horizontal ray in (numerically) homogeneous ice: infinite range
     return R - g.rho;
 }
 
-// Bracketed root of g on piece p between a and b (ga, gb of opposite strict sign): regula falsi with the Illinois
-// modification, bisection safeguard; converges superlinearly on the smooth pieces.
-NRMC_HD double solve_piece(const Curve &cv, int p, double a, double ga, double b, double gb)
+NRMC_HD double curve_g(const Curve &cv, int p, double t) { double d; return curve_eval<false>(cv, p, t, d); }
+NRMC_HD double curve_gd(const Curve &cv, int p, double t, double &dg) { return curve_eval<true>(cv, p, t, dg); }
+
+// Starting point for the root on piece p (NaN: none).  Direct rays (P0, P1): the straight line between the two points
+// in ice of the path-averaged index n_bar = n_ice - z0 (gamma2 - gamma1)/(z2 - z1) has beta = n_bar sin(theta);
+// reflected rays (P3): the same with the receiver mirrored at the surface.  Only used for k = 0.
+NRMC_HD double guess_t(const IceParams &ice, const PairGeom &g, int p)
+{
+    if (p == 2) return NAN;
+    const double dz = (p == 3) ? -g.z1 - g.z2 : g.z2 - g.z1;
+    if (!(dz > 0.0)) return NAN;
+    const double dgam = (p == 3) ? (ice.dn - g.g1) + (ice.dn - g.g2) : g.g2 - g.g1;
+    const double nbar = ice.n_ice - ice.z0 * dgam / dz;
+    const double b0 = nbar * g.rho / sqrt(g.rho * g.rho + dz * dz);
+    const double nX = (p == 1) ? g.n2 : ice.ns;
+    return (b0 < nX) ? t_of_beta(nX, b0) : NAN;
+}
+
+// Bracketed root of g on piece p between a and b (ga, gb of opposite strict sign): Newton steps with the closed-form
+// derivative, kept inside the bracket (bisection when a step leaves it).  x0: starting point (NaN: secant point).
+// Stops on |g| <= 1e-10 m or when the Newton step is below 1e-9 relative (the step is then applied unevaluated:
+// quadratic convergence puts the result at ~1e-16).
+NRMC_HD double solve_piece(const Curve &cv, int p, double a, double ga, double b, double gb, double x0)
 {
     const double gtol = 1e-10;
-    int side = 0;
-    double x = a;
+    double lo = fmin(a, b), hi = fmax(a, b);
+    double x = x0;
+    if (!(x > lo && x < hi)) x = (a * gb - b * ga) / (gb - ga);
+    if (!(x > lo && x < hi)) x = 0.5 * (a + b);
     for (int it = 0; it < 100; ++it) {
-        double denom = gb - ga;
-        x = (a * gb - b * ga) / denom;
-        double lo = fmin(a, b), hi = fmax(a, b);
-        if (!(x > lo && x < hi)) x = 0.5 * (a + b);
-        double gx = curve_g(cv, p, x);
+        double dg;
+        const double gx = curve_gd(cv, p, x, dg);
         if (fabs(gx) <= gtol) break;
-        if ((gx > 0) == (gb > 0)) { b = x; gb = gx; if (side == 1) ga *= 0.5; side = 1; }
-        else { a = x; ga = gx; if (side == -1) gb *= 0.5; side = -1; }
-        if (fabs(b - a) <= 4e-16 * (fabs(a) + fabs(b))) { x = (fabs(ga) < fabs(gb)) ? a : b; break; }
+        if ((gx > 0) == (gb > 0)) { b = x; gb = gx; } else { a = x; ga = gx; }
+        lo = fmin(a, b); hi = fmax(a, b);
+        double xn = x - gx / dg;
+        if (!(xn > lo && xn < hi)) xn = 0.5 * (a + b);
+        else if (fabs(xn - x) <= 1e-9 * (fabs(x) + 1e-3)) { x = xn; break; }
+        if (hi - lo <= 4e-16 * (fabs(lo) + fabs(hi))) { x = xn; break; }
+        x = xn;
     }
     return x;
 }
 
-// Look for an interior maximum of g on piece p (end values <= 0): bracket the sign change of dg/dv and close it
+// Look for an interior maximum of g on piece p (end values <= 0): bracket the sign change of dg/dt and close it
 // with Illinois steps on the derivative.  Returns true as soon as a point with g > 0 is found (xm, gm); false if the
 // maximum is at an end point or stays <= 0.  `interior` tells the caller whether this piece holds the curve's maximum.
 NRMC_HD bool maximise_piece(const Curve &cv, int p, double a, double b, double &xm, double &gm, bool &interior)
@@ -239,6 +281,7 @@ NRMC_HD bool maximise_piece(const Curve &cv, int p, double a, double b, double &
     double dlo, dhi;
     double glo = curve_gd(cv, p, lo, dlo);
     double ghi = curve_gd(cv, p, hi, dhi);
+    (void)ghi;
     interior = (dlo > 0.0) && (dhi < 0.0);
     xm = lo; gm = glo;
     if (!interior) return false;
@@ -262,68 +305,92 @@ NRMC_HD bool maximise_piece(const Curve &cv, int p, double a, double b, double &
 }
 
 struct Root { double v; int piece; double beta; };
+struct Bracket { double a, ga, b, gb; int piece; };
 
-// All roots (0 or 2; 1 only on a tangency) of one mode, ordered by increasing C0 = 1/beta.
-// Written so that the solver and the maximum search each have ONE call site: everything inlines into the kernel and
-// the pair geometry stays in registers.
-NRMC_HD int find_roots_mode(const IceParams &ice, const PairGeom &g, int k, int rcase, Root out[2])
+// piece end points in curve order: P0 t: 0 -> 1, P1 t: tmin -> 1, P2 t: 1 -> tmin, P3 t: 1 -> 0
+NRMC_HD double piece_begin(const PairGeom &g, int p) { return p == 0 ? 0.0 : (p == 1 ? g.tmin : 1.0); }
+NRMC_HD double piece_end(const PairGeom &g, int p) { return p <= 1 ? 1.0 : (p == 2 ? g.tmin : 0.0); }
+
+// Junction values of the curve (J0 = J4 = -rho at the vertical ray) and the brackets they give.  Returns the number of
+// brackets (0..2); need_hump: the whole curve was sampled below rho, the maximum has to be searched (hump_search).
+NRMC_HD int classify_mode(const Curve &cv, double &J1, double &J2, double &J3, Bracket br[2], bool &need_hump)
 {
-    Curve cv;
-    cv.ice = &ice; cv.g = &g;
-    cv.m_dir = mode_coeffs(k, rcase, false);
-    cv.m_trn = mode_coeffs(k, rcase, true);
+    const PairGeom &g = *cv.g;
     const bool has_band = g.s2max > 0.0;
-    // piece end points (parameter values) in curve order: P0 t:0->1, P1 s2:s2max->0, P2 s2:0->s2max, P3 t:1->0
     const double J0 = -g.rho, J4 = -g.rho;
-    const double J1 = curve_g(cv, 0, 1.0);
-    const double J3 = curve_g(cv, 3, 1.0);
-    const double J2 = has_band ? curve_g(cv, 1, 0.0) : J1;
-    // brackets: (piece, a, g(a), b, g(b)), at most two
-    int bp0 = 0, bp1 = 0, nb = 0;
-    double ba0 = 0, bga0 = 0, bb0 = 0, bgb0 = 0, ba1 = 0, bga1 = 0, bb1 = 0, bgb1 = 0;
-#define NRMC_PUSH_BRACKET(P, A, GA, B, GB)                                               \
-    do {                                                                                  \
-        if (nb == 0) { bp0 = (P); ba0 = (A); bga0 = (GA); bb0 = (B); bgb0 = (GB); }       \
-        else if (nb == 1) { bp1 = (P); ba1 = (A); bga1 = (GA); bb1 = (B); bgb1 = (GB); }  \
-        ++nb;                                                                             \
+    J1 = curve_g(cv, 0, 1.0);
+    J3 = curve_g(cv, 3, 1.0);
+    J2 = has_band ? curve_g(cv, 1, 1.0) : J1;
+    int nb = 0;
+#define NRMC_PUSH_BRACKET(P, A, GA, B, GB)                                                         \
+    do {                                                                                            \
+        if (nb < 2) { br[nb].piece = (P); br[nb].a = (A); br[nb].ga = (GA); br[nb].b = (B); br[nb].gb = (GB); } \
+        ++nb;                                                                                       \
     } while (0)
     // receiver exactly at the surface (no band): P0 and P3 coincide (py: one 'reflected' solution) -> only P3
     if (has_band && ((J0 > 0) != (J1 > 0))) NRMC_PUSH_BRACKET(0, 0.0, J0, 1.0, J1);
-    if (has_band && ((J1 > 0) != (J2 > 0))) NRMC_PUSH_BRACKET(1, g.s2max, J1, 0.0, J2);
-    if (has_band && ((J2 > 0) != (J3 > 0))) NRMC_PUSH_BRACKET(2, 0.0, J2, g.s2max, J3);
+    if (has_band && ((J1 > 0) != (J2 > 0))) NRMC_PUSH_BRACKET(1, g.tmin, J1, 1.0, J2);
+    if (has_band && ((J2 > 0) != (J3 > 0))) NRMC_PUSH_BRACKET(2, 1.0, J2, g.tmin, J3);
     if ((J3 > 0) != (J4 > 0)) NRMC_PUSH_BRACKET(3, 1.0, J3, 0.0, J4);
-    if (nb == 0 && J1 <= 0 && J2 <= 0 && J3 <= 0) {
-        // whole curve sampled below rho: look for a hump inside the pieces adjacent to the largest junction
-        int jm = 1;
-        double Jm = J1;
-        if (J2 > Jm) { jm = 2; Jm = J2; }
-        if (J3 > Jm) { jm = 3; Jm = J3; }
-        bool interior = false;
-        for (int side = 0; side < 2 && nb == 0 && !interior; ++side) {
-            const int p = jm - 1 + side;
-            if (!has_band && p != 3) continue;
-            const double pa = (p == 1) ? g.s2max : ((p == 3) ? 1.0 : 0.0);
-            const double pb = (p == 0) ? 1.0 : ((p == 2) ? g.s2max : 0.0);
-            const double ja = (p == 0) ? J0 : (p == 1 ? J1 : (p == 2 ? J2 : J3));
-            const double jb = (p == 0) ? J1 : (p == 1 ? J2 : (p == 2 ? J3 : J4));
-            double xm, gm;
-            if (maximise_piece(cv, p, pa, pb, xm, gm, interior)) {
-                NRMC_PUSH_BRACKET(p, pa, ja, xm, gm);
-                NRMC_PUSH_BRACKET(p, xm, gm, pb, jb);
-            }
+#undef NRMC_PUSH_BRACKET
+    need_hump = (nb == 0 && J1 <= 0 && J2 <= 0 && J3 <= 0);
+    return nb > 2 ? 2 : nb;
+}
+
+// The hump of a curve whose junctions all lie below rho: search the pieces adjacent to the largest junction.
+// Returns 2 (two brackets around the maximum) or 0.
+NRMC_HD int hump_search(const Curve &cv, double J1, double J2, double J3, Bracket br[2])
+{
+    const PairGeom &g = *cv.g;
+    const bool has_band = g.s2max > 0.0;
+    const double J0 = -g.rho, J4 = -g.rho;
+    int jm = 1;
+    double Jm = J1;
+    if (J2 > Jm) { jm = 2; Jm = J2; }
+    if (J3 > Jm) { jm = 3; Jm = J3; }
+    bool interior = false;
+    for (int side = 0; side < 2 && !interior; ++side) {
+        const int p = jm - 1 + side;
+        if (!has_band && p != 3) continue;
+        const double pa = piece_begin(g, p), pb = piece_end(g, p);
+        const double ja = (p == 0) ? J0 : (p == 1 ? J1 : (p == 2 ? J2 : J3));
+        const double jb = (p == 0) ? J1 : (p == 1 ? J2 : (p == 2 ? J3 : J4));
+        double xm, gm;
+        if (maximise_piece(cv, p, pa, pb, xm, gm, interior)) {
+            br[0].piece = p; br[0].a = pa; br[0].ga = ja; br[0].b = xm; br[0].gb = gm;
+            br[1].piece = p; br[1].a = xm; br[1].ga = gm; br[1].b = pb; br[1].gb = jb;
+            return 2;
         }
     }
-#undef NRMC_PUSH_BRACKET
-    if (nb > 2) nb = 2;
+    return 0;
+}
+
+NRMC_HD Root solve_bracket(const Curve &cv, const Bracket &b)
+{
+    Root r;
+    r.piece = b.piece;
+    // the straight-line starting points describe the whole piece; a bracket made by the hump search starts from its secant point
+    const bool whole = (b.a == piece_begin(*cv.g, b.piece) && b.b == piece_end(*cv.g, b.piece));
+    r.v = solve_piece(cv, b.piece, b.a, b.ga, b.b, b.gb, (cv.k == 0 && whole) ? guess_t(*cv.ice, *cv.g, b.piece) : NAN);
+    const double q = 1.0 / (1.0 + r.v * r.v);
+    r.beta = ((b.piece == 1 || b.piece == 2) ? cv.g->n2 : cv.ice->ns) * (2.0 * r.v) * q;
+    return r;
+}
+
+// All roots (0 or 2; 1 only on a tangency) of one mode, ordered by increasing C0 = 1/beta.
+NRMC_HD int find_roots_mode(const IceParams &ice, const PairGeom &g, int k, int rcase, Root out[2])
+{
+    Curve cv;
+    cv.ice = &ice; cv.g = &g; cv.k = k; cv.rcase = rcase;
+    double J1, J2, J3;
+    Bracket br[2];
+    bool need_hump;
+    int nb = classify_mode(cv, J1, J2, J3, br, need_hump);
+    if (need_hump) nb = hump_search(cv, J1, J2, J3, br);
     Root r0, r1;
     r0.v = r1.v = 0; r0.piece = r1.piece = 0; r0.beta = r1.beta = 0;
-    for (int i = 0; i < nb; ++i) {
-        const int p = i == 0 ? bp0 : bp1;
-        const double v = solve_piece(cv, p, i == 0 ? ba0 : ba1, i == 0 ? bga0 : bga1, i == 0 ? bb0 : bb1, i == 0 ? bgb0 : bgb1);
-        RayState rs;
-        ray_state(ice, g, (p == 1 || p == 2), v, rs);
-        if (i == 0) { r0.v = v; r0.piece = p; r0.beta = rs.beta; } else { r1.v = v; r1.piece = p; r1.beta = rs.beta; }
-    }
+    if (nb > 0) r0 = solve_bracket(cv, br[0]);
+    if (nb > 1) r1 = solve_bracket(cv, br[1]);
     if (nb == 2 && r0.beta < r1.beta) { Root t = r0; r0 = r1; r1 = t; }  // ascending C0 (py:1547)
     out[0] = r0; out[1] = r1;
     return nb;
@@ -436,17 +503,58 @@ NRMC_HD void make_frame(double ax, double ay, double az, double bx, double by, d
     f.z1 = az; f.z2 = bz; f.x1y = ax;
 }
 
+// empty slots: 0 / NaN (HDF5 writer convention, output_writer_hdf5.py:272-275)
+NRMC_HD void fill_empty_slot(const TraceOutputs &o, int64_t q, int K1)
+{
+    if (o.type) o.type[q] = 0;
+    if (o.reflection) o.reflection[q] = 0;
+    if (o.reflection_case) o.reflection_case[q] = 0;
+    if (o.C0) o.C0[q] = NAN;
+    if (o.C1) o.C1[q] = NAN;
+    if (o.path_length) o.path_length[q] = NAN;
+    if (o.travel_time) o.travel_time[q] = NAN;
+    if (o.launch) { o.launch[3 * q] = NAN; o.launch[3 * q + 1] = NAN; o.launch[3 * q + 2] = NAN; }
+    if (o.receive) { o.receive[3 * q] = NAN; o.receive[3 * q + 1] = NAN; o.receive[3 * q + 2] = NAN; }
+    if (o.reflection_angle) for (int t = 0; t < K1; ++t) o.reflection_angle[q * K1 + t] = NAN;
+}
+
+NRMC_HD void write_solution(const TraceOutputs &o, int64_t q, int K1, const Frame2D &f, int k, int rcase, const SolutionProps &p)
+{
+    if (o.type) o.type[q] = (int8_t)p.type;
+    if (o.reflection) o.reflection[q] = (int8_t)k;
+    if (o.reflection_case) o.reflection_case[q] = (int8_t)rcase;
+    if (o.C0) o.C0[q] = p.C0;
+    if (o.C1) o.C1[q] = p.C1;
+    if (o.path_length) o.path_length[q] = p.path_length;
+    if (o.travel_time) o.travel_time[q] = p.travel_time;
+    // 2-D vectors -> 3-D: R^T [vx,0,vz] = [vx ex, vx ey, vz]; roles exchanged when swapped (py:2583-2590,2617-2623)
+    double lx = p.sin_l, lz = p.cos_l, rx = -p.sin_r, rz = p.cos_r;
+    if (f.swap) { double tx = lx, tz = lz; lx = rx; lz = rz; rx = tx; rz = tz; }
+    if (o.launch) { o.launch[3 * q] = lx * f.ex; o.launch[3 * q + 1] = lx * f.ey; o.launch[3 * q + 2] = lz; }
+    if (o.receive) { o.receive[3 * q] = rx * f.ex; o.receive[3 * q + 1] = rx * f.ey; o.receive[3 * q + 2] = rz; }
+    if (o.reflection_angle)
+        for (int s = 0; s < K1; ++s) o.reflection_angle[q * K1 + s] = ((p.refl_mask >> s) & 1u) ? p.refl_angle : NAN;
+}
+
+// status of a pair before any ray is traced (0: traceable)
+NRMC_HD int pair_status(const IceParams &ice, const Frame2D &f)
+{
+    if (!(f.rho == f.rho) || !(f.z1 == f.z1) || !(f.z2 == f.z2) || isinf(f.rho) || isinf(f.z1)) return NRMC_STATUS_NONFINITE;
+    if (f.z2 > 0.0) return NRMC_STATUS_AIR;
+    if (ice.n_refl > 0 && f.z1 < ice.zr) return NRMC_STATUS_BELOW_REFLECTOR;
+    return 0;
+}
+
 // Returns the number of solutions; fills the SoA slots of pair i and (if recs != null) one SolRec per solution.
+// Thread-per-pair form: used by the generic kernel (bottom reflections) and by the CPU test harness.
 NRMC_HD int trace_pair(const IceParams &ice, double ax, double ay, double az, double bx, double by, double bz,
                         int64_t i, const TraceOutputs &o, SolRec *recs)
 {
     const int S = 2 + 4 * ice.n_refl, K1 = ice.n_refl + 1;
-    int status = 0, n = 0;
+    int n = 0;
     Frame2D f;
     make_frame(ax, ay, az, bx, by, bz, f);
-    if (!(f.rho == f.rho) || !(f.z1 == f.z1) || !(f.z2 == f.z2) || isinf(f.rho) || isinf(f.z1)) status |= NRMC_STATUS_NONFINITE;
-    else if (f.z2 > 0.0) status |= NRMC_STATUS_AIR;
-    else if (ice.n_refl > 0 && f.z1 < ice.zr) status |= NRMC_STATUS_BELOW_REFLECTOR;
+    const int status = pair_status(ice, f);
     if (status == 0) {
         PairGeom g;
         make_pair_geom(ice, f.z1, f.z2, fmax(f.rho, 1e-12), g);
@@ -458,22 +566,7 @@ NRMC_HD int trace_pair(const IceParams &ice, double ax, double ay, double az, do
             for (int j = 0; j < nr && n < S; ++j) {
                 SolutionProps p;
                 solution_props(ice, g, f.x1y, k, rcase, roots[j], p);
-                const int64_t q = i * S + n;
-                if (o.type) o.type[q] = (int8_t)p.type;
-                if (o.reflection) o.reflection[q] = (int8_t)k;
-                if (o.reflection_case) o.reflection_case[q] = (int8_t)rcase;
-                if (o.C0) o.C0[q] = p.C0;
-                if (o.C1) o.C1[q] = p.C1;
-                if (o.path_length) o.path_length[q] = p.path_length;
-                if (o.travel_time) o.travel_time[q] = p.travel_time;
-                // 2-D vectors -> 3-D: R^T [vx,0,vz] = [vx ex, vx ey, vz]; roles exchanged when swapped (py:2583-2590,2617-2623)
-                double lx = p.sin_l, lz = p.cos_l, rx = -p.sin_r, rz = p.cos_r;
-                if (f.swap) { double tx = lx, tz = lz; lx = rx; lz = rz; rx = tx; rz = tz; }
-                if (o.launch) { o.launch[3 * q] = lx * f.ex; o.launch[3 * q + 1] = lx * f.ey; o.launch[3 * q + 2] = lz; }
-                if (o.receive) { o.receive[3 * q] = rx * f.ex; o.receive[3 * q + 1] = rx * f.ey; o.receive[3 * q + 2] = rz; }
-                if (o.reflection_angle)
-                    for (int s = 0; s < K1; ++s)
-                        o.reflection_angle[q * K1 + s] = ((p.refl_mask >> s) & 1u) ? p.refl_angle : NAN;
+                write_solution(o, i * S + n, K1, f, k, rcase, p);
                 if (recs) { recs[n].v = roots[j].v; recs[n].pair = i; recs[n].slot = n; recs[n].piece = (uint8_t)roots[j].piece;
                             recs[n].k = (uint8_t)k; recs[n].rcase = (uint8_t)rcase; recs[n].pad = 0; }
                 ++n;
@@ -482,19 +575,7 @@ NRMC_HD int trace_pair(const IceParams &ice, double ax, double ay, double az, do
     }
     if (o.n_sol) o.n_sol[i] = n;
     if (o.status) o.status[i] = status;
-    for (int s = n; s < S; ++s) {   // empty slots: 0 / NaN (HDF5 writer convention, output_writer_hdf5.py:272-275)
-        const int64_t q = i * S + s;
-        if (o.type) o.type[q] = 0;
-        if (o.reflection) o.reflection[q] = 0;
-        if (o.reflection_case) o.reflection_case[q] = 0;
-        if (o.C0) o.C0[q] = NAN;
-        if (o.C1) o.C1[q] = NAN;
-        if (o.path_length) o.path_length[q] = NAN;
-        if (o.travel_time) o.travel_time[q] = NAN;
-        if (o.launch) { o.launch[3 * q] = NAN; o.launch[3 * q + 1] = NAN; o.launch[3 * q + 2] = NAN; }
-        if (o.receive) { o.receive[3 * q] = NAN; o.receive[3 * q + 1] = NAN; o.receive[3 * q + 2] = NAN; }
-        if (o.reflection_angle) for (int t = 0; t < K1; ++t) o.reflection_angle[q * K1 + t] = NAN;
-    }
+    for (int s = n; s < S; ++s) fill_empty_slot(o, i * S + s, K1);
     return n;
 }
 

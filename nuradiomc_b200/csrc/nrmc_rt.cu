@@ -80,6 +80,197 @@ K_solve(IceParams ice, KInput in, TraceOutputs out, SolRec *worklist, unsigned l
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Binned solver for media without bottom reflections (one mode per pair).  Pairs differ wildly in the work they need
+// (shadow zone: a maximum search; lit zone: two root solves), so a thread-per-pair kernel runs with half-empty warps.
+// Here the work is split at the points where it diverges and re-packed through queues in HBM (64-byte items, a few
+// GB/s -- HBM is idle in this workload):
+//   K_classify  thread per pair:  frame, gamma(z1), gamma(z2), the three junction values -> two bracket items
+//                                 (root queue), or one hump item (curve entirely below rho), or "no solution"
+//   K_hump      thread per hump item: maximum search with the closed-form derivative -> two bracket items or "no solution"
+//   K_roots     thread per bracket item: safeguarded Newton, closed-form properties, SoA stores, SolRec for K_att.
+//               The two brackets of a pair sit in adjacent lanes; one shuffle orders them by C0 (py:1547).
+// Queue appends are warp-aggregated (ballot + one atomic per warp).
+// ---------------------------------------------------------------------------------------------------------------
+struct RootItem { int64_t pair; double g1, g2, a, ga, b, gb; int32_t piece, valid; };   // 64 bytes
+struct HumpItem { int64_t pair; double g1, g2, J1, J2, J3; };                           // 48 bytes
+
+__device__ __forceinline__ void push_brackets(bool have, int64_t pair, const PairGeom &g, const Bracket *br, int nb, RootItem *rootq,
+                                              unsigned long long *root_count, unsigned lane)
+{
+    const unsigned m = __ballot_sync(0xffffffffu, have);
+    if (m == 0) return;
+    const int leader = __ffs(m) - 1;
+    unsigned long long base = 0;
+    if ((int)lane == leader) base = atomicAdd(root_count, 2ull * __popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (have) {
+        RootItem *dst = rootq + base + 2ull * __popc(m & ((1u << lane) - 1u));
+        for (int j = 0; j < 2; ++j) {
+            RootItem it;
+            const Bracket &b = br[j < nb ? j : 0];
+            it.pair = pair; it.g1 = g.g1; it.g2 = g.g2; it.a = b.a; it.ga = b.ga; it.b = b.b; it.gb = b.gb;
+            it.piece = b.piece; it.valid = j < nb ? 1 : 0;
+            dst[j] = it;
+        }
+    }
+}
+
+__device__ __forceinline__ void write_no_solution(const TraceOutputs &out, int64_t p, int status)
+{
+    if (out.n_sol) out.n_sol[p] = 0;
+    if (out.status) out.status[p] = status;
+    fill_empty_slot(out, 2 * p, 1);
+    fill_empty_slot(out, 2 * p + 1, 1);
+}
+
+#define CLASSIFY_THREADS 256
+__global__ void __launch_bounds__(CLASSIFY_THREADS)
+K_classify(IceParams ice, KInput in, TraceOutputs out, RootItem *rootq, unsigned long long *root_count, HumpItem *humpq,
+           unsigned long long *hump_count)
+{
+    const int64_t p = (int64_t)blockIdx.x * CLASSIFY_THREADS + threadIdx.x;
+    const unsigned lane = threadIdx.x & 31u;
+    int kind = 0;     // 0: nothing to queue, 1: brackets, 2: hump search
+    PairGeom g;
+    Bracket br[2];
+    int nb = 0;
+    double J1 = 0, J2 = 0, J3 = 0;
+    if (p < in.n_pairs) {
+        double x1, y1, z1, x2, y2, z2;
+        load_pair(in, p, x1, y1, z1, x2, y2, z2);
+        Frame2D f;
+        make_frame(x1, y1, z1, x2, y2, z2, f);
+        const int status = pair_status(ice, f);
+        if (status == 0) {
+            make_pair_geom(ice, f.z1, f.z2, fmax(f.rho, 1e-12), g);
+            Curve cv;
+            cv.ice = &ice; cv.g = &g; cv.k = 0; cv.rcase = 1;
+            bool need_hump;
+            nb = classify_mode(cv, J1, J2, J3, br, need_hump);
+            kind = nb > 0 ? 1 : (need_hump ? 2 : 0);
+        }
+        if (kind == 0) write_no_solution(out, p, status);
+        if (kind == 1) { if (out.n_sol) out.n_sol[p] = nb; if (out.status) out.status[p] = 0; }
+    }
+    push_brackets(kind == 1, p, g, br, nb, rootq, root_count, lane);
+    const unsigned mh = __ballot_sync(0xffffffffu, kind == 2);
+    if (mh) {
+        const int leader = __ffs(mh) - 1;
+        unsigned long long base = 0;
+        if ((int)lane == leader) base = atomicAdd(hump_count, (unsigned long long)__popc(mh));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (kind == 2) {
+            HumpItem it;
+            it.pair = p; it.g1 = g.g1; it.g2 = g.g2; it.J1 = J1; it.J2 = J2; it.J3 = J3;
+            humpq[base + __popc(mh & ((1u << lane) - 1u))] = it;
+        }
+    }
+}
+
+#define HUMP_THREADS 128
+__global__ void __launch_bounds__(HUMP_THREADS)
+K_hump(IceParams ice, KInput in, TraceOutputs out, const HumpItem *humpq, const unsigned long long *hump_count, RootItem *rootq,
+       unsigned long long *root_count)
+{
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned long long n = *hump_count;
+    const unsigned long long stride = (unsigned long long)gridDim.x * HUMP_THREADS;
+    for (unsigned long long w0 = (unsigned long long)blockIdx.x * HUMP_THREADS + (threadIdx.x & ~31u); w0 < n; w0 += stride) {
+        const unsigned long long w = w0 + lane;
+        const bool active = w < n;
+        PairGeom g;
+        Bracket br[2];
+        int nb = 0;
+        int64_t pair = 0;
+        if (active) {
+            const HumpItem it = humpq[w];
+            pair = it.pair;
+            double x1, y1, z1, x2, y2, z2;
+            load_pair(in, pair, x1, y1, z1, x2, y2, z2);
+            Frame2D f;
+            make_frame(x1, y1, z1, x2, y2, z2, f);
+            make_pair_geom_g(ice, f.z1, f.z2, fmax(f.rho, 1e-12), it.g1, it.g2, g);
+            Curve cv;
+            cv.ice = &ice; cv.g = &g; cv.k = 0; cv.rcase = 1;
+            nb = hump_search(cv, it.J1, it.J2, it.J3, br);
+            if (nb == 0) write_no_solution(out, pair, 0);
+            else { if (out.n_sol) out.n_sol[pair] = nb; if (out.status) out.status[pair] = 0; }
+        }
+        push_brackets(active && nb > 0, pair, g, br, nb, rootq, root_count, lane);
+    }
+}
+
+#define ROOTS_THREADS 128
+__global__ void __launch_bounds__(ROOTS_THREADS)
+K_roots(IceParams ice, KInput in, TraceOutputs out, const RootItem *rootq, const unsigned long long *root_count, SolRec *worklist,
+        unsigned long long *work_count)
+{
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned long long n = *root_count;     // even: items are pushed in pairs at even offsets
+    const unsigned long long stride = (unsigned long long)gridDim.x * ROOTS_THREADS;
+    for (unsigned long long w0 = (unsigned long long)blockIdx.x * ROOTS_THREADS + (threadIdx.x & ~31u); w0 < n; w0 += stride) {
+        const unsigned long long w = w0 + lane;
+        const bool active = w < n;
+        bool valid = false;
+        int64_t pair = 0;
+        Root root;
+        root.v = 0; root.piece = 0; root.beta = 0;
+        double g1 = 0, g2 = 0;
+        if (active) {
+            const RootItem it = rootq[w];
+            pair = it.pair; g1 = it.g1; g2 = it.g2;
+            valid = it.valid != 0;
+            if (valid) {
+                double x1, y1, z1, x2, y2, z2;
+                load_pair(in, pair, x1, y1, z1, x2, y2, z2);
+                Frame2D f;
+                make_frame(x1, y1, z1, x2, y2, z2, f);
+                PairGeom g;
+                make_pair_geom_g(ice, f.z1, f.z2, fmax(f.rho, 1e-12), g1, g2, g);
+                Curve cv;
+                cv.ice = &ice; cv.g = &g; cv.k = 0; cv.rcase = 1;
+                Bracket b;
+                b.a = it.a; b.ga = it.ga; b.b = it.b; b.gb = it.gb; b.piece = it.piece;
+                root = solve_bracket(cv, b);
+            }
+        }
+        // order the two roots of the pair by ascending C0 = descending beta (py:1547); the partner sits in lane ^ 1
+        const double beta_other = __shfl_xor_sync(0xffffffffu, valid ? root.beta : -1.0, 1);
+        int slot = lane & 1;
+        if (valid) slot = (root.beta > beta_other) ? 0 : ((root.beta < beta_other) ? 1 : (int)(lane & 1u));
+        if (active) {
+            if (valid) {
+                double x1, y1, z1, x2, y2, z2;
+                load_pair(in, pair, x1, y1, z1, x2, y2, z2);
+                Frame2D f;
+                make_frame(x1, y1, z1, x2, y2, z2, f);
+                PairGeom g;
+                make_pair_geom_g(ice, f.z1, f.z2, fmax(f.rho, 1e-12), g1, g2, g);
+                SolutionProps pr;
+                solution_props(ice, g, f.x1y, 0, 1, root, pr);
+                write_solution(out, 2 * pair + slot, 1, f, 0, 1, pr);
+            } else {
+                fill_empty_slot(out, 2 * pair + 1, 1);    // single root (tangency at the surface): second slot stays empty
+            }
+        }
+        if (worklist) {
+            const unsigned m = __ballot_sync(0xffffffffu, valid);
+            if (m) {
+                const int leader = __ffs(m) - 1;
+                unsigned long long base = 0;
+                if ((int)lane == leader) base = atomicAdd(work_count, (unsigned long long)__popc(m));
+                base = __shfl_sync(0xffffffffu, base, leader);
+                if (valid) {
+                    SolRec r;
+                    r.v = root.v; r.pair = pair; r.slot = slot; r.piece = (uint8_t)root.piece; r.k = 0; r.rcase = 1; r.pad = 0;
+                    worklist[base + __popc(m & ((1u << lane) - 1u))] = r;
+                }
+            }
+        }
+    }
+}
+
 // ---- TMA bulk copy helpers (1-D, global -> shared, completion on an mbarrier) --------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
@@ -450,7 +641,7 @@ struct DevBuf {
 struct Lane {               // one pipeline lane (stream + scratch) for host-memory calls
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    DevBuf in, out, work, fallback, sparse_tmp;
+    DevBuf in, out, work, fallback, sparse_tmp, rootq, humpq;
     bool timed = false;
 };
 
@@ -465,6 +656,7 @@ struct nrmc_rt_s {
     Sp1Tables sp1;
     bool have_sp1 = false;
     int grid_att = 0, grid_sp1 = 0;      // resident blocks (occupancy x SMs) of the persistent attenuation kernels
+    int grid_hump = 0, grid_roots = 0;   // the same for the persistent solver kernels
     size_t smem_att = 0, smem_sp1 = 0;
     DevBuf d_tables, d_gl3, d_sp1;
     bool have_freq = false;
@@ -526,7 +718,14 @@ int nrmc_rt_create(const nrmc_rt_config *cfg, nrmc_rt_t *out)
         if (cudaStreamCreateWithFlags(&h->lanes[l].stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return NRMC_ERR_CUDA; }
         for (int e = 0; e < 6; ++e) cudaEventCreate(&h->lanes[l].ev[e]);
     }
-    if (h->d_count.reserve(64) != cudaSuccess) { delete h; return NRMC_ERR_CUDA; }
+    if (h->d_count.reserve(256) != cudaSuccess) { delete h; return NRMC_ERR_CUDA; }
+    {
+        int nb = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, K_hump, HUMP_THREADS, 0) != cudaSuccess) { delete h; return NRMC_ERR_CUDA; }
+        h->grid_hump = std::max(1, nb) * h->n_sm;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, K_roots, ROOTS_THREADS, 0) != cudaSuccess) { delete h; return NRMC_ERR_CUDA; }
+        h->grid_roots = std::max(1, nb) * h->n_sm;
+    }
     if (cfg->attenuation_model == NRMC_ATT_GL3) {
         const size_t bytes = (size_t)cfg->gl3_rows * 3 * sizeof(double);
         if (h->d_gl3.reserve(bytes) != cudaSuccess ||
@@ -546,7 +745,7 @@ void nrmc_rt_destroy(nrmc_rt_t h)
         if (h->lanes[l].stream) { cudaStreamSynchronize(h->lanes[l].stream); cudaStreamDestroy(h->lanes[l].stream); }
         for (int e = 0; e < 6; ++e) if (h->lanes[l].ev[e]) cudaEventDestroy(h->lanes[l].ev[e]);
         h->lanes[l].in.release(); h->lanes[l].out.release(); h->lanes[l].work.release();
-        h->lanes[l].fallback.release(); h->lanes[l].sparse_tmp.release();
+        h->lanes[l].fallback.release(); h->lanes[l].sparse_tmp.release(); h->lanes[l].rootq.release(); h->lanes[l].humpq.release();
     }
     h->d_tables.release(); h->d_gl3.release(); h->d_sp1.release(); h->d_count.release(); h->d_ant.release();
     delete h;
@@ -695,9 +894,26 @@ static int launch_chunk(nrmc_rt_s *h, Lane &ln, int lane_id, const KInput &kin, 
         CK(cudaMemsetAsync(d_count, 0, sizeof(unsigned long long), ln.stream));
     }
     if (ln.timed) cudaEventRecord(ln.ev[0], ln.stream);
-    const int64_t blocks = (kin.n_pairs + SOLVE_THREADS - 1) / SOLVE_THREADS;
-    K_solve<<<(unsigned)blocks, SOLVE_THREADS, 0, ln.stream>>>(h->ice, kin, to, wl, d_count);
-    ++*n_launches;
+    if (h->ice.n_refl == 0) {
+        // binned solver: classify -> hump search -> roots, re-packed through queues (counters [4+lane], [6+lane])
+        unsigned long long *d_roots = (unsigned long long *)h->d_count.p + 4 + lane_id;
+        unsigned long long *d_humps = (unsigned long long *)h->d_count.p + 6 + lane_id;
+        CK(ln.rootq.reserve((size_t)kin.n_pairs * 2 * sizeof(RootItem)));
+        CK(ln.humpq.reserve((size_t)kin.n_pairs * sizeof(HumpItem)));
+        CK(cudaMemsetAsync(d_roots, 0, sizeof(unsigned long long), ln.stream));
+        CK(cudaMemsetAsync(d_humps, 0, sizeof(unsigned long long), ln.stream));
+        const int64_t blocks = (kin.n_pairs + CLASSIFY_THREADS - 1) / CLASSIFY_THREADS;
+        K_classify<<<(unsigned)blocks, CLASSIFY_THREADS, 0, ln.stream>>>(h->ice, kin, to, (RootItem *)ln.rootq.p, d_roots,
+                                                                         (HumpItem *)ln.humpq.p, d_humps);
+        K_hump<<<h->grid_hump, HUMP_THREADS, 0, ln.stream>>>(h->ice, kin, to, (const HumpItem *)ln.humpq.p, d_humps,
+                                                             (RootItem *)ln.rootq.p, d_roots);
+        K_roots<<<h->grid_roots, ROOTS_THREADS, 0, ln.stream>>>(h->ice, kin, to, (const RootItem *)ln.rootq.p, d_roots, wl, d_count);
+        *n_launches += 3;
+    } else {
+        const int64_t blocks = (kin.n_pairs + SOLVE_THREADS - 1) / SOLVE_THREADS;
+        K_solve<<<(unsigned)blocks, SOLVE_THREADS, 0, ln.stream>>>(h->ice, kin, to, wl, d_count);
+        ++*n_launches;
+    }
     if (ln.timed) cudaEventRecord(ln.ev[1], ln.stream);
     if (want_att) {
         const AttTables &tb = h->tb;
@@ -784,7 +1000,7 @@ extern "C" int nrmc_rt_trace(nrmc_rt_t h, const nrmc_rt_input *in, const nrmc_rt
         ln.timed = false;
         cudaEvent_t e0 = ln.ev[3], e1 = ln.ev[4];
         if (stats) cudaEventRecord(e0, user);
-        int64_t chunk = want_att ? (int64_t)1 << 24 : N;
+        int64_t chunk = std::min<int64_t>(N, (int64_t)1 << 24);     // bounds the queue / work-list scratch
         if (in->outer && chunk < N) chunk = std::max<int64_t>(in->n_antennas, (chunk / in->n_antennas) * in->n_antennas);
         float ms_solve = 0, ms_att = 0;
         int rc = NRMC_OK, n_chunks = 0;
@@ -855,6 +1071,7 @@ extern "C" int nrmc_rt_trace(nrmc_rt_t h, const nrmc_rt_input *in, const nrmc_rt
     const bool need_nsol_dev = want_att || want[0];
     for (int i = 0; i < 14; ++i) if (want[i] || (i == 0 && need_nsol_dev)) per_pair += elem[i] + 16;
     per_pair += h->S * sizeof(SolRec) + 48;
+    if (h->ice.n_refl == 0) per_pair += 2 * sizeof(RootItem) + sizeof(HumpItem);
     int64_t chunk = (int64_t)((size_t)1536 * 1024 * 1024 / per_pair);   // ~1.5 GB of device scratch per lane
     chunk = std::max<int64_t>(chunk, 1024);
     if (in->outer) chunk = std::max<int64_t>(na, (chunk / na) * na);
