@@ -230,7 +230,7 @@ def main():
     Vh = np.ascontiguousarray(Vr[:, :e2e_v].T)
     Ah = np.ascontiguousarray(A.T)
     hres = None
-    kwh = dict(outer=True, frequency=ff, max_detector_freq=FMAX, attenuation="sparse", pinned=True)
+    kwh = dict(outer=True, frequency=ff, max_detector_freq=FMAX, attenuation="sparse", pinned=True, compact=True)
     for _ in range(2):
         hres = rt.trace_batch(Vh, Ah, out=hres, **kwh)
     barrier()
@@ -273,7 +273,8 @@ def main():
         "solutions_per_s": n_solutions_total / (ms_per_step * 1e-3), "solutions_per_pair": n_solutions_total / n_pairs_total,
         "clocks": clk,
         "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": int(h2d) * world, "d2h_bytes_per_step": int(d2h) * world,
-                "pairs_per_step": e2e_pairs_total, "steps": e2e_steps, "timer": "host perf_counter around the blocking API call"},
+                "pairs_per_step": e2e_pairs_total, "steps": e2e_steps, "timer": "host perf_counter around the blocking API call",
+                "layout": "host numpy in, pinned numpy out, per-solution (CSR) rows: empty slots are not copied"},
         "gpu_launches": int(launches_per_step * args.steps * world),
         "roofline": {"bound": "fp64", "kernel": "K_att (attenuation integral, one warp per solution)",
                      "achieved": att_tflops, "peak": fp64_peak, "unit": "TFLOP/s", "frac": att_tflops / fp64_peak,

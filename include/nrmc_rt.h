@@ -30,6 +30,7 @@ extern "C" {
 #define NRMC_ERR_NO_DEVICE (-3)
 #define NRMC_ERR_UNSUPPORTED (-4)
 #define NRMC_ERR_NO_FREQUENCIES (-5)
+#define NRMC_ERR_CAPACITY (-6)
 
 /* attenuation model integers: NuRadioMC/utilities/attenuation.py:14 */
 #define NRMC_ATT_NONE 0
@@ -92,6 +93,14 @@ typedef struct {
     double *reflection_angle;  /* [N,S,n_reflections+1]  get_reflection_angle(iS), NaN = None          */
     double *attenuation_sparse;/* [N,S,Fs] attenuation factors at the Fs integration frequencies       */
     double *attenuation;       /* [N,S,F]  get_attenuation(iS, frequency, max_detector_freq)           */
+    /* Compact (per-solution) layout, NRMC_MEMORY_HOST only.  compact != 0: every [N,S,...] array above is written as
+     * [n_rows,...] with one row per EXISTING solution: the rows of pair i are sol_offset[i] .. sol_offset[i+1]-1, in slot
+     * order (CSR; sol_offset[N] = n_rows = sum of n_sol).  Empty slots are neither stored nor copied over PCIe.
+     * row_capacity = rows the per-solution arrays can hold (N*S always suffices); NRMC_ERR_CAPACITY if exceeded. */
+    int32_t compact;
+    int32_t reserved;
+    int64_t *sol_offset;       /* [N+1]    compact only (required then)                                */
+    int64_t row_capacity;
 } nrmc_rt_output;
 
 typedef struct {

@@ -110,13 +110,22 @@ class BatchResult(dict):
     `.frequencies_sparse`."""
     stats = None
     frequencies_sparse = None
+    compact = False
     _keep = None
+    _full = None
+
+    def rows(self, i):
+        """index of the per-slot arrays for the solutions of pair i: (i, slice) padded, slice of rows compact"""
+        if self.compact:
+            return slice(int(self["sol_offset"][i]), int(self["sol_offset"][i + 1]))
+        return (i, slice(0, int(self["n_sol"][i])))
 
     def solutions(self, i):
         """results of pair i in the reference's `get_results()` format"""
-        return [{'type': int(self["solution_type"][i, s]), 'C0': float(self["C0"][i, s]), 'C1': float(self["C1"][i, s]),
-                 'reflection': int(self["reflection"][i, s]), 'reflection_case': int(self["reflection_case"][i, s])}
-                for s in range(int(self["n_sol"][i]))]
+        r = self.rows(i)
+        return [{'type': int(t), 'C0': float(c0), 'C1': float(c1), 'reflection': int(k), 'reflection_case': int(rc)}
+                for t, c0, c1, k, rc in zip(self["solution_type"][r], self["C0"][r], self["C1"][r], self["reflection"][r],
+                                            self["reflection_case"][r])]
 
 
 class ray_tracing(ray_tracing_base):
@@ -199,7 +208,7 @@ class ray_tracing(ray_tracing_base):
     # batched entry points (new)
     # ------------------------------------------------------------------------------------------------------
     def trace_batch(self, X1, X2, frequency=None, max_detector_freq=None, outer=False, outputs=None,
-                    attenuation="dense", pinned=False, out=None):
+                    attenuation="dense", pinned=False, out=None, compact=False, row_capacity=None):
         """
         Trace all pairs in one device pass (host arrays in, host arrays out).
 
@@ -209,6 +218,9 @@ class ray_tracing(ray_tracing_base):
         (`attenuation` = "dense": on `frequency`; "sparse": at the integration frequencies; "both").
         outputs: iterable of field names (default: everything but attenuation).  pinned=True allocates page-locked
         result arrays; `out` may pass a previous BatchResult of the same shape to reuse its buffers.
+        compact=True: per-solution (CSR) layout -- every per-slot array has one row per EXISTING solution instead of
+        S slots per pair; the rows of pair i are res["sol_offset"][i] : res["sol_offset"][i+1] (slot order).  Empty
+        slots are neither stored nor copied from the device.  `row_capacity` bounds the rows allocated (default N*S).
         """
         X1 = np.asarray(X1, dtype=np.float64).reshape(-1, 3)
         X2 = np.asarray(X2, dtype=np.float64).reshape(-1, 3)
@@ -235,10 +247,22 @@ class ray_tracing(ray_tracing_base):
         res = out if out is not None else BatchResult()
         keep = []
         o = _lib.Output()
+        rows = N * S if row_capacity is None else int(row_capacity)
+        full = getattr(res, "_full", None) or {}
+        if compact:
+            if "n_sol" not in names:
+                names.insert(0, "n_sol")
+            names.append("sol_offset")
         for name in names:
-            dtype, trail = _OUT_SPECS[name]
-            shape = (N,) + trail(S, K1, Fs, F)
-            if name in res and res[name].shape == shape:
+            if name == "sol_offset":
+                dtype, shape = np.int64, (N + 1,)
+            else:
+                dtype, trail = _OUT_SPECS[name]
+                per_slot = len(trail(S, K1, Fs, F)) > 0
+                shape = ((rows,) + trail(S, K1, Fs, F)[1:]) if (compact and per_slot) else (N,) + trail(S, K1, Fs, F)
+            if name in full and full[name].shape == shape:
+                arr = full[name]
+            elif name in res and res[name].shape == shape:
                 arr = res[name]
             elif pinned:
                 pa = PinnedArray(shape, dtype)
@@ -247,9 +271,11 @@ class ray_tracing(ray_tracing_base):
             else:
                 arr = np.empty(shape, dtype=dtype)
             res[name] = arr
+            full[name] = arr
             setattr(o, name, arr.ctypes.data)
         if keep:
             res._keep = (res._keep or []) + keep
+        o.compact, o.row_capacity = int(bool(compact)), rows
         inp = _lib.Input()
         inp.n_vertices, inp.vx, inp.vy, inp.vz = X1.shape[0], v[0].ctypes.data, v[1].ctypes.data, v[2].ctypes.data
         inp.n_antennas, inp.ax, inp.ay, inp.az = X2.shape[0], a[0].ctypes.data, a[1].ctypes.data, a[2].ctypes.data
@@ -258,6 +284,13 @@ class ray_tracing(ray_tracing_base):
         _lib.check(_lib.load().nrmc_rt_trace(h.ptr, C.byref(inp), C.byref(o), None, C.byref(st)), h.ptr, "trace")
         res.stats = {k: getattr(st, k) for k, _ in _lib.Stats._fields_}
         res.frequencies_sparse = h.sparse if frequency is not None else None
+        res.compact = bool(compact)
+        if compact:     # expose the filled rows; the capacity-sized buffers are kept for reuse through `out=`
+            res._full = full
+            n_rows = int(res["sol_offset"][N])
+            for name in names:
+                if name not in ("n_sol", "status", "sol_offset"):
+                    res[name] = full[name][:n_rows]
         return res
 
     def trace_batch_device(self, v, a, frequency=None, max_detector_freq=None, outer=False, outputs=None,

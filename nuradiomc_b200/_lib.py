@@ -7,7 +7,7 @@ LIB_PATH = os.environ.get("NRMC_RT_LIB", os.path.join(HERE, "libnrmc_rt.so"))   
 
 NRMC_OK = 0
 ERRORS = {-1: "invalid argument", -2: "CUDA error", -3: "no CUDA device", -4: "unsupported configuration",
-          -5: "no frequencies set"}
+          -5: "no frequencies set", -6: "row capacity of the compact output arrays exceeded"}
 MEMORY_HOST, MEMORY_DEVICE = 0, 1
 PAIR_IN_AIR, PAIR_BELOW_REFLECTOR, PAIR_NONFINITE = 1, 2, 4
 
@@ -29,7 +29,8 @@ OUTPUT_FIELDS = ("n_sol", "status", "solution_type", "reflection", "reflection_c
 
 
 class Output(C.Structure):
-    _fields_ = [(k, C.c_void_p) for k in OUTPUT_FIELDS]
+    _fields_ = [(k, C.c_void_p) for k in OUTPUT_FIELDS] + [("compact", C.c_int32), ("reserved", C.c_int32),
+                                                          ("sol_offset", C.c_void_p), ("row_capacity", C.c_int64)]
 
 
 class Stats(C.Structure):

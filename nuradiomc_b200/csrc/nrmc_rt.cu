@@ -584,6 +584,108 @@ __global__ void K_att_fill(const int32_t *n_sol, int64_t n_pairs, int S, int Fs,
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// compact (per-solution, CSR) output for host calls: exclusive scan of n_sol, then a gather of the existing rows
+// ---------------------------------------------------------------------------------------------------------------
+#define PACK_PAIRS 1024
+#define PACK_THREADS 256
+struct PackArrays { const unsigned char *src[12]; unsigned char *dst[12]; int32_t row_bytes[12]; int32_t n; };
+
+__global__ void __launch_bounds__(PACK_THREADS)
+K_pack_count(const int32_t *n_sol, int64_t n_pairs, unsigned long long *block_sums)
+{
+    __shared__ int s_part[PACK_THREADS / 32];
+    const int64_t p0 = (int64_t)blockIdx.x * PACK_PAIRS + 4 * threadIdx.x;
+    int v = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) if (p0 + j < n_pairs) v += n_sol[p0 + j];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int w = 0; w < PACK_THREADS / 32; ++w) t += s_part[w];
+        block_sums[blockIdx.x] = (unsigned long long)t;
+    }
+}
+
+// single block: exclusive scan of the block sums in place; total -> block_sums[n_blocks]
+__global__ void __launch_bounds__(1024)
+K_pack_scan(unsigned long long *block_sums, int n_blocks)
+{
+    __shared__ unsigned long long s_warp[32];
+    __shared__ unsigned long long s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int base = 0; base < n_blocks; base += 1024) {
+        const int i = base + threadIdx.x;
+        const unsigned long long v = i < n_blocks ? block_sums[i] : 0ull;
+        unsigned long long incl = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            unsigned long long w = s_warp[lane], wi = w;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const unsigned long long t = __shfl_up_sync(0xffffffffu, wi, d); if (lane >= d) wi += t; }
+            s_warp[lane] = wi - w;     // exclusive over warps
+        }
+        __syncthreads();
+        const unsigned long long carry = s_carry;
+        if (i < n_blocks) block_sums[i] = carry + s_warp[warp] + incl - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = carry + s_warp[warp] + incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) block_sums[n_blocks] = s_carry;
+}
+
+__global__ void __launch_bounds__(PACK_THREADS)
+K_pack(const int32_t *n_sol, int64_t n_pairs, int S, const unsigned long long *block_off, int64_t row_base, int64_t *sol_offset,
+       PackArrays pa)
+{
+    __shared__ int s_off[PACK_PAIRS];
+    __shared__ int s_n[PACK_PAIRS];
+    __shared__ int s_part[PACK_THREADS / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t pb = (int64_t)blockIdx.x * PACK_PAIRS;
+    int nloc[4], v = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { const int64_t p = pb + 4 * threadIdx.x + j; nloc[j] = p < n_pairs ? n_sol[p] : 0; v += nloc[j]; }
+    int incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
+    if (lane == 31) s_part[warp] = incl;
+    __syncthreads();
+    int wbase = 0;
+    for (int w = 0; w < warp; ++w) wbase += s_part[w];
+    int run = wbase + incl - v;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { s_off[4 * threadIdx.x + j] = run; s_n[4 * threadIdx.x + j] = nloc[j]; run += nloc[j]; }
+    __syncthreads();
+    const int64_t row0 = row_base + (int64_t)block_off[blockIdx.x];
+    for (int i = threadIdx.x; i < PACK_PAIRS && pb + i < n_pairs; i += PACK_THREADS) sol_offset[pb + i] = row0 + s_off[i];
+    for (int i = warp; i < PACK_PAIRS && pb + i < n_pairs; i += PACK_THREADS / 32) {
+        const int n = s_n[i];
+        for (int sl = 0; sl < n; ++sl) {
+            const int64_t src_row = (pb + i) * S + sl, dst_row = (int64_t)block_off[blockIdx.x] + s_off[i] + sl;   // chunk-local rows
+            for (int a = 0; a < pa.n; ++a) {
+                const int rb = pa.row_bytes[a];
+                if ((rb & 7) == 0) {
+                    const double *src = reinterpret_cast<const double *>(pa.src[a]) + src_row * (rb >> 3);
+                    double *dst = reinterpret_cast<double *>(pa.dst[a]) + dst_row * (rb >> 3);
+                    for (int j = lane; j < (rb >> 3); j += 32) dst[j] = src[j];
+                } else {
+                    for (int j = lane; j < rb; j += 32) pa.dst[a][dst_row * rb + j] = pa.src[a][src_row * rb + j];
+                }
+            }
+        }
+    }
+}
+
 __global__ void K_att_length(IceParams ice, Gl3Table gl3, const double *z, const double *f, int64_t n, double *out)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -641,7 +743,7 @@ struct DevBuf {
 struct Lane {               // one pipeline lane (stream + scratch) for host-memory calls
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    DevBuf in, out, work, fallback, sparse_tmp, rootq, humpq;
+    DevBuf in, out, work, fallback, sparse_tmp, rootq, humpq, packed, pack_sums, pack_off;
     bool timed = false;
 };
 
@@ -746,6 +848,7 @@ void nrmc_rt_destroy(nrmc_rt_t h)
         for (int e = 0; e < 6; ++e) if (h->lanes[l].ev[e]) cudaEventDestroy(h->lanes[l].ev[e]);
         h->lanes[l].in.release(); h->lanes[l].out.release(); h->lanes[l].work.release();
         h->lanes[l].fallback.release(); h->lanes[l].sparse_tmp.release(); h->lanes[l].rootq.release(); h->lanes[l].humpq.release();
+        h->lanes[l].packed.release(); h->lanes[l].pack_sums.release(); h->lanes[l].pack_off.release();
     }
     h->d_tables.release(); h->d_gl3.release(); h->d_sp1.release(); h->d_count.release(); h->d_ant.release();
     delete h;
@@ -973,7 +1076,7 @@ extern "C" int nrmc_rt_trace(nrmc_rt_t h, const nrmc_rt_input *in, const nrmc_rt
     if (!in->outer && in->n_antennas != in->n_vertices) { h->err = "pair mode needs n_antennas == n_vertices"; return NRMC_ERR_INVALID_ARGUMENT; }
     const int64_t N = in->outer ? in->n_vertices * in->n_antennas : in->n_vertices;
     if (stats) memset(stats, 0, sizeof(*stats));
-    if (N == 0) return NRMC_OK;
+    if (N == 0) { if (out->compact && out->sol_offset) out->sol_offset[0] = 0; return NRMC_OK; }
     if (!in->vx || !in->vy || !in->vz || !in->ax || !in->ay || !in->az) return NRMC_ERR_INVALID_ARGUMENT;
     const bool want_att = out->attenuation_sparse || out->attenuation;
     if (want_att && h->ice.att_model == 0) { h->err = "attenuation requested but no attenuation model configured"; return NRMC_ERR_UNSUPPORTED; }
@@ -985,6 +1088,9 @@ extern "C" int nrmc_rt_trace(nrmc_rt_t h, const nrmc_rt_input *in, const nrmc_rt
         return NRMC_ERR_UNSUPPORTED;
     }
     if (want_att && !h->have_freq) { h->err = "attenuation requested before nrmc_rt_set_frequencies"; return NRMC_ERR_NO_FREQUENCIES; }
+    const bool compact = out->compact != 0;
+    if (compact && in->memory != NRMC_MEMORY_HOST) { h->err = "the compact output layout is available for NRMC_MEMORY_HOST calls only"; return NRMC_ERR_UNSUPPORTED; }
+    if (compact && (!out->sol_offset || out->row_capacity < 0)) { h->err = "compact output needs sol_offset[N+1] and row_capacity"; return NRMC_ERR_INVALID_ARGUMENT; }
     CK(cudaSetDevice(h->cfg.device));
     const int S = h->S, K1 = h->K1, Fs = h->tb.Fs, F = h->tb.F;
     const size_t elem[14] = {4, 4, (size_t)S, (size_t)S, (size_t)S, 8u * S, 8u * S, 8u * S, 8u * S, 24u * S, 24u * S,
@@ -1068,8 +1174,9 @@ extern "C" int nrmc_rt_trace(nrmc_rt_t h, const nrmc_rt_input *in, const nrmc_rt
     size_t per_pair = 0;
     bool want[14];
     for (int i = 0; i < 14; ++i) { want[i] = out_ptr(out, i) != nullptr; }
-    const bool need_nsol_dev = want_att || want[0];
+    const bool need_nsol_dev = want_att || want[0] || compact;
     for (int i = 0; i < 14; ++i) if (want[i] || (i == 0 && need_nsol_dev)) per_pair += elem[i] + 16;
+    if (compact) per_pair = 2 * per_pair + 16;      // second (packed) copy of every array + offsets
     per_pair += h->S * sizeof(SolRec) + 48;
     if (h->ice.n_refl == 0) per_pair += 2 * sizeof(RootItem) + sizeof(HumpItem);
     int64_t chunk = (int64_t)((size_t)1536 * 1024 * 1024 / per_pair);   // ~1.5 GB of device scratch per lane
@@ -1093,7 +1200,7 @@ extern "C" int nrmc_rt_trace(nrmc_rt_t h, const nrmc_rt_input *in, const nrmc_rt
     cudaEventRecord(e0, h->lanes[0].stream);
     float ms_solve = 0, ms_att = 0;
     int n_chunks = 0;
-    int64_t n_solutions = 0;
+    int64_t n_solutions = 0, row_base = 0;
     for (int64_t p0 = 0; p0 < N; p0 += chunk, ++n_chunks) {
         const int lid = n_chunks & 1;
         Lane &ln = h->lanes[lid];
@@ -1142,11 +1249,55 @@ extern "C" int nrmc_rt_trace(nrmc_rt_t h, const nrmc_rt_input *in, const nrmc_rt
         ln.timed = (stats != nullptr);
         int rc = launch_chunk(h, ln, lid, kin, to, (double *)dp(12), (double *)dp(13), &n_launches);
         if (rc != NRMC_OK) return rc;
-        for (int i = 0; i < 14; ++i) {
-            if (!want[i]) continue;
-            const size_t bytes = (size_t)np * elem[i];
-            CK(cudaMemcpyAsync((unsigned char *)out_ptr(out, i) + (size_t)p0 * elem[i], dout + off[i], bytes, cudaMemcpyDeviceToHost, ln.stream));
-            d2h += bytes;
+        if (!compact) {
+            for (int i = 0; i < 14; ++i) {
+                if (!want[i]) continue;
+                const size_t bytes = (size_t)np * elem[i];
+                CK(cudaMemcpyAsync((unsigned char *)out_ptr(out, i) + (size_t)p0 * elem[i], dout + off[i], bytes, cudaMemcpyDeviceToHost, ln.stream));
+                d2h += bytes;
+            }
+        } else {
+            // per-solution rows: scan n_sol, gather the existing rows into a second device block, copy only those
+            const int nblk = (int)((np + PACK_PAIRS - 1) / PACK_PAIRS);
+            CK(ln.packed.reserve(total));
+            CK(ln.pack_sums.reserve((size_t)(nblk + 1) * sizeof(unsigned long long)));
+            CK(ln.pack_off.reserve((size_t)np * sizeof(int64_t)));
+            unsigned char *dpk = (unsigned char *)ln.packed.p;
+            PackArrays pa;
+            pa.n = 0;
+            for (int i = 2; i < 14; ++i) {
+                if (!want[i]) continue;
+                pa.src[pa.n] = dout + off[i]; pa.dst[pa.n] = dpk + off[i]; pa.row_bytes[pa.n] = (int32_t)(elem[i] / S); ++pa.n;
+            }
+            unsigned long long *sums = (unsigned long long *)ln.pack_sums.p;
+            K_pack_count<<<nblk, PACK_THREADS, 0, ln.stream>>>(to.n_sol, np, sums);
+            K_pack_scan<<<1, 1024, 0, ln.stream>>>(sums, nblk);
+            K_pack<<<nblk, PACK_THREADS, 0, ln.stream>>>(to.n_sol, np, S, sums, row_base, (int64_t *)ln.pack_off.p, pa);
+            n_launches += 3;
+            CK(cudaGetLastError());
+            unsigned long long rows = 0;
+            CK(cudaMemcpyAsync(&rows, sums + nblk, sizeof(rows), cudaMemcpyDeviceToHost, ln.stream));
+            CK(cudaStreamSynchronize(ln.stream));      // the row count sizes the copies; the other lane's copies keep the link busy meanwhile
+            d2h += sizeof(rows);
+            if (row_base + (int64_t)rows > out->row_capacity) {
+                h->err = "compact output: row_capacity exceeded";
+                for (int l = 0; l < 2; ++l) cudaStreamSynchronize(h->lanes[l].stream);
+                return NRMC_ERR_CAPACITY;
+            }
+            for (int i = 0; i < 2; ++i) {
+                if (!want[i]) continue;
+                CK(cudaMemcpyAsync((unsigned char *)out_ptr(out, i) + (size_t)p0 * elem[i], dout + off[i], (size_t)np * elem[i], cudaMemcpyDeviceToHost, ln.stream));
+                d2h += (size_t)np * elem[i];
+            }
+            CK(cudaMemcpyAsync(out->sol_offset + p0, ln.pack_off.p, (size_t)np * sizeof(int64_t), cudaMemcpyDeviceToHost, ln.stream));
+            d2h += (size_t)np * sizeof(int64_t);
+            for (int i = 2; i < 14; ++i) {
+                if (!want[i] || rows == 0) continue;
+                const size_t rb = elem[i] / S;
+                CK(cudaMemcpyAsync((unsigned char *)out_ptr(out, i) + (size_t)row_base * rb, dpk + off[i], (size_t)rows * rb, cudaMemcpyDeviceToHost, ln.stream));
+                d2h += (size_t)rows * rb;
+            }
+            row_base += (int64_t)rows;
         }
     }
     for (int l = 0; l < 2; ++l) {
@@ -1161,12 +1312,14 @@ extern "C" int nrmc_rt_trace(nrmc_rt_t h, const nrmc_rt_input *in, const nrmc_rt
     }
     cudaEventRecord(e1, h->lanes[0].stream);
     CK(cudaEventSynchronize(e1));
+    if (compact) out->sol_offset[N] = row_base;
     if (stats) {
         cudaEventElapsedTime(&stats->ms_total, e0, e1);
         stats->ms_solve = ms_solve; stats->ms_attenuation = ms_att;
         stats->n_pairs = N; stats->n_launches = n_launches; stats->n_chunks = n_chunks;
         stats->h2d_bytes = h2d; stats->d2h_bytes = d2h;
-        if (out->n_sol) { for (int64_t i = 0; i < N; ++i) n_solutions += out->n_sol[i]; stats->n_solutions = n_solutions; }
+        if (compact) stats->n_solutions = row_base;
+        else if (out->n_sol) { for (int64_t i = 0; i < N; ++i) n_solutions += out->n_sol[i]; stats->n_solutions = n_solutions; }
     }
     return NRMC_OK;
 }

@@ -263,6 +263,34 @@ def test_pair_mode_equals_outer_mode_and_pinned_buffers(make):
     assert r_outer.stats["h2d_bytes"] < r_pairs.stats["h2d_bytes"]
 
 
+@pytest.mark.parametrize("ice,n_refl,model,zmin,rmax", [("southpole_2015", 0, "SP1", -2700, 6000), ("mooresbay_simple", 1, "MB1", -500, 1000)])
+def test_compact_layout_equals_padded_layout(make, ice, n_refl, model, zmin, rmax):
+    """per-solution (CSR) rows == the filled slots of the padded layout, bit for bit; several chunks, buffer reuse"""
+    rt = make(ice, attenuation_model=model, n_reflections=n_refl, n_frequencies_integration=10)
+    ff = np.fft.rfftfreq(64, 0.5)
+    V, A = cylinder(21, 3001, rmax, zmin), np.array([[0, 0, -5.], [400, 0, -160.], [0, -1500, -145.]])
+    pad = rt.trace_batch(V, A, outer=True, frequency=ff, attenuation="both")
+    cmp_ = None
+    for _ in range(2):   # second pass reuses the pinned capacity buffers
+        cmp_ = rt.trace_batch(V, A, outer=True, frequency=ff, attenuation="both", compact=True, pinned=True, out=cmp_)
+    N, S = pad["n_sol"].shape[0], pad["C0"].shape[1]
+    np.testing.assert_array_equal(cmp_["n_sol"], pad["n_sol"])
+    np.testing.assert_array_equal(cmp_["status"], pad["status"])
+    np.testing.assert_array_equal(cmp_["sol_offset"], np.concatenate([[0], np.cumsum(pad["n_sol"])]))
+    filled = np.arange(S)[None, :] < pad["n_sol"][:, None]
+    assert cmp_["C0"].shape[0] == filled.sum() == cmp_.stats["n_solutions"]
+    for k in pad:
+        if k in ("n_sol", "status"):
+            continue
+        np.testing.assert_array_equal(cmp_[k], pad[k][filled], err_msg=k)
+    assert cmp_.stats["d2h_bytes"] < pad.stats["d2h_bytes"]
+    assert cmp_.solutions(7) == pad.solutions(7)
+    with pytest.raises(RuntimeError, match="capacity"):
+        rt.trace_batch(V, A, outer=True, compact=True, row_capacity=10)
+    empty = rt.trace_batch(np.zeros((0, 3)), np.zeros((0, 3)), compact=True)
+    assert list(empty["sol_offset"]) == [0] and empty["C0"].shape[0] == 0
+
+
 def test_device_resident_path_equals_host_path(make):
     import torch
     rt = make("southpole_2015", attenuation_model="SP1", n_frequencies_integration=25)
