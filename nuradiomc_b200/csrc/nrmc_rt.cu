@@ -43,6 +43,22 @@ __device__ __forceinline__ void load_pair(const KInput &in, int64_t p, double &x
     x2 = __ldg(in.ax + ia); y2 = __ldg(in.ay + ia); z2 = __ldg(in.az + ia);
 }
 
+// The work list of the attenuation kernels is filled from both ends: solutions whose path has one quadrature panel
+// (direct rays) from the front, two-panel paths (refracted / reflected) from the back, so that the warps of the
+// thread-per-solution kernel are homogeneous.  counts[0] = front entries, counts[WL_BACK] = back entries.
+// Per-lane counter block (16 x u64): [0] work front, [1] work back, [2] fallback front, [3] fallback back (unused, 0),
+// [4] root queue, [5] hump queue.
+#define CNT_WORK 0
+#define CNT_FALLBACK 2
+#define CNT_ROOTS 4
+#define CNT_HUMPS 5
+#define CNT_STRIDE 16
+#define WL_BACK 1
+__device__ __forceinline__ SolRec worklist_get(const SolRec *wl, unsigned long long cap, unsigned long long n_front, unsigned long long w)
+{
+    return w < n_front ? wl[w] : wl[cap - 1ull - (w - n_front)];
+}
+
 #define SOLVE_THREADS 128
 #define MAX_S (2 + 4 * NRMC_MAX_REFLECTIONS)
 
@@ -204,7 +220,7 @@ K_hump(IceParams ice, KInput in, TraceOutputs out, const HumpItem *humpq, const 
 #define ROOTS_THREADS 128
 __global__ void __launch_bounds__(ROOTS_THREADS)
 K_roots(IceParams ice, KInput in, TraceOutputs out, const RootItem *rootq, const unsigned long long *root_count, SolRec *worklist,
-        unsigned long long *work_count)
+        unsigned long long *work_count, unsigned long long work_cap)
 {
     const unsigned lane = threadIdx.x & 31u;
     const unsigned long long n = *root_count;     // even: items are pushed in pairs at even offsets
@@ -255,17 +271,17 @@ K_roots(IceParams ice, KInput in, TraceOutputs out, const RootItem *rootq, const
             }
         }
         if (worklist) {
-            const unsigned m = __ballot_sync(0xffffffffu, valid);
-            if (m) {
-                const int leader = __ffs(m) - 1;
-                unsigned long long base = 0;
-                if ((int)lane == leader) base = atomicAdd(work_count, (unsigned long long)__popc(m));
-                base = __shfl_sync(0xffffffffu, base, leader);
-                if (valid) {
-                    SolRec r;
-                    r.v = root.v; r.pair = pair; r.slot = slot; r.piece = (uint8_t)root.piece; r.k = 0; r.rcase = 1; r.pad = 0;
-                    worklist[base + __popc(m & ((1u << lane) - 1u))] = r;
-                }
+            const bool two_panel = root.piece >= 2;
+            const unsigned mf = __ballot_sync(0xffffffffu, valid && !two_panel), mb = __ballot_sync(0xffffffffu, valid && two_panel);
+            unsigned long long bf = 0, bb = 0;
+            if (mf) { const int l = __ffs(mf) - 1; if ((int)lane == l) bf = atomicAdd(work_count, (unsigned long long)__popc(mf)); bf = __shfl_sync(0xffffffffu, bf, l); }
+            if (mb) { const int l = __ffs(mb) - 1; if ((int)lane == l) bb = atomicAdd(work_count + WL_BACK, (unsigned long long)__popc(mb)); bb = __shfl_sync(0xffffffffu, bb, l); }
+            if (valid) {
+                SolRec r;
+                r.v = root.v; r.pair = pair; r.slot = slot; r.piece = (uint8_t)root.piece; r.k = 0; r.rcase = 1; r.pad = 0;
+                const unsigned below = (1u << lane) - 1u;
+                if (!two_panel) worklist[bf + __popc(mf & below)] = r;
+                else worklist[work_cap - 1ull - (bb + __popc(mb & below))] = r;
             }
         }
     }
@@ -316,6 +332,9 @@ __constant__ double c_glw[16] = {0.0271524594117540948517805724560181, 0.0622535
     0.1495959888165767320815017305474785, 0.1246289712555338720524762821920164, 0.0951585116824927848099251076022462,
     0.0622535239386478928628438369943776, 0.0271524594117540948517805724560181};
 
+__constant__ double c_glx12[12] = {-9.81560634246719244e-01, -9.04117256370474798e-01, -7.69902674194304693e-01, -5.87317954286617483e-01, -3.67831498998180184e-01, -1.25233408511468913e-01, 1.25233408511468913e-01, 3.67831498998180184e-01, 5.87317954286617483e-01, 7.69902674194304693e-01, 9.04117256370474798e-01, 9.81560634246719244e-01};
+__constant__ double c_glw12[12] = {4.71753363865114114e-02, 1.06939325995319065e-01, 1.60078328543346415e-01, 2.03167426723065730e-01, 2.33492536538354611e-01, 2.49147045813402690e-01, 2.49147045813402690e-01, 2.33492536538354611e-01, 2.03167426723065730e-01, 1.60078328543346415e-01, 1.06939325995319065e-01, 4.71753363865114114e-02};
+
 struct AttTables {            // device pointers, every array padded to a multiple of 16 bytes
     const double *fa, *fb;    // [Fs_pad] per integration frequency constants (att_freq_consts)
     const double *it;         // [F_pad]  interpolation weight t of every output bin
@@ -363,8 +382,8 @@ __device__ __forceinline__ void rebuild_ray(const IceParams &ice, const KInput &
 // Generic attenuation kernel (all models, any number of bottom reflections): one warp per solution.
 // dynamic shared memory (doubles): fa[Fs_pad] fb[Fs_pad] it[F_pad] | ii[F_pad] (int32) | per warp: H[3][Fs_pad] fac[nseg][Fs_pad]
 __global__ void __launch_bounds__(ATT_THREADS)
-K_att(IceParams ice, KInput in, AttTables tb, const SolRec *worklist, const unsigned long long *work_count, int nseg_max,
-      double *att_sparse, double *att_dense)
+K_att(IceParams ice, KInput in, AttTables tb, const SolRec *worklist, const unsigned long long *work_count, unsigned long long work_cap,
+      int nseg_max, double *att_sparse, double *att_dense)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t bar;
@@ -384,11 +403,11 @@ K_att(IceParams ice, KInput in, AttTables tb, const SolRec *worklist, const unsi
 
     const int q = lane & 15, half = lane >> 4;
     const double xq = c_glx[q], wq = c_glw[q];
-    const unsigned long long n_work = *work_count;
+    const unsigned long long n_front = work_count[0], n_work = n_front + work_count[WL_BACK];
     const int S = 2 + 4 * ice.n_refl;
     for (unsigned long long w = (unsigned long long)blockIdx.x * ATT_WARPS + warp; w < n_work;
          w += (unsigned long long)gridDim.x * ATT_WARPS) {
-        const SolRec rec = worklist[w];
+        const SolRec rec = worklist_get(worklist, work_cap, n_front, w);
         PairGeom g;
         AttPlan plan;
         rebuild_ray(ice, in, rec, g, plan);
@@ -463,7 +482,8 @@ K_att(IceParams ice, KInput in, AttTables tb, const SolRec *worklist, const unsi
 // shared memory by TMA.  Solutions whose slopes leave the band where the SP1_K-term series is accurate to 1e-9, or that
 // could touch the 1 m floor of attenuation.py:252-255, are handed to the generic kernel (fallback list).
 // ---------------------------------------------------------------------------------------------------------------
-#define SP1_K 12
+#define SP1_K 10
+#define SP1_NQ 12             // Gauss-Legendre nodes per panel: <= 6e-6 on the factor (16: 1e-8; 10: 9e-5) -- scratch/attconv.cpp
 struct Sp1Tables {
     const double *wk;         // [Fs_pad][SP1_K]  w_j^k / k!
     const double *E;          // [Fs_pad]         exp(p_ref(band_j) * w_j)
@@ -475,9 +495,10 @@ struct Sp1Tables {
 };
 #define SP1_THREADS 128
 
+template <bool HAVE_HI>
 __global__ void __launch_bounds__(SP1_THREADS)
 K_att_sp1(IceParams ice, KInput in, AttTables tb, Sp1Tables sp, const SolRec *worklist, const unsigned long long *work_count,
-          double *att_sparse, SolRec *fallback, unsigned long long *fallback_count)
+          unsigned long long work_cap, double *att_sparse, SolRec *fallback, unsigned long long *fallback_count)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t bar;
@@ -486,11 +507,11 @@ K_att_sp1(IceParams ice, KInput in, AttTables tb, Sp1Tables sp, const SolRec *wo
     int32_t *s_band = reinterpret_cast<int32_t *>(s_E + tb.Fs_pad);
     stage_tables(&bar, s_wk, sp.wk, (uint32_t)tb.Fs_pad * SP1_K * 8u, s_E, sp.E, (uint32_t)tb.Fs_pad * 8u, s_band, sp.band,
                  (uint32_t)((tb.Fs_pad + 3) & ~3) * 4u, nullptr, nullptr, 0u);
-    const unsigned long long n_work = *work_count;
-    const double xlim = 0.9;     // 0.9^12 / 12! = 5.9e-10
+    const unsigned long long n_front = work_count[0], n_work = n_front + work_count[WL_BACK];
+    const double xlim = 0.9;     // 0.9^10 / 10! = 9.6e-8 relative on the exponent
     for (unsigned long long w = (unsigned long long)blockIdx.x * SP1_THREADS + threadIdx.x; w < n_work;
          w += (unsigned long long)gridDim.x * SP1_THREADS) {
-        const SolRec rec = worklist[w];
+        const SolRec rec = worklist_get(worklist, work_cap, n_front, w);
         PairGeom g;
         AttPlan plan;
         rebuild_ray(ice, in, rec, g, plan);
@@ -498,28 +519,27 @@ K_att_sp1(IceParams ice, KInput in, AttTables tb, Sp1Tables sp, const SolRec *wo
 #pragma unroll
         for (int k = 0; k < SP1_K; ++k) { Mlo[k] = 0.0; Mhi[k] = 0.0; }
         bool ok = true;
-        for (int slot = 0; slot < plan.n_slots; ++slot) {
-            double lo, hi;
-            int panel;
-            plan_slot(plan, slot, lo, hi, panel);
-            const double mult = (double)plan_mult(plan, 0, panel);
+        // k = 0 paths: panel 0 = [u_T, u_2] twice (after the turning point), panel 1 = [u_2, u_1] once
 #pragma unroll 1
-            for (int i = 0; i < 16; ++i) {
-                const double x = c_glx[i], wgt = c_glw[i];
+        for (int panel = plan.turned ? 0 : 1; panel < 2; ++panel) {
+            const double lo = panel == 0 ? plan.uT : plan.u2, hi = panel == 0 ? plan.u2 : plan.u1;
+            if (!(hi > lo)) continue;
+            const double mult = panel == 0 ? 2.0 : 1.0;
+#pragma unroll 1
+            for (int i = 0; i < SP1_NQ; ++i) {
                 double z, wds;
-                att_node_geometry(ice, plan, lo, hi, x, wgt, z, wds);
+                att_node_geometry(ice, plan, lo, hi, c_glx12[i], c_glw12[i], z, wds);
                 AttNode nd;
                 att_node(1, z, tb.gl3, nd);
                 const double c = mult * wds * exp(nd.p0);
                 const double dlo = nd.p1 - sp.pref_lo, dhi = nd.p2 - sp.pref_hi;
                 // series radius and the 1 m floor (1/L <= 1 <=> exponent <= 0 at the band edges)
-                ok = ok && (fabs(dlo) * sp.wabs_lo <= xlim) && (fabs(dhi) * sp.wabs_hi <= xlim);
-                if (sp.n_lo) ok = ok && (nd.p0 + fmax(nd.p1 * sp.wmin_lo, nd.p1 * sp.wmax_lo) < 0.0);
-                if (sp.n_hi) ok = ok && (nd.p0 + fmax(nd.p2 * sp.wmin_hi, nd.p2 * sp.wmax_hi) < 0.0);
+                ok = ok && (fabs(dlo) * sp.wabs_lo <= xlim) && (nd.p0 + fmax(nd.p1 * sp.wmin_lo, nd.p1 * sp.wmax_lo) < 0.0);
                 double t = c;
 #pragma unroll
                 for (int k = 0; k < SP1_K; ++k) { Mlo[k] += t; t *= dlo; }
-                if (sp.n_hi) {
+                if (HAVE_HI) {
+                    ok = ok && (fabs(dhi) * sp.wabs_hi <= xlim) && (nd.p0 + fmax(nd.p2 * sp.wmin_hi, nd.p2 * sp.wmax_hi) < 0.0);
                     t = c;
 #pragma unroll
                     for (int k = 0; k < SP1_K; ++k) { Mhi[k] += t; t *= dhi; }
@@ -536,7 +556,7 @@ K_att_sp1(IceParams ice, KInput in, AttTables tb, Sp1Tables sp, const SolRec *wo
         for (int j = 0; j < tb.Fs; ++j) {
             const double *wk = s_wk + j * SP1_K;
             double acc = 0.0;
-            if (s_band[j] == 0) {
+            if (!HAVE_HI || s_band[j] == 0) {
 #pragma unroll
                 for (int k = 0; k < SP1_K; ++k) acc = fma(Mlo[k], wk[k], acc);
             } else {
@@ -957,9 +977,13 @@ int nrmc_rt_set_frequencies(nrmc_rt_t h, const double *frequency, int32_t n, dou
         t.wk = (const double *)q; t.E = (const double *)(q + b_wk); t.band = (const int32_t *)(q + b_wk + b_E);
         h->smem_sp1 = b_wk + b_E + b_band;
         if (h->smem_sp1 <= 200 * 1024) {
-            if (h->smem_sp1 > 48 * 1024) CK(cudaFuncSetAttribute(K_att_sp1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_sp1));
+            if (h->smem_sp1 > 48 * 1024) {
+                CK(cudaFuncSetAttribute(K_att_sp1<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_sp1));
+                CK(cudaFuncSetAttribute(K_att_sp1<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_sp1));
+            }
             int nb = 0;
-            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, K_att_sp1, SP1_THREADS, h->smem_sp1));
+            if (t.n_hi > 0) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, K_att_sp1<true>, SP1_THREADS, h->smem_sp1));
+            else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, K_att_sp1<false>, SP1_THREADS, h->smem_sp1));
             h->grid_sp1 = std::max(1, nb) * h->n_sm;
             h->have_sp1 = true;
         }
@@ -989,28 +1013,27 @@ static int launch_chunk(nrmc_rt_s *h, Lane &ln, int lane_id, const KInput &kin, 
                         double *att_dense, int *n_launches)
 {
     const bool want_att = (att_sparse || att_dense);
-    unsigned long long *d_count = (unsigned long long *)h->d_count.p + lane_id;
+    unsigned long long *cnt = (unsigned long long *)h->d_count.p + CNT_STRIDE * lane_id;
+    unsigned long long *d_count = cnt + CNT_WORK;
+    const unsigned long long work_cap = (unsigned long long)kin.n_pairs * h->S;
     SolRec *wl = nullptr;
     if (want_att) {
-        CK(ln.work.reserve((size_t)kin.n_pairs * h->S * sizeof(SolRec)));
+        CK(ln.work.reserve((size_t)work_cap * sizeof(SolRec)));
         wl = (SolRec *)ln.work.p;
-        CK(cudaMemsetAsync(d_count, 0, sizeof(unsigned long long), ln.stream));
     }
+    CK(cudaMemsetAsync(cnt, 0, CNT_STRIDE * sizeof(unsigned long long), ln.stream));
     if (ln.timed) cudaEventRecord(ln.ev[0], ln.stream);
     if (h->ice.n_refl == 0) {
         // binned solver: classify -> hump search -> roots, re-packed through queues (counters [4+lane], [6+lane])
-        unsigned long long *d_roots = (unsigned long long *)h->d_count.p + 4 + lane_id;
-        unsigned long long *d_humps = (unsigned long long *)h->d_count.p + 6 + lane_id;
+        unsigned long long *d_roots = cnt + CNT_ROOTS, *d_humps = cnt + CNT_HUMPS;
         CK(ln.rootq.reserve((size_t)kin.n_pairs * 2 * sizeof(RootItem)));
         CK(ln.humpq.reserve((size_t)kin.n_pairs * sizeof(HumpItem)));
-        CK(cudaMemsetAsync(d_roots, 0, sizeof(unsigned long long), ln.stream));
-        CK(cudaMemsetAsync(d_humps, 0, sizeof(unsigned long long), ln.stream));
         const int64_t blocks = (kin.n_pairs + CLASSIFY_THREADS - 1) / CLASSIFY_THREADS;
         K_classify<<<(unsigned)blocks, CLASSIFY_THREADS, 0, ln.stream>>>(h->ice, kin, to, (RootItem *)ln.rootq.p, d_roots,
                                                                          (HumpItem *)ln.humpq.p, d_humps);
         K_hump<<<h->grid_hump, HUMP_THREADS, 0, ln.stream>>>(h->ice, kin, to, (const HumpItem *)ln.humpq.p, d_humps,
                                                              (RootItem *)ln.rootq.p, d_roots);
-        K_roots<<<h->grid_roots, ROOTS_THREADS, 0, ln.stream>>>(h->ice, kin, to, (const RootItem *)ln.rootq.p, d_roots, wl, d_count);
+        K_roots<<<h->grid_roots, ROOTS_THREADS, 0, ln.stream>>>(h->ice, kin, to, (const RootItem *)ln.rootq.p, d_roots, wl, d_count, work_cap);
         *n_launches += 3;
     } else {
         const int64_t blocks = (kin.n_pairs + SOLVE_THREADS - 1) / SOLVE_THREADS;
@@ -1025,17 +1048,20 @@ static int launch_chunk(nrmc_rt_s *h, Lane &ln, int lane_id, const KInput &kin, 
         ++*n_launches;
         if (h->have_sp1) {
             // SP1 moment kernel -> sparse factors; rare out-of-band solutions -> generic kernel; dense = interp(sparse)
-            unsigned long long *d_fb = (unsigned long long *)h->d_count.p + 2 + lane_id;
+            unsigned long long *d_fb = cnt + CNT_FALLBACK;
             CK(ln.fallback.reserve((size_t)kin.n_pairs * h->S * sizeof(SolRec)));
             double *sparse = att_sparse;
             if (!sparse) {
                 CK(ln.sparse_tmp.reserve((size_t)kin.n_pairs * h->S * tb.Fs * sizeof(double)));
                 sparse = (double *)ln.sparse_tmp.p;
             }
-            CK(cudaMemsetAsync(d_fb, 0, sizeof(unsigned long long), ln.stream));
-            K_att_sp1<<<h->grid_sp1, SP1_THREADS, h->smem_sp1, ln.stream>>>(h->ice, kin, tb, h->sp1, wl, d_count, sparse,
-                                                                            (SolRec *)ln.fallback.p, d_fb);
-            K_att<<<h->grid_att, ATT_THREADS, h->smem_att, ln.stream>>>(h->ice, kin, tb, (const SolRec *)ln.fallback.p, d_fb,
+            if (h->sp1.n_hi > 0)
+                K_att_sp1<true><<<h->grid_sp1, SP1_THREADS, h->smem_sp1, ln.stream>>>(h->ice, kin, tb, h->sp1, wl, d_count, work_cap, sparse,
+                                                                                      (SolRec *)ln.fallback.p, d_fb);
+            else
+                K_att_sp1<false><<<h->grid_sp1, SP1_THREADS, h->smem_sp1, ln.stream>>>(h->ice, kin, tb, h->sp1, wl, d_count, work_cap, sparse,
+                                                                                       (SolRec *)ln.fallback.p, d_fb);
+            K_att<<<h->grid_att, ATT_THREADS, h->smem_att, ln.stream>>>(h->ice, kin, tb, (const SolRec *)ln.fallback.p, d_fb, work_cap,
                                                                         nseg_max, sparse, nullptr);
             *n_launches += 2;
             if (att_dense) {
@@ -1043,7 +1069,7 @@ static int launch_chunk(nrmc_rt_s *h, Lane &ln, int lane_id, const KInput &kin, 
                 ++*n_launches;
             }
         } else {
-            K_att<<<h->grid_att, ATT_THREADS, h->smem_att, ln.stream>>>(h->ice, kin, tb, wl, d_count, nseg_max, att_sparse, att_dense);
+            K_att<<<h->grid_att, ATT_THREADS, h->smem_att, ln.stream>>>(h->ice, kin, tb, wl, d_count, work_cap, nseg_max, att_sparse, att_dense);
             ++*n_launches;
         }
     }
@@ -1147,9 +1173,9 @@ extern "C" int nrmc_rt_trace(nrmc_rt_t h, const nrmc_rt_input *in, const nrmc_rt
             if (rc == NRMC_OK && stats) {
                 cudaEventSynchronize(ln.ev[2]);
                 if (want_att) {
-                    unsigned long long cnt = 0;
-                    cudaMemcpy(&cnt, h->d_count.p, sizeof(cnt), cudaMemcpyDeviceToHost);
-                    stats->n_solutions += (int64_t)cnt;
+                    unsigned long long cnt2[2] = {0, 0};
+                    cudaMemcpy(cnt2, h->d_count.p, sizeof(cnt2), cudaMemcpyDeviceToHost);
+                    stats->n_solutions += (int64_t)(cnt2[0] + cnt2[WL_BACK]);
                 }
                 float a = 0, b = 0;
                 cudaEventElapsedTime(&a, ln.ev[0], ln.ev[1]);
