@@ -16,6 +16,54 @@
 
 namespace nrmc {
 
+// ---------------------------------------------------------------------------------------------------------------
+// exp / expm1 for the attenuation kernels.  CUDA's exp() materialises every polynomial coefficient with two UMOVs
+// (FP64 immediates do not fit the DFMA encoding), which costs more issue slots than the arithmetic; here the
+// coefficients sit in constant memory (one LDCU.128 per two coefficients), the polynomial is the degree-11 Taylor
+// series on |r| <= ln2/2 (truncation 6e-15 relative) and there is no slow path: the argument is clamped to [-700, 700],
+// far outside anything an attenuation exponent needs (exp(-700) = 1e-304 stands in for 0).
+// ---------------------------------------------------------------------------------------------------------------
+#if defined(__CUDACC__)
+__constant__ double c_expc[10] = {2.505210838544172e-08, 2.755731922398589e-07, 2.7557319223985893e-06, 2.48015873015873e-05, 0.0001984126984126984, 0.001388888888888889, 0.008333333333333333, 0.041666666666666664, 0.16666666666666666, 0.5};
+__device__ __forceinline__ double exp_reduce(double x, int &k)
+{
+    const double t = fma(x, 1.4426950408889634, 6755399441055744.0);
+    k = __double2loint(t);
+    const double kd = t - 6755399441055744.0;
+    double r = fma(kd, -6.93147180369123816490e-01, x);
+    return fma(kd, -1.90821492927058770002e-10, r);
+}
+__device__ __forceinline__ double expm1_poly(double r)     // e^r - 1 on |r| <= ln2/2
+{
+    double p = c_expc[0];
+#pragma unroll
+    for (int i = 1; i < 10; ++i) p = fma(p, r, c_expc[i]);
+    return fma(p * r, r, r);
+}
+__device__ __forceinline__ double exp_c(double x)
+{
+    int k;
+    const double r = exp_reduce(fmin(fmax(x, -700.0), 700.0), k);
+    const double p = expm1_poly(r) + 1.0;
+    return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+}
+__device__ __forceinline__ double expm1_c(double x)        // accurate for x -> 0: k = 0 returns the polynomial itself
+{
+    int k;
+    const double r = exp_reduce(fmin(fmax(x, -700.0), 700.0), k);
+    const double q = expm1_poly(r);
+    const double s = __hiloint2double((1023 + k) << 20, 0);
+    return fma(s, q, s - 1.0);
+}
+#endif
+#if defined(__CUDA_ARCH__)
+#define NRMC_EXP(x) exp_c(x)
+#define NRMC_EXPM1(x) expm1_c(x)
+#else
+#define NRMC_EXP(x) exp(x)
+#define NRMC_EXPM1(x) expm1(x)
+#endif
+
 #define NRMC_NQ 16            // Gauss-Legendre points per half-warp slot
 #define NRMC_MAX_SEG (NRMC_MAX_REFLECTIONS + 1)
 
@@ -172,7 +220,7 @@ NRMC_HD void att_node_geometry(const IceParams &ice, const AttPlan &p, double lo
     const double u = 0.5 * (hi + lo) + half * x;
     const double uu = u * u;
     z = fmin(p.zv - uu, 0.0);
-    const double em = -expm1(-uu * ice.inv_z0);
+    const double em = -NRMC_EXPM1(-uu * ice.inv_z0);
     const double n = p.beta + p.delta * em;
     wds = w * half * 2.0 * u * n / sqrt(p.delta * em * (n + p.beta));
 }

@@ -132,6 +132,23 @@ __device__ __forceinline__ void push_brackets(bool have, int64_t pair, const Pai
     }
 }
 
+// NaN rows of the attenuation outputs for pairs without solution, written by the whole warp (coalesced) inside the
+// compute-bound solver kernels, where the store traffic is free
+struct AttFill { double *sparse, *dense; int32_t Fs, F; };
+
+__device__ __forceinline__ void warp_fill_nan_rows(bool mine, int64_t pair, const AttFill &af, unsigned lane)
+{
+    if (!af.sparse && !af.dense) return;
+    unsigned m = __ballot_sync(0xffffffffu, mine);
+    while (m) {
+        const int l = __ffs(m) - 1;
+        m &= m - 1;
+        const int64_t pr = __shfl_sync(0xffffffffu, pair, l);
+        if (af.sparse) { double *d = af.sparse + pr * 2 * af.Fs; for (int j = lane; j < 2 * af.Fs; j += 32) d[j] = NAN; }
+        if (af.dense) { double *d = af.dense + pr * 2 * af.F; for (int j = lane; j < 2 * af.F; j += 32) d[j] = NAN; }
+    }
+}
+
 __device__ __forceinline__ void write_no_solution(const TraceOutputs &out, int64_t p, int status)
 {
     if (out.n_sol) out.n_sol[p] = 0;
@@ -142,7 +159,7 @@ __device__ __forceinline__ void write_no_solution(const TraceOutputs &out, int64
 
 #define CLASSIFY_THREADS 256
 __global__ void __launch_bounds__(CLASSIFY_THREADS)
-K_classify(IceParams ice, KInput in, TraceOutputs out, RootItem *rootq, unsigned long long *root_count, HumpItem *humpq,
+K_classify(IceParams ice, KInput in, TraceOutputs out, AttFill af, RootItem *rootq, unsigned long long *root_count, HumpItem *humpq,
            unsigned long long *hump_count)
 {
     const int64_t p = (int64_t)blockIdx.x * CLASSIFY_THREADS + threadIdx.x;
@@ -169,6 +186,7 @@ K_classify(IceParams ice, KInput in, TraceOutputs out, RootItem *rootq, unsigned
         if (kind == 0) write_no_solution(out, p, status);
         if (kind == 1) { if (out.n_sol) out.n_sol[p] = nb; if (out.status) out.status[p] = 0; }
     }
+    warp_fill_nan_rows(p < in.n_pairs && kind == 0, p, af, lane);
     push_brackets(kind == 1, p, g, br, nb, rootq, root_count, lane);
     const unsigned mh = __ballot_sync(0xffffffffu, kind == 2);
     if (mh) {
@@ -185,8 +203,8 @@ K_classify(IceParams ice, KInput in, TraceOutputs out, RootItem *rootq, unsigned
 }
 
 #define HUMP_THREADS 128
-__global__ void __launch_bounds__(HUMP_THREADS)
-K_hump(IceParams ice, KInput in, TraceOutputs out, const HumpItem *humpq, const unsigned long long *hump_count, RootItem *rootq,
+__global__ void __launch_bounds__(HUMP_THREADS, 4)
+K_hump(IceParams ice, KInput in, TraceOutputs out, AttFill af, const HumpItem *humpq, const unsigned long long *hump_count, RootItem *rootq,
        unsigned long long *root_count)
 {
     const unsigned lane = threadIdx.x & 31u;
@@ -213,13 +231,14 @@ K_hump(IceParams ice, KInput in, TraceOutputs out, const HumpItem *humpq, const 
             if (nb == 0) write_no_solution(out, pair, 0);
             else { if (out.n_sol) out.n_sol[pair] = nb; if (out.status) out.status[pair] = 0; }
         }
+        warp_fill_nan_rows(active && nb == 0, pair, af, lane);
         push_brackets(active && nb > 0, pair, g, br, nb, rootq, root_count, lane);
     }
 }
 
 #define ROOTS_THREADS 128
 __global__ void __launch_bounds__(ROOTS_THREADS)
-K_roots(IceParams ice, KInput in, TraceOutputs out, const RootItem *rootq, const unsigned long long *root_count, SolRec *worklist,
+K_roots(IceParams ice, KInput in, TraceOutputs out, AttFill af, const RootItem *rootq, const unsigned long long *root_count, SolRec *worklist,
         unsigned long long *work_count, unsigned long long work_cap)
 {
     const unsigned lane = threadIdx.x & 31u;
@@ -268,6 +287,8 @@ K_roots(IceParams ice, KInput in, TraceOutputs out, const RootItem *rootq, const
                 write_solution(out, 2 * pair + slot, 1, f, 0, 1, pr);
             } else {
                 fill_empty_slot(out, 2 * pair + 1, 1);    // single root (tangency at the surface): second slot stays empty
+                if (af.sparse) for (int j = 0; j < af.Fs; ++j) af.sparse[(2 * pair + 1) * af.Fs + j] = NAN;
+                if (af.dense) for (int j = 0; j < af.F; ++j) af.dense[(2 * pair + 1) * af.F + j] = NAN;
             }
         }
         if (worklist) {
@@ -332,8 +353,13 @@ __constant__ double c_glw[16] = {0.0271524594117540948517805724560181, 0.0622535
     0.1495959888165767320815017305474785, 0.1246289712555338720524762821920164, 0.0951585116824927848099251076022462,
     0.0622535239386478928628438369943776, 0.0271524594117540948517805724560181};
 
-__constant__ double c_glx12[12] = {-9.81560634246719244e-01, -9.04117256370474798e-01, -7.69902674194304693e-01, -5.87317954286617483e-01, -3.67831498998180184e-01, -1.25233408511468913e-01, 1.25233408511468913e-01, 3.67831498998180184e-01, 5.87317954286617483e-01, 7.69902674194304693e-01, 9.04117256370474798e-01, 9.81560634246719244e-01};
-__constant__ double c_glw12[12] = {4.71753363865114114e-02, 1.06939325995319065e-01, 1.60078328543346415e-01, 2.03167426723065730e-01, 2.33492536538354611e-01, 2.49147045813402690e-01, 2.49147045813402690e-01, 2.33492536538354611e-01, 2.03167426723065730e-01, 1.60078328543346415e-01, 1.06939325995319065e-01, 4.71753363865114114e-02};
+// 12-point Gauss-Legendre rule, positive half (the rule is symmetric)
+__constant__ double c_glx12h[6] = {1.25233408511468913e-01, 3.67831498998180184e-01, 5.87317954286617483e-01, 7.69902674194304693e-01, 9.04117256370474798e-01, 9.81560634246719244e-01};
+__constant__ double c_glw12h[6] = {2.49147045813402690e-01, 2.33492536538354611e-01, 2.03167426723065730e-01, 1.60078328543346415e-01, 1.06939325995319065e-01, 4.71753363865114114e-02};
+// SP1 depth dependence (attenuation.py:141-142 temperature profile, :176-178 b-coefficients) in constant memory
+__constant__ double c_sp1[16] = {1.83415e-09, -1.59061e-08, 0.00267687, -51.0696,
+                                 -6.74890, 0.026709, -0.000884, -6.22121, -0.070927, -0.001773, -4.09468, -0.002213, -0.000332,
+                                 1.0 / 9.210340371976182, 1.0 / 1.1505720275988207, 0.0};
 
 struct AttTables {            // device pointers, every array padded to a multiple of 16 bytes
     const double *fa, *fb;    // [Fs_pad] per integration frequency constants (att_freq_consts)
@@ -495,6 +521,63 @@ struct Sp1Tables {
 };
 #define SP1_THREADS 128
 
+// one quadrature node of the SP1 kernel: depth terms and the moment update
+template <bool HAVE_HI>
+__device__ __forceinline__ void sp1_node(const IceParams &ice, const AttPlan &plan, const Sp1Tables &sp, double u, double wscale,
+                                         double (&Mlo)[SP1_K], double (&Mhi)[SP1_K], bool &ok)
+{
+    const double uu = u * u;
+    const double z = fmin(plan.zv - uu, 0.0);
+    const double em = -expm1_c(-uu * ice.inv_z0);
+    const double n = plan.beta + plan.delta * em;
+    const double wds = wscale * u * n * rsqrt(plan.delta * em * (n + plan.beta));
+    const double a = fabs(z);
+    const double t = fma(fma(fma(c_sp1[0], a, c_sp1[1]), a, c_sp1[2]), a, c_sp1[3]);
+    const double b0 = fma(t, fma(t, c_sp1[6], c_sp1[5]), c_sp1[4]);
+    const double b1 = fma(t, fma(t, c_sp1[9], c_sp1[8]), c_sp1[7]);
+    const double b2 = fma(t, fma(t, c_sp1[12], c_sp1[11]), c_sp1[10]);
+    const double p1 = (b1 - b0) * c_sp1[13], p2 = (b2 - b1) * c_sp1[14];
+    const double c = wds * exp_c(b1);
+    const double dlo = p1 - sp.pref_lo;
+    // series radius and the 1 m floor (1/L <= 1 <=> exponent <= 0 at the band edges)
+    ok = ok && (fabs(dlo) * sp.wabs_lo <= 0.9) && (b1 + fmax(p1 * sp.wmin_lo, p1 * sp.wmax_lo) < 0.0);
+    double tk = c;
+#pragma unroll
+    for (int k = 0; k < SP1_K; ++k) { Mlo[k] += tk; tk *= dlo; }
+    if (HAVE_HI) {
+        const double dhi = p2 - sp.pref_hi;
+        ok = ok && (fabs(dhi) * sp.wabs_hi <= 0.9) && (b1 + fmax(p2 * sp.wmin_hi, p2 * sp.wmax_hi) < 0.0);
+        tk = c;
+#pragma unroll
+        for (int k = 0; k < SP1_K; ++k) { Mhi[k] += tk; tk *= dhi; }
+    }
+}
+
+// factors exp(-E_j sum_k M_k wk[j][k]) for the integration frequencies [j_begin, j_end), four at a time
+__device__ __forceinline__ void sp1_emit(const double (&M)[SP1_K], const double *s_wk, const double *s_E, int j_begin, int j_end, double *dst)
+{
+    for (int j0 = j_begin; j0 < j_end; j0 += 4) {
+        double acc[4];
+        int jj[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { jj[u] = min(j0 + u, j_end - 1); acc[u] = 0.0; }
+#pragma unroll
+        for (int k = 0; k < SP1_K; k += 2) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const double2 w2 = *reinterpret_cast<const double2 *>(s_wk + jj[u] * SP1_K + k);
+                acc[u] = fma(M[k], w2.x, acc[u]);
+                acc[u] = fma(M[k + 1], w2.y, acc[u]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const double val = exp_c(-acc[u] * s_E[jj[u]]);
+            if (j0 + u < j_end) dst[j0 + u] = val;
+        }
+    }
+}
+
 template <bool HAVE_HI>
 __global__ void __launch_bounds__(SP1_THREADS)
 K_att_sp1(IceParams ice, KInput in, AttTables tb, Sp1Tables sp, const SolRec *worklist, const unsigned long long *work_count,
@@ -504,11 +587,9 @@ K_att_sp1(IceParams ice, KInput in, AttTables tb, Sp1Tables sp, const SolRec *wo
     __shared__ __align__(8) uint64_t bar;
     double *s_wk = reinterpret_cast<double *>(smem_raw);
     double *s_E = s_wk + tb.Fs_pad * SP1_K;
-    int32_t *s_band = reinterpret_cast<int32_t *>(s_E + tb.Fs_pad);
-    stage_tables(&bar, s_wk, sp.wk, (uint32_t)tb.Fs_pad * SP1_K * 8u, s_E, sp.E, (uint32_t)tb.Fs_pad * 8u, s_band, sp.band,
-                 (uint32_t)((tb.Fs_pad + 3) & ~3) * 4u, nullptr, nullptr, 0u);
+    stage_tables(&bar, s_wk, sp.wk, (uint32_t)tb.Fs_pad * SP1_K * 8u, s_E, sp.E, (uint32_t)tb.Fs_pad * 8u, nullptr, nullptr, 0u,
+                 nullptr, nullptr, 0u);
     const unsigned long long n_front = work_count[0], n_work = n_front + work_count[WL_BACK];
-    const double xlim = 0.9;     // 0.9^10 / 10! = 9.6e-8 relative on the exponent
     for (unsigned long long w = (unsigned long long)blockIdx.x * SP1_THREADS + threadIdx.x; w < n_work;
          w += (unsigned long long)gridDim.x * SP1_THREADS) {
         const SolRec rec = worklist_get(worklist, work_cap, n_front, w);
@@ -524,26 +605,13 @@ K_att_sp1(IceParams ice, KInput in, AttTables tb, Sp1Tables sp, const SolRec *wo
         for (int panel = plan.turned ? 0 : 1; panel < 2; ++panel) {
             const double lo = panel == 0 ? plan.uT : plan.u2, hi = panel == 0 ? plan.u2 : plan.u1;
             if (!(hi > lo)) continue;
-            const double mult = panel == 0 ? 2.0 : 1.0;
+            const double half = 0.5 * (hi - lo), mid = 0.5 * (hi + lo);
+            const double scale = (panel == 0 ? 4.0 : 2.0) * half;      // multiplicity x du/dx x the 2 of ds = 2 u n / ... du
 #pragma unroll 1
-            for (int i = 0; i < SP1_NQ; ++i) {
-                double z, wds;
-                att_node_geometry(ice, plan, lo, hi, c_glx12[i], c_glw12[i], z, wds);
-                AttNode nd;
-                att_node(1, z, tb.gl3, nd);
-                const double c = mult * wds * exp(nd.p0);
-                const double dlo = nd.p1 - sp.pref_lo, dhi = nd.p2 - sp.pref_hi;
-                // series radius and the 1 m floor (1/L <= 1 <=> exponent <= 0 at the band edges)
-                ok = ok && (fabs(dlo) * sp.wabs_lo <= xlim) && (nd.p0 + fmax(nd.p1 * sp.wmin_lo, nd.p1 * sp.wmax_lo) < 0.0);
-                double t = c;
-#pragma unroll
-                for (int k = 0; k < SP1_K; ++k) { Mlo[k] += t; t *= dlo; }
-                if (HAVE_HI) {
-                    ok = ok && (fabs(dhi) * sp.wabs_hi <= xlim) && (nd.p0 + fmax(nd.p2 * sp.wmin_hi, nd.p2 * sp.wmax_hi) < 0.0);
-                    t = c;
-#pragma unroll
-                    for (int k = 0; k < SP1_K; ++k) { Mhi[k] += t; t *= dhi; }
-                }
+            for (int i = 0; i < SP1_NQ / 2; ++i) {                     // the symmetric node pair mid -+ half x_i: two independent chains
+                const double hx = half * c_glx12h[i], ws = scale * c_glw12h[i];
+                sp1_node<HAVE_HI>(ice, plan, sp, mid - hx, ws, Mlo, Mhi, ok);
+                sp1_node<HAVE_HI>(ice, plan, sp, mid + hx, ws, Mlo, Mhi, ok);
             }
         }
         if (!ok) {
@@ -551,20 +619,9 @@ K_att_sp1(IceParams ice, KInput in, AttTables tb, Sp1Tables sp, const SolRec *wo
             fallback[idx] = rec;
             continue;
         }
-        const int S = 2;
-        double *dst = att_sparse + (rec.pair * S + rec.slot) * (int64_t)tb.Fs;
-        for (int j = 0; j < tb.Fs; ++j) {
-            const double *wk = s_wk + j * SP1_K;
-            double acc = 0.0;
-            if (!HAVE_HI || s_band[j] == 0) {
-#pragma unroll
-                for (int k = 0; k < SP1_K; ++k) acc = fma(Mlo[k], wk[k], acc);
-            } else {
-#pragma unroll
-                for (int k = 0; k < SP1_K; ++k) acc = fma(Mhi[k], wk[k], acc);
-            }
-            dst[j] = exp(-acc * s_E[j]);
-        }
+        double *dst = att_sparse + (rec.pair * 2 + rec.slot) * (int64_t)tb.Fs;
+        sp1_emit(Mlo, s_wk, s_E, 0, HAVE_HI ? sp.n_lo : tb.Fs, dst);
+        if (HAVE_HI) sp1_emit(Mhi, s_wk, s_E, sp.n_lo, tb.Fs, dst);
     }
 }
 
@@ -968,6 +1025,8 @@ int nrmc_rt_set_frequencies(nrmc_rt_t h, const double *frequency, int32_t n, dou
             if (b) { ++t.n_hi; t.wabs_hi = std::max(t.wabs_hi, fabs(w)); t.wmin_hi = std::min(t.wmin_hi, w); t.wmax_hi = std::max(t.wmax_hi, w); }
             else { ++t.n_lo; t.wabs_lo = std::max(t.wabs_lo, fabs(w)); t.wmin_lo = std::min(t.wmin_lo, w); t.wmax_lo = std::max(t.wmax_lo, w); }
         }
+        bool banded_in_order = true;      // the kernel emits [0, n_lo) from the low-band moments and [n_lo, Fs) from the high-band ones
+        for (int j = 0; j < Fs; ++j) if (band[j] != (j < t.n_lo ? 0 : 1)) banded_in_order = false;
         const size_t b_wk = wk.size() * 8, b_E = E.size() * 8, b_band = band.size() * 4;
         CK(h->d_sp1.reserve(b_wk + b_E + b_band + 64));
         unsigned char *q = (unsigned char *)h->d_sp1.p;
@@ -975,8 +1034,8 @@ int nrmc_rt_set_frequencies(nrmc_rt_t h, const double *frequency, int32_t n, dou
         CK(cudaMemcpy(q + b_wk, E.data(), b_E, cudaMemcpyHostToDevice));
         CK(cudaMemcpy(q + b_wk + b_E, band.data(), b_band, cudaMemcpyHostToDevice));
         t.wk = (const double *)q; t.E = (const double *)(q + b_wk); t.band = (const int32_t *)(q + b_wk + b_E);
-        h->smem_sp1 = b_wk + b_E + b_band;
-        if (h->smem_sp1 <= 200 * 1024) {
+        h->smem_sp1 = b_wk + b_E;
+        if (h->smem_sp1 <= 200 * 1024 && banded_in_order) {
             if (h->smem_sp1 > 48 * 1024) {
                 CK(cudaFuncSetAttribute(K_att_sp1<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_sp1));
                 CK(cudaFuncSetAttribute(K_att_sp1<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_sp1));
@@ -1029,11 +1088,13 @@ static int launch_chunk(nrmc_rt_s *h, Lane &ln, int lane_id, const KInput &kin, 
         CK(ln.rootq.reserve((size_t)kin.n_pairs * 2 * sizeof(RootItem)));
         CK(ln.humpq.reserve((size_t)kin.n_pairs * sizeof(HumpItem)));
         const int64_t blocks = (kin.n_pairs + CLASSIFY_THREADS - 1) / CLASSIFY_THREADS;
-        K_classify<<<(unsigned)blocks, CLASSIFY_THREADS, 0, ln.stream>>>(h->ice, kin, to, (RootItem *)ln.rootq.p, d_roots,
+        AttFill af;
+        af.sparse = att_sparse; af.dense = att_dense; af.Fs = h->tb.Fs; af.F = h->tb.F;
+        K_classify<<<(unsigned)blocks, CLASSIFY_THREADS, 0, ln.stream>>>(h->ice, kin, to, af, (RootItem *)ln.rootq.p, d_roots,
                                                                          (HumpItem *)ln.humpq.p, d_humps);
-        K_hump<<<h->grid_hump, HUMP_THREADS, 0, ln.stream>>>(h->ice, kin, to, (const HumpItem *)ln.humpq.p, d_humps,
+        K_hump<<<h->grid_hump, HUMP_THREADS, 0, ln.stream>>>(h->ice, kin, to, af, (const HumpItem *)ln.humpq.p, d_humps,
                                                              (RootItem *)ln.rootq.p, d_roots);
-        K_roots<<<h->grid_roots, ROOTS_THREADS, 0, ln.stream>>>(h->ice, kin, to, (const RootItem *)ln.rootq.p, d_roots, wl, d_count, work_cap);
+        K_roots<<<h->grid_roots, ROOTS_THREADS, 0, ln.stream>>>(h->ice, kin, to, af, (const RootItem *)ln.rootq.p, d_roots, wl, d_count, work_cap);
         *n_launches += 3;
     } else {
         const int64_t blocks = (kin.n_pairs + SOLVE_THREADS - 1) / SOLVE_THREADS;
@@ -1044,8 +1105,10 @@ static int launch_chunk(nrmc_rt_s *h, Lane &ln, int lane_id, const KInput &kin, 
     if (want_att) {
         const AttTables &tb = h->tb;
         const int nseg_max = h->ice.n_refl + 1;
-        K_att_fill<<<h->n_sm * 8, 256, 0, ln.stream>>>(to.n_sol, kin.n_pairs, h->S, tb.Fs, tb.F, att_sparse, att_dense);
-        ++*n_launches;
+        if (h->ice.n_refl > 0) {     // the binned solver writes the NaN rows itself
+            K_att_fill<<<h->n_sm * 8, 256, 0, ln.stream>>>(to.n_sol, kin.n_pairs, h->S, tb.Fs, tb.F, att_sparse, att_dense);
+            ++*n_launches;
+        }
         if (h->have_sp1) {
             // SP1 moment kernel -> sparse factors; rare out-of-band solutions -> generic kernel; dense = interp(sparse)
             unsigned long long *d_fb = cnt + CNT_FALLBACK;
