@@ -104,16 +104,18 @@ NRMC_HD void plan_slot(const AttPlan &p, int slot, double &lo, double &hi, int &
     hi = (sub == p.spp - 1) ? phi : plo + (sub + 1) * w;
 }
 
-NRMC_HD void att_plan(const IceParams &ice, const PairGeom &g, int piece, int k, int rcase, const RayState &r, AttPlan &p)
+NRMC_HD void att_plan_core(const IceParams &ice, double z1, double z2, int piece, int k, int rcase, double beta, double delta, double zv,
+                           AttPlan &p)
 {
+    const bool reflected = (piece == 0 || piece == 3);    // sub pieces: the turning point is the surface
     p.turned = piece >= 2;
     p.k = k; p.rcase = rcase; p.nseg = k + 1;
-    p.beta = r.beta;
-    p.delta = (r.rc * r.rc) / (ice.n_ice + r.beta);      // n_ice - beta without cancellation
-    p.zv = ice.z0 * log(p.delta / ice.dn);
-    p.uT = r.reflected ? sqrt(fmax(p.zv, 0.0)) : 0.0;
-    p.u2 = sqrt(fmax(p.zv - g.z2, 0.0));
-    p.u1 = sqrt(fmax(p.zv - g.z1, 0.0));
+    p.beta = beta;
+    p.delta = delta;
+    p.zv = zv;
+    p.uT = reflected ? sqrt(fmax(p.zv, 0.0)) : 0.0;
+    p.u2 = sqrt(fmax(p.zv - z2, 0.0));
+    p.u1 = sqrt(fmax(p.zv - z1, 0.0));
     p.ur = (k > 0) ? sqrt(fmax(p.zv - ice.zr, 0.0)) : p.u1;
     p.na = 0; p.act0 = p.act1 = p.act2 = 0;
     for (int q = 0; q < 3; ++q) {
@@ -131,6 +133,17 @@ NRMC_HD void att_plan(const IceParams &ice, const PairGeom &g, int piece, int k,
     p.spp = (ice.att_model == 2 || ice.att_model == 5) ? 8 : 1;
     if (p.na == 1) p.spp *= 2;
     p.n_slots = p.na * p.spp;
+}
+
+NRMC_HD void att_plan(const IceParams &ice, const PairGeom &g, int piece, int k, int rcase, const RayState &r, AttPlan &p)
+{
+    const double delta = (r.rc * r.rc) / (ice.n_ice + r.beta);      // n_ice - beta without cancellation
+    att_plan_core(ice, g.z1, g.z2, piece, k, rcase, r.beta, delta, ice.z0 * log(delta / ice.dn), p);
+}
+
+NRMC_HD void att_plan_rec(const IceParams &ice, const SolRec &rec, AttPlan &p)
+{
+    att_plan_core(ice, rec.z1, rec.z2, rec.piece, rec.k, rec.rcase, rec.beta, rec.delta, rec.zv, p);
 }
 
 // ---------------------------------------------------------------------------------------------------------------

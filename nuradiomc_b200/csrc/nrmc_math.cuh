@@ -479,12 +479,30 @@ struct TraceOutputs {          // all [N,S] pair-major, S = 2 + 4 n_refl; any po
     double *reflection_angle;  // [N,S,n_refl+1], NaN = None
 };
 
-struct SolRec {                // what the attenuation kernel needs to rebuild the ray
-    double v;                  // curve parameter of the root
+struct SolRec {                // everything the attenuation kernels need about one solution: one aligned 64-byte load
     int64_t pair;
+    double beta;               // Snell invariant of the ray
+    double delta;              // n_ice - beta, formed without cancellation: (n_ice^2 - beta^2)/(n_ice + beta)
+    double zv;                 // z0 ln(delta/dn): depth of the (possibly virtual, > 0) apex
+    double z1, z2;             // depths of the deeper / shallower end point
     int32_t slot;
     uint8_t piece, k, rcase, pad;
+    double v;                  // curve parameter of the root (kept for diagnostics)
 };
+
+NRMC_HD void make_solrec(const IceParams &ice, const PairGeom &g, int64_t pair, int slot, int k, int rcase, const Root &root, SolRec &r)
+{
+    r.pair = pair; r.slot = slot; r.piece = (uint8_t)root.piece; r.k = (uint8_t)k; r.rcase = (uint8_t)rcase; r.pad = 0; r.v = root.v;
+    r.beta = root.beta;
+    // c = n_ice^2 - beta^2 = c0 + sigma^2 with sigma from the curve parameter (ray_state)
+    const bool band = (root.piece == 1 || root.piece == 2);
+    const double q = 1.0 / (1.0 + root.v * root.v);
+    const double sig = (band ? g.n2 : ice.ns) * ((1.0 - root.v) * (1.0 + root.v)) * q;
+    const double c = (band ? g.c0_band : g.c0_sub) + sig * sig;
+    r.delta = c / (ice.n_ice + r.beta);
+    r.zv = ice.z0 * log(r.delta / ice.dn);
+    r.z1 = g.z1; r.z2 = g.z2;
+}
 
 #define NRMC_STATUS_AIR 1
 #define NRMC_STATUS_BELOW_REFLECTOR 2
@@ -567,8 +585,7 @@ NRMC_HD int trace_pair(const IceParams &ice, double ax, double ay, double az, do
                 SolutionProps p;
                 solution_props(ice, g, f.x1y, k, rcase, roots[j], p);
                 write_solution(o, i * S + n, K1, f, k, rcase, p);
-                if (recs) { recs[n].v = roots[j].v; recs[n].pair = i; recs[n].slot = n; recs[n].piece = (uint8_t)roots[j].piece;
-                            recs[n].k = (uint8_t)k; recs[n].rcase = (uint8_t)rcase; recs[n].pad = 0; }
+                if (recs) make_solrec(ice, g, i, n, k, rcase, roots[j], recs[n]);
                 ++n;
             }
         }

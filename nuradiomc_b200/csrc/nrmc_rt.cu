@@ -274,6 +274,17 @@ K_roots(IceParams ice, KInput in, TraceOutputs out, AttFill af, const RootItem *
         const double beta_other = __shfl_xor_sync(0xffffffffu, valid ? root.beta : -1.0, 1);
         int slot = lane & 1;
         if (valid) slot = (root.beta > beta_other) ? 0 : ((root.beta < beta_other) ? 1 : (int)(lane & 1u));
+        // work-list slot of this solution (front: one quadrature panel, back: two), one atomic per warp and list end
+        SolRec *rec_dst = nullptr;
+        if (worklist) {
+            const bool two_panel = root.piece >= 2;
+            const unsigned mf = __ballot_sync(0xffffffffu, valid && !two_panel), mb = __ballot_sync(0xffffffffu, valid && two_panel);
+            unsigned long long bf = 0, bb = 0;
+            if (mf) { const int l = __ffs(mf) - 1; if ((int)lane == l) bf = atomicAdd(work_count, (unsigned long long)__popc(mf)); bf = __shfl_sync(0xffffffffu, bf, l); }
+            if (mb) { const int l = __ffs(mb) - 1; if ((int)lane == l) bb = atomicAdd(work_count + WL_BACK, (unsigned long long)__popc(mb)); bb = __shfl_sync(0xffffffffu, bb, l); }
+            const unsigned below = (1u << lane) - 1u;
+            if (valid) rec_dst = two_panel ? worklist + (work_cap - 1ull - (bb + __popc(mb & below))) : worklist + (bf + __popc(mf & below));
+        }
         if (active) {
             if (valid) {
                 double x1, y1, z1, x2, y2, z2;
@@ -282,6 +293,11 @@ K_roots(IceParams ice, KInput in, TraceOutputs out, AttFill af, const RootItem *
                 make_frame(x1, y1, z1, x2, y2, z2, f);
                 PairGeom g;
                 make_pair_geom_g(ice, f.z1, f.z2, fmax(f.rho, 1e-12), g1, g2, g);
+                if (rec_dst) {
+                    SolRec rec;
+                    make_solrec(ice, g, pair, slot, 0, 1, root, rec);
+                    *rec_dst = rec;
+                }
                 SolutionProps pr;
                 solution_props(ice, g, f.x1y, 0, 1, root, pr);
                 write_solution(out, 2 * pair + slot, 1, f, 0, 1, pr);
@@ -289,20 +305,6 @@ K_roots(IceParams ice, KInput in, TraceOutputs out, AttFill af, const RootItem *
                 fill_empty_slot(out, 2 * pair + 1, 1);    // single root (tangency at the surface): second slot stays empty
                 if (af.sparse) for (int j = 0; j < af.Fs; ++j) af.sparse[(2 * pair + 1) * af.Fs + j] = NAN;
                 if (af.dense) for (int j = 0; j < af.F; ++j) af.dense[(2 * pair + 1) * af.F + j] = NAN;
-            }
-        }
-        if (worklist) {
-            const bool two_panel = root.piece >= 2;
-            const unsigned mf = __ballot_sync(0xffffffffu, valid && !two_panel), mb = __ballot_sync(0xffffffffu, valid && two_panel);
-            unsigned long long bf = 0, bb = 0;
-            if (mf) { const int l = __ffs(mf) - 1; if ((int)lane == l) bf = atomicAdd(work_count, (unsigned long long)__popc(mf)); bf = __shfl_sync(0xffffffffu, bf, l); }
-            if (mb) { const int l = __ffs(mb) - 1; if ((int)lane == l) bb = atomicAdd(work_count + WL_BACK, (unsigned long long)__popc(mb)); bb = __shfl_sync(0xffffffffu, bb, l); }
-            if (valid) {
-                SolRec r;
-                r.v = root.v; r.pair = pair; r.slot = slot; r.piece = (uint8_t)root.piece; r.k = 0; r.rcase = 1; r.pad = 0;
-                const unsigned below = (1u << lane) - 1u;
-                if (!two_panel) worklist[bf + __popc(mf & below)] = r;
-                else worklist[work_cap - 1ull - (bb + __popc(mb & below))] = r;
             }
         }
     }
@@ -392,19 +394,6 @@ __device__ __forceinline__ void stage_tables(uint64_t *bar, void *dst0, const vo
     mbar_wait(bar, 0);
 }
 
-// rebuild the ray of a work-list record (uniform per warp in K_att, per thread in K_att_sp1)
-__device__ __forceinline__ void rebuild_ray(const IceParams &ice, const KInput &in, const SolRec &rec, PairGeom &g, AttPlan &plan)
-{
-    double x1, y1, z1, x2, y2, z2;
-    load_pair(in, rec.pair, x1, y1, z1, x2, y2, z2);
-    Frame2D f;
-    make_frame(x1, y1, z1, x2, y2, z2, f);
-    make_pair_geom(ice, f.z1, f.z2, fmax(f.rho, 1e-12), g);
-    RayState rs;
-    ray_state(ice, g, (rec.piece == 1 || rec.piece == 2), rec.v, rs);
-    att_plan(ice, g, rec.piece, rec.k, rec.rcase, rs, plan);
-}
-
 // Generic attenuation kernel (all models, any number of bottom reflections): one warp per solution.
 // dynamic shared memory (doubles): fa[Fs_pad] fb[Fs_pad] it[F_pad] | ii[F_pad] (int32) | per warp: H[3][Fs_pad] fac[nseg][Fs_pad]
 __global__ void __launch_bounds__(ATT_THREADS)
@@ -434,9 +423,8 @@ K_att(IceParams ice, KInput in, AttTables tb, const SolRec *worklist, const unsi
     for (unsigned long long w = (unsigned long long)blockIdx.x * ATT_WARPS + warp; w < n_work;
          w += (unsigned long long)gridDim.x * ATT_WARPS) {
         const SolRec rec = worklist_get(worklist, work_cap, n_front, w);
-        PairGeom g;
         AttPlan plan;
-        rebuild_ray(ice, in, rec, g, plan);
+        att_plan_rec(ice, rec, plan);
         for (int j = lane; j < 3 * tb.Fs_pad; j += 32) H[j] = 0.0;
         __syncwarp();
         // quadrature: each half-warp integrates one 16-node slot per pass; slot sums are added to their panel
@@ -593,9 +581,8 @@ K_att_sp1(IceParams ice, KInput in, AttTables tb, Sp1Tables sp, const SolRec *wo
     for (unsigned long long w = (unsigned long long)blockIdx.x * SP1_THREADS + threadIdx.x; w < n_work;
          w += (unsigned long long)gridDim.x * SP1_THREADS) {
         const SolRec rec = worklist_get(worklist, work_cap, n_front, w);
-        PairGeom g;
         AttPlan plan;
-        rebuild_ray(ice, in, rec, g, plan);
+        att_plan_rec(ice, rec, plan);
         double Mlo[SP1_K], Mhi[SP1_K];
 #pragma unroll
         for (int k = 0; k < SP1_K; ++k) { Mlo[k] = 0.0; Mhi[k] = 0.0; }
