@@ -27,6 +27,12 @@ numba_available = False
 cuda_available = True     # resolved lazily: the library is loaded on first use
 
 
+def _stats_dict(st):
+    d = {k: getattr(st, k) for k, _ in _lib.Stats._fields_ if k != "ms_kernel"}
+    d["ms_kernel"] = dict(zip(("classify", "hump", "roots", "attenuation_main", "attenuation_other"), list(st.ms_kernel)[:5]))
+    return d
+
+
 class _Handle:
     """owns one nrmc_rt_t"""
 
@@ -282,7 +288,7 @@ class ray_tracing(ray_tracing_base):
         inp.outer, inp.memory = int(bool(outer)), _lib.MEMORY_HOST
         st = _lib.Stats()
         _lib.check(_lib.load().nrmc_rt_trace(h.ptr, C.byref(inp), C.byref(o), None, C.byref(st)), h.ptr, "trace")
-        res.stats = {k: getattr(st, k) for k, _ in _lib.Stats._fields_}
+        res.stats = _stats_dict(st)
         res.frequencies_sparse = h.sparse if frequency is not None else None
         res.compact = bool(compact)
         if compact:     # expose the filled rows; the capacity-sized buffers are kept for reuse through `out=`
@@ -333,7 +339,7 @@ class ray_tracing(ray_tracing_base):
         st = _lib.Stats()
         _lib.check(_lib.load().nrmc_rt_trace(h.ptr, C.byref(inp), C.byref(o), C.c_void_p(stream),
                                              C.byref(st) if sync_stats else None), h.ptr, "trace")
-        res.stats = {k: getattr(st, k) for k, _ in _lib.Stats._fields_} if sync_stats else None
+        res.stats = _stats_dict(st) if sync_stats else None
         res.frequencies_sparse = h.sparse if frequency is not None else None
         return res
 

@@ -36,7 +36,7 @@ class Output(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("n_pairs", C.c_int64), ("n_solutions", C.c_int64), ("ms_solve", C.c_float), ("ms_attenuation", C.c_float),
                 ("ms_total", C.c_float), ("n_launches", C.c_int32), ("n_chunks", C.c_int32), ("h2d_bytes", C.c_int64),
-                ("d2h_bytes", C.c_int64)]
+                ("d2h_bytes", C.c_int64), ("ms_kernel", C.c_float * 6)]
 
 
 EXPORTS = ("nrmc_rt_create", "nrmc_rt_destroy", "nrmc_rt_last_error", "nrmc_rt_max_solutions", "nrmc_rt_set_frequencies",

@@ -824,6 +824,7 @@ struct DevBuf {
 struct Lane {               // one pipeline lane (stream + scratch) for host-memory calls
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t kev[3] = {nullptr, nullptr, nullptr};   // after K_classify, after K_hump, after the main attenuation kernel
     DevBuf in, out, work, fallback, sparse_tmp, rootq, humpq, packed, pack_sums, pack_off;
     bool timed = false;
 };
@@ -900,6 +901,7 @@ int nrmc_rt_create(const nrmc_rt_config *cfg, nrmc_rt_t *out)
     for (int l = 0; l < 2; ++l) {
         if (cudaStreamCreateWithFlags(&h->lanes[l].stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return NRMC_ERR_CUDA; }
         for (int e = 0; e < 6; ++e) cudaEventCreate(&h->lanes[l].ev[e]);
+        for (int e = 0; e < 3; ++e) cudaEventCreate(&h->lanes[l].kev[e]);
     }
     if (h->d_count.reserve(256) != cudaSuccess) { delete h; return NRMC_ERR_CUDA; }
     {
@@ -927,6 +929,7 @@ void nrmc_rt_destroy(nrmc_rt_t h)
     for (int l = 0; l < 2; ++l) {
         if (h->lanes[l].stream) { cudaStreamSynchronize(h->lanes[l].stream); cudaStreamDestroy(h->lanes[l].stream); }
         for (int e = 0; e < 6; ++e) if (h->lanes[l].ev[e]) cudaEventDestroy(h->lanes[l].ev[e]);
+        for (int e = 0; e < 3; ++e) if (h->lanes[l].kev[e]) cudaEventDestroy(h->lanes[l].kev[e]);
         h->lanes[l].in.release(); h->lanes[l].out.release(); h->lanes[l].work.release();
         h->lanes[l].fallback.release(); h->lanes[l].sparse_tmp.release(); h->lanes[l].rootq.release(); h->lanes[l].humpq.release();
         h->lanes[l].packed.release(); h->lanes[l].pack_sums.release(); h->lanes[l].pack_off.release();
@@ -1096,14 +1099,17 @@ static int launch_chunk(nrmc_rt_s *h, Lane &ln, int lane_id, const KInput &kin, 
         af.sparse = att_sparse; af.dense = att_dense; af.Fs = h->tb.Fs; af.F = h->tb.F;
         K_classify<<<(unsigned)blocks, CLASSIFY_THREADS, 0, ln.stream>>>(h->ice, kin, to, af, (RootItem *)ln.rootq.p, d_roots,
                                                                          (HumpItem *)ln.humpq.p, d_humps);
+        if (ln.timed) cudaEventRecord(ln.kev[0], ln.stream);
         K_hump<<<h->grid_hump, HUMP_THREADS, 0, ln.stream>>>(h->ice, kin, to, af, (const HumpItem *)ln.humpq.p, d_humps,
                                                              (RootItem *)ln.rootq.p, d_roots);
+        if (ln.timed) cudaEventRecord(ln.kev[1], ln.stream);
         K_roots<<<h->grid_roots, ROOTS_THREADS, 0, ln.stream>>>(h->ice, kin, to, af, (const RootItem *)ln.rootq.p, d_roots, wl, d_count, work_cap);
         *n_launches += 3;
     } else {
         const int64_t blocks = (kin.n_pairs + SOLVE_THREADS - 1) / SOLVE_THREADS;
         K_solve<<<(unsigned)blocks, SOLVE_THREADS, 0, ln.stream>>>(h->ice, kin, to, wl, d_count);
         ++*n_launches;
+        if (ln.timed) { cudaEventRecord(ln.kev[0], ln.stream); cudaEventRecord(ln.kev[1], ln.stream); }
     }
     if (ln.timed) cudaEventRecord(ln.ev[1], ln.stream);
     if (want_att) {
@@ -1128,6 +1134,7 @@ static int launch_chunk(nrmc_rt_s *h, Lane &ln, int lane_id, const KInput &kin, 
             else
                 K_att_sp1<false><<<h->grid_sp1, SP1_THREADS, h->smem_sp1, ln.stream>>>(h->ice, kin, tb, h->sp1, wl, d_count, work_cap, sparse,
                                                                                        (SolRec *)ln.fallback.p, d_fb);
+            if (ln.timed) cudaEventRecord(ln.kev[2], ln.stream);
             K_att<<<h->grid_att, ATT_THREADS, h->smem_att, ln.stream>>>(h->ice, kin, tb, (const SolRec *)ln.fallback.p, d_fb, work_cap,
                                                                         nseg_max, sparse, nullptr);
             *n_launches += 2;
@@ -1138,11 +1145,32 @@ static int launch_chunk(nrmc_rt_s *h, Lane &ln, int lane_id, const KInput &kin, 
         } else {
             K_att<<<h->grid_att, ATT_THREADS, h->smem_att, ln.stream>>>(h->ice, kin, tb, wl, d_count, work_cap, nseg_max, att_sparse, att_dense);
             ++*n_launches;
+            if (ln.timed) cudaEventRecord(ln.kev[2], ln.stream);
         }
-    }
+    } else if (ln.timed) cudaEventRecord(ln.kev[2], ln.stream);
     if (ln.timed) cudaEventRecord(ln.ev[2], ln.stream);
     CK(cudaGetLastError());
     return NRMC_OK;
+}
+
+// adds the CUDA-event durations of the chunk last run on this lane: ms[0] solver, ms[1] attenuation, ms[2..6] per kernel
+static void accumulate_lane_times(Lane &ln, float *ms)
+{
+    cudaEventSynchronize(ln.ev[2]);
+    float t = 0;
+    cudaEventElapsedTime(&t, ln.ev[0], ln.ev[1]); ms[0] += t;
+    cudaEventElapsedTime(&t, ln.ev[1], ln.ev[2]); ms[1] += t;
+    cudaEventElapsedTime(&t, ln.ev[0], ln.kev[0]); ms[2] += t;    // K_classify (or the generic K_solve)
+    cudaEventElapsedTime(&t, ln.kev[0], ln.kev[1]); ms[3] += t;   // K_hump
+    cudaEventElapsedTime(&t, ln.kev[1], ln.ev[1]); ms[4] += t;    // K_roots
+    cudaEventElapsedTime(&t, ln.ev[1], ln.kev[2]); ms[5] += t;    // main attenuation kernel (+ NaN fill for bottom reflections)
+    cudaEventElapsedTime(&t, ln.kev[2], ln.ev[2]); ms[6] += t;    // fallback / dense expansion kernels
+}
+
+static void store_times(nrmc_rt_stats *stats, const float *ms)
+{
+    stats->ms_solve = ms[0]; stats->ms_attenuation = ms[1];
+    for (int i = 0; i < 5; ++i) stats->ms_kernel[i] = ms[2 + i];
 }
 
 struct OutLayout {           // byte offsets of every output inside one contiguous per-chunk device block
@@ -1201,7 +1229,7 @@ extern "C" int nrmc_rt_trace(nrmc_rt_t h, const nrmc_rt_input *in, const nrmc_rt
         if (stats) cudaEventRecord(e0, user);
         int64_t chunk = std::min<int64_t>(N, (int64_t)1 << 24);     // bounds the queue / work-list scratch
         if (in->outer && chunk < N) chunk = std::max<int64_t>(in->n_antennas, (chunk / in->n_antennas) * in->n_antennas);
-        float ms_solve = 0, ms_att = 0;
+        float ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         int rc = NRMC_OK, n_chunks = 0;
         for (int64_t p0 = 0; p0 < N && rc == NRMC_OK; p0 += chunk, ++n_chunks) {
             const int64_t np = std::min(chunk, N - p0);
@@ -1238,23 +1266,19 @@ extern "C" int nrmc_rt_trace(nrmc_rt_t h, const nrmc_rt_input *in, const nrmc_rt
             rc = launch_chunk(h, ln, 0, kin, to, out->attenuation_sparse ? out->attenuation_sparse + p0 * S * Fs : nullptr,
                               out->attenuation ? out->attenuation + p0 * S * F : nullptr, &n_launches);
             if (rc == NRMC_OK && stats) {
-                cudaEventSynchronize(ln.ev[2]);
+                accumulate_lane_times(ln, ms);
                 if (want_att) {
                     unsigned long long cnt2[2] = {0, 0};
                     cudaMemcpy(cnt2, h->d_count.p, sizeof(cnt2), cudaMemcpyDeviceToHost);
                     stats->n_solutions += (int64_t)(cnt2[0] + cnt2[WL_BACK]);
                 }
-                float a = 0, b = 0;
-                cudaEventElapsedTime(&a, ln.ev[0], ln.ev[1]);
-                cudaEventElapsedTime(&b, ln.ev[1], ln.ev[2]);
-                ms_solve += a; ms_att += b;
             }
         }
         if (stats && rc == NRMC_OK) {
             cudaEventRecord(e1, user);
             CK(cudaEventSynchronize(e1));
             cudaEventElapsedTime(&stats->ms_total, e0, e1);
-            stats->ms_solve = ms_solve; stats->ms_attenuation = ms_att;
+            store_times(stats, ms);
             stats->n_pairs = N; stats->n_launches = n_launches; stats->n_chunks = n_chunks;
         }
         ln.stream = saved;
@@ -1291,19 +1315,14 @@ extern "C" int nrmc_rt_trace(nrmc_rt_t h, const nrmc_rt_input *in, const nrmc_rt
     }
     cudaEvent_t e0 = h->lanes[0].ev[3], e1 = h->lanes[0].ev[4];
     cudaEventRecord(e0, h->lanes[0].stream);
-    float ms_solve = 0, ms_att = 0;
+    float ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     int n_chunks = 0;
     int64_t n_solutions = 0, row_base = 0;
     for (int64_t p0 = 0; p0 < N; p0 += chunk, ++n_chunks) {
         const int lid = n_chunks & 1;
         Lane &ln = h->lanes[lid];
         const int64_t np = std::min(chunk, N - p0);
-        if (n_chunks >= 2 && stats && ln.timed) {   // collect the timing of the chunk that used this lane before
-            cudaEventSynchronize(ln.ev[2]);
-            float a = 0, b = 0;
-            cudaEventElapsedTime(&a, ln.ev[0], ln.ev[1]); cudaEventElapsedTime(&b, ln.ev[1], ln.ev[2]);
-            ms_solve += a; ms_att += b;
-        }
+        if (n_chunks >= 2 && stats && ln.timed) accumulate_lane_times(ln, ms);   // the chunk that used this lane before
         // inputs
         KInput kin;
         kin.outer = in->outer; kin.n_antennas = na; kin.n_pairs = np;
@@ -1396,11 +1415,7 @@ extern "C" int nrmc_rt_trace(nrmc_rt_t h, const nrmc_rt_input *in, const nrmc_rt
     for (int l = 0; l < 2; ++l) {
         Lane &ln = h->lanes[l];
         CK(cudaStreamSynchronize(ln.stream));
-        if (stats && ln.timed && l < n_chunks) {
-            float a = 0, b = 0;
-            cudaEventElapsedTime(&a, ln.ev[0], ln.ev[1]); cudaEventElapsedTime(&b, ln.ev[1], ln.ev[2]);
-            ms_solve += a; ms_att += b;
-        }
+        if (stats && ln.timed && l < n_chunks) accumulate_lane_times(ln, ms);
         ln.timed = false;
     }
     cudaEventRecord(e1, h->lanes[0].stream);
@@ -1408,7 +1423,7 @@ extern "C" int nrmc_rt_trace(nrmc_rt_t h, const nrmc_rt_input *in, const nrmc_rt
     if (compact) out->sol_offset[N] = row_base;
     if (stats) {
         cudaEventElapsedTime(&stats->ms_total, e0, e1);
-        stats->ms_solve = ms_solve; stats->ms_attenuation = ms_att;
+        store_times(stats, ms);
         stats->n_pairs = N; stats->n_launches = n_launches; stats->n_chunks = n_chunks;
         stats->h2d_bytes = h2d; stats->d2h_bytes = d2h;
         if (compact) stats->n_solutions = row_base;
