@@ -394,8 +394,114 @@ __device__ __forceinline__ void stage_tables(uint64_t *bar, void *dst0, const vo
     mbar_wait(bar, 0);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// GL3: the reference does not integrate ds/L for this model (300 rows of measured, rough data) but DEFINES the result
+// by a discretisation (analyticraytracing.py:62, :458, :998-1064): per path segment, in the mirrored depth coordinate
+// t in [z_a, t_b], np.linspace cells of ~10 m, ds at the cell centre times the cell width over L(z_centre, f); the
+// cell around the turning point (+-10 m) is replaced by its exact path length over L(z_turn, f).  Reproduced cell for
+// cell: lanes = cells, warp reduction per frequency.  fac[s][j] receives exp(-I) of segment s.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int gl3_n_steps(double a, double b) { const int n = (int)floor(fabs(a - b) / 10.0); return n > 3 ? n : 3; }  // py:65-67
+
+// path-length antiderivative F(z) of the ray (py:602-690), z <= apex, with n - beta formed without cancellation
+__device__ __forceinline__ double gl3_F(const IceParams &ice, double beta, double delta, double zv, double c, double rc, double z)
+{
+    const double nmb = -delta * expm1(-(zv - z) * ice.inv_z0);      // n(z) - beta >= 0
+    const double n = beta + nmb;
+    const double sz = sqrt(fmax(nmb * (n + beta), 0.0));
+    const double k1 = rc * sz + (c - ice.n_ice * (ice.n_ice - n));
+    const double k2 = sz + n;
+    return ice.n_ice / rc * (z - ice.z0 * log(k1)) + ice.z0 * log(k2);
+}
+
+__device__ __forceinline__ void gl3_path(const IceParams &ice, const SolRec &rec, const Gl3Table &gl3, const double *s_f, int Fs, int Fs_pad,
+                                         double *fac, int lane)
+{
+    const double zT = fmin(rec.zv, 0.0);                            // get_turning_point clamps to the surface (py:152-156)
+    const double beta = rec.beta, delta = rec.delta;
+    const double c = delta * (ice.n_ice + beta), rc = sqrt(c);
+    const int k = rec.k;
+    const bool turned_last = rec.piece >= 2;
+    for (int s = 0; s <= k; ++s) {
+        // the segment as the reference integrates it (get_path_segments py:1091-1159, first-segment mirroring py:943-950)
+        double za, zb;
+        bool turned;
+        if (k == 0) { za = rec.z1; zb = rec.z2; turned = turned_last; }
+        else if (s == 0) {
+            if (rec.rcase == 1) { za = rec.z1; zb = ice.zr; turned = true; }
+            else { za = ice.zr; zb = rec.z1; turned = false; }
+        } else if (s < k) { za = ice.zr; zb = ice.zr; turned = true; }
+        else { za = ice.zr; zb = rec.z2; turned = turned_last; }
+        const double ta = za, tb = turned ? 2.0 * zT - zb : zb;       // get_z_mirrored (py:496-511)
+        for (int j = lane; j < Fs; j += 32) fac[s * Fs_pad + j] = 0.0;
+        __syncwarp();
+        const bool fallback = (ta - 10.0 < zT) && (zT < tb + 10.0);
+        double w0 = ta, w1 = tb;
+        int nA = 1, nB = 1, n_cells;
+        if (fallback) {
+            w0 = fmax(ta, zT - 10.0); w1 = fmin(zT + 10.0, tb);
+            nA = (ta == w0) ? 1 : gl3_n_steps(ta, w0);
+            nB = (w1 == tb) ? 1 : gl3_n_steps(w1, tb);
+            n_cells = nA + nB - 1;
+        } else {
+            nA = (ta == tb) ? 1 : gl3_n_steps(ta, tb);
+            n_cells = nA - 1;
+        }
+        for (int base = 0; base < n_cells; base += 32) {
+            const int cell = base + lane;
+            const bool live = cell < n_cells;
+            double w = 0.0, slope = 0.0, off = 1.0;
+            if (live) {
+                double lo, hi;
+                bool window = false;
+                if (!fallback) {
+                    const double step = (tb - ta) / (nA - 1);
+                    lo = ta + cell * step; hi = (cell + 1 == nA - 1) ? tb : ta + (cell + 1) * step;
+                } else if (cell < nA - 1) {
+                    const double step = (w0 - ta) / (nA - 1);
+                    lo = ta + cell * step; hi = (cell + 1 == nA - 1) ? w0 : ta + (cell + 1) * step;
+                } else if (cell == nA - 1) {
+                    lo = w0; hi = w1; window = true;
+                } else {
+                    const int i = cell - nA;
+                    const double step = (tb - w1) / (nB - 1);
+                    lo = w1 + i * step; hi = (i + 1 == nB - 1) ? tb : w1 + (i + 1) * step;
+                }
+                double depth;
+                if (!window) {
+                    const double mid = lo + (hi - lo) / 2.0;
+                    const double z = mid > zT ? 2.0 * zT - mid : mid;            // get_z_unmirrored (py:293-304)
+                    const double nmb = -delta * expm1(-(rec.zv - z) * ice.inv_z0);
+                    const double n = beta + nmb;
+                    w = n / sqrt(nmb * (n + beta)) * (hi - lo);                 // ds(mid) * dx   (py:513-517, :1030-1035)
+                    depth = -z;
+                } else {
+                    const double zl = lo > zT ? 2.0 * zT - lo : lo, zh = hi > zT ? 2.0 * zT - hi : hi;
+                    const double Fl = gl3_F(ice, beta, delta, rec.zv, c, rc, zl), Fh = gl3_F(ice, beta, delta, rec.zv, c, rc, zh);
+                    if (hi <= zT) w = Fh - Fl;
+                    else if (lo >= zT) w = Fl - Fh;
+                    else w = 2.0 * gl3_F(ice, beta, delta, rec.zv, c, rc, zT) - Fl - Fh;   // integral of ds over the cell (py:1058)
+                    depth = -zT;
+                }
+                slope = gl3_lookup(gl3, depth, 1);
+                off = gl3_lookup(gl3, depth, 2);
+            }
+            for (int j = 0; j < Fs; ++j) {
+                double term = w / fmax(slope * s_f[j] + off, 1.0);             // attenuation.py:206-222, 1 m floor :252-255
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) term += __shfl_xor_sync(0xffffffffu, term, d);
+                if (lane == 0) fac[s * Fs_pad + j] += term;
+            }
+            __syncwarp();
+        }
+        for (int j = lane; j < Fs; j += 32) fac[s * Fs_pad + j] = exp(-fac[s * Fs_pad + j]);
+        __syncwarp();
+    }
+}
+
 // Generic attenuation kernel (all models, any number of bottom reflections): one warp per solution.
 // dynamic shared memory (doubles): fa[Fs_pad] fb[Fs_pad] it[F_pad] | ii[F_pad] (int32) | per warp: H[3][Fs_pad] fac[nseg][Fs_pad]
+template <bool GL3>
 __global__ void __launch_bounds__(ATT_THREADS)
 K_att(IceParams ice, KInput in, AttTables tb, const SolRec *worklist, const unsigned long long *work_count, unsigned long long work_cap,
       int nseg_max, double *att_sparse, double *att_dense)
@@ -425,6 +531,15 @@ K_att(IceParams ice, KInput in, AttTables tb, const SolRec *worklist, const unsi
         const SolRec rec = worklist_get(worklist, work_cap, n_front, w);
         AttPlan plan;
         att_plan_rec(ice, rec, plan);
+        const int64_t slot_index = rec.pair * S + rec.slot;
+        if (GL3) {
+            gl3_path(ice, rec, tb.gl3, s_fa, tb.Fs, tb.Fs_pad, fac, lane);
+            for (int j = lane; j < tb.Fs; j += 32) {
+                double prod = 1.0;
+                for (int s = 0; s < plan.nseg; ++s) prod *= fac[s * tb.Fs_pad + j];
+                if (att_sparse) att_sparse[slot_index * tb.Fs + j] = prod;
+            }
+        } else {
         for (int j = lane; j < 3 * tb.Fs_pad; j += 32) H[j] = 0.0;
         __syncwarp();
         // quadrature: each half-warp integrates one 16-node slot per pass; slot sums are added to their panel
@@ -455,7 +570,6 @@ K_att(IceParams ice, KInput in, AttTables tb, const SolRec *worklist, const unsi
             __syncwarp();
         }
         // per segment: I_seg = sum_panel mult[seg][panel] * H[panel];  factor = exp(-I_seg)   (py:1075)
-        const int64_t slot_index = rec.pair * S + rec.slot;
         for (int j = lane; j < tb.Fs; j += 32) {
             const double h0 = H[j], h1 = H[tb.Fs_pad + j], h2 = H[2 * tb.Fs_pad + j];
             double prod = 1.0;
@@ -466,6 +580,7 @@ K_att(IceParams ice, KInput in, AttTables tb, const SolRec *worklist, const unsi
                 prod *= e;
             }
             if (att_sparse) att_sparse[slot_index * tb.Fs + j] = prod;
+        }
         }
         __syncwarp();
         if (dense) {
@@ -1007,9 +1122,13 @@ int nrmc_rt_set_frequencies(nrmc_rt_t h, const double *frequency, int32_t n, dou
     {
         const int nseg_max = h->ice.n_refl + 1;
         h->smem_att = (size_t)Fs_pad * 16 + (size_t)F_pad * 12 + (size_t)ATT_WARPS * (3 + nseg_max) * Fs_pad * 8;
-        if (h->smem_att > 48 * 1024) CK(cudaFuncSetAttribute(K_att, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_att));
+        if (h->smem_att > 48 * 1024) {
+            CK(cudaFuncSetAttribute(K_att<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_att));
+            CK(cudaFuncSetAttribute(K_att<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_att));
+        }
         int nb = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, K_att, ATT_THREADS, h->smem_att));
+        if (h->ice.att_model == NRMC_ATT_GL3) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, K_att<true>, ATT_THREADS, h->smem_att));
+        else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, K_att<false>, ATT_THREADS, h->smem_att));
         h->grid_att = std::max(1, nb) * h->n_sm;
     }
     h->have_sp1 = false;
@@ -1135,15 +1254,18 @@ static int launch_chunk(nrmc_rt_s *h, Lane &ln, int lane_id, const KInput &kin, 
                 K_att_sp1<false><<<h->grid_sp1, SP1_THREADS, h->smem_sp1, ln.stream>>>(h->ice, kin, tb, h->sp1, wl, d_count, work_cap, sparse,
                                                                                        (SolRec *)ln.fallback.p, d_fb);
             if (ln.timed) cudaEventRecord(ln.kev[2], ln.stream);
-            K_att<<<h->grid_att, ATT_THREADS, h->smem_att, ln.stream>>>(h->ice, kin, tb, (const SolRec *)ln.fallback.p, d_fb, work_cap,
-                                                                        nseg_max, sparse, nullptr);
+            K_att<false><<<h->grid_att, ATT_THREADS, h->smem_att, ln.stream>>>(h->ice, kin, tb, (const SolRec *)ln.fallback.p, d_fb, work_cap,
+                                                                               nseg_max, sparse, nullptr);
             *n_launches += 2;
             if (att_dense) {
                 K_att_expand<<<h->n_sm * 8, 256, 0, ln.stream>>>(tb, to.n_sol, kin.n_pairs, h->S, sparse, att_dense);
                 ++*n_launches;
             }
         } else {
-            K_att<<<h->grid_att, ATT_THREADS, h->smem_att, ln.stream>>>(h->ice, kin, tb, wl, d_count, work_cap, nseg_max, att_sparse, att_dense);
+            if (h->ice.att_model == NRMC_ATT_GL3)
+                K_att<true><<<h->grid_att, ATT_THREADS, h->smem_att, ln.stream>>>(h->ice, kin, tb, wl, d_count, work_cap, nseg_max, att_sparse, att_dense);
+            else
+                K_att<false><<<h->grid_att, ATT_THREADS, h->smem_att, ln.stream>>>(h->ice, kin, tb, wl, d_count, work_cap, nseg_max, att_sparse, att_dense);
             ++*n_launches;
             if (ln.timed) cudaEventRecord(ln.kev[2], ln.stream);
         }
@@ -1201,13 +1323,6 @@ extern "C" int nrmc_rt_trace(nrmc_rt_t h, const nrmc_rt_input *in, const nrmc_rt
     if (!in->vx || !in->vy || !in->vz || !in->ax || !in->ay || !in->az) return NRMC_ERR_INVALID_ARGUMENT;
     const bool want_att = out->attenuation_sparse || out->attenuation;
     if (want_att && h->ice.att_model == 0) { h->err = "attenuation requested but no attenuation model configured"; return NRMC_ERR_UNSUPPORTED; }
-    if (want_att && h->ice.att_model == NRMC_ATT_GL3) {
-        // GL3 is a 300-row table of rough measured data: the smooth Gauss-Legendre panels used for the other models
-        // do not integrate it to the stated tolerance, and the reference itself switches to a 10 m midpoint sum for it
-        // (analyticraytracing.py:998-1064).  Not built in this round -- refuse instead of returning inaccurate numbers.
-        h->err = "attenuation along the path is not available for the GL3 model in this version";
-        return NRMC_ERR_UNSUPPORTED;
-    }
     if (want_att && !h->have_freq) { h->err = "attenuation requested before nrmc_rt_set_frequencies"; return NRMC_ERR_NO_FREQUENCIES; }
     const bool compact = out->compact != 0;
     if (compact && in->memory != NRMC_MEMORY_HOST) { h->err = "the compact output layout is available for NRMC_MEMORY_HOST calls only"; return NRMC_ERR_UNSUPPORTED; }

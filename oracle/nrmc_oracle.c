@@ -484,6 +484,18 @@ static double att_integrand(double v, void *p)                                  
     return jac * ds / ora_attenuation_length(c->m, z, c->f);
 }
 
+/* ds alone in the substituted variable (window cell of the optimized discretisation) */
+static double att_integrand_ds(double v, void *p)
+{
+    att_ctx *c = (att_ctx *)p;
+    double t = v, jac = 1;
+    if (c->sub < 0) { t = c->z_turn - v * v; jac = 2 * v; }
+    else if (c->sub > 0) { t = c->z_turn + v * v; jac = 2 * v; }
+    double ds = ds_of_t(t, c->C_0, c->m);
+    if (!isfinite(ds)) return 0.0;
+    return jac * ds;
+}
+
 /* numpy.linspace(start, stop, n) */
 static void linspace(double a, double b, int n, double *out)
 {
@@ -526,6 +538,87 @@ static double interp1(double x, const double *xp, const double *fp, int n)
     return slope * (x - xp[lo]) + fp[lo];
 }
 
+/* ---- the "optimized" discretisation the reference switches to for GL3 (py:62, :458, :998-1064) ---- */
+
+/* py:65-67 */
+static int get_n_steps(double x1, double x2, double dx)
+{
+    int n = (int)floor(fabs(x1 - x2) / dx);   /* int(abs(x1 - x2) // dx) */
+    return n > 3 ? n : 3;
+}
+
+/* py:70-76: np.linspace(x1, x2, get_n_steps(...)), or the single point if x1 == x2; returns the count */
+static int get_equidistant_steps(double x1, double x2, double dx, double *out)
+{
+    if (x1 == x2) { out[0] = x1; return 1; }
+    int n = get_n_steps(x1, x2, dx);
+    linspace(x1, x2, n, out);
+    return n;
+}
+
+static double ds_ctx(double t, void *p) { att_ctx *c = (att_ctx *)p; return ds_of_t(t, c->C_0, c->m); }
+
+/* exponent of the attenuation factor of one segment for the sparse frequencies: 10 m midpoint sum of ds/L in the
+ * mirrored depth coordinate, the cell that holds the turning point replaced by (integral of ds) / L(z_turn)  (py:998-1064) */
+#define ORA_MAX_STEPS 4096
+static void optimized_exponent(const double x1[2], const double x2m[2], double z_turn, double C_0, const ora_cfg *m,
+                               const double *freqs, int nsp, double *expo, long *neval)
+{
+    const double dx = 10.0, window = 20.0;
+    static __thread double steps[ORA_MAX_STEPS];
+    int n = 0;
+    int fallback = (x1[1] - window / 2 < z_turn && z_turn < x2m[1] + window / 2);
+    if (fallback) {
+        double w0 = fmax(x1[1], z_turn - window / 2), w1 = fmin(z_turn + window / 2, x2m[1]);
+        n = get_equidistant_steps(x1[1], w0, dx, steps);
+        n += get_equidistant_steps(w1, x2m[1], dx, steps + n);
+    } else {
+        n = get_equidistant_steps(x1[1], x2m[1], dx, steps);
+    }
+    for (int k = 0; k < nsp; ++k) expo[k] = 0.0;
+    int idx = -2;
+    if (fallback) {
+        /* np.digitize(z_turn, path_steps) - 1 for increasing bins, clamped (py:1044-1050) */
+        int d = 0;
+        while (d < n && steps[d] <= z_turn) ++d;
+        idx = d - 1;
+        if (idx == n - 1) idx -= 1;
+        else if (idx == -1) idx = 0;
+    }
+    for (int i = 0; i + 1 < n; ++i) {
+        double dxa = steps[i + 1] - steps[i];
+        if (i == idx) {
+            att_ctx c = {m, C_0, 0, z_turn, 0};
+            double S;
+            if (m->quad_mode == 0) {
+                double br[3] = {steps[i], z_turn, steps[i + 1]};
+                if (steps[i] < z_turn && z_turn < steps[i + 1]) S = quad_adaptive(ds_ctx, &c, br, 3, 1.49e-8, 1e-2, neval);
+                else { double b2[2] = {steps[i], steps[i + 1]}; S = quad_adaptive(ds_ctx, &c, b2, 2, 1.49e-8, 1e-2, neval); }
+            } else {
+                /* tight: ds = 1/sqrt(1 - (beta/n)^2) has a 1/sqrt singularity at a refracted apex: substitute t = z_turn -+ u^2 */
+                S = 0;
+                const double a = steps[i], b = steps[i + 1];
+                if (a < z_turn) {
+                    double lo_t = b < z_turn ? b : z_turn;
+                    double b2[2] = {sqrt(z_turn - lo_t), sqrt(z_turn - a)};
+                    c.sub = -1; S += quad_adaptive(att_integrand_ds, &c, b2, 2, 0, 1e-12, neval);
+                }
+                if (b > z_turn) {
+                    double lo_t = a > z_turn ? a : z_turn;
+                    double b2[2] = {sqrt(lo_t - z_turn), sqrt(b - z_turn)};
+                    c.sub = +1; S += quad_adaptive(att_integrand_ds, &c, b2, 2, 0, 1e-12, neval);
+                }
+            }
+            for (int k = 0; k < nsp; ++k) expo[k] += S / ora_attenuation_length(m, z_turn, freqs[k]);
+        } else {
+            double mid = steps[i] + dxa / 2;
+            double z = get_z_unmirrored(mid, C_0, m);
+            double ds = ds_of_t(mid, C_0, m);
+            for (int k = 0; k < nsp; ++k) expo[k] += ds / ora_attenuation_length(m, z, freqs[k]) * dxa;
+        }
+    }
+}
+
 /* py:933-1089 (python branch, not the GL3 "optimized" discretisation).  out[nf] dense factors on `frequency`;
  * if sparse_out != NULL it additionally receives the product over segments of the factors at the sparse
  * frequencies (what a consumer that interpolates later needs). */
@@ -548,6 +641,11 @@ static void attenuation_along_path(const double x1_in[2], const double x2_in[2],
         get_turning_point(m->n_ice * m->n_ice - pow(C_0, -2), m, &gamma_turn, &z_turn);
         int interior = (x1[1] < z_turn && z_turn < x2m[1]);
         int refracted_apex = (z_turn < 0); /* unclamped turning point -> 1/sqrt singularity of ds */
+        if (m->att_model == 5) {   /* speedup_attenuation_models = ["GL3"] (py:62, :458) */
+            double expo[4096];
+            optimized_exponent(x1, x2m, z_turn, C_0, m, freqs, nsp, expo, neval);
+            for (int k = 0; k < nsp; ++k) fac[k] = exp(-expo[k]);
+        } else
         for (int k = 0; k < nsp; ++k) {
             att_ctx c = {m, C_0, freqs[k], z_turn, 0};
             double I = 0;

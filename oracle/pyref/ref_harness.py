@@ -148,6 +148,21 @@ def tight_attenuation_factor(r, iS, frequency, max_detector_freq):
     import copy
     ray, _, att = load_reference()
     r2 = r._r2d
+    if getattr(r2, "_use_optimized_calculation", False):
+        # GL3 (analyticraytracing.py:62, :998-1064): the result is DEFINED by the 10 m midpoint sum; the only tolerance in it
+        # is quad(ds, epsrel=1e-2) over the cell that holds the turning point (:1058).  "Tight" = the same algorithm with that
+        # one quadrature at epsrel=1e-11.
+        _quad = ray.integrate.quad
+
+        def _tight_quad(f, a, b, args=(), **kw):
+            kw.update(epsrel=1e-11, epsabs=0, limit=400)
+            return _quad(f, a, b, args=args, **kw)
+
+        ray.integrate.quad = _tight_quad
+        try:
+            return r.get_attenuation(iS, np.asarray(frequency, float), max_detector_freq)
+        finally:
+            ray.integrate.quad = _quad
     med = r2.medium
     b = 2 * med.n_ice
     res = r.get_results()[iS]

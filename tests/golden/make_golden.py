@@ -84,6 +84,12 @@ def cases():
     V, A = pairs(cylinder(6, 16, 3000., -2500.), np.array([[0, 0, -100.]]))
     c["greenland_GL2"] = dict(ice="greenland_simple", att="GL2", n_refl=0, n_freq=20, X1=V, X2=A,
                               freqs=np.fft.rfftfreq(256, 0.5), fmax=None)
+    V, A = pairs(cylinder(7, 24, 3000., -2700.), RNOG[[0, 13]])
+    c["greenland_GL3"] = dict(ice="greenland_simple", att="GL3", n_refl=0, n_freq=15, X1=V, X2=A,
+                              freqs=np.fft.rfftfreq(256, 0.5), fmax=None)
+    V, A = pairs(cylinder(8, 10, 800., -550.), np.array([[3, 3, -5.]]))
+    c["mooresbay_GL3"] = dict(ice="mooresbay_simple", att="GL3", n_refl=1, n_freq=10, X1=V, X2=A,
+                              freqs=np.fft.rfftfreq(128, 0.5), fmax=None)
     return c
 
 

@@ -53,7 +53,8 @@ def test_T06_golden_through_kernel(make):
 
 
 @pytest.mark.parametrize("name", ["sp_simple_T05", "sp2015_cfg2", "mooresbay_cfg4", "mooresbay_T06", "sp1_cfg1",
-                                  "greenland_cfg3", "mooresbay_cfg4_MB1", "sp2015_cfg5_SP1", "greenland_GL2"])
+                                  "greenland_cfg3", "mooresbay_cfg4_MB1", "sp2015_cfg5_SP1", "greenland_GL2", "greenland_GL3",
+                                  "mooresbay_GL3"])
 def test_python_reference_fixtures(make, name):
     """fixtures produced by the reference's own Python path (tests/golden/make_golden.py)"""
     g = load_golden(name)
@@ -119,10 +120,19 @@ def test_attenuation_vs_tight_oracle(make, oracle_mod, ice, model, n_refl, rmax,
     assert (res["attenuation"][:, :, freqs <= 0][res["n_sol"] > 0][:, 0] == 1.0).all()   # the 0 Hz bin is 1 (py:1077)
 
 
-def test_gl3_path_attenuation_is_refused_not_approximated(make):
-    rt = make("greenland_simple", attenuation_model="GL3")
-    with pytest.raises(RuntimeError, match="GL3"):
-        rt.trace_batch(np.array([[100., 0, -500.]]), np.array([[0, 0, -100.]]), frequency=np.linspace(0, 1, 33))
+def test_gl3_discretised_path_attenuation_vs_oracle(make, oracle_mod):
+    """GL3: the reference defines the result by its 10 m midpoint discretisation (analyticraytracing.py:998-1064); the kernel
+    reproduces it cell for cell.  Seeded pairs against the oracle (tight window quadrature), deep and shallow receivers."""
+    from nuradiomc_b200.utilities import attenuation
+    ff = np.fft.rfftfreq(256, 0.5)
+    V = cylinder(31, 300, 3500, -2900)
+    for ant in ([0, 20, -97.], [1.5, 11, -2.], [0, 0, -1500.]):
+        X2 = np.repeat([ant], len(V), 0)
+        res = make("greenland_simple", attenuation_model="GL3", n_frequencies_integration=12).trace_batch(V, X2, frequency=ff)
+        ora = oracle_mod.Oracle("greenland_simple", attenuation_model="GL3", n_freq=12, tight=True,
+                                gl3_table=attenuation.gl3_parameters()).trace(V, X2, ff, None)
+        assert np.array_equal(res["n_sol"], ora["n_sol"])
+        assert_attenuation_parity(res["attenuation"], ora["attenuation"], rtol=1e-6, atol=1e-9)
 
 
 def test_attenuation_length_models(make, oracle_mod):
