@@ -131,6 +131,34 @@ int nrmc_rt_get_sparse_frequencies(nrmc_rt_t h, double *out, int32_t capacity);
  * and the call returns after enqueueing unless `stats` is non-NULL (then it synchronises to fill it). */
 int nrmc_rt_trace(nrmc_rt_t h, const nrmc_rt_input *in, const nrmc_rt_output *out, void *stream, nrmc_rt_stats *stats);
 
+/* Propagation effects on electric-field spectra, the step after the ray trace
+ * (ray_tracing.apply_propagation_effects, analyticraytracing.py:2937-3033, in-ice branch; Fresnel coefficients
+ * NuRadioReco/utilities/geometryUtilities.py:211-263).  One row = one ray-tracing solution with a spectrum of 3 components
+ * (eR, eTheta, ePhi) x F complex bins:
+ *   all components          *= attenuation factor of the row (if given)
+ *   eTheta, ePhi            *= r_p, r_s of every surface reflection of the path (reflection_angle[row, 0..K1-1], NaN = none)
+ *                              with n_1 = n(z = -1 cm), n_2 = 1 (complex beyond total internal reflection)
+ *   eTheta, ePhi            *= (reflection_coefficient * exp(i * phase))^k for k = reflection[row] bottom reflections.
+ * Attenuation comes from `attenuation` ([n_rows, F], already on the spectrum's frequency grid) or, for single-segment
+ * paths, is interpolated on the fly from `attenuation_sparse` ([n_rows, Fs]) with the tables of nrmc_rt_set_frequencies
+ * (F must then equal the length of that frequency vector): the dense factors are never materialised.
+ * All pointers are DEVICE pointers; the work is enqueued on `stream`.  Optional outputs r_theta / r_phi
+ * ([n_rows] complex, interleaved re/im): the coefficients the reference stores on the field object (:2993-2994). */
+typedef struct {
+    int64_t n_rows;
+    int32_t n_freq;                    /* F */
+    int32_t reserved;
+    double *spectrum;                  /* [n_rows, 3, F] complex128 (interleaved re, im), modified in place */
+    const double *attenuation;         /* [n_rows, F] or NULL */
+    const double *attenuation_sparse;  /* [n_rows, Fs] or NULL */
+    const double *reflection_angle;    /* [n_rows, K1], K1 = n_reflections + 1; NULL: no surface reflection anywhere */
+    const int8_t *reflection;          /* [n_rows] number of bottom reflections; NULL: none */
+    double reflection_coefficient;     /* medium.reflection_coefficient (medium_base.py:61) */
+    double reflection_phase_shift;     /* medium.reflection_phase_shift [rad] */
+    double *r_theta, *r_phi;           /* [n_rows] complex, or NULL */
+} nrmc_rt_effects;
+int nrmc_rt_apply_propagation_effects(nrmc_rt_t h, const nrmc_rt_effects *fx, void *stream);
+
 /* pinned host memory for fast NRMC_MEMORY_HOST transfers */
 int nrmc_rt_host_alloc(void **ptr, uint64_t bytes);
 int nrmc_rt_host_free(void *ptr);

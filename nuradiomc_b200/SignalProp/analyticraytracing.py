@@ -343,6 +343,101 @@ class ray_tracing(ray_tracing_base):
         res.frequencies_sparse = h.sparse if frequency is not None else None
         return res
 
+    def apply_propagation_effects_batch(self, spectra, reflection_angle=None, reflection=None, attenuation=None,
+                                        attenuation_sparse=None, return_coefficients=False):
+        """
+        Batched `apply_propagation_effects` (reference :2937-3033, in-ice branch; focusing / birefringence are out of
+        scope): one row per ray-tracing solution.
+
+        spectra: (R, 3, F) complex128 -- eR, eTheta, ePhi spectra; a CUDA torch tensor is modified in place (and
+        returned), a numpy array is copied to the device and the result is returned as a new numpy array.
+        reflection_angle: (R, n_reflections+1) as returned by `trace_batch` (NaN = no surface reflection on that segment);
+        reflection: (R,) number of bottom reflections; attenuation: (R, F) factors on the spectra's frequency grid, or
+        attenuation_sparse: (R, Fs) factors at the integration frequencies (single-segment paths; interpolated on the fly
+        with the tables of the last `frequency` passed to trace_batch*).
+        """
+        import torch
+        h = self._h()
+        dev = torch.device("cuda", self._device)
+        is_np = isinstance(spectra, np.ndarray)
+
+        def dev_tensor(x, dtype):
+            if x is None:
+                return None
+            if isinstance(x, np.ndarray):
+                return torch.as_tensor(np.ascontiguousarray(x), dtype=dtype).to(dev)
+            assert x.is_cuda and x.dtype == dtype and x.is_contiguous()
+            return x
+        spec = dev_tensor(spectra, torch.complex128)
+        if spec.dim() != 3 or spec.shape[1] != 3:
+            raise ValueError("spectra must have the shape (rows, 3, n_frequencies)")
+        R, F = spec.shape[0], spec.shape[2]
+        ang = dev_tensor(reflection_angle, torch.float64)
+        refl = dev_tensor(reflection, torch.int8)
+        att = dev_tensor(attenuation, torch.float64)
+        att_sp = dev_tensor(attenuation_sparse, torch.float64)
+        K1 = self._n_reflections + 1
+        if ang is not None and tuple(ang.shape) != (R, K1):
+            raise ValueError(f"reflection_angle must have the shape ({R}, {K1})")
+        if att is not None and tuple(att.shape) != (R, F):
+            raise ValueError(f"attenuation must have the shape ({R}, {F})")
+        fx = _lib.Effects()
+        fx.n_rows, fx.n_freq = R, F
+        fx.spectrum = spec.data_ptr()
+        fx.attenuation = att.data_ptr() if att is not None else None
+        fx.attenuation_sparse = att_sp.data_ptr() if att_sp is not None else None
+        fx.reflection_angle = ang.data_ptr() if ang is not None else None
+        fx.reflection = refl.data_ptr() if refl is not None else None
+        rc, ph = getattr(self._medium, "reflection_coefficient", None), getattr(self._medium, "reflection_phase_shift", None)
+        fx.reflection_coefficient = 1.0 if rc is None else float(rc)
+        fx.reflection_phase_shift = 0.0 if ph is None else float(ph)
+        r_t = r_p = None
+        if return_coefficients:
+            r_t = torch.empty(R, dtype=torch.complex128, device=dev)
+            r_p = torch.empty(R, dtype=torch.complex128, device=dev)
+            fx.r_theta, fx.r_phi = r_t.data_ptr(), r_p.data_ptr()
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _lib.check(_lib.load().nrmc_rt_apply_propagation_effects(h.ptr, C.byref(fx), C.c_void_p(stream)), h.ptr,
+                   "apply_propagation_effects")
+        out = spec.cpu().numpy() if is_np else spec
+        if return_coefficients:
+            return (out, r_t.cpu().numpy(), r_p.cpu().numpy()) if is_np else (out, r_t, r_p)
+        return out
+
+    def apply_propagation_effects(self, efield, i_solution):
+        """
+        Apply propagation effects to the electric field (reference :2937-3033): attenuation, Fresnel coefficients of
+        surface reflections, bottom-reflection amplitude and phase.  `efield` is a NuRadioReco ElectricField or any object
+        with get_frequency_spectrum / get_frequencies / get_sampling_rate / set_frequency_spectrum (and item assignment).
+        """
+        self._check(i_solution)
+        self._need_cache()
+        if self._config['propagation'].get('focusing', False) or self._config['propagation'].get('birefringence', False):
+            raise NotImplementedError("focusing and birefringence are outside the scope of nuradiomc_b200 (SURVEY.md section 8a)")
+        if self._X2[2] > 0 or self._X1[2] > 0:
+            raise NotImplementedError("air/ice transmission is experimental in the reference (:2971) and not provided")
+        spec = np.array(efield.get_frequency_spectrum(), dtype=np.complex128)
+        ff = np.asarray(efield.get_frequencies(), dtype=np.float64)
+        att = None
+        if self._config['propagation']['attenuate_ice']:
+            max_freq = np.max(ff) if self._max_detector_frequency is None else self._max_detector_frequency
+            att = self.get_attenuation(i_solution, ff, max_freq)[None, :]
+        k = self._results[i_solution]['reflection']
+        out, r_t, r_p = self.apply_propagation_effects_batch(
+            spec[None], reflection_angle=np.ascontiguousarray(self._cache["reflection_angle"][i_solution][None, :]),
+            reflection=np.array([k], np.int8), attenuation=att, return_coefficients=True)
+        if not np.all(np.isnan(self._cache["reflection_angle"][i_solution][:k + 1])):
+            try:    # the reference stores the coefficients on the field object (:2993-2994)
+                try:
+                    from NuRadioReco.framework.parameters import electricFieldParameters as efp
+                    efield[efp.reflection_coefficient_theta], efield[efp.reflection_coefficient_phi] = r_t[0], r_p[0]
+                except ImportError:
+                    efield["reflection_coefficient_theta"], efield["reflection_coefficient_phi"] = r_t[0], r_p[0]
+            except (TypeError, KeyError, AttributeError):
+                pass
+        efield.set_frequency_spectrum(out[0], efield.get_sampling_rate())
+        return efield
+
     def prepare_batch(self, X1, X2, outer=False, **kwargs):
         """
         Trace many pairs ahead of a scalar loop (e.g. all (shower, channel) pairs of an event group in

@@ -39,9 +39,16 @@ class Stats(C.Structure):
                 ("d2h_bytes", C.c_int64), ("ms_kernel", C.c_float * 6)]
 
 
+class Effects(C.Structure):
+    _fields_ = [("n_rows", C.c_int64), ("n_freq", C.c_int32), ("reserved", C.c_int32), ("spectrum", C.c_void_p),
+                ("attenuation", C.c_void_p), ("attenuation_sparse", C.c_void_p), ("reflection_angle", C.c_void_p),
+                ("reflection", C.c_void_p), ("reflection_coefficient", C.c_double), ("reflection_phase_shift", C.c_double),
+                ("r_theta", C.c_void_p), ("r_phi", C.c_void_p)]
+
+
 EXPORTS = ("nrmc_rt_create", "nrmc_rt_destroy", "nrmc_rt_last_error", "nrmc_rt_max_solutions", "nrmc_rt_set_frequencies",
            "nrmc_rt_get_sparse_frequencies", "nrmc_rt_trace", "nrmc_rt_host_alloc", "nrmc_rt_host_free",
-           "nrmc_rt_attenuation_length", "nrmc_rt_measure_fp64_peak", "nrmc_rt_device_count", "nrmc_rt_version")
+           "nrmc_rt_attenuation_length", "nrmc_rt_apply_propagation_effects", "nrmc_rt_measure_fp64_peak", "nrmc_rt_device_count", "nrmc_rt_version")
 
 _lib = None
 
@@ -75,6 +82,8 @@ def load():
     lib.nrmc_rt_host_free.restype = C.c_int
     lib.nrmc_rt_attenuation_length.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
     lib.nrmc_rt_attenuation_length.restype = C.c_int
+    lib.nrmc_rt_apply_propagation_effects.argtypes = [C.c_void_p, C.POINTER(Effects), C.c_void_p]
+    lib.nrmc_rt_apply_propagation_effects.restype = C.c_int
     lib.nrmc_rt_measure_fp64_peak.argtypes = [C.c_int32, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     lib.nrmc_rt_measure_fp64_peak.restype = C.c_int
     lib.nrmc_rt_device_count.argtypes = []

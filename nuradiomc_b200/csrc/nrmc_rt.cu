@@ -882,6 +882,84 @@ K_pack(const int32_t *n_sol, int64_t n_pairs, int S, const unsigned long long *b
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// propagation effects on spectra (analyticraytracing.py:2937-3033, in-ice branch): one block per solution row
+// ---------------------------------------------------------------------------------------------------------------
+struct cplx { double re, im; };
+__device__ __forceinline__ cplx cmul(cplx a, cplx b) { return {a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re}; }
+__device__ __forceinline__ cplx cdiv(cplx a, cplx b)
+{
+    const double d = b.re * b.re + b.im * b.im;
+    return {(a.re * b.re + a.im * b.im) / d, (a.im * b.re - a.re * b.im) / d};
+}
+
+// Fresnel reflection coefficients for an interface n_1 -> n_2 at incidence angle a (geometryUtilities.py:211-263):
+// r_p = conj((n^2 cos a - sqrt(n^2 - sin^2 a)) / (n^2 cos a + sqrt(...))), r_s = conj((cos a - sqrt(...)) / (cos a + sqrt(...))),
+// n = n_2 / n_1, sqrt on the complex branch (scimath) beyond total internal reflection.
+__device__ __forceinline__ void fresnel_r(double a, double n, cplx &rp, cplx &rs)
+{
+    const double ca = cos(a), sa = sin(a);
+    const double rad = n * n - sa * sa;
+    cplx sq = rad >= 0.0 ? cplx{sqrt(rad), 0.0} : cplx{0.0, sqrt(-rad)};
+    cplx p = cdiv(cplx{n * n * ca - sq.re, -sq.im}, cplx{n * n * ca + sq.re, sq.im});
+    cplx q = cdiv(cplx{ca - sq.re, -sq.im}, cplx{ca + sq.re, sq.im});
+    rp = {p.re, -p.im};
+    rs = {q.re, -q.im};
+}
+
+#define FX_THREADS 128
+__global__ void __launch_bounds__(FX_THREADS)
+K_apply_effects(nrmc_rt_effects fx, AttTables tb, int K1, double n_surface)
+{
+    __shared__ cplx s_c[2];      // total factor on eTheta and ePhi
+    for (int64_t row = blockIdx.x; row < fx.n_rows; row += gridDim.x) {
+        if (threadIdx.x == 0) {
+            cplx ct = {1.0, 0.0}, cp = {1.0, 0.0};
+            if (fx.reflection_angle) {
+                for (int s = 0; s < K1; ++s) {
+                    const double a = fx.reflection_angle[row * K1 + s];
+                    if (a == a) {
+                        cplx rp, rs;
+                        fresnel_r(a, 1.0 / n_surface, rp, rs);
+                        ct = cmul(ct, rp); cp = cmul(cp, rs);
+                    }
+                }
+            }
+            if (fx.r_theta) { fx.r_theta[2 * row] = ct.re; fx.r_theta[2 * row + 1] = ct.im; }
+            if (fx.r_phi) { fx.r_phi[2 * row] = cp.re; fx.r_phi[2 * row + 1] = cp.im; }
+            const int k = fx.reflection ? fx.reflection[row] : 0;
+            if (k > 0) {   // analyticraytracing.py:3002-3010
+                const double amp = pow(fx.reflection_coefficient, (double)k);
+                const double ph = fmod(k * fx.reflection_phase_shift, 2.0 * 3.14159265358979323846);
+                const cplx b = {amp * cos(ph), amp * sin(ph)};
+                ct = cmul(ct, b); cp = cmul(cp, b);
+            }
+            s_c[0] = ct; s_c[1] = cp;
+        }
+        __syncthreads();
+        const cplx ct = s_c[0], cp = s_c[1];
+        cplx *spec = reinterpret_cast<cplx *>(fx.spectrum) + row * 3 * (int64_t)fx.n_freq;
+        for (int b = threadIdx.x; b < fx.n_freq; b += FX_THREADS) {
+            double att = 1.0;
+            if (fx.attenuation) att = fx.attenuation[row * fx.n_freq + b];
+            else if (fx.attenuation_sparse) {
+                const int i0 = __ldg(tb.ii + b);
+                if (i0 >= 0) {
+                    const double *src = fx.attenuation_sparse + row * tb.Fs;
+                    const double f0 = src[i0], f1 = src[i0 + 1];
+                    att = (f1 - f0) * __ldg(tb.it + b) + f0;
+                }
+            }
+            cplx e0 = spec[b], e1 = spec[fx.n_freq + b], e2 = spec[2 * fx.n_freq + b];
+            e0.re *= att; e0.im *= att;
+            e1 = cmul(cplx{e1.re * att, e1.im * att}, ct);
+            e2 = cmul(cplx{e2.re * att, e2.im * att}, cp);
+            spec[b] = e0; spec[fx.n_freq + b] = e1; spec[2 * fx.n_freq + b] = e2;
+        }
+        __syncthreads();
+    }
+}
+
 __global__ void K_att_length(IceParams ice, Gl3Table gl3, const double *z, const double *f, int64_t n, double *out)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1544,6 +1622,27 @@ extern "C" int nrmc_rt_trace(nrmc_rt_t h, const nrmc_rt_input *in, const nrmc_rt
         if (compact) stats->n_solutions = row_base;
         else if (out->n_sol) { for (int64_t i = 0; i < N; ++i) n_solutions += out->n_sol[i]; stats->n_solutions = n_solutions; }
     }
+    return NRMC_OK;
+}
+
+extern "C" int nrmc_rt_apply_propagation_effects(nrmc_rt_t h, const nrmc_rt_effects *fx, void *stream)
+{
+    if (!h || !fx || fx->n_rows < 0 || fx->n_freq <= 0) return NRMC_ERR_INVALID_ARGUMENT;
+    if (fx->n_rows == 0) return NRMC_OK;
+    if (!fx->spectrum) return NRMC_ERR_INVALID_ARGUMENT;
+    if (!fx->attenuation && fx->attenuation_sparse) {
+        if (!h->have_freq) { h->err = "sparse attenuation needs nrmc_rt_set_frequencies"; return NRMC_ERR_NO_FREQUENCIES; }
+        if (fx->n_freq != h->tb.F) { h->err = "n_freq differs from the frequency vector of nrmc_rt_set_frequencies"; return NRMC_ERR_INVALID_ARGUMENT; }
+        if (h->ice.n_refl > 0) {
+            h->err = "with bottom reflections the factors of the path segments are interpolated separately (py:1077-1086): pass the dense attenuation";
+            return NRMC_ERR_UNSUPPORTED;
+        }
+    }
+    CK(cudaSetDevice(h->cfg.device));
+    const double n_surface = h->ice.n_ice - h->ice.dn * exp(-0.01 * h->ice.inv_z0);    // n(z = -1 cm), py:2990
+    const int64_t blocks = std::min<int64_t>(fx->n_rows, (int64_t)h->n_sm * 16);
+    K_apply_effects<<<(unsigned)blocks, FX_THREADS, 0, (cudaStream_t)stream>>>(*fx, h->tb, h->K1, n_surface);
+    CK(cudaGetLastError());
     return NRMC_OK;
 }
 

@@ -217,3 +217,40 @@ def arbiter_roots(r, X1, X2, reflection=0, reflection_case=1, n_scan=20001, lo=-
             x = optimize.brentq(r2.obj_delta_y, ls[k], ls[k + 1], args=(r._x1, r._x2, reflection, reflection_case), xtol=1e-14)
             roots.append(ray.get_C0_from_log(x, r2.medium.n_ice))
     return np.array(sorted(roots))
+
+
+class _FieldStub:
+    """duck-typed stand-in for NuRadioReco.framework.electric_field.ElectricField: exactly the members
+    ray_tracing.apply_propagation_effects touches (analyticraytracing.py:2954-3031)"""
+
+    def __init__(self, spectrum, frequencies, sampling_rate):
+        self._spec, self._ff, self._sr, self.params = np.array(spectrum, complex), np.asarray(frequencies, float), sampling_rate, {}
+
+    def get_sampling_rate(self):
+        return self._sr
+
+    def get_frequency_spectrum(self):
+        return self._spec
+
+    def get_frequencies(self):
+        return self._ff
+
+    def set_frequency_spectrum(self, spec, sampling_rate):
+        self._spec = np.array(spec, complex)
+
+    def __setitem__(self, key, value):
+        self.params[getattr(key, "name", str(key))] = value
+
+
+def apply_effects(r, X1, X2, spectra, frequencies, sampling_rate):
+    """the reference's apply_propagation_effects on every solution of one pair; spectra: (S, 3, F) complex"""
+    r.set_start_and_end_point(X1, X2)
+    r.find_solutions()
+    out, rt, rp = [], [], []
+    for iS in range(r.get_number_of_solutions()):
+        ef = _FieldStub(spectra[iS], frequencies, sampling_rate)
+        r.apply_propagation_effects(ef, iS)
+        out.append(ef.get_frequency_spectrum())
+        rt.append(ef.params.get("reflection_coefficient_theta", np.nan))
+        rp.append(ef.params.get("reflection_coefficient_phi", np.nan))
+    return np.array(out), np.array(rt, complex), np.array(rp, complex)

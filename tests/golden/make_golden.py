@@ -160,5 +160,45 @@ def main(names):
             np.save(os.path.join(HERE, fn.replace(".pkl", ".npy")), np.asarray(arr, float))
 
 
+def make_effects_golden():
+    """fixtures of ray_tracing.apply_propagation_effects (analyticraytracing.py:2937-3033): random spectra in, spectra out"""
+    import ref_harness as rh
+    rng = np.random.default_rng(77)
+    out = {}
+    for tag, ice, att, n_refl, V, A in (
+            ("sp", "southpole_2015", "SP1", 0, cylinder(41, 10, 2500., -2000.), np.array([[0, 0, -150.]])),
+            ("mb", "mooresbay_simple", "MB1", 1, cylinder(42, 5, 600., -400.), np.array([[3, 3, -5.]]))):
+        r = rh.make_tracer(ice, attenuation_model=att, n_freq=12, n_reflections=n_refl)
+        S = r.get_number_of_raytracing_solutions()
+        n_samples, sr = 128, 2.0
+        ff = np.fft.rfftfreq(n_samples, 1. / sr)
+        spec_in = rng.normal(size=(len(V), S, 3, len(ff))) + 1j * rng.normal(size=(len(V), S, 3, len(ff)))
+        spec_out = np.full_like(spec_in, np.nan)
+        r_theta = np.full((len(V), S), np.nan, complex)
+        r_phi = np.full((len(V), S), np.nan, complex)
+        n_sol = np.zeros(len(V), np.int32)
+        for i in range(len(V)):
+            o, rt, rp = rh.apply_effects(r, V[i], A[0], spec_in[i], ff, sr)
+            n_sol[i] = len(o)
+            if len(o) == 0:
+                continue
+            spec_out[i, :len(o)] = o
+            r_theta[i, :len(o)], r_phi[i, :len(o)] = rt, rp
+        out.update({f"{tag}_X1": V, f"{tag}_X2": np.repeat(A, len(V), 0), f"{tag}_frequencies": ff, f"{tag}_spec_in": spec_in,
+                    f"{tag}_spec_out": spec_out, f"{tag}_r_theta": r_theta, f"{tag}_r_phi": r_phi, f"{tag}_n_sol": n_sol})
+    # Fresnel coefficients straight from the reference's helpers (NuRadioReco/utilities/geometryUtilities.py:211-263)
+    from NuRadioReco.utilities import geometryUtilities as gu
+    ang = np.linspace(0.01, np.pi / 2 - 0.01, 60)
+    n1 = 1.3587
+    out["fresnel_angle"], out["fresnel_n1"] = ang, np.array(n1)
+    out["fresnel_r_p"] = np.array([gu.get_fresnel_r_p(a, n_2=1., n_1=n1) for a in ang], complex)
+    out["fresnel_r_s"] = np.array([gu.get_fresnel_r_s(a, n_2=1., n_1=n1) for a in ang], complex)
+    np.savez_compressed(os.path.join(HERE, "propagation_effects.npz"), **out)
+    print("propagation_effects: solutions", int(out["sp_n_sol"].sum()), int(out["mb_n_sol"].sum()))
+
+
 if __name__ == "__main__":
-    main(sys.argv[1:])
+    if sys.argv[1:] == ["effects"]:
+        make_effects_golden()
+    else:
+        main(sys.argv[1:])

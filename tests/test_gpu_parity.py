@@ -316,6 +316,65 @@ def test_device_resident_path_equals_host_path(make):
 
 
 # ---------------------------------------------------------------------------------------------------------------
+# the step after the trace: propagation effects on spectra
+# ---------------------------------------------------------------------------------------------------------------
+class _Field:
+    """minimal ElectricField stand-in (the members apply_propagation_effects uses)"""
+
+    def __init__(self, spec, ff, sr):
+        self.spec, self.ff, self.sr, self.params = np.array(spec), ff, sr, {}
+
+    def get_sampling_rate(self): return self.sr
+    def get_frequency_spectrum(self): return self.spec
+    def get_frequencies(self): return self.ff
+    def set_frequency_spectrum(self, spec, sr): self.spec = np.array(spec)
+    def __setitem__(self, k, v): self.params[getattr(k, "name", str(k))] = v
+
+
+@pytest.mark.parametrize("tag,ice,att,n_refl", [("sp", "southpole_2015", "SP1", 0), ("mb", "mooresbay_simple", "MB1", 1)])
+def test_propagation_effects_kernel(make, oracle_mod, tag, ice, att, n_refl):
+    """K_apply_effects against the numpy restatement (bit-level: 1e-12) and the reference's own outputs (its attenuation
+    carries quad(epsrel=1e-2) noise: 1e-2 band, as the reference's T01 test); sparse on-the-fly interpolation == dense"""
+    from oracle import propagation_effects as pe
+    g = load_golden("propagation_effects")
+    ff = g[f"{tag}_frequencies"]
+    rt = make(ice, attenuation_model=att, n_reflections=n_refl, n_frequencies_integration=12)
+    X1, X2 = g[f"{tag}_X1"], g[f"{tag}_X2"]
+    res = rt.trace_batch(X1, X2, frequency=ff, max_detector_freq=float(ff.max()), attenuation="both", compact=True)
+    assert np.array_equal(res["n_sol"], g[f"{tag}_n_sol"])
+    S = g[f"{tag}_spec_in"].shape[1]
+    filled = np.arange(S)[None, :] < res["n_sol"][:, None]
+    spec_in, ref = g[f"{tag}_spec_in"][filled], g[f"{tag}_spec_out"][filled]
+    out, r_t, r_p = rt.apply_propagation_effects_batch(spec_in, reflection_angle=res["reflection_angle"], reflection=res["reflection"],
+                                                       attenuation=res["attenuation"], return_coefficients=True)
+    n_ice, dn, z0, _ = oracle_mod.ICE_MODELS[ice]
+    med = rt._medium
+    for r in range(len(spec_in)):
+        k = int(res["reflection"][r])
+        exp, et, ep = pe.apply_propagation_effects(spec_in[r], res["attenuation"][r], res["reflection_angle"][r, :k + 1], k,
+                                                   n_ice - dn * np.exp(-0.01 / z0), med.reflection_coefficient, med.reflection_phase_shift)
+        np.testing.assert_allclose(out[r], exp, rtol=1e-12, atol=1e-14)
+        np.testing.assert_allclose([r_t[r], r_p[r]], [et, ep], rtol=1e-12)
+        np.testing.assert_allclose(out[r], ref[r], rtol=1e-2, atol=1e-3 * np.abs(ref[r]).max())
+    if n_refl == 0:
+        out2 = rt.apply_propagation_effects_batch(spec_in, reflection_angle=res["reflection_angle"], reflection=res["reflection"],
+                                                  attenuation_sparse=res["attenuation_sparse"])
+        np.testing.assert_allclose(out2, out, rtol=1e-13, atol=1e-300)
+        # scalar API, as simulation.py uses it
+        i = int(np.nonzero(res["n_sol"] == 2)[0][0])
+        rt.set_start_and_end_point(X1[i], X2[i])
+        rt.find_solutions()
+        r0 = int(res["sol_offset"][i])
+        for iS in range(2):
+            f = _Field(spec_in[r0 + iS], ff, 2.0)
+            rt.apply_propagation_effects(f, iS)
+            np.testing.assert_allclose(f.spec, out[r0 + iS], rtol=1e-12, atol=1e-14)
+    else:
+        with pytest.raises(RuntimeError, match="dense"):
+            rt.apply_propagation_effects_batch(spec_in, attenuation_sparse=res["attenuation_sparse"])
+
+
+# ---------------------------------------------------------------------------------------------------------------
 # BASELINE sizes: size-independent properties
 # ---------------------------------------------------------------------------------------------------------------
 def test_full_size_properties_cfg2(make):
