@@ -74,6 +74,12 @@ typedef struct {
     const double *ax, *ay, *az;        /* SoA end points (the reference's x2) */
     int32_t outer;
     int32_t memory;                    /* NRMC_MEMORY_HOST or NRMC_MEMORY_DEVICE: where ALL input and output pointers live */
+    /* Optional viewing-angle cut of the simulation loop (NuRadioMC/simulation/simulation.py:175-208).  sx, sy, sz: SoA
+     * [n_vertices] propagation direction of the shower at each vertex (-shower axis); NULL: no cut.  A solution whose
+     * launch vector makes an angle with it that differs from the Cherenkov angle arccos(1/n(vertex)) by more than
+     * delta_C_cut [rad] keeps its geometric outputs but gets NO attenuation (NaN rows): the reference skips it. */
+    const double *sx, *sy, *sz;
+    double delta_C_cut;
 } nrmc_rt_input;
 
 /* SoA outputs, pair-major, S = nrmc_rt_max_solutions() slots per pair ordered as the reference orders
@@ -93,6 +99,7 @@ typedef struct {
     double *reflection_angle;  /* [N,S,n_reflections+1]  get_reflection_angle(iS), NaN = None          */
     double *attenuation_sparse;/* [N,S,Fs] attenuation factors at the Fs integration frequencies       */
     double *attenuation;       /* [N,S,F]  get_attenuation(iS, frequency, max_detector_freq)           */
+    double *viewing_angle;     /* [N,S]    angle(shower direction, launch vector) (simulation.py:191); NaN without sx/sy/sz */
     /* Compact (per-solution) layout, NRMC_MEMORY_HOST only.  compact != 0: every [N,S,...] array above is written as
      * [n_rows,...] with one row per EXISTING solution: the rows of pair i are sol_offset[i] .. sol_offset[i+1]-1, in slot
      * order (CSR; sol_offset[N] = n_rows = sum of n_sol).  Empty slots are neither stored nor copied over PCIe.

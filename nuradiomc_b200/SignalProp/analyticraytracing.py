@@ -106,6 +106,7 @@ _OUT_SPECS = {  # name -> (dtype, trailing shape as function of (S, K1, Fs, F))
     "reflection_angle": (np.float64, lambda S, K1, Fs, F: (S, K1)),
     "attenuation_sparse": (np.float64, lambda S, K1, Fs, F: (S, Fs)),
     "attenuation": (np.float64, lambda S, K1, Fs, F: (S, F)),
+    "viewing_angle": (np.float64, lambda S, K1, Fs, F: (S,)),
 }
 DEFAULT_OUTPUTS = ("n_sol", "status", "solution_type", "reflection", "reflection_case", "C0", "C1", "path_length",
                    "travel_time", "launch_vector", "receive_vector", "reflection_angle")
@@ -214,7 +215,8 @@ class ray_tracing(ray_tracing_base):
     # batched entry points (new)
     # ------------------------------------------------------------------------------------------------------
     def trace_batch(self, X1, X2, frequency=None, max_detector_freq=None, outer=False, outputs=None,
-                    attenuation="dense", pinned=False, out=None, compact=False, row_capacity=None):
+                    attenuation="dense", pinned=False, out=None, compact=False, row_capacity=None, shower_axis=None,
+                    delta_C_cut=None):
         """
         Trace all pairs in one device pass (host arrays in, host arrays out).
 
@@ -227,6 +229,9 @@ class ray_tracing(ray_tracing_base):
         compact=True: per-solution (CSR) layout -- every per-slot array has one row per EXISTING solution instead of
         S slots per pair; the rows of pair i are res["sol_offset"][i] : res["sol_offset"][i+1] (slot order).  Empty
         slots are neither stored nor copied from the device.  `row_capacity` bounds the rows allocated (default N*S).
+        shower_axis: (Nv, 3) propagation direction of the shower at every vertex (simulation.py:175 uses -shower.get_axis());
+        adds the output "viewing_angle" and, with delta_C_cut [rad], applies the reference's viewing-angle cut
+        (simulation.py:195-208): solutions further than delta_C_cut from the Cherenkov cone get no attenuation (NaN).
         """
         X1 = np.asarray(X1, dtype=np.float64).reshape(-1, 3)
         X2 = np.asarray(X2, dtype=np.float64).reshape(-1, 3)
@@ -250,6 +255,13 @@ class ray_tracing(ray_tracing_base):
         elif any(n in ("attenuation", "attenuation_sparse") for n in names):
             raise ValueError("attenuation outputs need `frequency`")
         S, K1 = self.get_number_of_raytracing_solutions(), self._n_reflections + 1
+        sax = None
+        if shower_axis is not None:
+            sax = np.ascontiguousarray(np.asarray(shower_axis, dtype=np.float64).reshape(-1, 3).T)
+            if sax.shape[1] != X1.shape[0]:
+                raise ValueError("shower_axis needs one direction per start point")
+            if "viewing_angle" not in names:
+                names.append("viewing_angle")
         res = out if out is not None else BatchResult()
         keep = []
         o = _lib.Output()
@@ -286,6 +298,9 @@ class ray_tracing(ray_tracing_base):
         inp.n_vertices, inp.vx, inp.vy, inp.vz = X1.shape[0], v[0].ctypes.data, v[1].ctypes.data, v[2].ctypes.data
         inp.n_antennas, inp.ax, inp.ay, inp.az = X2.shape[0], a[0].ctypes.data, a[1].ctypes.data, a[2].ctypes.data
         inp.outer, inp.memory = int(bool(outer)), _lib.MEMORY_HOST
+        if sax is not None:
+            inp.sx, inp.sy, inp.sz = sax[0].ctypes.data, sax[1].ctypes.data, sax[2].ctypes.data
+            inp.delta_C_cut = float(np.pi) if delta_C_cut is None else float(delta_C_cut)
         st = _lib.Stats()
         _lib.check(_lib.load().nrmc_rt_trace(h.ptr, C.byref(inp), C.byref(o), None, C.byref(st)), h.ptr, "trace")
         res.stats = _stats_dict(st)
@@ -522,9 +537,24 @@ class ray_tracing(ray_tracing_base):
             raise IndexError
 
     def _need_cache(self):
+        if self._cache is None and self._X1 is not None and self._results:
+            self._rebuild_cache_from_results()
         if self._cache is None:
-            raise AttributeError("find_solutions has to be called first (solutions injected with set_solution carry no "
-                                 "geometry; call set_start_and_end_point + find_solutions)")
+            raise AttributeError("find_solutions (or set_start_and_end_point + set_solution) has to be called first")
+
+    def _rebuild_cache_from_results(self):
+        """solutions injected with `set_solution` (reference :2092-2116; speedup.redo_raytracing = False) carry C0 / type
+        only: trace the pair once and keep, in the injected order, the solutions that were injected"""
+        src = self.trace_batch(self._X1[None, :], self._X2[None, :])
+        n = int(src["n_sol"][0])
+        pick = []
+        for r in self._results:
+            cand = [s for s in range(n) if int(src["reflection"][0, s]) == int(r['reflection'])
+                    and abs(src["C0"][0, s] - r['C0']) <= 1e-6 * abs(r['C0'])]
+            if not cand:
+                raise AttributeError("the injected ray-tracing solution (C0 = {}) does not belong to this pair of points".format(r['C0']))
+            pick.append(cand[0])
+        self._cache = {k: np.array(src[k][0][pick]) for k in DEFAULT_OUTPUTS if k in src and np.ndim(src[k][0]) > 0}
 
     def get_solution_type(self, iS):
         self._check(iS)

@@ -21,11 +21,13 @@ class Config(C.Structure):
 class Input(C.Structure):
     _fields_ = [("n_vertices", C.c_int64), ("vx", C.c_void_p), ("vy", C.c_void_p), ("vz", C.c_void_p),
                 ("n_antennas", C.c_int64), ("ax", C.c_void_p), ("ay", C.c_void_p), ("az", C.c_void_p),
-                ("outer", C.c_int32), ("memory", C.c_int32)]
+                ("outer", C.c_int32), ("memory", C.c_int32), ("sx", C.c_void_p), ("sy", C.c_void_p), ("sz", C.c_void_p),
+                ("delta_C_cut", C.c_double)]
 
 
 OUTPUT_FIELDS = ("n_sol", "status", "solution_type", "reflection", "reflection_case", "C0", "C1", "path_length",
-                 "travel_time", "launch_vector", "receive_vector", "reflection_angle", "attenuation_sparse", "attenuation")
+                 "travel_time", "launch_vector", "receive_vector", "reflection_angle", "attenuation_sparse", "attenuation",
+                 "viewing_angle")
 
 
 class Output(C.Structure):

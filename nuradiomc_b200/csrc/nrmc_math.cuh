@@ -477,7 +477,27 @@ struct TraceOutputs {          // all [N,S] pair-major, S = 2 + 4 n_refl; any po
     double *C0, *C1, *path_length, *travel_time;
     double *launch, *receive;  // [N,S,3]
     double *reflection_angle;  // [N,S,n_refl+1], NaN = None
+    double *viewing_angle;     // [N,S] angle between the shower's propagation direction and the launch vector (simulation.py:191)
 };
+
+// Viewing-angle cut of the simulation loop (NuRadioMC/simulation/simulation.py:175-208): solutions whose launch direction
+// is further than delta_C_cut from the Cherenkov cone of the shower are dropped before any further work.
+struct ShowerCut { double sx, sy, sz, cut; bool on; };
+
+// angle between the shower propagation direction and the launch vector (lx ex, lx ey, lz); radiotools.helper.get_angle
+NRMC_HD double viewing_angle_of(const ShowerCut &sc, double ex, double ey, double lx, double lz)
+{
+    const double nrm = sqrt(sc.sx * sc.sx + sc.sy * sc.sy + sc.sz * sc.sz);
+    double c = (sc.sx * lx * ex + sc.sy * lx * ey + sc.sz * lz) / nrm;
+    c = fmin(fmax(c, -1.0), 1.0);
+    return acos(c);
+}
+
+// |viewing angle - Cherenkov angle| <= cut, Cherenkov angle = arccos(1 / n(vertex))   (simulation.py:176-177, :195-208)
+NRMC_HD bool passes_cut(const ShowerCut &sc, double viewing, double n_vertex)
+{
+    return fabs(viewing - acos(1.0 / n_vertex)) <= sc.cut;
+}
 
 struct SolRec {                // everything the attenuation kernels need about one solution: one aligned 64-byte load
     int64_t pair;
@@ -534,6 +554,14 @@ NRMC_HD void fill_empty_slot(const TraceOutputs &o, int64_t q, int K1)
     if (o.launch) { o.launch[3 * q] = NAN; o.launch[3 * q + 1] = NAN; o.launch[3 * q + 2] = NAN; }
     if (o.receive) { o.receive[3 * q] = NAN; o.receive[3 * q + 1] = NAN; o.receive[3 * q + 2] = NAN; }
     if (o.reflection_angle) for (int t = 0; t < K1; ++t) o.reflection_angle[q * K1 + t] = NAN;
+    if (o.viewing_angle) o.viewing_angle[q] = NAN;
+}
+
+// launch direction in the 2-D frame (x along rho, z up): roles of launch and receive exchanged when the points were swapped
+NRMC_HD void launch_2d(const Frame2D &f, const SolutionProps &p, double &lx, double &lz)
+{
+    lx = f.swap ? -p.sin_r : p.sin_l;
+    lz = f.swap ? p.cos_r : p.cos_l;
 }
 
 NRMC_HD void write_solution(const TraceOutputs &o, int64_t q, int K1, const Frame2D &f, int k, int rcase, const SolutionProps &p)
@@ -566,10 +594,12 @@ NRMC_HD int pair_status(const IceParams &ice, const Frame2D &f)
 // Returns the number of solutions; fills the SoA slots of pair i and (if recs != null) one SolRec per solution.
 // Thread-per-pair form: used by the generic kernel (bottom reflections) and by the CPU test harness.
 NRMC_HD int trace_pair(const IceParams &ice, double ax, double ay, double az, double bx, double by, double bz,
-                        int64_t i, const TraceOutputs &o, SolRec *recs)
+                        int64_t i, const TraceOutputs &o, SolRec *recs, const ShowerCut *sc = nullptr, int *n_recs = nullptr,
+                        uint32_t *cut_mask = nullptr)
 {
     const int S = 2 + 4 * ice.n_refl, K1 = ice.n_refl + 1;
-    int n = 0;
+    int n = 0, nrec = 0;
+    uint32_t cut = 0;
     Frame2D f;
     make_frame(ax, ay, az, bx, by, bz, f);
     const int status = pair_status(ice, f);
@@ -585,7 +615,16 @@ NRMC_HD int trace_pair(const IceParams &ice, double ax, double ay, double az, do
                 SolutionProps p;
                 solution_props(ice, g, f.x1y, k, rcase, roots[j], p);
                 write_solution(o, i * S + n, K1, f, k, rcase, p);
-                if (recs) make_solrec(ice, g, i, n, k, rcase, roots[j], recs[n]);
+                bool keep = true;
+                if (sc && sc->on) {
+                    double lx, lz;
+                    launch_2d(f, p, lx, lz);
+                    const double va = viewing_angle_of(*sc, f.ex, f.ey, lx, lz);
+                    if (o.viewing_angle) o.viewing_angle[i * S + n] = va;
+                    keep = passes_cut(*sc, va, f.swap ? g.n2 : g.n1);
+                    if (!keep) cut |= (1u << n);
+                } else if (o.viewing_angle) o.viewing_angle[i * S + n] = NAN;
+                if (recs && keep) make_solrec(ice, g, i, n, k, rcase, roots[j], recs[nrec++]);
                 ++n;
             }
         }
@@ -593,6 +632,8 @@ NRMC_HD int trace_pair(const IceParams &ice, double ax, double ay, double az, do
     if (o.n_sol) o.n_sol[i] = n;
     if (o.status) o.status[i] = status;
     for (int s = n; s < S; ++s) fill_empty_slot(o, i * S + s, K1);
+    if (n_recs) *n_recs = nrec;
+    if (cut_mask) *cut_mask = cut;
     return n;
 }
 

@@ -32,7 +32,21 @@ struct KInput {
     int64_t n_pairs;       // pairs in this launch
     int64_t n_antennas;    // outer-product divisor (1 pair = vertex p / n_antennas, antenna p % n_antennas) if outer
     int32_t outer;
+    const double *sx, *sy, *sz;   // optional, per vertex: propagation direction of the shower (viewing-angle cut)
+    double delta_C_cut;
 };
+
+__device__ __forceinline__ ShowerCut load_cut(const KInput &in, int64_t p)
+{
+    ShowerCut sc;
+    sc.on = in.sx != nullptr;
+    sc.sx = sc.sy = sc.sz = 0.0; sc.cut = in.delta_C_cut;
+    if (sc.on) {
+        const int64_t iv = in.outer ? p / in.n_antennas : p;
+        sc.sx = __ldg(in.sx + iv); sc.sy = __ldg(in.sy + iv); sc.sz = __ldg(in.sz + iv);
+    }
+    return sc;
+}
 
 __device__ __forceinline__ void load_pair(const KInput &in, int64_t p, double &x1, double &y1, double &z1, double &x2,
                                           double &y2, double &z2)
@@ -59,6 +73,7 @@ __device__ __forceinline__ SolRec worklist_get(const SolRec *wl, unsigned long l
     return w < n_front ? wl[w] : wl[cap - 1ull - (w - n_front)];
 }
 
+#define N_OUT 15            // output arrays of nrmc_rt_output (out_ptr)
 #define SOLVE_THREADS 128
 #define MAX_S (2 + 4 * NRMC_MAX_REFLECTIONS)
 
@@ -66,16 +81,25 @@ __device__ __forceinline__ SolRec worklist_get(const SolRec *wl, unsigned long l
 #define SOLVE_MIN_BLOCKS 4
 #endif
 __global__ void __launch_bounds__(SOLVE_THREADS, SOLVE_MIN_BLOCKS)
-K_solve(IceParams ice, KInput in, TraceOutputs out, SolRec *worklist, unsigned long long *work_count)
+K_solve(IceParams ice, KInput in, TraceOutputs out, SolRec *worklist, unsigned long long *work_count, double *att_sparse,
+        double *att_dense, int Fs, int F)
 {
     const int64_t p = (int64_t)blockIdx.x * SOLVE_THREADS + threadIdx.x;
     const unsigned lane = threadIdx.x & 31u;
     SolRec recs[MAX_S];
-    int n = 0;
+    int n = 0;     // records for the attenuation kernel (solutions that pass the viewing-angle cut)
     if (p < in.n_pairs) {
         double x1, y1, z1, x2, y2, z2;
         load_pair(in, p, x1, y1, z1, x2, y2, z2);
-        n = trace_pair(ice, x1, y1, z1, x2, y2, z2, p, out, worklist ? recs : nullptr);
+        const ShowerCut sc = load_cut(in, p);
+        uint32_t cut_mask = 0;
+        trace_pair(ice, x1, y1, z1, x2, y2, z2, p, out, worklist ? recs : nullptr, &sc, &n, &cut_mask);
+        const int S = 2 + 4 * ice.n_refl;
+        for (int sl = 0; cut_mask >> sl; ++sl) {      // cut solutions get NaN attenuation rows
+            if (!((cut_mask >> sl) & 1u)) continue;
+            if (att_sparse) for (int j = 0; j < Fs; ++j) att_sparse[(p * S + sl) * Fs + j] = NAN;
+            if (att_dense) for (int j = 0; j < F; ++j) att_dense[(p * S + sl) * F + j] = NAN;
+        }
     }
     if (worklist) {
         // warp-aggregated append: inclusive scan of the per-lane counts, one atomic per warp
@@ -146,6 +170,19 @@ __device__ __forceinline__ void warp_fill_nan_rows(bool mine, int64_t pair, cons
         const int64_t pr = __shfl_sync(0xffffffffu, pair, l);
         if (af.sparse) { double *d = af.sparse + pr * 2 * af.Fs; for (int j = lane; j < 2 * af.Fs; j += 32) d[j] = NAN; }
         if (af.dense) { double *d = af.dense + pr * 2 * af.F; for (int j = lane; j < 2 * af.F; j += 32) d[j] = NAN; }
+    }
+}
+
+__device__ __forceinline__ void warp_fill_nan_slot(bool mine, int64_t q, const AttFill &af, unsigned lane)
+{
+    if (!af.sparse && !af.dense) return;
+    unsigned m = __ballot_sync(0xffffffffu, mine);
+    while (m) {
+        const int l = __ffs(m) - 1;
+        m &= m - 1;
+        const int64_t qq = __shfl_sync(0xffffffffu, q, l);
+        if (af.sparse) { double *d = af.sparse + qq * af.Fs; for (int j = lane; j < af.Fs; j += 32) d[j] = NAN; }
+        if (af.dense) { double *d = af.dense + qq * af.F; for (int j = lane; j < af.F; j += 32) d[j] = NAN; }
     }
 }
 
@@ -237,6 +274,7 @@ K_hump(IceParams ice, KInput in, TraceOutputs out, AttFill af, const HumpItem *h
 }
 
 #define ROOTS_THREADS 128
+template <bool CUT>
 __global__ void __launch_bounds__(ROOTS_THREADS)
 K_roots(IceParams ice, KInput in, TraceOutputs out, AttFill af, const RootItem *rootq, const unsigned long long *root_count, SolRec *worklist,
         unsigned long long *work_count, unsigned long long work_cap)
@@ -251,7 +289,8 @@ K_roots(IceParams ice, KInput in, TraceOutputs out, AttFill af, const RootItem *
         int64_t pair = 0;
         Root root;
         root.v = 0; root.piece = 0; root.beta = 0;
-        double g1 = 0, g2 = 0;
+        double g1 = 0, g2 = 0, viewing = NAN;
+        bool keep = true;      // passes the viewing-angle cut (always, when no shower axes were given)
         if (active) {
             const RootItem it = rootq[w];
             pair = it.pair; g1 = it.g1; g2 = it.g2;
@@ -268,6 +307,16 @@ K_roots(IceParams ice, KInput in, TraceOutputs out, AttFill af, const RootItem *
                 Bracket b;
                 b.a = it.a; b.ga = it.ga; b.b = it.b; b.gb = it.gb; b.piece = it.piece;
                 root = solve_bracket(cv, b);
+                if (CUT) {
+                    // launch direction from Snell's invariant: sin = beta / n, cos = s / n at the emitter (py:1161-1199, :2583-2590)
+                    const ShowerCut sc = load_cut(in, pair);
+                    const double nl = f.swap ? g.n2 : g.n1;
+                    const double sl = sqrt(fmax((nl - root.beta) * (nl + root.beta), 0.0));
+                    const double lx = f.swap ? -root.beta / nl : root.beta / nl;
+                    const double lz = f.swap ? (root.piece >= 2 ? sl / nl : -sl / nl) : sl / nl;
+                    viewing = viewing_angle_of(sc, f.ex, f.ey, lx, lz);
+                    keep = passes_cut(sc, viewing, nl);
+                }
             }
         }
         // order the two roots of the pair by ascending C0 = descending beta (py:1547); the partner sits in lane ^ 1
@@ -278,13 +327,14 @@ K_roots(IceParams ice, KInput in, TraceOutputs out, AttFill af, const RootItem *
         SolRec *rec_dst = nullptr;
         if (worklist) {
             const bool two_panel = root.piece >= 2;
-            const unsigned mf = __ballot_sync(0xffffffffu, valid && !two_panel), mb = __ballot_sync(0xffffffffu, valid && two_panel);
+            const unsigned mf = __ballot_sync(0xffffffffu, valid && keep && !two_panel), mb = __ballot_sync(0xffffffffu, valid && keep && two_panel);
             unsigned long long bf = 0, bb = 0;
             if (mf) { const int l = __ffs(mf) - 1; if ((int)lane == l) bf = atomicAdd(work_count, (unsigned long long)__popc(mf)); bf = __shfl_sync(0xffffffffu, bf, l); }
             if (mb) { const int l = __ffs(mb) - 1; if ((int)lane == l) bb = atomicAdd(work_count + WL_BACK, (unsigned long long)__popc(mb)); bb = __shfl_sync(0xffffffffu, bb, l); }
             const unsigned below = (1u << lane) - 1u;
-            if (valid) rec_dst = two_panel ? worklist + (work_cap - 1ull - (bb + __popc(mb & below))) : worklist + (bf + __popc(mf & below));
+            if (valid && keep) rec_dst = two_panel ? worklist + (work_cap - 1ull - (bb + __popc(mb & below))) : worklist + (bf + __popc(mf & below));
         }
+        if (CUT) warp_fill_nan_slot(valid && !keep, 2 * pair + slot, af, lane);     // cut solutions: NaN attenuation rows
         if (active) {
             if (valid) {
                 double x1, y1, z1, x2, y2, z2;
@@ -301,6 +351,7 @@ K_roots(IceParams ice, KInput in, TraceOutputs out, AttFill af, const RootItem *
                 SolutionProps pr;
                 solution_props(ice, g, f.x1y, 0, 1, root, pr);
                 write_solution(out, 2 * pair + slot, 1, f, 0, 1, pr);
+                if (out.viewing_angle) out.viewing_angle[2 * pair + slot] = viewing;
             } else {
                 fill_empty_slot(out, 2 * pair + 1, 1);    // single root (tangency at the surface): second slot stays empty
                 if (af.sparse) for (int j = 0; j < af.Fs; ++j) af.sparse[(2 * pair + 1) * af.Fs + j] = NAN;
@@ -756,11 +807,12 @@ K_att_expand(AttTables tb, const int32_t *n_sol, int64_t n_pairs, int S, const d
         if ((int)(qi - p * S) >= n_sol[p]) continue;
         const double *src = att_sparse + qi * tb.Fs;
         double *dst = att_dense + qi * tb.F;
+        const bool dropped = src[0] != src[0];      // solution removed by the viewing-angle cut: the whole row stays NaN
         for (int b = lane; b < tb.F; b += 32) {
             const int i0 = __ldg(tb.ii + b);
             double val = 1.0;
             if (i0 >= 0) { const double f0 = src[i0], f1 = src[i0 + 1]; val = (f1 - f0) * __ldg(tb.it + b) + f0; }
-            dst[b] = val;
+            dst[b] = dropped ? NAN : val;
         }
     }
 }
@@ -785,7 +837,7 @@ __global__ void K_att_fill(const int32_t *n_sol, int64_t n_pairs, int S, int Fs,
 // ---------------------------------------------------------------------------------------------------------------
 #define PACK_PAIRS 1024
 #define PACK_THREADS 256
-struct PackArrays { const unsigned char *src[12]; unsigned char *dst[12]; int32_t row_bytes[12]; int32_t n; };
+struct PackArrays { const unsigned char *src[N_OUT - 2]; unsigned char *dst[N_OUT - 2]; int32_t row_bytes[N_OUT - 2]; int32_t n; };
 
 __global__ void __launch_bounds__(PACK_THREADS)
 K_pack_count(const int32_t *n_sol, int64_t n_pairs, unsigned long long *block_sums)
@@ -1101,7 +1153,7 @@ int nrmc_rt_create(const nrmc_rt_config *cfg, nrmc_rt_t *out)
         int nb = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, K_hump, HUMP_THREADS, 0) != cudaSuccess) { delete h; return NRMC_ERR_CUDA; }
         h->grid_hump = std::max(1, nb) * h->n_sm;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, K_roots, ROOTS_THREADS, 0) != cudaSuccess) { delete h; return NRMC_ERR_CUDA; }
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, K_roots<false>, ROOTS_THREADS, 0) != cudaSuccess) { delete h; return NRMC_ERR_CUDA; }
         h->grid_roots = std::max(1, nb) * h->n_sm;
     }
     if (cfg->attenuation_model == NRMC_ATT_GL3) {
@@ -1300,11 +1352,14 @@ static int launch_chunk(nrmc_rt_s *h, Lane &ln, int lane_id, const KInput &kin, 
         K_hump<<<h->grid_hump, HUMP_THREADS, 0, ln.stream>>>(h->ice, kin, to, af, (const HumpItem *)ln.humpq.p, d_humps,
                                                              (RootItem *)ln.rootq.p, d_roots);
         if (ln.timed) cudaEventRecord(ln.kev[1], ln.stream);
-        K_roots<<<h->grid_roots, ROOTS_THREADS, 0, ln.stream>>>(h->ice, kin, to, af, (const RootItem *)ln.rootq.p, d_roots, wl, d_count, work_cap);
+        if (kin.sx)
+            K_roots<true><<<h->grid_roots, ROOTS_THREADS, 0, ln.stream>>>(h->ice, kin, to, af, (const RootItem *)ln.rootq.p, d_roots, wl, d_count, work_cap);
+        else
+            K_roots<false><<<h->grid_roots, ROOTS_THREADS, 0, ln.stream>>>(h->ice, kin, to, af, (const RootItem *)ln.rootq.p, d_roots, wl, d_count, work_cap);
         *n_launches += 3;
     } else {
         const int64_t blocks = (kin.n_pairs + SOLVE_THREADS - 1) / SOLVE_THREADS;
-        K_solve<<<(unsigned)blocks, SOLVE_THREADS, 0, ln.stream>>>(h->ice, kin, to, wl, d_count);
+        K_solve<<<(unsigned)blocks, SOLVE_THREADS, 0, ln.stream>>>(h->ice, kin, to, wl, d_count, att_sparse, att_dense, h->tb.Fs, h->tb.F);
         ++*n_launches;
         if (ln.timed) { cudaEventRecord(ln.kev[0], ln.stream); cudaEventRecord(ln.kev[1], ln.stream); }
     }
@@ -1374,8 +1429,8 @@ static void store_times(nrmc_rt_stats *stats, const float *ms)
 }
 
 struct OutLayout {           // byte offsets of every output inside one contiguous per-chunk device block
-    size_t off[14];
-    size_t elem[14];         // bytes per pair
+    size_t off[N_OUT];
+    size_t elem[N_OUT];         // bytes per pair
     size_t total;
 };
 
@@ -1386,6 +1441,7 @@ static void *out_ptr(const nrmc_rt_output *o, int i)
     case 4: return o->reflection_case; case 5: return o->C0; case 6: return o->C1; case 7: return o->path_length;
     case 8: return o->travel_time; case 9: return o->launch_vector; case 10: return o->receive_vector;
     case 11: return o->reflection_angle; case 12: return o->attenuation_sparse; case 13: return o->attenuation;
+    case 14: return o->viewing_angle;
     }
     return nullptr;
 }
@@ -1399,6 +1455,7 @@ extern "C" int nrmc_rt_trace(nrmc_rt_t h, const nrmc_rt_input *in, const nrmc_rt
     if (stats) memset(stats, 0, sizeof(*stats));
     if (N == 0) { if (out->compact && out->sol_offset) out->sol_offset[0] = 0; return NRMC_OK; }
     if (!in->vx || !in->vy || !in->vz || !in->ax || !in->ay || !in->az) return NRMC_ERR_INVALID_ARGUMENT;
+    if (in->sx && (!in->sy || !in->sz || !(in->delta_C_cut >= 0.0))) { h->err = "the viewing-angle cut needs sx, sy, sz and delta_C_cut >= 0"; return NRMC_ERR_INVALID_ARGUMENT; }
     const bool want_att = out->attenuation_sparse || out->attenuation;
     if (want_att && h->ice.att_model == 0) { h->err = "attenuation requested but no attenuation model configured"; return NRMC_ERR_UNSUPPORTED; }
     if (want_att && !h->have_freq) { h->err = "attenuation requested before nrmc_rt_set_frequencies"; return NRMC_ERR_NO_FREQUENCIES; }
@@ -1407,8 +1464,8 @@ extern "C" int nrmc_rt_trace(nrmc_rt_t h, const nrmc_rt_input *in, const nrmc_rt
     if (compact && (!out->sol_offset || out->row_capacity < 0)) { h->err = "compact output needs sol_offset[N+1] and row_capacity"; return NRMC_ERR_INVALID_ARGUMENT; }
     CK(cudaSetDevice(h->cfg.device));
     const int S = h->S, K1 = h->K1, Fs = h->tb.Fs, F = h->tb.F;
-    const size_t elem[14] = {4, 4, (size_t)S, (size_t)S, (size_t)S, 8u * S, 8u * S, 8u * S, 8u * S, 24u * S, 24u * S,
-                             8u * S * K1, 8u * (size_t)S * Fs, 8u * (size_t)S * F};
+    const size_t elem[N_OUT] = {4, 4, (size_t)S, (size_t)S, (size_t)S, 8u * S, 8u * S, 8u * S, 8u * S, 24u * S, 24u * S,
+                                8u * S * K1, 8u * (size_t)S * Fs, 8u * (size_t)S * F, 8u * S};
     int n_launches = 0;
 
     if (in->memory == NRMC_MEMORY_DEVICE) {
@@ -1428,6 +1485,11 @@ extern "C" int nrmc_rt_trace(nrmc_rt_t h, const nrmc_rt_input *in, const nrmc_rt
             const int64_t np = std::min(chunk, N - p0);
             KInput kin;
             kin.outer = in->outer; kin.n_antennas = in->n_antennas; kin.n_pairs = np;
+            kin.sx = kin.sy = kin.sz = nullptr; kin.delta_C_cut = in->delta_C_cut;
+            if (in->sx) {
+                const int64_t v0s = in->outer ? p0 / in->n_antennas : p0;
+                kin.sx = in->sx + v0s; kin.sy = in->sy + v0s; kin.sz = in->sz + v0s;
+            }
             if (in->outer) {
                 // chunk boundaries must fall on whole vertices
                 if (p0 % in->n_antennas != 0) { rc = NRMC_ERR_INVALID_ARGUMENT; break; }
@@ -1451,6 +1513,7 @@ extern "C" int nrmc_rt_trace(nrmc_rt_t h, const nrmc_rt_input *in, const nrmc_rt
             to.launch = out->launch_vector ? out->launch_vector + p0 * S * 3 : nullptr;
             to.receive = out->receive_vector ? out->receive_vector + p0 * S * 3 : nullptr;
             to.reflection_angle = out->reflection_angle ? out->reflection_angle + p0 * S * K1 : nullptr;
+            to.viewing_angle = out->viewing_angle ? out->viewing_angle + p0 * S : nullptr;
             if (want_att && !to.n_sol) {   // the fill kernel needs n_sol
                 CK(ln.out.reserve((size_t)np * 4));
                 to.n_sol = (int32_t *)ln.out.p;
@@ -1482,10 +1545,10 @@ extern "C" int nrmc_rt_trace(nrmc_rt_t h, const nrmc_rt_input *in, const nrmc_rt
     // ---------------- host memory: chunked, two lanes (streams) so copies of one chunk overlap kernels of the other --------
     const int64_t na = in->n_antennas;
     size_t per_pair = 0;
-    bool want[14];
-    for (int i = 0; i < 14; ++i) { want[i] = out_ptr(out, i) != nullptr; }
+    bool want[N_OUT];
+    for (int i = 0; i < N_OUT; ++i) { want[i] = out_ptr(out, i) != nullptr; }
     const bool need_nsol_dev = want_att || want[0] || compact;
-    for (int i = 0; i < 14; ++i) if (want[i] || (i == 0 && need_nsol_dev)) per_pair += elem[i] + 16;
+    for (int i = 0; i < N_OUT; ++i) if (want[i] || (i == 0 && need_nsol_dev)) per_pair += elem[i] + 16;
     if (compact) per_pair = 2 * per_pair + 16;      // second (packed) copy of every array + offsets
     per_pair += h->S * sizeof(SolRec) + 48;
     if (h->ice.n_refl == 0) per_pair += 2 * sizeof(RootItem) + sizeof(HumpItem);
@@ -1519,8 +1582,9 @@ extern "C" int nrmc_rt_trace(nrmc_rt_t h, const nrmc_rt_input *in, const nrmc_rt
         // inputs
         KInput kin;
         kin.outer = in->outer; kin.n_antennas = na; kin.n_pairs = np;
+        kin.sx = kin.sy = kin.sz = nullptr; kin.delta_C_cut = in->delta_C_cut;
         const int64_t nv = in->outer ? np / na : np, v0 = in->outer ? p0 / na : p0;
-        const size_t in_bytes = (size_t)nv * 24 + (in->outer ? 0 : (size_t)np * 24);
+        const size_t in_bytes = (size_t)nv * 24 + (in->outer ? 0 : (size_t)np * 24) + (in->sx ? (size_t)nv * 24 : 0);
         CK(ln.in.reserve(in_bytes));
         double *din = (double *)ln.in.p;
         CK(cudaMemcpyAsync(din, in->vx + v0, nv * 8, cudaMemcpyHostToDevice, ln.stream));
@@ -1528,6 +1592,14 @@ extern "C" int nrmc_rt_trace(nrmc_rt_t h, const nrmc_rt_input *in, const nrmc_rt
         CK(cudaMemcpyAsync(din + 2 * nv, in->vz + v0, nv * 8, cudaMemcpyHostToDevice, ln.stream));
         kin.vx = din; kin.vy = din + nv; kin.vz = din + 2 * nv;
         h2d += nv * 24;
+        if (in->sx) {
+            double *ds = din + 3 * nv + (in->outer ? 0 : 3 * np);
+            CK(cudaMemcpyAsync(ds, in->sx + v0, nv * 8, cudaMemcpyHostToDevice, ln.stream));
+            CK(cudaMemcpyAsync(ds + nv, in->sy + v0, nv * 8, cudaMemcpyHostToDevice, ln.stream));
+            CK(cudaMemcpyAsync(ds + 2 * nv, in->sz + v0, nv * 8, cudaMemcpyHostToDevice, ln.stream));
+            kin.sx = ds; kin.sy = ds + nv; kin.sz = ds + 2 * nv;
+            h2d += nv * 24;
+        }
         if (in->outer) { kin.ax = d_ax; kin.ay = d_ay; kin.az = d_az; }
         else {
             double *da = din + 3 * nv;
@@ -1538,8 +1610,8 @@ extern "C" int nrmc_rt_trace(nrmc_rt_t h, const nrmc_rt_input *in, const nrmc_rt
             h2d += np * 24;
         }
         // outputs: one device block per lane, every array 16-byte aligned
-        size_t off[14], total = 0;
-        for (int i = 0; i < 14; ++i) {
+        size_t off[N_OUT], total = 0;
+        for (int i = 0; i < N_OUT; ++i) {
             off[i] = total;
             if (want[i] || (i == 0 && need_nsol_dev)) total += ((size_t)np * elem[i] + 15) & ~(size_t)15;
         }
@@ -1551,11 +1623,12 @@ extern "C" int nrmc_rt_trace(nrmc_rt_t h, const nrmc_rt_input *in, const nrmc_rt
         to.reflection_case = (int8_t *)dp(4); to.C0 = (double *)dp(5); to.C1 = (double *)dp(6); to.path_length = (double *)dp(7);
         to.travel_time = (double *)dp(8); to.launch = (double *)dp(9); to.receive = (double *)dp(10);
         to.reflection_angle = (double *)dp(11);
+        to.viewing_angle = (double *)dp(14);
         ln.timed = (stats != nullptr);
         int rc = launch_chunk(h, ln, lid, kin, to, (double *)dp(12), (double *)dp(13), &n_launches);
         if (rc != NRMC_OK) return rc;
         if (!compact) {
-            for (int i = 0; i < 14; ++i) {
+            for (int i = 0; i < N_OUT; ++i) {
                 if (!want[i]) continue;
                 const size_t bytes = (size_t)np * elem[i];
                 CK(cudaMemcpyAsync((unsigned char *)out_ptr(out, i) + (size_t)p0 * elem[i], dout + off[i], bytes, cudaMemcpyDeviceToHost, ln.stream));
@@ -1570,7 +1643,7 @@ extern "C" int nrmc_rt_trace(nrmc_rt_t h, const nrmc_rt_input *in, const nrmc_rt
             unsigned char *dpk = (unsigned char *)ln.packed.p;
             PackArrays pa;
             pa.n = 0;
-            for (int i = 2; i < 14; ++i) {
+            for (int i = 2; i < N_OUT; ++i) {
                 if (!want[i]) continue;
                 pa.src[pa.n] = dout + off[i]; pa.dst[pa.n] = dpk + off[i]; pa.row_bytes[pa.n] = (int32_t)(elem[i] / S); ++pa.n;
             }
@@ -1596,7 +1669,7 @@ extern "C" int nrmc_rt_trace(nrmc_rt_t h, const nrmc_rt_input *in, const nrmc_rt
             }
             CK(cudaMemcpyAsync(out->sol_offset + p0, ln.pack_off.p, (size_t)np * sizeof(int64_t), cudaMemcpyDeviceToHost, ln.stream));
             d2h += (size_t)np * sizeof(int64_t);
-            for (int i = 2; i < 14; ++i) {
+            for (int i = 2; i < N_OUT; ++i) {
                 if (!want[i] || rows == 0) continue;
                 const size_t rb = elem[i] / S;
                 CK(cudaMemcpyAsync((unsigned char *)out_ptr(out, i) + (size_t)row_base * rb, dpk + off[i], (size_t)rows * rb, cudaMemcpyDeviceToHost, ln.stream));

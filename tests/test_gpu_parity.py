@@ -375,6 +375,98 @@ def test_propagation_effects_kernel(make, oracle_mod, tag, ice, att, n_refl):
 
 
 # ---------------------------------------------------------------------------------------------------------------
+# the callers either side of the path
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("ice,att,n_refl,rmax,zmin", [("southpole_2015", "SP1", 0, 3000, -2500), ("mooresbay_simple", "MB1", 1, 800, -500)])
+def test_viewing_angle_cut(make, ice, att, n_refl, rmax, zmin):
+    """simulation.py:175-208: viewing angle = angle(-shower axis, launch vector); solutions further than delta_C_cut from the
+    Cherenkov cone keep their geometry but get no attenuation; everything else is unchanged by the cut"""
+    rt = make(ice, attenuation_model=att, n_reflections=n_refl, n_frequencies_integration=8)
+    ff = np.fft.rfftfreq(64, 0.5)
+    V, A = cylinder(51, 400, rmax, zmin), np.array([[0, 0, -5.], [200, 0, -150.]])
+    rng = np.random.default_rng(52)
+    axes = rng.normal(size=(len(V), 3))
+    cut = np.deg2rad(40.)
+    plain = rt.trace_batch(V, A, outer=True, frequency=ff, attenuation="both")
+    res = rt.trace_batch(V, A, outer=True, frequency=ff, attenuation="both", shower_axis=axes, delta_C_cut=cut)
+    S = plain["C0"].shape[1]
+    filled = np.arange(S)[None, :] < plain["n_sol"][:, None]
+    ax = np.repeat(axes, len(A), axis=0)
+    cosv = np.einsum("nk,nsk->ns", ax, plain["launch_vector"]) / np.linalg.norm(ax, axis=1)[:, None]
+    va = np.arccos(np.clip(cosv, -1, 1))
+    np.testing.assert_allclose(res["viewing_angle"][filled], va[filled], atol=1e-9)
+    assert np.isnan(res["viewing_angle"][~filled]).all()
+    n_vertex = np.repeat(rt._medium.get_index_of_refraction(V), len(A))
+    keep = np.abs(va - np.arccos(1. / n_vertex)[:, None]) <= cut
+    margin = np.abs(np.abs(va - np.arccos(1. / n_vertex)[:, None]) - cut) > 1e-9
+    for k in plain:
+        if k.startswith("attenuation"):
+            sel = filled & keep & margin
+            np.testing.assert_array_equal(res[k][sel], plain[k][sel], err_msg=k)
+            assert np.isnan(res[k][filled & ~keep & margin]).all(), k
+        else:
+            np.testing.assert_array_equal(res[k], plain[k], err_msg=k)
+    assert 0.05 < keep[filled].mean() < 0.95
+    from nuradiomc_b200 import simulation
+    np.testing.assert_array_equal(simulation.cherenkov_mask(res, rt._medium, V, len(A), cut)[filled & margin], keep[filled & margin])
+
+
+def test_simulation_hooks_and_hdf5_datasets(make):
+    """pretrace of an event group serves the scalar loop of simulation.py:155-210 from the cache; the HDF5 ray-tracing
+    datasets (output_writer_hdf5.py:267-294) round-trip through set_solution (analyticraytracing.py:2092-2116)"""
+    from nuradiomc_b200 import simulation
+    rt = make("mooresbay_simple", n_reflections=1)
+    V, A = cylinder(61, 12, 800, -500), np.array([[3, 3, -5.], [-3, 0, -1.], [0, 3, -1.]])
+    res = simulation.pretrace_event_group(rt, V, A)
+    ds = simulation.raytracing_datasets(res, len(V), len(A))
+    S = rt.get_number_of_raytracing_solutions()
+    assert ds["travel_times"].shape == (12, 3, S) and ds["launch_vectors"].shape == (12, 3, S, 3)
+    fresh = make("mooresbay_simple", n_reflections=1)
+    for i in range(len(V)):
+        for j in range(len(A)):
+            rt.set_start_and_end_point(V[i], A[j])
+            rt.find_solutions()
+            assert rt._batch_index == i * len(A) + j          # served from the batch, no kernel launch
+            n = rt.get_number_of_solutions()
+            assert np.isnan(ds["ray_tracing_C0"][i, j, n:]).all() and not np.isnan(ds["ray_tracing_C0"][i, j, :n]).any()
+            for iS in range(n):
+                assert rt.get_travel_time(iS) == ds["travel_times"][i, j, iS]
+                assert rt.get_path_length(iS) == ds["travel_distances"][i, j, iS]
+                np.testing.assert_array_equal(rt.get_launch_vector(iS), ds["launch_vectors"][i, j, iS])
+                assert rt.get_raytracing_output(iS)["ray_tracing_C0"] == ds["ray_tracing_C0"][i, j, iS]
+            if n and (i + j) % 5 == 0:       # reload: a fresh propagator fed from the stored datasets
+                fresh.set_start_and_end_point(V[i], A[j])
+                fresh.set_solution(simulation.solutions_from_datasets(ds, i, j))
+                assert fresh.get_number_of_solutions() == n
+                for iS in range(n):
+                    assert fresh.get_solution_type(iS) == rt.get_solution_type(iS)
+                    np.testing.assert_allclose(fresh.get_receive_vector(iS), rt.get_receive_vector(iS), atol=1e-12)
+                    assert fresh.get_travel_time(iS) == pytest.approx(rt.get_travel_time(iS), rel=1e-12)
+    fresh.set_start_and_end_point(V[0], A[0])
+    fresh.set_solution({"ray_tracing_C0": np.array([7.7]), "ray_tracing_C1": np.array([0.]), "ray_tracing_solution_type": np.array([1])})
+    with pytest.raises(AttributeError):
+        fresh.get_launch_vector(0)
+
+
+def test_lookup_table_vs_oracle(make, oracle_mod):
+    """create_lookup_table.py:62-107 as one batched pass: travel time per solution type on an (r, z) grid"""
+    from nuradiomc_b200 import lookup_table
+    tab = lookup_table.create_lookup_table(100., r_min=10, r_max=2010, z_min=2000, z_max=50, d_r=100, d_z=130, ice_model="greenland_simple")
+    hdr, t = tab["header"], tab["antenna_100.0"]
+    x_pos, z_pos = np.arange(10, 2010, 100.), np.arange(-2000, -50, 130.)
+    assert t["direct"].shape == (len(x_pos), len(z_pos)) and hdr["d_x"] == 100 and hdr["z_min"] == -2000
+    V = np.array([[x, 0, z] for x in x_pos for z in z_pos])
+    ora = oracle_mod.Oracle("greenland_simple").trace(V, np.repeat([[0, 0, -100.]], len(V), 0))
+    for typ, name in ((1, "direct"), (2, "refracted"), (3, "reflected")):
+        exp = np.zeros(len(V))
+        for s in range(2):
+            m = (s < ora["n_sol"]) & (ora["type"][:, s] == typ)
+            exp[m] = ora["travel_time"][m, s]
+        np.testing.assert_allclose(t[name].ravel(), exp, rtol=1e-6)
+        assert (exp > 0).any()
+
+
+# ---------------------------------------------------------------------------------------------------------------
 # BASELINE sizes: size-independent properties
 # ---------------------------------------------------------------------------------------------------------------
 def test_full_size_properties_cfg2(make):
