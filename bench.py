@@ -32,8 +32,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-    os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's version banner / warnings go to stderr: stdout carries ONE JSON line
 
 N_VERTICES = 1_000_000
 ICE, ATT_MODEL, N_FREQ, FMAX = "southpole_2015", "SP1", 25, 1.2
@@ -197,12 +196,12 @@ def main():
         torch.cuda.synchronize(dev)
 
     out = None
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()          # sampled from the warm-up on (same load): short timed regions still get several samples under load
     for _ in range(args.warmup):
         out = rt.trace_batch_device(dv, da, out=out, **kw)
     barrier()
-    clocks = ClockSampler(local)
-    if rank == 0:
-        clocks.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()

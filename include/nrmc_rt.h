@@ -166,6 +166,10 @@ typedef struct {
 } nrmc_rt_effects;
 int nrmc_rt_apply_propagation_effects(nrmc_rt_t h, const nrmc_rt_effects *fx, void *stream);
 
+/* Pairs per internal chunk (device scratch and the host-call pipeline are sized per chunk).  0 = automatic (2^24 pairs for
+ * device-resident calls, ~1.5 GB of scratch per stream for host calls).  A tuning / testing knob: results do not depend on it. */
+int nrmc_rt_set_chunk_pairs(nrmc_rt_t h, int64_t pairs);
+
 /* pinned host memory for fast NRMC_MEMORY_HOST transfers */
 int nrmc_rt_host_alloc(void **ptr, uint64_t bytes);
 int nrmc_rt_host_free(void *ptr);

@@ -197,6 +197,11 @@ class ray_tracing(ray_tracing_base):
                                         self._n_frequencies_integration, self._device)
         return self._handle
 
+    def set_chunk_pairs(self, pairs):
+        """pairs per internal chunk of the batched calls (0 = automatic); results do not depend on it"""
+        h = self._h()
+        _lib.check(_lib.load().nrmc_rt_set_chunk_pairs(h.ptr, int(pairs)), h.ptr, "set_chunk_pairs")
+
     def _set_frequencies(self, frequency, max_detector_freq):
         h = self._h()
         frequency = np.ascontiguousarray(frequency, dtype=np.float64)

@@ -49,7 +49,7 @@ class Effects(C.Structure):
 
 
 EXPORTS = ("nrmc_rt_create", "nrmc_rt_destroy", "nrmc_rt_last_error", "nrmc_rt_max_solutions", "nrmc_rt_set_frequencies",
-           "nrmc_rt_get_sparse_frequencies", "nrmc_rt_trace", "nrmc_rt_host_alloc", "nrmc_rt_host_free",
+           "nrmc_rt_get_sparse_frequencies", "nrmc_rt_trace", "nrmc_rt_set_chunk_pairs", "nrmc_rt_host_alloc", "nrmc_rt_host_free",
            "nrmc_rt_attenuation_length", "nrmc_rt_apply_propagation_effects", "nrmc_rt_measure_fp64_peak", "nrmc_rt_device_count", "nrmc_rt_version")
 
 _lib = None
@@ -78,6 +78,8 @@ def load():
     lib.nrmc_rt_get_sparse_frequencies.restype = C.c_int
     lib.nrmc_rt_trace.argtypes = [C.c_void_p, C.POINTER(Input), C.POINTER(Output), C.c_void_p, C.POINTER(Stats)]
     lib.nrmc_rt_trace.restype = C.c_int
+    lib.nrmc_rt_set_chunk_pairs.argtypes = [C.c_void_p, C.c_int64]
+    lib.nrmc_rt_set_chunk_pairs.restype = C.c_int
     lib.nrmc_rt_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_uint64]
     lib.nrmc_rt_host_alloc.restype = C.c_int
     lib.nrmc_rt_host_free.argtypes = [C.c_void_p]

@@ -1086,6 +1086,7 @@ struct nrmc_rt_s {
     bool have_sp1 = false;
     int grid_att = 0, grid_sp1 = 0;      // resident blocks (occupancy x SMs) of the persistent attenuation kernels
     int grid_hump = 0, grid_roots = 0;   // the same for the persistent solver kernels
+    int64_t chunk_pairs = 0;             // 0: automatic; > 0: pairs per chunk (nrmc_rt_set_chunk_pairs)
     size_t smem_att = 0, smem_sp1 = 0;
     DevBuf d_tables, d_gl3, d_sp1;
     bool have_freq = false;
@@ -1314,6 +1315,13 @@ int nrmc_rt_get_sparse_frequencies(nrmc_rt_t h, double *out, int32_t capacity)
     return n;
 }
 
+int nrmc_rt_set_chunk_pairs(nrmc_rt_t h, int64_t pairs)
+{
+    if (!h || pairs < 0) return NRMC_ERR_INVALID_ARGUMENT;
+    h->chunk_pairs = pairs;
+    return NRMC_OK;
+}
+
 int nrmc_rt_host_alloc(void **ptr, uint64_t bytes)
 {
     if (!ptr) return NRMC_ERR_INVALID_ARGUMENT;
@@ -1477,7 +1485,7 @@ extern "C" int nrmc_rt_trace(nrmc_rt_t h, const nrmc_rt_input *in, const nrmc_rt
         ln.timed = false;
         cudaEvent_t e0 = ln.ev[3], e1 = ln.ev[4];
         if (stats) cudaEventRecord(e0, user);
-        int64_t chunk = std::min<int64_t>(N, (int64_t)1 << 24);     // bounds the queue / work-list scratch
+        int64_t chunk = std::min<int64_t>(N, h->chunk_pairs > 0 ? h->chunk_pairs : (int64_t)1 << 24);     // bounds the queue / work-list scratch
         if (in->outer && chunk < N) chunk = std::max<int64_t>(in->n_antennas, (chunk / in->n_antennas) * in->n_antennas);
         float ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         int rc = NRMC_OK, n_chunks = 0;
@@ -1554,9 +1562,10 @@ extern "C" int nrmc_rt_trace(nrmc_rt_t h, const nrmc_rt_input *in, const nrmc_rt
     if (h->ice.n_refl == 0) per_pair += 2 * sizeof(RootItem) + sizeof(HumpItem);
     int64_t chunk = (int64_t)((size_t)1536 * 1024 * 1024 / per_pair);   // ~1.5 GB of device scratch per lane
     chunk = std::max<int64_t>(chunk, 1024);
+    if (h->chunk_pairs > 0) chunk = h->chunk_pairs;
     if (in->outer) chunk = std::max<int64_t>(na, (chunk / na) * na);
     chunk = std::min(chunk, N);
-    if (N > chunk && N < 2 * chunk) { chunk = (N + 1) / 2; if (in->outer) chunk = ((chunk + na - 1) / na) * na; }
+    if (h->chunk_pairs <= 0 && N > chunk && N < 2 * chunk) { chunk = (N + 1) / 2; if (in->outer) chunk = ((chunk + na - 1) / na) * na; }
     const double *d_ax = nullptr, *d_ay = nullptr, *d_az = nullptr;
     int64_t h2d = 0, d2h = 0;
     if (in->outer) {

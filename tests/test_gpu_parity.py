@@ -315,6 +315,55 @@ def test_device_resident_path_equals_host_path(make):
     assert dev.stats["n_solutions"] == int(host["n_sol"].sum())
 
 
+def test_results_do_not_depend_on_chunking(make):
+    """the device path (2^24-pair chunks) and the host pipeline (two streams, per-chunk scan for the compact layout) cut
+    the batch at arbitrary places: force tiny chunks and compare bit for bit with the single-chunk result"""
+    import torch
+    ff = np.fft.rfftfreq(128, 0.5)
+    V, A = cylinder(71, 1300, 6000, -2700), np.array([[0, 0, -150.], [1500, 0, -160.], [0, -1500, -145.]])
+    rt = make("southpole_2015", attenuation_model="SP1", n_frequencies_integration=10)
+    one = rt.trace_batch(V, A, outer=True, frequency=ff, max_detector_freq=0.6, attenuation="both")
+    one_c = rt.trace_batch(V, A, outer=True, frequency=ff, max_detector_freq=0.6, attenuation="both", compact=True)
+    dv = torch.tensor(np.ascontiguousarray(V.T), device="cuda:0")
+    da = torch.tensor(np.ascontiguousarray(A.T), device="cuda:0")
+    for chunk in (300, 999, 1024):
+        rt.set_chunk_pairs(chunk)
+        many = rt.trace_batch(V, A, outer=True, frequency=ff, max_detector_freq=0.6, attenuation="both")
+        assert many.stats["n_chunks"] >= 3
+        for k in one:
+            np.testing.assert_array_equal(many[k], one[k], err_msg=f"host {chunk} {k}")
+        many_c = rt.trace_batch(V, A, outer=True, frequency=ff, max_detector_freq=0.6, attenuation="both", compact=True)
+        for k in one_c:
+            np.testing.assert_array_equal(many_c[k], one_c[k], err_msg=f"compact {chunk} {k}")
+        dev = rt.trace_batch_device(dv, da, outer=True, frequency=ff, max_detector_freq=0.6, attenuation="both", sync_stats=True)
+        assert dev.stats["n_chunks"] >= 3
+        for k in one:
+            np.testing.assert_array_equal(dev[k].cpu().numpy(), one[k], err_msg=f"device {chunk} {k}")
+    rt.set_chunk_pairs(0)
+    # pair mode with bottom reflections (generic solver + generic attenuation kernel)
+    rtm = make("mooresbay_simple", attenuation_model="MB1", n_reflections=1, n_frequencies_integration=8)
+    Vm = cylinder(72, 700, 900, -550)
+    Am = np.repeat([[3, 3, -5.]], len(Vm), 0)
+    one = rtm.trace_batch(Vm, Am, frequency=ff)
+    rtm.set_chunk_pairs(128)
+    many = rtm.trace_batch(Vm, Am, frequency=ff)
+    for k in one:
+        np.testing.assert_array_equal(many[k], one[k], err_msg=f"mooresbay {k}")
+
+
+def test_sp1_series_fallback_path(make, oracle_mod):
+    """frequencies far below the band where the SP1 moment series converges (|ln f| large) push solutions to the generic
+    quadrature kernel: same tolerance against the tight oracle"""
+    ff = np.linspace(0, 0.02, 65)          # first bin 0.3 MHz: |ln f| = 8.1
+    V = cylinder(73, 400, 4000, -2700)
+    X2 = np.repeat([[0, 0, -150.]], len(V), 0)
+    rt = make("southpole_2015", attenuation_model="SP1", n_frequencies_integration=20)
+    res = rt.trace_batch(V, X2, frequency=ff)
+    ora = oracle_mod.Oracle("southpole_2015", attenuation_model="SP1", n_freq=20, tight=True).trace(V, X2, ff, None)
+    assert np.array_equal(res["n_sol"], ora["n_sol"])
+    assert_attenuation_parity(res["attenuation"], ora["attenuation"])
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # the step after the trace: propagation effects on spectra (SURVEY.md 8(f) N1)
 # ---------------------------------------------------------------------------------------------------------------
