@@ -591,3 +591,63 @@ def test_full_size_properties_attenuation_cfg5_slice(make, oracle_mod):
     sub = {k: v.cpu().numpy()[idx] for k, v in res.items()}
     assert_parity(sub, ora)
     assert_attenuation_parity(sub["attenuation_sparse"], ora["attenuation_sparse"])
+
+
+def test_full_size_properties_cfg3_gl1_dense(make, oracle_mod):
+    """cfg3 set-up (greenland_simple, 24-channel RNO-G station, GL1, 512-bin dense output) on 5e4 vertices = 1.2e6 pairs:
+    invariants at size + oracle parity (tight quadrature) on a random subsample"""
+    import torch
+    rt = make("greenland_simple", attenuation_model="GL1", n_frequencies_integration=25)
+    ff = np.fft.rfftfreq(1022, 0.2)
+    V = cylinder(3, 50_000, 4000, -2700)
+    dv = torch.tensor(np.ascontiguousarray(V.T), device="cuda:0")
+    da = torch.tensor(np.ascontiguousarray(RNOG.T), device="cuda:0")
+    res = rt.trace_batch_device(dv, da, outer=True, frequency=ff, max_detector_freq=1.2, attenuation="both")
+    torch.cuda.synchronize()
+    n_sol = res["n_sol"].cpu().numpy()
+    assert set(np.unique(n_sol)) <= {0, 2}
+    has = torch.tensor(n_sol == 2, device="cuda:0")
+    dense = res["attenuation"]
+    assert dense.shape == (1_200_000, 2, 512)
+    assert bool(torch.isnan(dense[~has]).all())
+    d = dense[has]
+    assert bool((d[..., 0] == 1).all())                                  # the 0 Hz bin keeps factor 1 (py:1077)
+    assert bool(((d >= 0) & (d <= 1)).all())                           # above ~2 GHz the GL1 length hits its 1 m floor: exp(-km) = 0.0
+    assert bool((d[..., 1:245].diff(dim=-1) <= 1e-15).all())              # GL1: attenuation grows with frequency (detector band)
+    idx = np.random.default_rng(3).choice(len(n_sol), 200, replace=False)
+    X1, X2 = V[idx // len(RNOG)], RNOG[idx % len(RNOG)]
+    ora = oracle_mod.Oracle("greenland_simple", attenuation_model="GL1", n_freq=25, tight=True).trace(X1, X2, ff, 1.2)
+    sub = {k: v[torch.tensor(idx, device="cuda:0")].cpu().numpy() for k, v in res.items()}
+    assert_parity(sub, ora)
+    assert_attenuation_parity(sub["attenuation"], ora["attenuation"])
+
+
+def test_full_size_properties_cfg4_bottom_reflections(make, oracle_mod):
+    """cfg4 set-up (mooresbay_simple, n_reflections = 1, 8 channels) on 1e5 vertices = 8e5 pairs, up to 6 solutions"""
+    import torch
+    rt = make("mooresbay_simple", n_reflections=1)
+    V = cylinder(4, 100_000, 1000, -500)
+    A = np.array([[-3, 0, -1.], [0, 3, -1.], [3, 0, -1.], [0, -3, -1.], [3, 3, -5.], [3, -3, -5.], [-3, -3, -5.], [-3, 3, -5.]])
+    dv = torch.tensor(np.ascontiguousarray(V.T), device="cuda:0")
+    da = torch.tensor(np.ascontiguousarray(A.T), device="cuda:0")
+    res = {k: v.cpu().numpy() for k, v in rt.trace_batch_device(dv, da, outer=True).items()}
+    n_sol, S = res["n_sol"], 6
+    assert set(np.unique(n_sol)) <= {0, 2, 4, 6} and (n_sol == 6).mean() > 0.1 and (n_sol >= 4).mean() > 0.9
+    filled = np.arange(S)[None, :] < n_sol[:, None]
+    refl, case, C0 = res["reflection"], res["reflection_case"], res["C0"]
+    assert np.isnan(C0[~filled]).all() and not np.isnan(C0[filled]).any()
+    # result order of the reference: mode (reflection, case) first, then C0 ascending (py:2122-2125, :1547)
+    key = refl.astype(np.int64) * 4 + case
+    key[~filled] = 99
+    assert (np.diff(key, axis=1) >= 0).all()
+    same_mode = filled[:, 1:] & filled[:, :-1] & (key[:, 1:] == key[:, :-1])
+    assert (C0[:, 1:][same_mode] > C0[:, :-1][same_mode]).all()
+    # a bottom-reflected path is longer than the straight line to the mirror image of the receiver below the reflector
+    X1, X2 = np.repeat(V, len(A), axis=0), np.tile(A, (len(V), 1))
+    rho = np.hypot(X1[:, 0] - X2[:, 0], X1[:, 1] - X2[:, 1])
+    image = np.sqrt(rho ** 2 + ((X1[:, 2] + 576.) + (X2[:, 2] + 576.)) ** 2)
+    bounced = filled & (refl == 1)
+    assert (res["path_length"][bounced] >= np.broadcast_to(image[:, None], bounced.shape)[bounced] * (1 - 1e-12)).all()
+    idx = np.random.default_rng(4).choice(len(n_sol), 300, replace=False)
+    ora = oracle_mod.Oracle("mooresbay_simple", n_reflections=1).trace(X1[idx], X2[idx])
+    assert_parity({k: v[idx] for k, v in res.items()}, ora)
