@@ -365,6 +365,44 @@ NRMC_HD int hump_search(const Curve &cv, double J1, double J2, double J3, Bracke
     return 0;
 }
 
+// Largest horizontal range any ray of the k = 0 mode reaches between the depths of g (g.rho is ignored).  Every direct
+// ray is shorter than the turned ray of the same beta (R_dir = I(z1) - I(z2) <= I(z1) + I(z2) = R_trn, I(z) = integral of
+// beta/s from z to the turning point), so the maximum lies on the pieces P2 / P3 or at their junctions.  R_max grows with the
+// depth of either end point (each I grows, and so does the admissible range beta <= n(z2)): a table of R_max on a depth
+// grid bounds it from above at the deeper grid corner -- used by K_classify to discard shadow-zone pairs without a search.
+NRMC_HD double range_max(const IceParams &ice, const PairGeom &g_in)
+{
+    PairGeom g = g_in;
+    g.rho = 0.0;
+    Curve cv;
+    cv.ice = &ice; cv.g = &g; cv.k = 0; cv.rcase = 1;
+    const bool has_band = g.s2max > 0.0;
+    double best = curve_g(cv, 3, 1.0);                       // beta = n_s, reflected
+    if (has_band) best = fmax(best, curve_g(cv, 2, 1.0));    // beta = n(z2): apex at the receiver
+    for (int p = has_band ? 2 : 3; p <= 3; ++p) {
+        double lo = fmin(piece_begin(g, p), piece_end(g, p)), hi = fmax(piece_begin(g, p), piece_end(g, p));
+        if (p == 3) lo = 1e-9;                                // the vertical ray has range 0
+        double dlo, dhi;
+        const double glo = curve_gd(cv, p, lo, dlo), ghi = curve_gd(cv, p, hi, dhi);
+        best = fmax(best, fmax(glo, ghi));
+        if (!(dlo > 0.0 && dhi < 0.0)) continue;              // no interior maximum on this piece
+        int side = 0;
+        for (int it = 0; it < 200; ++it) {
+            double x = (lo * dhi - hi * dlo) / (dhi - dlo);
+            if (!(x > lo && x < hi)) x = 0.5 * (lo + hi);
+            double dx;
+            const double gx = curve_gd(cv, p, x, dx);
+            best = fmax(best, gx);
+            if (dx > 0.0) { lo = x; dlo = dx; if (side == 1) dhi *= 0.5; side = 1; }
+            else if (dx < 0.0) { hi = x; dhi = dx; if (side == -1) dlo *= 0.5; side = -1; }
+            else break;
+            if (fmax(fabs(dlo), fabs(dhi)) * (hi - lo) < 1e-9 || (hi - lo) <= 4e-16 * (fabs(lo) + fabs(hi))) break;
+        }
+        best += fmax(fabs(dlo), fabs(dhi)) * (hi - lo);      // what the unconverged bracket could still add
+    }
+    return best;
+}
+
 NRMC_HD Root solve_bracket(const Curve &cv, const Bracket &b)
 {
     Root r;

@@ -135,6 +135,25 @@ K_solve(IceParams ice, KInput in, TraceOutputs out, SolRec *worklist, unsigned l
 struct RootItem { int64_t pair; double g1, g2, a, ga, b, gb; int32_t piece, valid; };   // 64 bytes
 struct HumpItem { int64_t pair; double g1, g2, J1, J2, J3; };                           // 48 bytes
 
+// Upper bounds of the maximal range on a depth grid (range_max): entry [i1, i2] belongs to the depths (-i1 dz, -i2 dz).
+struct RmaxTable { const double *t; int32_t n; double dz; };
+#define RMAX_DZ 8.0
+#define RMAX_N 401            // 0 ... 3200 m
+
+__global__ void K_rmax_table(IceParams ice, int n, double dz, double *table)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * n) return;
+    const int i1 = i / n, i2 = i - i1 * n;
+    if (i1 < i2) return;                                     // filled by the symmetric entry
+    PairGeom g;
+    make_pair_geom(ice, -i1 * dz, -i2 * dz, 0.0, g);
+    double r = range_max(ice, g);
+    if (!(r < 1e6)) r = INFINITY;      // deep, numerically homogeneous ice: a horizontal ray reaches any distance
+    table[i1 * n + i2] = r;
+    table[i2 * n + i1] = r;
+}
+
 __device__ __forceinline__ void push_brackets(bool have, int64_t pair, const PairGeom &g, const Bracket *br, int nb, RootItem *rootq,
                                               unsigned long long *root_count, unsigned lane)
 {
@@ -196,8 +215,8 @@ __device__ __forceinline__ void write_no_solution(const TraceOutputs &out, int64
 
 #define CLASSIFY_THREADS 256
 __global__ void __launch_bounds__(CLASSIFY_THREADS)
-K_classify(IceParams ice, KInput in, TraceOutputs out, AttFill af, RootItem *rootq, unsigned long long *root_count, HumpItem *humpq,
-           unsigned long long *hump_count)
+K_classify(IceParams ice, KInput in, TraceOutputs out, AttFill af, RmaxTable rmax, RootItem *rootq, unsigned long long *root_count,
+           HumpItem *humpq, unsigned long long *hump_count)
 {
     const int64_t p = (int64_t)blockIdx.x * CLASSIFY_THREADS + threadIdx.x;
     const unsigned lane = threadIdx.x & 31u;
@@ -218,6 +237,14 @@ K_classify(IceParams ice, KInput in, TraceOutputs out, AttFill af, RootItem *roo
             cv.ice = &ice; cv.g = &g; cv.k = 0; cv.rcase = 1;
             bool need_hump;
             nb = classify_mode(cv, J1, J2, J3, br, need_hump);
+            if (need_hump && rmax.t) {
+                // shadow zone: the range cannot exceed R_max at the deeper grid corner (monotone in both depths, range_max)
+                const int i1 = (int)ceil(-f.z1 / rmax.dz), i2 = (int)ceil(-f.z2 / rmax.dz);
+                if (i1 < rmax.n && i2 < rmax.n && i1 >= 0 && i2 >= 0) {
+                    const double bound = __ldg(rmax.t + i1 * rmax.n + i2);
+                    if (f.rho > bound * (1.0 + 1e-9) + 1e-6) need_hump = false;
+                }
+            }
             kind = nb > 0 ? 1 : (need_hump ? 2 : 0);
         }
         if (kind == 0) write_no_solution(out, p, status);
@@ -1092,6 +1119,8 @@ struct nrmc_rt_s {
     bool have_freq = false;
     Lane lanes[2];
     DevBuf d_count;       // work-list counters (one per lane)
+    DevBuf d_rmax;        // R_max table of the shadow-zone test
+    RmaxTable rmax;
     DevBuf d_ant;         // antenna table for outer-product host calls
 };
 
@@ -1157,6 +1186,26 @@ int nrmc_rt_create(const nrmc_rt_config *cfg, nrmc_rt_t *out)
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, K_roots<false>, ROOTS_THREADS, 0) != cudaSuccess) { delete h; return NRMC_ERR_CUDA; }
         h->grid_roots = std::max(1, nb) * h->n_sm;
     }
+    h->rmax.t = nullptr; h->rmax.n = 0; h->rmax.dz = RMAX_DZ;
+    if (n_refl == 0) {
+        // R_max on a depth grid: lets K_classify discard pairs far in the shadow zone without a maximum search
+        if (h->d_rmax.reserve((size_t)RMAX_N * RMAX_N * sizeof(double)) != cudaSuccess) { delete h; return NRMC_ERR_CUDA; }
+        K_rmax_table<<<(RMAX_N * RMAX_N + 127) / 128, 128>>>(ice, RMAX_N, RMAX_DZ, (double *)h->d_rmax.p);
+        // R_max is monotone in both depths: a running maximum over the shallower corners keeps the table an upper bound
+        // even where rounding noise of the search would dent it
+        std::vector<double> t((size_t)RMAX_N * RMAX_N);
+        if (cudaMemcpy(t.data(), h->d_rmax.p, t.size() * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess) { delete h; return NRMC_ERR_CUDA; }
+        for (int i1 = 0; i1 < RMAX_N; ++i1)
+            for (int i2 = 0; i2 < RMAX_N; ++i2) {
+                double v = t[(size_t)i1 * RMAX_N + i2];
+                if (!(v == v)) v = INFINITY;
+                if (i1 > 0) v = std::max(v, t[(size_t)(i1 - 1) * RMAX_N + i2]);
+                if (i2 > 0) v = std::max(v, t[(size_t)i1 * RMAX_N + i2 - 1]);
+                t[(size_t)i1 * RMAX_N + i2] = v;
+            }
+        if (cudaMemcpy(h->d_rmax.p, t.data(), t.size() * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) { delete h; return NRMC_ERR_CUDA; }
+        h->rmax.t = (const double *)h->d_rmax.p; h->rmax.n = RMAX_N;
+    }
     if (cfg->attenuation_model == NRMC_ATT_GL3) {
         const size_t bytes = (size_t)cfg->gl3_rows * 3 * sizeof(double);
         if (h->d_gl3.reserve(bytes) != cudaSuccess ||
@@ -1180,7 +1229,7 @@ void nrmc_rt_destroy(nrmc_rt_t h)
         h->lanes[l].fallback.release(); h->lanes[l].sparse_tmp.release(); h->lanes[l].rootq.release(); h->lanes[l].humpq.release();
         h->lanes[l].packed.release(); h->lanes[l].pack_sums.release(); h->lanes[l].pack_off.release();
     }
-    h->d_tables.release(); h->d_gl3.release(); h->d_sp1.release(); h->d_count.release(); h->d_ant.release();
+    h->d_tables.release(); h->d_gl3.release(); h->d_sp1.release(); h->d_count.release(); h->d_ant.release(); h->d_rmax.release();
     delete h;
 }
 
@@ -1354,7 +1403,7 @@ static int launch_chunk(nrmc_rt_s *h, Lane &ln, int lane_id, const KInput &kin, 
         const int64_t blocks = (kin.n_pairs + CLASSIFY_THREADS - 1) / CLASSIFY_THREADS;
         AttFill af;
         af.sparse = att_sparse; af.dense = att_dense; af.Fs = h->tb.Fs; af.F = h->tb.F;
-        K_classify<<<(unsigned)blocks, CLASSIFY_THREADS, 0, ln.stream>>>(h->ice, kin, to, af, (RootItem *)ln.rootq.p, d_roots,
+        K_classify<<<(unsigned)blocks, CLASSIFY_THREADS, 0, ln.stream>>>(h->ice, kin, to, af, h->rmax, (RootItem *)ln.rootq.p, d_roots,
                                                                          (HumpItem *)ln.humpq.p, d_humps);
         if (ln.timed) cudaEventRecord(ln.kev[0], ln.stream);
         K_hump<<<h->grid_hump, HUMP_THREADS, 0, ln.stream>>>(h->ice, kin, to, af, (const HumpItem *)ln.humpq.p, d_humps,

@@ -4,5 +4,6 @@ for lib in "$@"; do
   NRMC_RT_LIB=$PWD/$lib python bench.py --no-cpu-baseline --e2e-vertices 2000 --steps 3 2>/dev/null | python -c "
 import json,sys
 d=json.load(sys.stdin)
-print('$lib', 'pairs/s %.3e' % d['value'], 'ms/step %.1f' % d['ms_per_step'], 'att_ms %.1f' % d['roofline']['kernel_ms'], 'solve_ms %.1f' % d['roofline']['K_solve']['kernel_ms'])"
+r=d['roofline']; s=r['solver']
+print('$lib', 'pairs/s %.3e' % d['value'], 'ms/step %.1f' % d['ms_per_step'], 'att %.1f' % r['kernel_ms'], 'classify %.1f hump %.1f roots %.1f' % (s['K_classify']['kernel_ms'], s['K_hump']['kernel_ms'], s['K_roots']['kernel_ms']))"
 done
