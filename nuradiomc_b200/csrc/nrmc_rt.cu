@@ -187,8 +187,10 @@ __device__ __forceinline__ void warp_fill_nan_rows(bool mine, int64_t pair, cons
         const int l = __ffs(m) - 1;
         m &= m - 1;
         const int64_t pr = __shfl_sync(0xffffffffu, pair, l);
-        if (af.sparse) { double *d = af.sparse + pr * 2 * af.Fs; for (int j = lane; j < 2 * af.Fs; j += 32) d[j] = NAN; }
-        if (af.dense) { double *d = af.dense + pr * 2 * af.F; for (int j = lane; j < 2 * af.F; j += 32) d[j] = NAN; }
+        // both slots of the pair: 2 Fs doubles = Fs 16-byte stores (the pair's rows start on a 16-byte boundary), streaming
+        const double2 nan2 = make_double2(NAN, NAN);
+        if (af.sparse) { double2 *d = reinterpret_cast<double2 *>(af.sparse + pr * 2 * af.Fs); for (int j = lane; j < af.Fs; j += 32) __stcs(d + j, nan2); }
+        if (af.dense) { double2 *d = reinterpret_cast<double2 *>(af.dense + pr * 2 * af.F); for (int j = lane; j < af.F; j += 32) __stcs(d + j, nan2); }
     }
 }
 
@@ -200,8 +202,8 @@ __device__ __forceinline__ void warp_fill_nan_slot(bool mine, int64_t q, const A
         const int l = __ffs(m) - 1;
         m &= m - 1;
         const int64_t qq = __shfl_sync(0xffffffffu, q, l);
-        if (af.sparse) { double *d = af.sparse + qq * af.Fs; for (int j = lane; j < af.Fs; j += 32) d[j] = NAN; }
-        if (af.dense) { double *d = af.dense + qq * af.F; for (int j = lane; j < af.F; j += 32) d[j] = NAN; }
+        if (af.sparse) { double *d = af.sparse + qq * af.Fs; for (int j = lane; j < af.Fs; j += 32) __stcs(d + j, NAN); }
+        if (af.dense) { double *d = af.dense + qq * af.F; for (int j = lane; j < af.F; j += 32) __stcs(d + j, NAN); }
     }
 }
 
@@ -767,7 +769,7 @@ __device__ __forceinline__ void sp1_emit(const double (&M)[SP1_K], const double 
 #pragma unroll 4
     for (int r = 0; r < 32; ++r) {
         double *row = reinterpret_cast<double *>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(dst), r));
-        if (row != nullptr && (int)lane < len) row[j_begin + lane] = stage[r * SP1_ROW + lane];
+        if (row != nullptr && (int)lane < len) __stcs(row + j_begin + lane, stage[r * SP1_ROW + lane]);
     }
     __syncwarp();
 }
