@@ -142,8 +142,8 @@ def config_dict(n_vertices, e2e_vertices):
     return {"workload": "cfg5 (BASELINE.json configs[4]): %d vertices in r<6 km, z in [-2700,0] m x 100 channels (5x5 stations, "
                         "1.5 km pitch, 4 depths) = %d pairs; southpole_2015; SP1; 512-bin grid 0-2.5 GHz, max_detector_freq 1.2 GHz, "
                         "n_freq 25 -> 37 integration frequencies; sparse attenuation output" % (n_vertices, n_vertices * 100),
-            "pairs_per_step": n_vertices * 100, "outputs": "n_sol,status,type,reflection,reflection_case,C0,C1,path_length,"
-            "travel_time,launch_vector,receive_vector,reflection_angle,attenuation_sparse[37]",
+            "pairs_per_step": n_vertices * 100, "outputs": "n_sol,status,sol_offset per pair; per solution row (CSR): type,reflection,"
+            "reflection_case,C0,C1,path_length,travel_time,launch_vector,receive_vector,reflection_angle,attenuation_sparse[37]",
             "l2": "inputs+outputs per step (>= GBs) far exceed the 126 MB L2; no explicit flush",
             "e2e_vertices": e2e_vertices, "parallelism": "vertices sharded over ranks, no data-path collective"}
 
@@ -188,7 +188,7 @@ def main():
     rt = propagation.get_propagation_module("analytic")(medium.get_ice_model(ICE), attenuation_model=ATT_MODEL,
                                                           n_frequencies_integration=N_FREQ, device=local)
     dv, da = torch.tensor(Vr, device=dev), torch.tensor(A, device=dev)
-    kw = dict(outer=True, frequency=ff, max_detector_freq=FMAX, attenuation="sparse")
+    kw = dict(outer=True, frequency=ff, max_detector_freq=FMAX, attenuation="sparse", compact=True)
 
     def barrier():
         if world > 1:
@@ -266,7 +266,8 @@ def main():
     except Exception:
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
-    out_bytes = n_pairs_rank * bytes_per_pair_out
+    bytes_per_row = 3 + 4 * 8 + 2 * 24 + 8 + 37 * 8                  # type/reflection/case, C0/C1/path/time, vectors, angle, 37 factors
+    out_bytes = n_pairs_rank * (4 + 4 + 8) + n_sol_launch * bytes_per_row     # n_sol, status, sol_offset per pair + the rows
     mk = meas["ms_kernel"]
 
     def kernel_entry(name, ms, units, alg_flops_per_unit, unit_name):
@@ -312,7 +313,7 @@ def main():
                 "solver": solver,
                 "hbm": {"achieved": out_bytes / (meas["ms_total"] * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                         "frac": out_bytes / (meas["ms_total"] * 1e-3) / 1e9 / hbm_peak,
-                        "algorithmic_bytes_per_pair": bytes_per_pair_out}}
+                        "algorithmic_bytes_per_pair": out_bytes / n_pairs_rank}}
     line = {
         "metric": "ray-trace pairs/s (vertex x antenna pairs, with attenuation)", "value": value, "unit": "pairs/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,

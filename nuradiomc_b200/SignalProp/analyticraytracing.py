@@ -121,6 +121,10 @@ class BatchResult(dict):
     _keep = None
     _full = None
 
+    def n_rows(self):
+        """number of per-solution rows of a compact result (synchronises a device-resident result)"""
+        return int(self["sol_offset"][-1])
+
     def rows(self, i):
         """index of the per-slot arrays for the solutions of pair i: (i, slice) padded, slice of rows compact"""
         if self.compact:
@@ -320,11 +324,14 @@ class ray_tracing(ray_tracing_base):
         return res
 
     def trace_batch_device(self, v, a, frequency=None, max_detector_freq=None, outer=False, outputs=None,
-                           attenuation="sparse", out=None, sync_stats=False):
+                           attenuation="sparse", out=None, sync_stats=False, compact=False, row_capacity=None):
         """
         Device-resident variant: `v` (3, Nv) and `a` (3, Na) are contiguous float64 CUDA torch tensors (SoA); the results
         are CUDA torch tensors, the kernels are enqueued on torch's current stream.  Used by bench.py for the
         HBM-resident number and by callers that keep the next stage on the GPU.
+        compact=True (media without bottom reflections): per-solution rows as in `trace_batch`; the per-slot tensors keep
+        their capacity (`row_capacity`, default N*S) and only the first `res["sol_offset"][N]` rows are defined -- reading
+        that number is the caller's synchronisation point (`res.n_rows()`).
         """
         import torch
         assert v.is_cuda and a.is_cuda and v.dtype == torch.float64 and a.dtype == torch.float64
@@ -345,12 +352,21 @@ class ray_tracing(ray_tracing_base):
         res = out if out is not None else BatchResult()
         o = _lib.Output()
         tdt = {np.int32: torch.int32, np.int8: torch.int8, np.float64: torch.float64}
+        rows = N * S if row_capacity is None else int(row_capacity)
+        if compact and "n_sol" not in names:
+            names.insert(0, "n_sol")
         for name in names:
             dtype, trail = _OUT_SPECS[name]
-            shape = (N,) + trail(S, K1, Fs, F)
+            per_slot = len(trail(S, K1, Fs, F)) > 0
+            shape = ((rows,) + trail(S, K1, Fs, F)[1:]) if (compact and per_slot) else (N,) + trail(S, K1, Fs, F)
             if not (name in res and tuple(res[name].shape) == shape):
                 res[name] = torch.empty(shape, dtype=tdt[dtype], device=v.device)
             setattr(o, name, res[name].data_ptr())
+        if compact:
+            if not ("sol_offset" in res and tuple(res["sol_offset"].shape) == (N + 1,)):
+                res["sol_offset"] = torch.empty(N + 1, dtype=torch.int64, device=v.device)
+            o.compact, o.sol_offset, o.row_capacity = 1, res["sol_offset"].data_ptr(), rows
+        res.compact = bool(compact)
         inp = _lib.Input()
         inp.n_vertices, inp.vx, inp.vy, inp.vz = Nv, v[0].data_ptr(), v[1].data_ptr(), v[2].data_ptr()
         inp.n_antennas, inp.ax, inp.ay, inp.az = Na, a[0].data_ptr(), a[1].data_ptr(), a[2].data_ptr()

@@ -516,7 +516,15 @@ struct TraceOutputs {          // all [N,S] pair-major, S = 2 + 4 n_refl; any po
     double *launch, *receive;  // [N,S,3]
     double *reflection_angle;  // [N,S,n_refl+1], NaN = None
     double *viewing_angle;     // [N,S] angle between the shower's propagation direction and the launch vector (simulation.py:191)
+    const int64_t *row_offset; // compact layout: row of slot s of pair i = row_offset[i] + s (per-slot arrays are [rows,...]);
+                               // null: padded layout, row = i * S + s
+    int64_t row_limit;         // compact layout: rows the per-slot arrays can hold (solutions beyond it are dropped)
 };
+
+NRMC_HD int64_t row_of(const TraceOutputs &o, int64_t pair, int slot, int S)
+{
+    return o.row_offset ? o.row_offset[pair] + slot : pair * S + slot;
+}
 
 // Viewing-angle cut of the simulation loop (NuRadioMC/simulation/simulation.py:175-208): solutions whose launch direction
 // is further than delta_C_cut from the Cherenkov cone of the shower are dropped before any further work.
@@ -545,12 +553,13 @@ struct SolRec {                // everything the attenuation kernels need about 
     double z1, z2;             // depths of the deeper / shallower end point
     int32_t slot;
     uint8_t piece, k, rcase, pad;
-    double v;                  // curve parameter of the root (kept for diagnostics)
+    int64_t row;               // row of the solution in the per-slot output arrays (padded: pair * S + slot)
 };
 
-NRMC_HD void make_solrec(const IceParams &ice, const PairGeom &g, int64_t pair, int slot, int k, int rcase, const Root &root, SolRec &r)
+NRMC_HD void make_solrec(const IceParams &ice, const PairGeom &g, int64_t pair, int slot, int64_t row, int k, int rcase, const Root &root,
+                         SolRec &r)
 {
-    r.pair = pair; r.slot = slot; r.piece = (uint8_t)root.piece; r.k = (uint8_t)k; r.rcase = (uint8_t)rcase; r.pad = 0; r.v = root.v;
+    r.pair = pair; r.slot = slot; r.piece = (uint8_t)root.piece; r.k = (uint8_t)k; r.rcase = (uint8_t)rcase; r.pad = 0; r.row = row;
     r.beta = root.beta;
     // c = n_ice^2 - beta^2 = c0 + sigma^2 with sigma from the curve parameter (ray_state)
     const bool band = (root.piece == 1 || root.piece == 2);
@@ -662,7 +671,7 @@ NRMC_HD int trace_pair(const IceParams &ice, double ax, double ay, double az, do
                     keep = passes_cut(*sc, va, f.swap ? g.n2 : g.n1);
                     if (!keep) cut |= (1u << n);
                 } else if (o.viewing_angle) o.viewing_angle[i * S + n] = NAN;
-                if (recs && keep) make_solrec(ice, g, i, n, k, rcase, roots[j], recs[nrec++]);
+                if (recs && keep) make_solrec(ice, g, i, n, i * S + n, k, rcase, roots[j], recs[nrec++]);
                 ++n;
             }
         }

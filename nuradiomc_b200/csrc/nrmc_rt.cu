@@ -67,6 +67,7 @@ __device__ __forceinline__ void load_pair(const KInput &in, int64_t p, double &x
 #define CNT_ROOTS 4
 #define CNT_HUMPS 5
 #define CNT_STRIDE 16
+#define CNT_ROWBASE 32          // running row base of a compact device-resident call (not per lane, not reset per chunk)
 #define WL_BACK 1
 __device__ __forceinline__ SolRec worklist_get(const SolRec *wl, unsigned long long cap, unsigned long long n_front, unsigned long long w)
 {
@@ -211,6 +212,7 @@ __device__ __forceinline__ void write_no_solution(const TraceOutputs &out, int64
 {
     if (out.n_sol) out.n_sol[p] = 0;
     if (out.status) out.status[p] = status;
+    if (out.row_offset) return;          // compact layout: empty slots have no rows
     fill_empty_slot(out, 2 * p, 1);
     fill_empty_slot(out, 2 * p + 1, 1);
 }
@@ -252,7 +254,7 @@ K_classify(IceParams ice, KInput in, TraceOutputs out, AttFill af, RmaxTable rma
         if (kind == 0) write_no_solution(out, p, status);
         if (kind == 1) { if (out.n_sol) out.n_sol[p] = nb; if (out.status) out.status[p] = 0; }
     }
-    warp_fill_nan_rows(p < in.n_pairs && kind == 0, p, af, lane);
+    if (!out.row_offset) warp_fill_nan_rows(p < in.n_pairs && kind == 0, p, af, lane);
     push_brackets(kind == 1, p, g, br, nb, rootq, root_count, lane);
     const unsigned mh = __ballot_sync(0xffffffffu, kind == 2);
     if (mh) {
@@ -297,7 +299,7 @@ K_hump(IceParams ice, KInput in, TraceOutputs out, AttFill af, const HumpItem *h
             if (nb == 0) write_no_solution(out, pair, 0);
             else { if (out.n_sol) out.n_sol[pair] = nb; if (out.status) out.status[pair] = 0; }
         }
-        warp_fill_nan_rows(active && nb == 0, pair, af, lane);
+        if (!out.row_offset) warp_fill_nan_rows(active && nb == 0, pair, af, lane);
         push_brackets(active && nb > 0, pair, g, br, nb, rootq, root_count, lane);
     }
 }
@@ -352,6 +354,8 @@ K_roots(IceParams ice, KInput in, TraceOutputs out, AttFill af, const RootItem *
         const double beta_other = __shfl_xor_sync(0xffffffffu, valid ? root.beta : -1.0, 1);
         int slot = lane & 1;
         if (valid) slot = (root.beta > beta_other) ? 0 : ((root.beta < beta_other) ? 1 : (int)(lane & 1u));
+        const int64_t row = valid ? row_of(out, pair, slot, 2) : 0;
+        if (out.row_offset && row >= out.row_limit) valid = false;      // caller's compact arrays are full: drop (reported as NRMC_ERR_CAPACITY)
         // work-list slot of this solution (front: one quadrature panel, back: two), one atomic per warp and list end
         SolRec *rec_dst = nullptr;
         if (worklist) {
@@ -363,7 +367,7 @@ K_roots(IceParams ice, KInput in, TraceOutputs out, AttFill af, const RootItem *
             const unsigned below = (1u << lane) - 1u;
             if (valid && keep) rec_dst = two_panel ? worklist + (work_cap - 1ull - (bb + __popc(mb & below))) : worklist + (bf + __popc(mf & below));
         }
-        if (CUT) warp_fill_nan_slot(valid && !keep, 2 * pair + slot, af, lane);     // cut solutions: NaN attenuation rows
+        if (CUT) warp_fill_nan_slot(valid && !keep, row, af, lane);     // cut solutions: NaN attenuation rows
         if (active) {
             if (valid) {
                 double x1, y1, z1, x2, y2, z2;
@@ -374,14 +378,14 @@ K_roots(IceParams ice, KInput in, TraceOutputs out, AttFill af, const RootItem *
                 make_pair_geom_g(ice, f.z1, f.z2, fmax(f.rho, 1e-12), g1, g2, g);
                 if (rec_dst) {
                     SolRec rec;
-                    make_solrec(ice, g, pair, slot, 0, 1, root, rec);
+                    make_solrec(ice, g, pair, slot, row, 0, 1, root, rec);
                     *rec_dst = rec;
                 }
                 SolutionProps pr;
                 solution_props(ice, g, f.x1y, 0, 1, root, pr);
-                write_solution(out, 2 * pair + slot, 1, f, 0, 1, pr);
-                if (out.viewing_angle) out.viewing_angle[2 * pair + slot] = viewing;
-            } else {
+                write_solution(out, row, 1, f, 0, 1, pr);
+                if (out.viewing_angle) out.viewing_angle[row] = viewing;
+            } else if (!out.row_offset) {
                 fill_empty_slot(out, 2 * pair + 1, 1);    // single root (tangency at the surface): second slot stays empty
                 if (af.sparse) for (int j = 0; j < af.Fs; ++j) af.sparse[(2 * pair + 1) * af.Fs + j] = NAN;
                 if (af.dense) for (int j = 0; j < af.F; ++j) af.dense[(2 * pair + 1) * af.F + j] = NAN;
@@ -611,7 +615,7 @@ K_att(IceParams ice, KInput in, AttTables tb, const SolRec *worklist, const unsi
         const SolRec rec = worklist_get(worklist, work_cap, n_front, w);
         AttPlan plan;
         att_plan_rec(ice, rec, plan);
-        const int64_t slot_index = rec.pair * S + rec.slot;
+        const int64_t slot_index = rec.row;
         if (GL3) {
             gl3_path(ice, rec, tb.gl3, s_fa, tb.Fs, tb.Fs_pad, fac, lane);
             for (int j = lane; j < tb.Fs; j += 32) {
@@ -777,7 +781,7 @@ __device__ __forceinline__ void sp1_emit(const double (&M)[SP1_K], const double 
 template <bool HAVE_HI>
 __global__ void __launch_bounds__(SP1_THREADS)
 K_att_sp1(IceParams ice, KInput in, AttTables tb, Sp1Tables sp, const SolRec *worklist, const unsigned long long *work_count,
-          unsigned long long work_cap, double *att_sparse, SolRec *fallback, unsigned long long *fallback_count)
+          unsigned long long work_cap, int sparse_is_tmp, double *att_sparse, SolRec *fallback, unsigned long long *fallback_count)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t bar;
@@ -796,7 +800,8 @@ K_att_sp1(IceParams ice, KInput in, AttTables tb, Sp1Tables sp, const SolRec *wo
         for (int k = 0; k < SP1_K; ++k) { Mlo[k] = 0.0; Mhi[k] = 0.0; }
         double *dst = nullptr;
         if (w < n_work) {
-            const SolRec rec = worklist_get(worklist, work_cap, n_front, w);
+            SolRec rec = worklist_get(worklist, work_cap, n_front, w);
+            if (sparse_is_tmp) rec.row = (int64_t)(w < n_front ? w : work_cap - 1ull - (w - n_front));   // scratch rows: work-list position
             AttPlan plan;
             att_plan_rec(ice, rec, plan);
             bool ok = true;
@@ -814,7 +819,7 @@ K_att_sp1(IceParams ice, KInput in, AttTables tb, Sp1Tables sp, const SolRec *wo
                     sp1_node<HAVE_HI>(ice, plan, sp, mid + hx, ws, Mlo, Mhi, ok);
                 }
             }
-            if (ok) dst = att_sparse + (rec.pair * 2 + rec.slot) * (int64_t)tb.Fs;
+            if (ok) dst = att_sparse + rec.row * (int64_t)tb.Fs;
             else fallback[atomicAdd(fallback_count, 1ull)] = rec;          // out of the series' band: generic kernel
         }
         const int n_lo = HAVE_HI ? sp.n_lo : tb.Fs;
@@ -824,24 +829,24 @@ K_att_sp1(IceParams ice, KInput in, AttTables tb, Sp1Tables sp, const SolRec *wo
     }
 }
 
-// dense expansion for single-segment paths: np.interp of the sparse factors onto the output grid (py:1077-1078)
+// dense expansion for single-segment paths: np.interp of the sparse factors onto the output grid (py:1077-1078).
+// One warp per work-list record; sparse_is_tmp: the sparse factors sit in scratch rows indexed by the work-list position.
 __global__ void __launch_bounds__(256)
-K_att_expand(AttTables tb, const int32_t *n_sol, int64_t n_pairs, int S, const double *att_sparse, double *att_dense)
+K_att_expand(AttTables tb, const SolRec *worklist, const unsigned long long *work_count, unsigned long long work_cap, int sparse_is_tmp,
+             const double *att_sparse, double *att_dense)
 {
     const int lane = threadIdx.x & 31;
-    const int64_t total = n_pairs * S;
-    for (int64_t qi = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); qi < total;
-         qi += (int64_t)gridDim.x * (blockDim.x >> 5)) {
-        const int64_t p = qi / S;
-        if ((int)(qi - p * S) >= n_sol[p]) continue;
-        const double *src = att_sparse + qi * tb.Fs;
-        double *dst = att_dense + qi * tb.F;
-        const bool dropped = src[0] != src[0];      // solution removed by the viewing-angle cut: the whole row stays NaN
+    const unsigned long long n_front = work_count[0], n_work = n_front + work_count[WL_BACK];
+    for (unsigned long long w = (unsigned long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w < n_work;
+         w += (unsigned long long)gridDim.x * (blockDim.x >> 5)) {
+        const int64_t row = worklist_get(worklist, work_cap, n_front, w).row;
+        const double *src = att_sparse + (sparse_is_tmp ? (int64_t)(w < n_front ? w : work_cap - 1ull - (w - n_front)) : row) * tb.Fs;
+        double *dst = att_dense + row * tb.F;
         for (int b = lane; b < tb.F; b += 32) {
             const int i0 = __ldg(tb.ii + b);
             double val = 1.0;
             if (i0 >= 0) { const double f0 = src[i0], f1 = src[i0 + 1]; val = (f1 - f0) * __ldg(tb.it + b) + f0; }
-            dst[b] = dropped ? NAN : val;
+            dst[b] = val;
         }
     }
 }
@@ -889,7 +894,7 @@ K_pack_count(const int32_t *n_sol, int64_t n_pairs, unsigned long long *block_su
 
 // single block: exclusive scan of the block sums in place; total -> block_sums[n_blocks]
 __global__ void __launch_bounds__(1024)
-K_pack_scan(unsigned long long *block_sums, int n_blocks)
+K_pack_scan(unsigned long long *block_sums, int n_blocks, unsigned long long *base_dev)
 {
     __shared__ unsigned long long s_warp[32];
     __shared__ unsigned long long s_carry;
@@ -917,13 +922,21 @@ K_pack_scan(unsigned long long *block_sums, int n_blocks)
         if (threadIdx.x == 1023) s_carry = carry + s_warp[warp] + incl;
         __syncthreads();
     }
-    if (threadIdx.x == 0) block_sums[n_blocks] = s_carry;
+    if (threadIdx.x == 0) {
+        block_sums[n_blocks] = s_carry;                       // rows of this chunk
+        if (base_dev) {                                       // running row base of a multi-chunk device call
+            const unsigned long long old = *base_dev;
+            block_sums[n_blocks + 1] = old;
+            *base_dev = old + s_carry;
+        }
+    }
 }
 
 __global__ void __launch_bounds__(PACK_THREADS)
-K_pack(const int32_t *n_sol, int64_t n_pairs, int S, const unsigned long long *block_off, int64_t row_base, int64_t *sol_offset,
-       PackArrays pa)
+K_pack(const int32_t *n_sol, int64_t n_pairs, int S, const unsigned long long *block_off, int64_t row_base, int base_from_scan,
+       int64_t *sol_offset, PackArrays pa)
 {
+    if (base_from_scan) row_base = (int64_t)block_off[gridDim.x + 1];     // K_pack_scan left the device-side row base there
     __shared__ int s_off[PACK_PAIRS];
     __shared__ int s_n[PACK_PAIRS];
     __shared__ int s_part[PACK_THREADS / 32];
@@ -1180,7 +1193,7 @@ int nrmc_rt_create(const nrmc_rt_config *cfg, nrmc_rt_t *out)
         for (int e = 0; e < 6; ++e) cudaEventCreate(&h->lanes[l].ev[e]);
         for (int e = 0; e < 3; ++e) cudaEventCreate(&h->lanes[l].kev[e]);
     }
-    if (h->d_count.reserve(256) != cudaSuccess) { delete h; return NRMC_ERR_CUDA; }
+    if (h->d_count.reserve(512) != cudaSuccess) { delete h; return NRMC_ERR_CUDA; }
     {
         int nb = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, K_hump, HUMP_THREADS, 0) != cudaSuccess) { delete h; return NRMC_ERR_CUDA; }
@@ -1383,9 +1396,21 @@ int nrmc_rt_host_free(void *ptr) { return cudaFreeHost(ptr) == cudaSuccess ? NRM
 }  // extern "C"
 
 // enqueue the kernels for one chunk of pairs whose inputs/outputs are device resident
-static int launch_chunk(nrmc_rt_s *h, Lane &ln, int lane_id, const KInput &kin, const TraceOutputs &to, double *att_sparse,
-                        double *att_dense, int *n_launches)
+// compact layout inside the binned solver: rows are assigned by a scan of n_sol between K_hump and K_roots
+struct CompactCtx {
+    bool on = false;
+    int64_t *sol_offset = nullptr;          // [n_pairs of the chunk] device, receives GLOBAL rows
+    unsigned long long *base_dev = nullptr; // device-side running row base (device-resident calls), or
+    int64_t base_host = 0;                  // the row base known on the host (host calls)
+    int64_t row_limit = 0;                  // rows the caller's per-slot arrays hold
+};
+
+static int launch_chunk(nrmc_rt_s *h, Lane &ln, int lane_id, const KInput &kin, const TraceOutputs &to_in, double *att_sparse,
+                        double *att_dense, int *n_launches, const CompactCtx &cc = CompactCtx())
 {
+    TraceOutputs to = to_in;
+    to.row_offset = cc.on ? cc.sol_offset : nullptr;
+    to.row_limit = cc.row_limit;
     const bool want_att = (att_sparse || att_dense);
     unsigned long long *cnt = (unsigned long long *)h->d_count.p + CNT_STRIDE * lane_id;
     unsigned long long *d_count = cnt + CNT_WORK;
@@ -1410,6 +1435,17 @@ static int launch_chunk(nrmc_rt_s *h, Lane &ln, int lane_id, const KInput &kin, 
         if (ln.timed) cudaEventRecord(ln.kev[0], ln.stream);
         K_hump<<<h->grid_hump, HUMP_THREADS, 0, ln.stream>>>(h->ice, kin, to, af, (const HumpItem *)ln.humpq.p, d_humps,
                                                              (RootItem *)ln.rootq.p, d_roots);
+        if (cc.on) {
+            const int nblk = (int)((kin.n_pairs + PACK_PAIRS - 1) / PACK_PAIRS);
+            CK(ln.pack_sums.reserve((size_t)(nblk + 2) * sizeof(unsigned long long)));
+            unsigned long long *sums = (unsigned long long *)ln.pack_sums.p;
+            PackArrays none;
+            none.n = 0;
+            K_pack_count<<<nblk, PACK_THREADS, 0, ln.stream>>>(to.n_sol, kin.n_pairs, sums);
+            K_pack_scan<<<1, 1024, 0, ln.stream>>>(sums, nblk, cc.base_dev);
+            K_pack<<<nblk, PACK_THREADS, 0, ln.stream>>>(to.n_sol, kin.n_pairs, h->S, sums, cc.base_host, cc.base_dev ? 1 : 0, cc.sol_offset, none);
+            *n_launches += 3;
+        }
         if (ln.timed) cudaEventRecord(ln.kev[1], ln.stream);
         if (kin.sx)
             K_roots<true><<<h->grid_roots, ROOTS_THREADS, 0, ln.stream>>>(h->ice, kin, to, af, (const RootItem *)ln.rootq.p, d_roots, wl, d_count, work_cap);
@@ -1435,22 +1471,23 @@ static int launch_chunk(nrmc_rt_s *h, Lane &ln, int lane_id, const KInput &kin, 
             unsigned long long *d_fb = cnt + CNT_FALLBACK;
             CK(ln.fallback.reserve((size_t)kin.n_pairs * h->S * sizeof(SolRec)));
             double *sparse = att_sparse;
+            const int sparse_is_tmp = sparse ? 0 : 1;
             if (!sparse) {
                 CK(ln.sparse_tmp.reserve((size_t)kin.n_pairs * h->S * tb.Fs * sizeof(double)));
                 sparse = (double *)ln.sparse_tmp.p;
             }
             if (h->sp1.n_hi > 0)
-                K_att_sp1<true><<<h->grid_sp1, SP1_THREADS, h->smem_sp1, ln.stream>>>(h->ice, kin, tb, h->sp1, wl, d_count, work_cap, sparse,
-                                                                                      (SolRec *)ln.fallback.p, d_fb);
+                K_att_sp1<true><<<h->grid_sp1, SP1_THREADS, h->smem_sp1, ln.stream>>>(h->ice, kin, tb, h->sp1, wl, d_count, work_cap, sparse_is_tmp,
+                                                                                      sparse, (SolRec *)ln.fallback.p, d_fb);
             else
-                K_att_sp1<false><<<h->grid_sp1, SP1_THREADS, h->smem_sp1, ln.stream>>>(h->ice, kin, tb, h->sp1, wl, d_count, work_cap, sparse,
-                                                                                       (SolRec *)ln.fallback.p, d_fb);
+                K_att_sp1<false><<<h->grid_sp1, SP1_THREADS, h->smem_sp1, ln.stream>>>(h->ice, kin, tb, h->sp1, wl, d_count, work_cap, sparse_is_tmp,
+                                                                                       sparse, (SolRec *)ln.fallback.p, d_fb);
             if (ln.timed) cudaEventRecord(ln.kev[2], ln.stream);
             K_att<false><<<h->grid_att, ATT_THREADS, h->smem_att, ln.stream>>>(h->ice, kin, tb, (const SolRec *)ln.fallback.p, d_fb, work_cap,
                                                                                nseg_max, sparse, nullptr);
             *n_launches += 2;
             if (att_dense) {
-                K_att_expand<<<h->n_sm * 8, 256, 0, ln.stream>>>(tb, to.n_sol, kin.n_pairs, h->S, sparse, att_dense);
+                K_att_expand<<<h->n_sm * 8, 256, 0, ln.stream>>>(tb, wl, d_count, work_cap, sparse_is_tmp, sparse, att_dense);
                 ++*n_launches;
             }
         } else {
@@ -1519,7 +1556,10 @@ extern "C" int nrmc_rt_trace(nrmc_rt_t h, const nrmc_rt_input *in, const nrmc_rt
     if (want_att && h->ice.att_model == 0) { h->err = "attenuation requested but no attenuation model configured"; return NRMC_ERR_UNSUPPORTED; }
     if (want_att && !h->have_freq) { h->err = "attenuation requested before nrmc_rt_set_frequencies"; return NRMC_ERR_NO_FREQUENCIES; }
     const bool compact = out->compact != 0;
-    if (compact && in->memory != NRMC_MEMORY_HOST) { h->err = "the compact output layout is available for NRMC_MEMORY_HOST calls only"; return NRMC_ERR_UNSUPPORTED; }
+    if (compact && in->memory != NRMC_MEMORY_HOST && h->ice.n_refl > 0) {
+        h->err = "device-resident calls offer the compact output layout only without bottom reflections";
+        return NRMC_ERR_UNSUPPORTED;
+    }
     if (compact && (!out->sol_offset || out->row_capacity < 0)) { h->err = "compact output needs sol_offset[N+1] and row_capacity"; return NRMC_ERR_INVALID_ARGUMENT; }
     CK(cudaSetDevice(h->cfg.device));
     const int S = h->S, K1 = h->K1, Fs = h->tb.Fs, F = h->tb.F;
@@ -1540,8 +1580,11 @@ extern "C" int nrmc_rt_trace(nrmc_rt_t h, const nrmc_rt_input *in, const nrmc_rt
         if (in->outer && chunk < N) chunk = std::max<int64_t>(in->n_antennas, (chunk / in->n_antennas) * in->n_antennas);
         float ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         int rc = NRMC_OK, n_chunks = 0;
+        unsigned long long *row_base_dev = (unsigned long long *)h->d_count.p + CNT_ROWBASE;
+        if (compact) CK(cudaMemsetAsync(row_base_dev, 0, sizeof(unsigned long long), user));
         for (int64_t p0 = 0; p0 < N && rc == NRMC_OK; p0 += chunk, ++n_chunks) {
             const int64_t np = std::min(chunk, N - p0);
+            const int64_t ps = compact ? 0 : p0 * S;        // first row of the chunk in the per-slot arrays (compact: rows are global)
             KInput kin;
             kin.outer = in->outer; kin.n_antennas = in->n_antennas; kin.n_pairs = np;
             kin.sx = kin.sy = kin.sz = nullptr; kin.delta_C_cut = in->delta_C_cut;
@@ -1562,24 +1605,27 @@ extern "C" int nrmc_rt_trace(nrmc_rt_t h, const nrmc_rt_input *in, const nrmc_rt
             TraceOutputs to;
             to.n_sol = out->n_sol ? out->n_sol + p0 : nullptr;
             to.status = out->status ? out->status + p0 : nullptr;
-            to.type = out->solution_type ? out->solution_type + p0 * S : nullptr;
-            to.reflection = out->reflection ? out->reflection + p0 * S : nullptr;
-            to.reflection_case = out->reflection_case ? out->reflection_case + p0 * S : nullptr;
-            to.C0 = out->C0 ? out->C0 + p0 * S : nullptr;
-            to.C1 = out->C1 ? out->C1 + p0 * S : nullptr;
-            to.path_length = out->path_length ? out->path_length + p0 * S : nullptr;
-            to.travel_time = out->travel_time ? out->travel_time + p0 * S : nullptr;
-            to.launch = out->launch_vector ? out->launch_vector + p0 * S * 3 : nullptr;
-            to.receive = out->receive_vector ? out->receive_vector + p0 * S * 3 : nullptr;
-            to.reflection_angle = out->reflection_angle ? out->reflection_angle + p0 * S * K1 : nullptr;
-            to.viewing_angle = out->viewing_angle ? out->viewing_angle + p0 * S : nullptr;
-            if (want_att && !to.n_sol) {   // the fill kernel needs n_sol
+            to.type = out->solution_type ? out->solution_type + ps : nullptr;
+            to.reflection = out->reflection ? out->reflection + ps : nullptr;
+            to.reflection_case = out->reflection_case ? out->reflection_case + ps : nullptr;
+            to.C0 = out->C0 ? out->C0 + ps : nullptr;
+            to.C1 = out->C1 ? out->C1 + ps : nullptr;
+            to.path_length = out->path_length ? out->path_length + ps : nullptr;
+            to.travel_time = out->travel_time ? out->travel_time + ps : nullptr;
+            to.launch = out->launch_vector ? out->launch_vector + ps * 3 : nullptr;
+            to.receive = out->receive_vector ? out->receive_vector + ps * 3 : nullptr;
+            to.reflection_angle = out->reflection_angle ? out->reflection_angle + ps * K1 : nullptr;
+            to.viewing_angle = out->viewing_angle ? out->viewing_angle + ps : nullptr;
+            to.row_offset = nullptr;
+            if ((want_att || compact) && !to.n_sol) {   // the fill kernel / the row scan need n_sol
                 CK(ln.out.reserve((size_t)np * 4));
                 to.n_sol = (int32_t *)ln.out.p;
             }
             ln.timed = (stats != nullptr);
-            rc = launch_chunk(h, ln, 0, kin, to, out->attenuation_sparse ? out->attenuation_sparse + p0 * S * Fs : nullptr,
-                              out->attenuation ? out->attenuation + p0 * S * F : nullptr, &n_launches);
+            CompactCtx cc;
+            if (compact) { cc.on = true; cc.sol_offset = out->sol_offset + p0; cc.base_dev = row_base_dev; cc.row_limit = out->row_capacity; }
+            rc = launch_chunk(h, ln, 0, kin, to, out->attenuation_sparse ? out->attenuation_sparse + ps * Fs : nullptr,
+                              out->attenuation ? out->attenuation + ps * F : nullptr, &n_launches, cc);
             if (rc == NRMC_OK && stats) {
                 accumulate_lane_times(ln, ms);
                 if (want_att) {
@@ -1589,12 +1635,20 @@ extern "C" int nrmc_rt_trace(nrmc_rt_t h, const nrmc_rt_input *in, const nrmc_rt
                 }
             }
         }
+        if (compact && rc == NRMC_OK)      // sol_offset[N] = number of rows
+            CK(cudaMemcpyAsync(out->sol_offset + N, row_base_dev, sizeof(int64_t), cudaMemcpyDeviceToDevice, user));
         if (stats && rc == NRMC_OK) {
             cudaEventRecord(e1, user);
             CK(cudaEventSynchronize(e1));
             cudaEventElapsedTime(&stats->ms_total, e0, e1);
             store_times(stats, ms);
             stats->n_pairs = N; stats->n_launches = n_launches; stats->n_chunks = n_chunks;
+            if (compact) {
+                unsigned long long rows = 0;
+                cudaMemcpy(&rows, row_base_dev, sizeof(rows), cudaMemcpyDeviceToHost);
+                if ((int64_t)rows > out->row_capacity) { h->err = "compact output: row_capacity exceeded"; rc = NRMC_ERR_CAPACITY; }
+                if (!want_att) stats->n_solutions = (int64_t)rows;
+            }
         }
         ln.stream = saved;
         ln.timed = false;
@@ -1608,7 +1662,8 @@ extern "C" int nrmc_rt_trace(nrmc_rt_t h, const nrmc_rt_input *in, const nrmc_rt
     for (int i = 0; i < N_OUT; ++i) { want[i] = out_ptr(out, i) != nullptr; }
     const bool need_nsol_dev = want_att || want[0] || compact;
     for (int i = 0; i < N_OUT; ++i) if (want[i] || (i == 0 && need_nsol_dev)) per_pair += elem[i] + 16;
-    if (compact) per_pair = 2 * per_pair + 16;      // second (packed) copy of every array + offsets
+    const bool direct = compact && h->ice.n_refl == 0;   // the binned solver assigns compact rows itself; otherwise scan + gather
+    if (compact && !direct) per_pair = 2 * per_pair + 16;      // second (packed) copy of every array + offsets
     per_pair += h->S * sizeof(SolRec) + 48;
     if (h->ice.n_refl == 0) per_pair += 2 * sizeof(RootItem) + sizeof(HumpItem);
     int64_t chunk = (int64_t)((size_t)1536 * 1024 * 1024 / per_pair);   // ~1.5 GB of device scratch per lane
@@ -1678,16 +1733,54 @@ extern "C" int nrmc_rt_trace(nrmc_rt_t h, const nrmc_rt_input *in, const nrmc_rt
         CK(ln.out.reserve(total));
         unsigned char *dout = (unsigned char *)ln.out.p;
         auto dp = [&](int i) -> void * { return (want[i] || (i == 0 && need_nsol_dev)) ? (void *)(dout + off[i]) : nullptr; };
+        // per-slot arrays as the kernels address them: in direct compact mode rows are GLOBAL, the chunk's block holds the rows
+        // [row_base, row_base + rows), so the base pointers are shifted back by row_base rows
+        auto dps = [&](int i) -> void * {
+            unsigned char *q = (unsigned char *)dp(i);
+            return (q && direct) ? (void *)(q - (size_t)row_base * (elem[i] / S)) : (void *)q;
+        };
         TraceOutputs to;
-        to.n_sol = (int32_t *)dp(0); to.status = (int32_t *)dp(1); to.type = (int8_t *)dp(2); to.reflection = (int8_t *)dp(3);
-        to.reflection_case = (int8_t *)dp(4); to.C0 = (double *)dp(5); to.C1 = (double *)dp(6); to.path_length = (double *)dp(7);
-        to.travel_time = (double *)dp(8); to.launch = (double *)dp(9); to.receive = (double *)dp(10);
-        to.reflection_angle = (double *)dp(11);
-        to.viewing_angle = (double *)dp(14);
+        to.n_sol = (int32_t *)dp(0); to.status = (int32_t *)dp(1); to.type = (int8_t *)dps(2); to.reflection = (int8_t *)dps(3);
+        to.reflection_case = (int8_t *)dps(4); to.C0 = (double *)dps(5); to.C1 = (double *)dps(6); to.path_length = (double *)dps(7);
+        to.travel_time = (double *)dps(8); to.launch = (double *)dps(9); to.receive = (double *)dps(10);
+        to.reflection_angle = (double *)dps(11);
+        to.viewing_angle = (double *)dps(14);
+        to.row_offset = nullptr; to.row_limit = 0;
         ln.timed = (stats != nullptr);
-        int rc = launch_chunk(h, ln, lid, kin, to, (double *)dp(12), (double *)dp(13), &n_launches);
+        CompactCtx cc;
+        if (direct) {
+            CK(ln.pack_off.reserve((size_t)np * sizeof(int64_t)));
+            cc.on = true; cc.sol_offset = (int64_t *)ln.pack_off.p; cc.base_host = row_base;
+            cc.row_limit = std::min<int64_t>(out->row_capacity, row_base + np * S);
+        }
+        int rc = launch_chunk(h, ln, lid, kin, to, (double *)dps(12), (double *)dps(13), &n_launches, cc);
         if (rc != NRMC_OK) return rc;
-        if (!compact) {
+        if (direct) {
+            const int nblk = (int)((np + PACK_PAIRS - 1) / PACK_PAIRS);
+            unsigned long long rows = 0;
+            CK(cudaMemcpyAsync(&rows, (unsigned long long *)ln.pack_sums.p + nblk, sizeof(rows), cudaMemcpyDeviceToHost, ln.stream));
+            CK(cudaStreamSynchronize(ln.stream));      // the row count sizes the copies; the other lane's copies keep the link busy meanwhile
+            d2h += sizeof(rows);
+            if (row_base + (int64_t)rows > out->row_capacity) {
+                h->err = "compact output: row_capacity exceeded";
+                for (int l = 0; l < 2; ++l) cudaStreamSynchronize(h->lanes[l].stream);
+                return NRMC_ERR_CAPACITY;
+            }
+            for (int i = 0; i < 2; ++i) {
+                if (!want[i]) continue;
+                CK(cudaMemcpyAsync((unsigned char *)out_ptr(out, i) + (size_t)p0 * elem[i], dout + off[i], (size_t)np * elem[i], cudaMemcpyDeviceToHost, ln.stream));
+                d2h += (size_t)np * elem[i];
+            }
+            CK(cudaMemcpyAsync(out->sol_offset + p0, ln.pack_off.p, (size_t)np * sizeof(int64_t), cudaMemcpyDeviceToHost, ln.stream));
+            d2h += (size_t)np * sizeof(int64_t);
+            for (int i = 2; i < N_OUT; ++i) {
+                if (!want[i] || rows == 0) continue;
+                const size_t rb = elem[i] / S;
+                CK(cudaMemcpyAsync((unsigned char *)out_ptr(out, i) + (size_t)row_base * rb, dout + off[i], (size_t)rows * rb, cudaMemcpyDeviceToHost, ln.stream));
+                d2h += (size_t)rows * rb;
+            }
+            row_base += (int64_t)rows;
+        } else if (!compact) {
             for (int i = 0; i < N_OUT; ++i) {
                 if (!want[i]) continue;
                 const size_t bytes = (size_t)np * elem[i];
@@ -1698,7 +1791,7 @@ extern "C" int nrmc_rt_trace(nrmc_rt_t h, const nrmc_rt_input *in, const nrmc_rt
             // per-solution rows: scan n_sol, gather the existing rows into a second device block, copy only those
             const int nblk = (int)((np + PACK_PAIRS - 1) / PACK_PAIRS);
             CK(ln.packed.reserve(total));
-            CK(ln.pack_sums.reserve((size_t)(nblk + 1) * sizeof(unsigned long long)));
+            CK(ln.pack_sums.reserve((size_t)(nblk + 2) * sizeof(unsigned long long)));
             CK(ln.pack_off.reserve((size_t)np * sizeof(int64_t)));
             unsigned char *dpk = (unsigned char *)ln.packed.p;
             PackArrays pa;
@@ -1709,8 +1802,8 @@ extern "C" int nrmc_rt_trace(nrmc_rt_t h, const nrmc_rt_input *in, const nrmc_rt
             }
             unsigned long long *sums = (unsigned long long *)ln.pack_sums.p;
             K_pack_count<<<nblk, PACK_THREADS, 0, ln.stream>>>(to.n_sol, np, sums);
-            K_pack_scan<<<1, 1024, 0, ln.stream>>>(sums, nblk);
-            K_pack<<<nblk, PACK_THREADS, 0, ln.stream>>>(to.n_sol, np, S, sums, row_base, (int64_t *)ln.pack_off.p, pa);
+            K_pack_scan<<<1, 1024, 0, ln.stream>>>(sums, nblk, nullptr);
+            K_pack<<<nblk, PACK_THREADS, 0, ln.stream>>>(to.n_sol, np, S, sums, row_base, 0, (int64_t *)ln.pack_off.p, pa);
             n_launches += 3;
             CK(cudaGetLastError());
             unsigned long long rows = 0;
