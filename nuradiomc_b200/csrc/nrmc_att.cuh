@@ -47,6 +47,30 @@ __device__ __forceinline__ double exp_c(double x)
     const double p = expm1_poly(r) + 1.0;
     return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
 }
+// arguments known to lie in (-700, 700): no clamp
+__device__ __forceinline__ double exp_c_bounded(double x)
+{
+    int k;
+    const double r = exp_reduce(x, k);
+    const double p = expm1_poly(r) + 1.0;
+    return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+}
+// x <= 0 of any size (attenuation exponents): clamp from below only
+__device__ __forceinline__ double exp_c_neg(double x)
+{
+    int k;
+    const double r = exp_reduce(fmax(x, -700.0), k);
+    const double p = expm1_poly(r) + 1.0;
+    return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+}
+__device__ __forceinline__ double expm1_c_neg(double x)    // -700 < x <= 0
+{
+    int k;
+    const double r = exp_reduce(fmax(x, -700.0), k);
+    const double q = expm1_poly(r);
+    const double s = __hiloint2double((1023 + k) << 20, 0);
+    return fma(s, q, s - 1.0);
+}
 __device__ __forceinline__ double expm1_c(double x)        // accurate for x -> 0: k = 0 returns the polynomial itself
 {
     int k;

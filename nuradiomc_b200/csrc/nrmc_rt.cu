@@ -715,7 +715,7 @@ __device__ __forceinline__ void sp1_node(const IceParams &ice, const AttPlan &pl
 {
     const double uu = u * u;
     const double z = fmin(plan.zv - uu, 0.0);
-    const double em = -expm1_c(-uu * ice.inv_z0);
+    const double em = -expm1_c_neg(-uu * ice.inv_z0);
     const double n = plan.beta + plan.delta * em;
     const double wds = wscale * u * n * rsqrt(plan.delta * em * (n + plan.beta));
     const double a = fabs(z);
@@ -724,7 +724,7 @@ __device__ __forceinline__ void sp1_node(const IceParams &ice, const AttPlan &pl
     const double b1 = fma(t, fma(t, c_sp1[9], c_sp1[8]), c_sp1[7]);
     const double b2 = fma(t, fma(t, c_sp1[12], c_sp1[11]), c_sp1[10]);
     const double p1 = (b1 - b0) * c_sp1[13], p2 = (b2 - b1) * c_sp1[14];
-    const double c = wds * exp_c(b1);
+    const double c = wds * exp_c_neg(b1);              // b1 = ln(1/L at 1 GHz) <= -5.5 for any temperature
     const double dlo = p1 - sp.pref_lo;
     // series radius and the 1 m floor (1/L <= 1 <=> exponent <= 0 at the band edges)
     ok = ok && (fabs(dlo) * sp.wabs_lo <= 0.9) && (b1 + fmax(p1 * sp.wmin_lo, p1 * sp.wmax_lo) < 0.0);
@@ -766,7 +766,7 @@ __device__ __forceinline__ void sp1_emit(const double (&M)[SP1_K], const double 
             }
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) mine[jj[u] - j_begin] = exp_c(-acc[u] * s_E[jj[u]]);
+        for (int u = 0; u < 4; ++u) mine[jj[u] - j_begin] = exp_c_neg(-acc[u] * s_E[jj[u]]);
     }
     __syncwarp();
     const int len = j_end - j_begin;
