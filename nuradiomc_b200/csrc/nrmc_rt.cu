@@ -705,13 +705,36 @@ struct Sp1Tables {
     double wabs_lo, wabs_hi;  // max |ln f| per band (series radius)
     double wmin_lo, wmax_lo, wmin_hi, wmax_hi;
     int32_t n_lo, n_hi;
+    // validity of the moment form as six quadratics of the ice temperature T that must stay inside [lo, hi] along the path:
+    // slopes within the series radius (2), exponent below the 1 m floor at the band edges (4); tv = vertex of the quadratic
+    double qa[6], qb[6], qc[6], qlo[6], qhi[6], qtv[6];
 };
 #define SP1_THREADS 128
+
+// Is the moment form valid along the whole path?  Every condition (slope inside the series radius, exponent below the 1 m
+// floor of attenuation.py:252-255) is a quadratic in the ice temperature T, and T(depth) is monotone, so the extrema over the
+// path are at the shallowest / deepest point or at the quadratic's vertex: checked once per solution instead of per node.
+__device__ __forceinline__ bool sp1_path_ok(const Sp1Tables &sp, double z_top, double z_deep)
+{
+    const double at = fabs(z_top), ad = fabs(z_deep);
+    const double Tl = fma(fma(fma(c_sp1[0], at, c_sp1[1]), at, c_sp1[2]), at, c_sp1[3]);
+    const double Th = fma(fma(fma(c_sp1[0], ad, c_sp1[1]), ad, c_sp1[2]), ad, c_sp1[3]);
+    bool ok = Th >= Tl;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        const double tv = fmin(fmax(sp.qtv[i], Tl), Th);
+        const double v1 = fma(fma(sp.qa[i], Tl, sp.qb[i]), Tl, sp.qc[i]);
+        const double v2 = fma(fma(sp.qa[i], Th, sp.qb[i]), Th, sp.qc[i]);
+        const double v3 = fma(fma(sp.qa[i], tv, sp.qb[i]), tv, sp.qc[i]);
+        ok = ok && fmin(v1, fmin(v2, v3)) >= sp.qlo[i] && fmax(v1, fmax(v2, v3)) <= sp.qhi[i];
+    }
+    return ok;
+}
 
 // one quadrature node of the SP1 kernel: depth terms and the moment update
 template <bool HAVE_HI>
 __device__ __forceinline__ void sp1_node(const IceParams &ice, const AttPlan &plan, const Sp1Tables &sp, double u, double wscale,
-                                         double (&Mlo)[SP1_K], double (&Mhi)[SP1_K], bool &ok)
+                                         double (&Mlo)[SP1_K], double (&Mhi)[SP1_K])
 {
     const double uu = u * u;
     const double z = fmin(plan.zv - uu, 0.0);
@@ -726,14 +749,11 @@ __device__ __forceinline__ void sp1_node(const IceParams &ice, const AttPlan &pl
     const double p1 = (b1 - b0) * c_sp1[13], p2 = (b2 - b1) * c_sp1[14];
     const double c = wds * exp_c_neg(b1);              // b1 = ln(1/L at 1 GHz) <= -5.5 for any temperature
     const double dlo = p1 - sp.pref_lo;
-    // series radius and the 1 m floor (1/L <= 1 <=> exponent <= 0 at the band edges)
-    ok = ok && (fabs(dlo) * sp.wabs_lo <= 0.9) && (b1 + fmax(p1 * sp.wmin_lo, p1 * sp.wmax_lo) < 0.0);
     double tk = c;
 #pragma unroll
     for (int k = 0; k < SP1_K; ++k) { Mlo[k] += tk; tk *= dlo; }
     if (HAVE_HI) {
         const double dhi = p2 - sp.pref_hi;
-        ok = ok && (fabs(dhi) * sp.wabs_hi <= 0.9) && (b1 + fmax(p2 * sp.wmin_hi, p2 * sp.wmax_hi) < 0.0);
         tk = c;
 #pragma unroll
         for (int k = 0; k < SP1_K; ++k) { Mhi[k] += tk; tk *= dhi; }
@@ -804,10 +824,10 @@ K_att_sp1(IceParams ice, KInput in, AttTables tb, Sp1Tables sp, const SolRec *wo
             if (sparse_is_tmp) rec.row = (int64_t)(w < n_front ? w : work_cap - 1ull - (w - n_front));   // scratch rows: work-list position
             AttPlan plan;
             att_plan_rec(ice, rec, plan);
-            bool ok = true;
+            const bool ok = sp1_path_ok(sp, plan.turned ? fmin(rec.zv, 0.0) : rec.z2, rec.z1);
             // k = 0 paths: panel 0 = [u_T, u_2] twice (after the turning point), panel 1 = [u_2, u_1] once
 #pragma unroll 1
-            for (int panel = plan.turned ? 0 : 1; panel < 2; ++panel) {
+            for (int panel = plan.turned ? 0 : 1; panel < 2 && ok; ++panel) {
                 const double lo = panel == 0 ? plan.uT : plan.u2, hi = panel == 0 ? plan.u2 : plan.u1;
                 if (!(hi > lo)) continue;
                 const double half = 0.5 * (hi - lo), mid = 0.5 * (hi + lo);
@@ -815,8 +835,8 @@ K_att_sp1(IceParams ice, KInput in, AttTables tb, Sp1Tables sp, const SolRec *wo
 #pragma unroll 1
                 for (int i = 0; i < SP1_NQ / 2; ++i) {                     // the symmetric node pair mid -+ half x_i: two independent chains
                     const double hx = half * c_glx12h[i], ws = scale * c_glw12h[i];
-                    sp1_node<HAVE_HI>(ice, plan, sp, mid - hx, ws, Mlo, Mhi, ok);
-                    sp1_node<HAVE_HI>(ice, plan, sp, mid + hx, ws, Mlo, Mhi, ok);
+                    sp1_node<HAVE_HI>(ice, plan, sp, mid - hx, ws, Mlo, Mhi);
+                    sp1_node<HAVE_HI>(ice, plan, sp, mid + hx, ws, Mlo, Mhi);
                 }
             }
             if (ok) dst = att_sparse + rec.row * (int64_t)tb.Fs;
@@ -1345,6 +1365,29 @@ int nrmc_rt_set_frequencies(nrmc_rt_t h, const double *frequency, int32_t n, dou
             for (int k = 0; k < SP1_K; ++k) { wk[(size_t)j * SP1_K + k] = term; term *= w / (k + 1); }
             if (b) { ++t.n_hi; t.wabs_hi = std::max(t.wabs_hi, fabs(w)); t.wmin_hi = std::min(t.wmin_hi, w); t.wmax_hi = std::max(t.wmax_hi, w); }
             else { ++t.n_lo; t.wabs_lo = std::max(t.wabs_lo, fabs(w)); t.wmin_lo = std::min(t.wmin_lo, w); t.wmax_lo = std::max(t.wmax_lo, w); }
+        }
+        {
+            // SP1 coefficients (attenuation.py:176-178): b_i(T) = c0 + c1 T + c2 T^2
+            const double B0[3] = {-6.74890, 0.026709, -0.000884}, B1[3] = {-6.22121, -0.070927, -0.001773}, B2[3] = {-4.09468, -0.002213, -0.000332};
+            const double s1 = 1.0 / 9.210340371976182, s2 = 1.0 / 1.1505720275988207;
+            double P1[3], P2[3];
+            for (int m = 0; m < 3; ++m) { P1[m] = (B1[m] - B0[m]) * s1; P2[m] = (B2[m] - B1[m]) * s2; }
+            auto set = [&](int i, const double *q, double lo, double hi) {
+                t.qc[i] = q[0]; t.qb[i] = q[1]; t.qa[i] = q[2]; t.qlo[i] = lo; t.qhi[i] = hi;
+                t.qtv[i] = q[2] != 0.0 ? -q[1] / (2.0 * q[2]) : 0.0;
+            };
+            const double inf = INFINITY;
+            const double r_lo = t.n_lo ? 0.9 / std::max(t.wabs_lo, 1e-300) : inf, r_hi = t.n_hi ? 0.9 / std::max(t.wabs_hi, 1e-300) : inf;
+            set(0, P1, t.pref_lo - r_lo, t.pref_lo + r_lo);
+            set(1, P2, t.pref_hi - r_hi, t.pref_hi + r_hi);
+            const double wl[4] = {t.wmin_lo, t.wmax_lo, t.wmin_hi, t.wmax_hi};
+            for (int j = 0; j < 4; ++j) {
+                const double *P = j < 2 ? P1 : P2;
+                const bool used = j < 2 ? t.n_lo > 0 : t.n_hi > 0;
+                double q[3];
+                for (int m = 0; m < 3; ++m) q[m] = B1[m] + (used ? P[m] * wl[j] : 0.0);
+                set(2 + j, q, -inf, -1e-300);      // exponent strictly below 0: 1/L < 1 / m
+            }
         }
         bool banded_in_order = true;      // the kernel emits [0, n_lo) from the low-band moments and [n_lo, Fs) from the high-band ones
         for (int j = 0; j < Fs; ++j) if (band[j] != (j < t.n_lo ? 0 : 1)) banded_in_order = false;
