@@ -662,6 +662,94 @@ class ray_tracing(ray_tracing_base):
             self._config = config
 
 
+class ray_tracing_2D:
+    """
+    The 2-D interface the bulk consumers call directly (reference :372-1929; NuRadioReco's vertex reconstructors,
+    create_lookup_table.py:62-107, channelTimeOffsetCalculator.py:109-120): points are [y, z] in the propagation plane.
+    A thin facade over `ray_tracing.trace_batch`: every call is one pair on the GPU; for bulk work use
+    `find_solutions_batch`, which serves millions of pairs in one pass.
+
+    Like the reference's solver, rays propagate towards +y: a receiver to the left of the emitter has no solution.
+    """
+
+    def __init__(self, medium, attenuation_model=None, log_level=logging.NOTSET, n_frequencies_integration=25,
+                 use_optimized_start_values=False, overwrite_speedup=None, use_cpp=None, compile_numba=None, n_reflections=None,
+                 device=0):
+        self.medium = medium
+        self.attenuation_model = attenuation_model or "SP1"
+        self._n_reflections = 0 if (n_reflections is None or getattr(medium, "reflection", None) is None) else int(n_reflections)
+        self._tracer = {}
+        self._kw = dict(attenuation_model=self.attenuation_model, log_level=log_level,
+                        n_frequencies_integration=n_frequencies_integration, device=device)
+
+    def _rt(self, reflection):
+        n = max(self._n_reflections, int(reflection))
+        if n not in self._tracer:
+            self._tracer[n] = ray_tracing(self.medium, n_reflections=n, **self._kw)
+        return self._tracer[n]
+
+    @staticmethod
+    def _xyz(x):
+        x = np.asarray(x, dtype=np.float64)
+        return np.stack([x[..., 0], np.zeros_like(x[..., 0]), x[..., 1]], axis=-1)
+
+    def find_solutions_batch(self, x1, x2, reflection=0, reflection_case=1, outputs=None):
+        """all pairs x1[i] -> x2[i] ((N, 2) arrays [y, z]) in one device pass: the padded SoA result of `trace_batch`,
+        restricted to the requested (reflection, reflection_case) mode through the mask `res["mode"]`"""
+        x1, x2 = np.atleast_2d(np.asarray(x1, float)), np.atleast_2d(np.asarray(x2, float))
+        res = self._rt(reflection).trace_batch(self._xyz(x1), self._xyz(x2), outputs=outputs)
+        S = res["C0"].shape[1]
+        filled = np.arange(S)[None, :] < res["n_sol"][:, None]
+        forward = (np.broadcast_to(x2[:, 0], res["n_sol"].shape) >= np.broadcast_to(x1[:, 0], res["n_sol"].shape))[:, None]
+        if reflection == 0:
+            res["mode"] = filled & forward & (res["reflection"] == 0)
+        else:
+            res["mode"] = filled & forward & (res["reflection"] == reflection) & (res["reflection_case"] == reflection_case)
+        return res
+
+    def find_solutions(self, x1, x2, plot=False, reflection=0, reflection_case=1):
+        """list of {'type', 'C0', 'C1', 'reflection', 'reflection_case'} sorted by C0 (reference :1400-1547)"""
+        res = self.find_solutions_batch(np.asarray(x1, float)[None], np.asarray(x2, float)[None], reflection, reflection_case)
+        out = []
+        for s in np.nonzero(res["mode"][0])[0]:
+            out.append({'type': int(res["solution_type"][0, s]), 'C0': float(res["C0"][0, s]), 'C1': float(res["C1"][0, s]),
+                        'reflection': int(reflection), 'reflection_case': int(reflection_case)})
+        return sorted(out, key=lambda d: d['C0'])
+
+    def _lookup(self, x1, x2, C_0, key, reflection, reflection_case):
+        res = self.find_solutions_batch(np.asarray(x1, float)[None], np.asarray(x2, float)[None], reflection, reflection_case)
+        cand = np.nonzero(res["mode"][0])[0]
+        if len(cand) == 0:
+            return None
+        s = cand[np.argmin(np.abs(res["C0"][0, cand] - C_0))]
+        if abs(res["C0"][0, s] - C_0) > 1e-6 * abs(C_0):
+            return None          # not a solution of this pair of points
+        return res[key][0, s]
+
+    def get_travel_time_analytic(self, x1, x2, C_0, reflection=0, reflection_case=1):
+        v = self._lookup(x1, x2, C_0, "travel_time", reflection, reflection_case)
+        return None if v is None else float(v)
+
+    def get_path_length_analytic(self, x1, x2, C_0, reflection=0, reflection_case=1):
+        v = self._lookup(x1, x2, C_0, "path_length", reflection, reflection_case)
+        return None if v is None else float(v)
+
+    # the reference's numerical versions (:519-599) integrate the same quantities with quad; the closed forms agree to 1e-12
+    get_travel_time = get_travel_time_analytic
+    get_path_length = get_path_length_analytic
+
+    def get_launch_angle(self, x1, C_0, reflection=0, reflection_case=1, x2=None):
+        """launch zenith angle (:1195); needs the end point as well here because the ray is identified through the trace"""
+        if x2 is None:
+            raise TypeError("nuradiomc_b200.ray_tracing_2D.get_launch_angle needs x2 (the ray is looked up by its end points)")
+        v = self._lookup(x1, x2, C_0, "launch_vector", reflection, reflection_case)
+        return None if v is None else float(np.arctan2(v[0], v[2]))
+
+    def get_receive_angle(self, x1, x2, C_0, reflection=0, reflection_case=1):
+        v = self._lookup(x1, x2, C_0, "receive_vector", reflection, reflection_case)
+        return None if v is None else float(np.arctan2(-v[0], v[2]))
+
+
 def measure_fp64_peak(device=0, seconds=1.0):
     """measured FP64 FMA peak [TFLOP/s] of the device (roofline denominator), and the nominal SM clock [MHz]"""
     t, clk = C.c_double(), C.c_double()

@@ -673,3 +673,27 @@ def test_full_size_properties_cfg4_bottom_reflections(make, oracle_mod):
     idx = np.random.default_rng(4).choice(len(n_sol), 300, replace=False)
     ora = oracle_mod.Oracle("mooresbay_simple", n_reflections=1).trace(X1[idx], X2[idx])
     assert_parity({k: v[idx] for k, v in res.items()}, ora)
+
+
+def test_ray_tracing_2D_facade(make, oracle_mod):
+    """the 2-D interface of the bulk consumers (create_lookup_table.py:92-100): find_solutions / get_travel_time on [y, z] points"""
+    from nuradiomc_b200.SignalProp.analyticraytracing import ray_tracing_2D
+    from nuradiomc_b200.utilities import medium
+    r2 = ray_tracing_2D(medium.get_ice_model("greenland_simple"))
+    x1, x2 = [-500., -1000.], [0., -100.]
+    sol = r2.find_solutions(x1, x2)
+    ora = oracle_mod.Oracle("greenland_simple").trace(np.array([[-500., 0, -1000.]]), np.array([[0, 0, -100.]]))
+    assert [s['type'] for s in sol] == list(ora["type"][0, :2]) and len(sol) == 2
+    np.testing.assert_allclose([s['C0'] for s in sol], ora["C0"][0, :2], rtol=1e-6)
+    # values of the reference's own 2-D class for this pair (run in the build container): 6108.0149791931 / 7037.4611398640 ns
+    np.testing.assert_allclose([r2.get_travel_time(x1, x2, s['C0']) for s in sol], [6108.0149791931035, 7037.461139863954], rtol=1e-9)
+    np.testing.assert_allclose(r2.get_path_length(x1, x2, sol[0]['C0']), ora["path_length"][0, 0], rtol=1e-6)
+    assert r2.find_solutions([500., -1000.], [0., -100.]) == []          # receiver to the left: none, as the reference
+    assert r2.get_travel_time(x1, x2, 7.7) is None
+    rb = ray_tracing_2D(medium.get_ice_model("mooresbay_simple"), n_reflections=1)
+    got = rb.find_solutions([0., -300.], [200., -5.], reflection=1, reflection_case=2)
+    om = oracle_mod.Oracle("mooresbay_simple", n_reflections=1).trace(np.array([[0., 0, -300.]]), np.array([[200., 0, -5.]]))
+    exp = [c for c, k, cs in zip(om["C0"][0], om["reflection"][0], om["reflection_case"][0]) if k == 1 and cs == 2]
+    np.testing.assert_allclose([s['C0'] for s in got], exp, rtol=1e-6)
+    batch = r2.find_solutions_batch(np.array([[-500., -1000.], [-50., -2000.]]), np.array([[0., -100.], [0., -100.]]))
+    assert batch["mode"].shape == (2, 2) and batch["mode"][0].all()
