@@ -785,8 +785,24 @@ __device__ __forceinline__ void sp1_emit(const double (&M)[SP1_K], const double 
                 acc[u] = fma(M[k + 1], w2.y, acc[u]);
             }
         }
+        // four exponentials as interleaved chains (values first, the shared-memory stores after: a store between them would
+        // order the chains, the compiler cannot prove that the staging row does not alias the tables)
+        double x[4], r[4], pv[4];
+        int kk[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) mine[jj[u] - j_begin] = exp_c_neg(-acc[u] * s_E[jj[u]]);
+        for (int u = 0; u < 4; ++u) { x[u] = fmax(-acc[u] * s_E[jj[u]], -700.0); r[u] = exp_reduce(x[u], kk[u]); pv[u] = c_expc[0]; }
+#pragma unroll
+        for (int i = 1; i < 10; ++i) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) pv[u] = fma(pv[u], r[u], c_expc[i]);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const double p1 = fma(pv[u] * r[u], r[u], r[u]) + 1.0;
+            pv[u] = __hiloint2double(__double2hiint(p1) + (kk[u] << 20), __double2loint(p1));
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) mine[jj[u] - j_begin] = pv[u];
     }
     __syncwarp();
     const int len = j_end - j_begin;
