@@ -765,21 +765,24 @@ __device__ __forceinline__ void sp1_node(const IceParams &ice, const AttPlan &pl
 // staging rows in shared memory; the warp then writes row after row with consecutive lanes on consecutive frequencies.
 // (A lane storing its own row directly makes every 8-byte store a separate 32-byte sector write: measured 60 % of the
 // kernel's time.)
+#ifndef SP1_EW
+#define SP1_EW 4             // frequencies per lane and emit step (independent chains)
+#endif
 #define SP1_SEG 24
 #define SP1_ROW (SP1_SEG + 1)        // odd row pitch: conflict-free column writes
 __device__ __forceinline__ void sp1_emit(const double (&M)[SP1_K], const double *s_wk, const double *s_E, int j_begin, int j_end,
                                          double *stage, double *dst, unsigned lane)
 {
     double *mine = stage + lane * SP1_ROW;
-    for (int j0 = j_begin; j0 < j_end; j0 += 4) {
-        double acc[4];
-        int jj[4];
+    for (int j0 = j_begin; j0 < j_end; j0 += SP1_EW) {
+        double acc[SP1_EW];
+        int jj[SP1_EW];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) { jj[u] = min(j0 + u, j_end - 1); acc[u] = 0.0; }
+        for (int u = 0; u < SP1_EW; ++u) { jj[u] = min(j0 + u, j_end - 1); acc[u] = 0.0; }
 #pragma unroll
         for (int k = 0; k < SP1_K; k += 2) {
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < SP1_EW; ++u) {
                 const double2 w2 = *reinterpret_cast<const double2 *>(s_wk + jj[u] * SP1_K + k);
                 acc[u] = fma(M[k], w2.x, acc[u]);
                 acc[u] = fma(M[k + 1], w2.y, acc[u]);
@@ -787,22 +790,22 @@ __device__ __forceinline__ void sp1_emit(const double (&M)[SP1_K], const double 
         }
         // four exponentials as interleaved chains (values first, the shared-memory stores after: a store between them would
         // order the chains, the compiler cannot prove that the staging row does not alias the tables)
-        double x[4], r[4], pv[4];
-        int kk[4];
+        double x[SP1_EW], r[SP1_EW], pv[SP1_EW];
+        int kk[SP1_EW];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) { x[u] = fmax(-acc[u] * s_E[jj[u]], -700.0); r[u] = exp_reduce(x[u], kk[u]); pv[u] = c_expc[0]; }
+        for (int u = 0; u < SP1_EW; ++u) { x[u] = fmax(-acc[u] * s_E[jj[u]], -700.0); r[u] = exp_reduce(x[u], kk[u]); pv[u] = c_expc[0]; }
 #pragma unroll
         for (int i = 1; i < 10; ++i) {
 #pragma unroll
-            for (int u = 0; u < 4; ++u) pv[u] = fma(pv[u], r[u], c_expc[i]);
+            for (int u = 0; u < SP1_EW; ++u) pv[u] = fma(pv[u], r[u], c_expc[i]);
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < SP1_EW; ++u) {
             const double p1 = fma(pv[u] * r[u], r[u], r[u]) + 1.0;
             pv[u] = __hiloint2double(__double2hiint(p1) + (kk[u] << 20), __double2loint(p1));
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) mine[jj[u] - j_begin] = pv[u];
+        for (int u = 0; u < SP1_EW; ++u) mine[jj[u] - j_begin] = pv[u];
     }
     __syncwarp();
     const int len = j_end - j_begin;
