@@ -273,8 +273,9 @@ NRMC_HD double solve_piece(const Curve &cv, int p, double a, double ga, double b
 }
 
 // Look for an interior maximum of g on piece p (end values <= 0): bracket the sign change of dg/dt and close it
-// with Illinois steps on the derivative.  Returns true as soon as a point with g > 0 is found (xm, gm); false if the
-// maximum is at an end point or stays <= 0.  `interior` tells the caller whether this piece holds the curve's maximum.
+// with Illinois steps on the derivative (the Illinois weights only steer the next abscissa; the bracket keeps the TRUE
+// derivatives, which is what the termination test needs).  Returns true as soon as a point with g > 0 is found (xm, gm);
+// false if the maximum is at an end point or stays <= 0.  `interior`: this piece holds the curve's maximum.
 NRMC_HD bool maximise_piece(const Curve &cv, int p, double a, double b, double &xm, double &gm, bool &interior)
 {
     double lo = fmin(a, b), hi = fmax(a, b);
@@ -285,21 +286,21 @@ NRMC_HD bool maximise_piece(const Curve &cv, int p, double a, double b, double &
     interior = (dlo > 0.0) && (dhi < 0.0);
     xm = lo; gm = glo;
     if (!interior) return false;
+    double wlo = 1.0, whi = 1.0;
     int side = 0;
-    for (int it = 0; it < 60; ++it) {
-        double x = (lo * dhi - hi * dlo) / (dhi - dlo);
+    for (int it = 0; it < 100; ++it) {
+        const double ea = wlo * dlo, eb = whi * dhi;
+        double x = (lo * eb - hi * ea) / (eb - ea);
         if (!(x > lo && x < hi)) x = 0.5 * (lo + hi);
         double dx;
         const double gx = curve_gd(cv, p, x, dx);
         if (gx > gm || it == 0) { xm = x; gm = gx; }
         if (gx > 0.0) return true;
-        if (dx > 0.0) { lo = x; dlo = dx; if (side == 1) dhi *= 0.5; side = 1; }
-        else if (dx < 0.0) { hi = x; dhi = dx; if (side == -1) dlo *= 0.5; side = -1; }
+        if (dx > 0.0) { lo = x; dlo = dx; wlo = 1.0; if (side == 1) whi *= 0.5; side = 1; }
+        else if (dx < 0.0) { hi = x; dhi = dx; whi = 1.0; if (side == -1) wlo *= 0.5; side = -1; }
         else break;
-        // the remaining gain is bounded by |slope| x bracket once the bracket lies in the concave cap around the maximum
-        const double gain = fmax(fabs(dlo), fabs(dhi)) * (hi - lo);
-        if (gain < 1e-11 || (hi - lo) <= 4e-16 * (fabs(lo) + fabs(hi))) break;
-        if (it >= 2 && gm + 4.0 * gain < 0.0) break;     // deep in the shadow zone: cannot reach rho any more
+        // between lo and hi the derivative falls from dlo to dhi: g cannot rise above gm by more than slope x width
+        if (fmax(dlo, -dhi) * (hi - lo) < 1e-11 || (hi - lo) <= 4e-16 * (fabs(lo) + fabs(hi))) break;
     }
     return gm > 0.0;
 }
@@ -387,16 +388,18 @@ NRMC_HD double range_max(const IceParams &ice, const PairGeom &g_in)
         best = fmax(best, fmax(glo, ghi));
         if (!(dlo > 0.0 && dhi < 0.0)) continue;              // no interior maximum on this piece
         int side = 0;
+        double wlo = 1.0, whi = 1.0;                          // Illinois weights; dlo / dhi stay the true derivatives
         for (int it = 0; it < 200; ++it) {
-            double x = (lo * dhi - hi * dlo) / (dhi - dlo);
+            const double ea = wlo * dlo, eb = whi * dhi;
+            double x = (lo * eb - hi * ea) / (eb - ea);
             if (!(x > lo && x < hi)) x = 0.5 * (lo + hi);
             double dx;
             const double gx = curve_gd(cv, p, x, dx);
             best = fmax(best, gx);
-            if (dx > 0.0) { lo = x; dlo = dx; if (side == 1) dhi *= 0.5; side = 1; }
-            else if (dx < 0.0) { hi = x; dhi = dx; if (side == -1) dlo *= 0.5; side = -1; }
+            if (dx > 0.0) { lo = x; dlo = dx; wlo = 1.0; if (side == 1) whi *= 0.5; side = 1; }
+            else if (dx < 0.0) { hi = x; dhi = dx; whi = 1.0; if (side == -1) wlo *= 0.5; side = -1; }
             else break;
-            if (fmax(fabs(dlo), fabs(dhi)) * (hi - lo) < 1e-9 || (hi - lo) <= 4e-16 * (fabs(lo) + fabs(hi))) break;
+            if (fmax(dlo, -dhi) * (hi - lo) < 1e-9 || (hi - lo) <= 4e-16 * (fabs(lo) + fabs(hi))) break;
         }
         best += fmax(fabs(dlo), fabs(dhi)) * (hi - lo);      // what the unconverged bracket could still add
     }

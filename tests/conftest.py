@@ -71,6 +71,10 @@ def assert_parity(a, b, exact_count=True, n_ice=1.78):
     returns 2998.04 m for two points 3000 m apart at -1000 m -- so the tolerance on path length / travel time is
     1e-6 + 3e-9 / (C0 n_ice - 1); the kernel itself is verified there against 40-digit quadrature
     (test_near_horizontal_rays_against_mpmath) and against the straight-line bound.
+    A second one: an absolute floor of 2e-5 m (1.2e-4 ns).  The reference closes its roots with brentq(xtol=2e-12) on
+    log C0 (analyticraytracing.py:1504, :1526); for short near-caustic rays (two points metres apart at almost the same depth)
+    dR/dC0 reaches 4e5 m, so ITS ray misses the receiver by up to ~5e-6 m and its path is off by as much (checked against
+    40-digit quadrature: the kernel's root is the converged one, scratch/stress_parity.py).
     """
     same = a["n_sol"] == b["n_sol"]
     if exact_count:
@@ -86,8 +90,9 @@ def assert_parity(a, b, exact_count=True, n_ice=1.78):
     for k in ("path_length", "travel_time"):
         x, y = a[k][m], b[k][m]
         assert np.array_equal(np.isnan(x), np.isnan(y)), k
+        floor = 2e-5 if k == "path_length" else 2e-5 * n_ice / 0.299792458
         with np.errstate(invalid="ignore"):
-            bad = np.abs(x - y) > tol * np.abs(y)
+            bad = np.abs(x - y) > tol * np.abs(y) + floor
         assert not bad.any(), (k, np.argwhere(bad)[:5], x[bad][:5], y[bad][:5])
     for k in ("launch", "receive"):
         np.testing.assert_allclose(_get(a, k)[m], _get(b, k)[m], atol=1e-6, equal_nan=True, err_msg=k)

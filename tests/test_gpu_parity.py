@@ -697,3 +697,26 @@ def test_ray_tracing_2D_facade(make, oracle_mod):
     np.testing.assert_allclose([s['C0'] for s in got], exp, rtol=1e-6)
     batch = r2.find_solutions_batch(np.array([[-500., -1000.], [-50., -2000.]]), np.array([[0., -100.], [0., -100.]]))
     assert batch["mode"].shape == (2, 2) and batch["mode"][0].all()
+
+
+
+def test_wide_geometry_stress_and_far_field_hump(make, oracle_mod):
+    """log-uniform depths and distances (1 cm - 12 km) against the oracle, plus the far-field pairs whose range curve has a sharp
+    hump next to the beta = n(z2) junction (regression: an early-exit heuristic of the maximum search once lost them)"""
+    from test_kernel_math_cpu import FAR_FIELD_HUMP
+    rng = np.random.default_rng(123)
+    N = 60000
+    for ice in ("greenland_simple", "mooresbay_simple"):
+        rt = make(ice)
+        zr = -np.exp(rng.uniform(np.log(0.5), np.log(3000.), N))
+        ze = -np.exp(rng.uniform(np.log(0.5), np.log(3100.), N))
+        rho = np.exp(rng.uniform(np.log(0.01), np.log(12000.), N))
+        phi = rng.uniform(0, 2 * np.pi, N)
+        X1 = np.concatenate([np.stack([rho * np.cos(phi), rho * np.sin(phi), ze], 1), np.array(FAR_FIELD_HUMP[ice][0], float)])
+        X2 = np.concatenate([np.stack([np.zeros(N), np.zeros(N), zr], 1), np.array(FAR_FIELD_HUMP[ice][1], float)])
+        res = rt.trace_batch(X1, X2)
+        ora = oracle_mod.Oracle(ice).trace(X1, X2, n_threads=16)
+        assert (res["n_sol"][N:] == 2).all()
+        bad = np.nonzero(res["n_sol"] != ora["n_sol"])[0]
+        assert len(bad) <= 2 and (res["n_sol"][bad] > ora["n_sol"][bad]).all()     # only roots the oracle's scan window misses
+        assert_parity(res, ora, exact_count=False)

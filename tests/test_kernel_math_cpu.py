@@ -136,3 +136,46 @@ def test_near_horizontal_rays_against_mpmath(harness, oracle_mod):
     assert abs(float(ctime) / 0.299792458 - a["travel_time"][0, 0]) / (float(ctime) / 0.299792458) < 1e-8
     b = oracle_mod.Oracle(ice).trace(X1, X2)
     assert abs(b["path_length"][0, 0] - float(path)) / float(path) > 1e-7   # documents the reference's own loss of digits
+
+
+FAR_FIELD_HUMP = {   # pairs ~10 km apart at a few hundred metres depth: the range curve has a sharp hump next to the beta = n(z2)
+    # junction (all three junction values far below rho); an early-exit heuristic of the maximum search once lost them
+    "greenland_simple": ([[-9180.4207706, 1164.20989001, -262.20068663], [-8629.38431682, -7236.22619227, -514.73425153],
+                          [-6384.5831188, -8814.6125283, -604.84198019]],
+                         [[0, 0, -404.48022707], [0, 0, -241.39690073], [0, 0, -218.40253047]]),
+    "mooresbay_simple": ([[-5563.01357923, 8648.34810806, -318.91790404], [7929.90411936, 8613.46890284, -340.82411275]],
+                         [[0, 0, -303.14734287], [0, 0, -341.08483289]]),
+}
+
+
+@pytest.mark.parametrize("ice", sorted(FAR_FIELD_HUMP))
+def test_far_field_sharp_hump_regression(harness, oracle_mod, ice):
+    X1, X2 = (np.array(a, float) for a in FAR_FIELD_HUMP[ice])
+    out = harness(ice, 0, X1, X2)
+    ora = oracle_mod.Oracle(ice).trace(X1, X2)
+    assert list(out["n_sol"]) == [2] * len(X1) == list(ora["n_sol"])
+    _assert_parity(out, ora)
+
+
+def test_wide_geometry_stress_counts(harness, oracle_mod):
+    """log-uniform depths (0.5 m - 3 km) and distances (1 cm - 15 km): solution counts must equal the oracle's; where they do
+    not, the oracle's roots must be a subset of ours (its scan window in log C0 misses rays within 1e-10 of horizontal in
+    numerically homogeneous deep ice -- SURVEY.md 8(c) protocol: 'oracle missed a root')"""
+    rng = np.random.default_rng(11)
+    N = 40000
+    for ice in ("southpole_2015", "greenland_simple"):
+        zr = -np.exp(rng.uniform(np.log(0.5), np.log(3000.), N))
+        ze = -np.exp(rng.uniform(np.log(0.5), np.log(3100.), N))
+        rho = np.exp(rng.uniform(np.log(0.01), np.log(15000.), N))
+        phi = rng.uniform(0, 2 * np.pi, N)
+        X1 = np.stack([rho * np.cos(phi), rho * np.sin(phi), ze], 1)
+        X2 = np.stack([np.zeros(N), np.zeros(N), zr], 1)
+        out = harness(ice, 0, X1, X2)
+        ora = oracle_mod.Oracle(ice).trace(X1, X2, n_threads=8)
+        bad = np.nonzero(out["n_sol"] != ora["n_sol"])[0]
+        assert len(bad) <= 2
+        for i in bad:
+            assert out["n_sol"][i] > ora["n_sol"][i]
+            for c in ora["C0"][i][:ora["n_sol"][i]]:
+                assert np.nanmin(np.abs(out["C0"][i] - c)) < 1e-6 * c
+        _assert_parity(out, ora, exact_count=False)
