@@ -89,6 +89,12 @@ __device__ __forceinline__ double expm1_c(double x)        // accurate for x -> 
 #endif
 
 #define NRMC_NQ 16            // Gauss-Legendre points per half-warp slot
+#ifndef NRMC_GL1_SPP
+#define NRMC_GL1_SPP 32       // sub-panels per panel for the rational GL1 model where a frequency comes within 60 m of the pole of
+                              // 1/(A(z) - s_f) or crosses the 1 m floor along the path; worst dense-bin deviation on wide random
+                              // geometry (scratch/stress_att.py): 8 -> 1.2e-4, 16 -> 1.0e-4, 32 -> 5e-5; cost is linear in it
+#define NRMC_GL1_SPP_EASY 4   // everywhere else the integrand is smooth (2 already give 4e-6)
+#endif
 #define NRMC_MAX_SEG (NRMC_MAX_REFLECTIONS + 1)
 
 struct AttPlan {                          // all scalars: nothing here is indexed dynamically (no local memory)
@@ -150,11 +156,12 @@ NRMC_HD void att_plan_core(const IceParams &ice, double z1, double z2, int piece
         }
     }
     // every active panel is cut into `spp` equal sub-panels of 16 nodes: 1 for the entire-function models (SP1, GL2,
-    // MB1: <= 2e-7 measured), 8 for the rational GL1 (1/max(A(z) - s_f, 1) has poles close to the path and kinks at
-    // the 1 m / 100 m floors: on bins above 1e-3 two sub-panels already leave 4e-6, but the absolute error of the
-    // strongly attenuated bins only falls to 1e-7 with 4 and 9e-9 with 8).  A path with a single panel gets twice as
-    // many so that no half-warp idles.
-    p.spp = (ice.att_model == 2 || ice.att_model == 5) ? 8 : 1;
+    // MB1: <= 2e-7 measured), 32 for the rational GL1: 1/max(A(z) - s_f, 1) has a pole next to the path and a kink at
+    // the 1 m floor once f approaches 75 MHz + A(z)/0.55 m (0.8-2 GHz, beyond the model's range).  Bins above 1e-3 are
+    // good to 4e-6 with two sub-panels already; what needs resolution are the strongly attenuated bins (factor 1e-6) next to
+    // them, because np.interp mixes them into dense bins that are still above 1e-3.  A path with a single panel gets twice
+    // as many so that no half-warp idles.
+    p.spp = (ice.att_model == 2) ? NRMC_GL1_SPP_EASY : 1;      // GL1: raised to NRMC_GL1_SPP by the kernel where a frequency needs it
     if (p.na == 1) p.spp *= 2;
     p.n_slots = p.na * p.spp;
 }

@@ -583,6 +583,9 @@ __device__ __forceinline__ void gl3_path(const IceParams &ice, const SolRec &rec
     }
 }
 
+// deepest point of the path of a work-list record: the emitter side end point, or the reflective layer for bottom-reflected paths
+__device__ __forceinline__ double k_deepest(const IceParams &ice, const SolRec &rec) { return rec.k > 0 ? ice.zr : rec.z1; }
+
 // Generic attenuation kernel (all models, any number of bottom reflections): one warp per solution.
 // dynamic shared memory (doubles): fa[Fs_pad] fb[Fs_pad] it[F_pad] | ii[F_pad] (int32) | per warp: H[3][Fs_pad] fac[nseg][Fs_pad]
 template <bool GL3>
@@ -615,6 +618,22 @@ K_att(IceParams ice, KInput in, AttTables tb, const SolRec *worklist, const unsi
         const SolRec rec = worklist_get(worklist, work_cap, n_front, w);
         AttPlan plan;
         att_plan_rec(ice, rec, plan);
+        if (ice.att_model == NRMC_ATT_GL1) {
+            // hard for a frequency: 1/max(A(z) - s_f, 1) comes close to its pole or crosses the 1 m floor somewhere on the path.
+            // A(z) (the 75 MHz length) falls with depth below ~1 km and is flat above: its extremes sit at the ends of the path
+            // or at the surface value; 1200 m bounds it from above everywhere.
+            AttNode a_deep, a_top;
+            const double z_lo = k_deepest(ice, rec), z_top = rec.piece >= 2 ? fmin(rec.zv, 0.0) : rec.z2;
+            att_node(NRMC_ATT_GL1, z_lo, tb.gl3, a_deep);
+            att_node(NRMC_ATT_GL1, z_top, tb.gl3, a_top);
+            const double a_min = fmin(a_deep.p0, a_top.p0), a_max = 1200.0;
+            bool hard = false;
+            for (int j = lane; j < tb.Fs; j += 32) hard = hard || (s_fa[j] > a_min - 60.0 && s_fa[j] < a_max - 1.0);
+            if (__any_sync(0xffffffffu, hard)) {
+                plan.spp = (plan.spp / NRMC_GL1_SPP_EASY) * NRMC_GL1_SPP;
+                plan.n_slots = plan.na * plan.spp;
+            }
+        }
         const int64_t slot_index = rec.row;
         if (GL3) {
             gl3_path(ice, rec, tb.gl3, s_fa, tb.Fs, tb.Fs_pad, fac, lane);
