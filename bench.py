@@ -32,7 +32,11 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's version banner / warnings go to stderr: stdout carries ONE JSON line
+# stdout carries ONE JSON line.  NCCL prints its version banner to stdout at NCCL_DEBUG=VERSION and honours NCCL_DEBUG_FILE only
+# above that level: raise VERSION to WARN and send the log to stderr.
+if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
+    os.environ["NCCL_DEBUG"] = "WARN"
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 N_VERTICES = 1_000_000
 ICE, ATT_MODEL, N_FREQ, FMAX = "southpole_2015", "SP1", 25, 1.2
