@@ -618,21 +618,19 @@ K_att(IceParams ice, KInput in, AttTables tb, const SolRec *worklist, const unsi
         const SolRec rec = worklist_get(worklist, work_cap, n_front, w);
         AttPlan plan;
         att_plan_rec(ice, rec, plan);
+        // GL1: frequencies [j_hard, Fs) come close to the pole of 1/max(A(z) - s_f, 1) or cross its 1 m floor somewhere on the
+        // path and are integrated on NRMC_GL1_SPP sub-panels; the others on NRMC_GL1_SPP_EASY (s_f ascends with frequency).
+        // A(z) (the 75 MHz length) falls with depth below ~1 km and is flat above: its minimum sits at an end of the path.
+        int j_hard = tb.Fs;
         if (ice.att_model == NRMC_ATT_GL1) {
-            // hard for a frequency: 1/max(A(z) - s_f, 1) comes close to its pole or crosses the 1 m floor somewhere on the path.
-            // A(z) (the 75 MHz length) falls with depth below ~1 km and is flat above: its extremes sit at the ends of the path
-            // or at the surface value; 1200 m bounds it from above everywhere.
             AttNode a_deep, a_top;
             const double z_lo = k_deepest(ice, rec), z_top = rec.piece >= 2 ? fmin(rec.zv, 0.0) : rec.z2;
             att_node(NRMC_ATT_GL1, z_lo, tb.gl3, a_deep);
             att_node(NRMC_ATT_GL1, z_top, tb.gl3, a_top);
-            const double a_min = fmin(a_deep.p0, a_top.p0), a_max = 1200.0;
-            bool hard = false;
-            for (int j = lane; j < tb.Fs; j += 32) hard = hard || (s_fa[j] > a_min - 60.0 && s_fa[j] < a_max - 1.0);
-            if (__any_sync(0xffffffffu, hard)) {
-                plan.spp = (plan.spp / NRMC_GL1_SPP_EASY) * NRMC_GL1_SPP;
-                plan.n_slots = plan.na * plan.spp;
-            }
+            const double a_min = fmin(a_deep.p0, a_top.p0);
+            for (int j = lane; j < tb.Fs; j += 32) if (s_fa[j] > a_min - 60.0) j_hard = min(j_hard, j);
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) j_hard = min(j_hard, __shfl_xor_sync(0xffffffffu, j_hard, d));
         }
         const int64_t slot_index = rec.row;
         if (GL3) {
@@ -645,7 +643,15 @@ K_att(IceParams ice, KInput in, AttTables tb, const SolRec *worklist, const unsi
         } else {
         for (int j = lane; j < 3 * tb.Fs_pad; j += 32) H[j] = 0.0;
         __syncwarp();
-        // quadrature: each half-warp integrates one 16-node slot per pass; slot sums are added to their panel
+        // quadrature: each half-warp integrates one 16-node slot per pass; slot sums are added to their panel.
+        // Phase 0: all frequencies below j_hard on the plan's sub-panels; phase 1 (GL1 only): the hard ones on the fine ones.
+        for (int phase = 0; phase < 2; ++phase) {
+            const int j_begin = phase == 0 ? 0 : j_hard, j_end = phase == 0 ? j_hard : tb.Fs;
+            if (j_begin >= j_end) continue;
+            if (phase == 1) {
+                plan.spp = (plan.spp / NRMC_GL1_SPP_EASY) * NRMC_GL1_SPP;
+                plan.n_slots = plan.na * plan.spp;
+            }
         for (int pass = 0; pass * 2 < plan.n_slots; ++pass) {
             const int slot = pass * 2 + half;
             const bool live = slot < plan.n_slots;
@@ -660,7 +666,7 @@ K_att(IceParams ice, KInput in, AttTables tb, const SolRec *worklist, const unsi
             }
             const int panel_other = __shfl_xor_sync(0xffffffffu, live ? panel : -1, 16);
             const bool merge = (panel_other == panel);       // both half-warps work on the same panel
-            for (int j = 0; j < tb.Fs; ++j) {
+            for (int j = j_begin; j < j_end; ++j) {
                 double term = live ? wds * att_inv_length(ice.att_model, nd, s_fa[j], s_fb[j]) : 0.0;
                 term += __shfl_xor_sync(0xffffffffu, term, 8);
                 term += __shfl_xor_sync(0xffffffffu, term, 4);
@@ -671,6 +677,7 @@ K_att(IceParams ice, KInput in, AttTables tb, const SolRec *worklist, const unsi
                 else if (q == 0 && live) H[panel * tb.Fs_pad + j] += term;
             }
             __syncwarp();
+        }
         }
         // per segment: I_seg = sum_panel mult[seg][panel] * H[panel];  factor = exp(-I_seg)   (py:1075)
         for (int j = lane; j < tb.Fs; j += 32) {
