@@ -643,9 +643,50 @@ K_att(IceParams ice, KInput in, AttTables tb, const SolRec *worklist, const unsi
         } else {
         for (int j = lane; j < 3 * tb.Fs_pad; j += 32) H[j] = 0.0;
         __syncwarp();
+        // MB1 and GL2 are separable, L(z, f) = fa(f) p0(z) (attenuation.py:198-204, :229-244): away from the 1 m floor the
+        // exponent of every frequency is ONE depth integral over fa(f), G = int ds / p0; where fa p0 <= 1 on the whole path
+        // (GL2 above 1.58 GHz: negative length, floored) it is the path length S = int ds.  Only a frequency whose floor is
+        // crossed ON the path needs the per-(node, frequency) loop below.
+        bool need_loop = true;
+        if (ice.att_model == NRMC_ATT_MB1 || ice.att_model == NRMC_ATT_GL2) {
+            double Gp0 = 0, Gp1 = 0, Gp2 = 0, Sp0 = 0, Sp1 = 0, Sp2 = 0, pmin = INFINITY, pmax = -INFINITY;
+            for (int pass = 0; pass * 2 < plan.n_slots; ++pass) {
+                const int slot = pass * 2 + half;
+                const bool live = slot < plan.n_slots;
+                double lo = 0.0, hi = 0.0, z = 0.0, wds = 0.0, g = 0.0;
+                int panel = -1;
+                if (live) {
+                    AttNode nd;
+                    plan_slot(plan, slot, lo, hi, panel);
+                    att_node_geometry(ice, plan, lo, hi, xq, wq, z, wds);
+                    att_node(ice.att_model, z, tb.gl3, nd);
+                    g = wds / nd.p0;
+                    pmin = fmin(pmin, nd.p0); pmax = fmax(pmax, nd.p0);
+                }
+#pragma unroll
+                for (int d = 8; d > 0; d >>= 1) { g += __shfl_xor_sync(0xffffffffu, g, d); wds += __shfl_xor_sync(0xffffffffu, wds, d); }
+                const double g_o = __shfl_xor_sync(0xffffffffu, g, 16), w_o = __shfl_xor_sync(0xffffffffu, wds, 16);
+                const int panel_o = __shfl_xor_sync(0xffffffffu, panel, 16);
+                // every lane keeps the panel sums (its own half-warp's slot and the other one's)
+                if (panel == 0) { Gp0 += g; Sp0 += wds; } else if (panel == 1) { Gp1 += g; Sp1 += wds; } else if (panel == 2) { Gp2 += g; Sp2 += wds; }
+                if (panel_o == 0) { Gp0 += g_o; Sp0 += w_o; } else if (panel_o == 1) { Gp1 += g_o; Sp1 += w_o; } else if (panel_o == 2) { Gp2 += g_o; Sp2 += w_o; }
+            }
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) { pmin = fmin(pmin, __shfl_xor_sync(0xffffffffu, pmin, d)); pmax = fmax(pmax, __shfl_xor_sync(0xffffffffu, pmax, d)); }
+            bool mixed = false;
+            for (int j = lane; j < tb.Fs; j += 32) {
+                const double fa = s_fa[j];
+                if (fa * pmin >= 1.0 && fa * pmax >= 1.0) { const double inv = 1.0 / fa; H[j] = Gp0 * inv; H[tb.Fs_pad + j] = Gp1 * inv; H[2 * tb.Fs_pad + j] = Gp2 * inv; }
+                else if (fa * pmin <= 1.0 && fa * pmax <= 1.0) { H[j] = Sp0; H[tb.Fs_pad + j] = Sp1; H[2 * tb.Fs_pad + j] = Sp2; }
+                else mixed = true;
+            }
+            need_loop = __any_sync(0xffffffffu, mixed);
+            __syncwarp();
+            if (need_loop) { for (int j = lane; j < 3 * tb.Fs_pad; j += 32) H[j] = 0.0; __syncwarp(); }
+        }
         // quadrature: each half-warp integrates one 16-node slot per pass; slot sums are added to their panel.
         // Phase 0: all frequencies below j_hard on the plan's sub-panels; phase 1 (GL1 only): the hard ones on the fine ones.
-        for (int phase = 0; phase < 2; ++phase) {
+        for (int phase = 0; phase < 2 && need_loop; ++phase) {
             const int j_begin = phase == 0 ? 0 : j_hard, j_end = phase == 0 ? j_hard : tb.Fs;
             if (j_begin >= j_end) continue;
             if (phase == 1) {
