@@ -118,7 +118,7 @@ typedef struct {
     int32_t n_launches;        /* kernels launched by this call                                         */
     int32_t n_chunks;
     int64_t h2d_bytes, d2h_bytes;
-    float ms_kernel[6];        /* device time per kernel: [0] K_classify (or the generic K_solve), [1] K_hump, [2] K_roots,
+    float ms_kernel[6];        /* device time per kernel: [0] K_classify, [1] K_hump (+ row scan / slot offsets), [2] K_roots,
                                   [3] main attenuation kernel, [4] fallback / dense-expansion kernels, [5] reserved      */
 } nrmc_rt_stats;
 

@@ -1,12 +1,14 @@
 // nrmc_rt.cu -- sm_100a kernels and the C ABI (include/nrmc_rt.h) of the batched analytic ray tracer.
 //
-//   K_solve        one thread per (vertex, antenna) pair: 2-D frame, all (reflection, case) modes, bracketed FP64 root
-//                  finding on Snell's invariant, closed-form properties, SoA stores; warp-aggregated (ballot/shuffle)
-//                  compaction of the found solutions into a work list for K_att.
-//   K_att          one warp per solution: 2 x 16 Gauss-Legendre nodes per pass (half-warp per u-panel), per-frequency
-//                  constants staged in shared memory with a TMA bulk copy (cp.async.bulk + mbarrier), half-warp shuffle
-//                  reduction of the path integral, exp, np.interp-equivalent expansion to the output frequency grid.
-//   K_fp64_peak    independent DFMA chains: measures the FP64 roofline denominator.
+//   K_classify / K_hump / K_roots (+ _m variants for media with a reflective bottom)
+//                  binned solver: junction values of the range curve per (pair, mode) -> bracket / hump items in HBM queues
+//                  (warp-aggregated appends) -> maximum search -> safeguarded Newton per bracket, closed-form properties,
+//                  SoA stores, 64-byte solution records for the attenuation kernels.
+//   K_att_sp1      SP1: thread per solution, 12-node panels, frequency-independent moments, tables staged by TMA bulk copies
+//                  (cp.async.bulk + mbarrier), staged coalesced row stores.
+//   K_att          other models and multi-segment paths: warp per solution, half-warp per 16-node slot, shuffle reductions;
+//                  separable fast path for MB1 / GL2; GL3: the reference's 10 m discretisation cell for cell.
+//   K_apply_effects, K_pack_*, K_att_expand, K_rmax_table, K_att_length, K_fp64_peak: see the comments at each kernel.
 //
 // No tensor cores: nothing here is a contraction.  There is no CPU fallback: every entry point
 // fails with NRMC_ERR_NO_DEVICE / NRMC_ERR_CUDA if the device path is unavailable.
@@ -75,52 +77,6 @@ __device__ __forceinline__ SolRec worklist_get(const SolRec *wl, unsigned long l
 }
 
 #define N_OUT 15            // output arrays of nrmc_rt_output (out_ptr)
-#define SOLVE_THREADS 128
-#define MAX_S (2 + 4 * NRMC_MAX_REFLECTIONS)
-
-#ifndef SOLVE_MIN_BLOCKS
-#define SOLVE_MIN_BLOCKS 4
-#endif
-__global__ void __launch_bounds__(SOLVE_THREADS, SOLVE_MIN_BLOCKS)
-K_solve(IceParams ice, KInput in, TraceOutputs out, SolRec *worklist, unsigned long long *work_count, double *att_sparse,
-        double *att_dense, int Fs, int F)
-{
-    const int64_t p = (int64_t)blockIdx.x * SOLVE_THREADS + threadIdx.x;
-    const unsigned lane = threadIdx.x & 31u;
-    SolRec recs[MAX_S];
-    int n = 0;     // records for the attenuation kernel (solutions that pass the viewing-angle cut)
-    if (p < in.n_pairs) {
-        double x1, y1, z1, x2, y2, z2;
-        load_pair(in, p, x1, y1, z1, x2, y2, z2);
-        const ShowerCut sc = load_cut(in, p);
-        uint32_t cut_mask = 0;
-        trace_pair(ice, x1, y1, z1, x2, y2, z2, p, out, worklist ? recs : nullptr, &sc, &n, &cut_mask);
-        const int S = 2 + 4 * ice.n_refl;
-        for (int sl = 0; cut_mask >> sl; ++sl) {      // cut solutions get NaN attenuation rows
-            if (!((cut_mask >> sl) & 1u)) continue;
-            if (att_sparse) for (int j = 0; j < Fs; ++j) att_sparse[(p * S + sl) * Fs + j] = NAN;
-            if (att_dense) for (int j = 0; j < F; ++j) att_dense[(p * S + sl) * F + j] = NAN;
-        }
-    }
-    if (worklist) {
-        // warp-aggregated append: inclusive scan of the per-lane counts, one atomic per warp
-        int incl = n;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            int t = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= (unsigned)d) incl += t;
-        }
-        const int total = __shfl_sync(0xffffffffu, incl, 31);
-        unsigned long long base = 0;
-        if (lane == 31 && total > 0) base = atomicAdd(work_count, (unsigned long long)total);
-        base = __shfl_sync(0xffffffffu, base, 31);
-        if (total > 0) {
-            SolRec *dst = worklist + base + (unsigned long long)(incl - n);
-            for (int j = 0; j < n; ++j) dst[j] = recs[j];
-        }
-    }
-}
-
 // ---------------------------------------------------------------------------------------------------------------
 // Binned solver for media without bottom reflections (one mode per pair).  Pairs differ wildly in the work they need
 // (shadow zone: a maximum search; lit zone: two root solves), so a thread-per-pair kernel runs with half-empty warps.
@@ -133,8 +89,11 @@ K_solve(IceParams ice, KInput in, TraceOutputs out, SolRec *worklist, unsigned l
 //               The two brackets of a pair sit in adjacent lanes; one shuffle orders them by C0 (py:1547).
 // Queue appends are warp-aggregated (ballot + one atomic per warp).
 // ---------------------------------------------------------------------------------------------------------------
-struct RootItem { int64_t pair; double g1, g2, a, ga, b, gb; int32_t piece, valid; };   // 64 bytes
-struct HumpItem { int64_t pair; double g1, g2, J1, J2, J3; };                           // 48 bytes
+struct RootItem { int64_t pair; double g1, g2, a, ga, b, gb; int32_t piece, valid; };   // 64 bytes; valid: bit 0, mode bits above
+struct HumpItem { int64_t pair; double g1, g2, J1, J2, J3; int32_t mode, pad; };        // 56 bytes
+// mode of a work item for media with bottom reflections: k bounces (bits 8-15), launch case (16-23), mode index (24-31)
+__device__ __forceinline__ int mode_bits(int k, int rcase, int md) { return (k << 8) | (rcase << 16) | (md << 24); }
+__device__ __forceinline__ void mode_of(int md, int &k, int &rcase) { k = md == 0 ? 0 : (md - 1) / 2 + 1; rcase = md == 0 ? 1 : (md - 1) % 2 + 1; }
 
 // Upper bounds of the maximal range on a depth grid (range_max): entry [i1, i2] belongs to the depths (-i1 dz, -i2 dz).
 struct RmaxTable { const double *t; int32_t n; double dz; };
@@ -156,7 +115,7 @@ __global__ void K_rmax_table(IceParams ice, int n, double dz, double *table)
 }
 
 __device__ __forceinline__ void push_brackets(bool have, int64_t pair, const PairGeom &g, const Bracket *br, int nb, RootItem *rootq,
-                                              unsigned long long *root_count, unsigned lane)
+                                              unsigned long long *root_count, unsigned lane, int mode = 0)
 {
     const unsigned m = __ballot_sync(0xffffffffu, have);
     if (m == 0) return;
@@ -170,7 +129,7 @@ __device__ __forceinline__ void push_brackets(bool have, int64_t pair, const Pai
             RootItem it;
             const Bracket &b = br[j < nb ? j : 0];
             it.pair = pair; it.g1 = g.g1; it.g2 = g.g2; it.a = b.a; it.ga = b.ga; it.b = b.b; it.gb = b.gb;
-            it.piece = b.piece; it.valid = j < nb ? 1 : 0;
+            it.piece = b.piece; it.valid = (j < nb ? 1 : 0) | mode;
             dst[j] = it;
         }
     }
@@ -264,7 +223,7 @@ K_classify(IceParams ice, KInput in, TraceOutputs out, AttFill af, RmaxTable rma
         base = __shfl_sync(0xffffffffu, base, leader);
         if (kind == 2) {
             HumpItem it;
-            it.pair = p; it.g1 = g.g1; it.g2 = g.g2; it.J1 = J1; it.J2 = J2; it.J3 = J3;
+            it.pair = p; it.g1 = g.g1; it.g2 = g.g2; it.J1 = J1; it.J2 = J2; it.J3 = J3; it.mode = 0; it.pad = 0;
             humpq[base + __popc(mh & ((1u << lane) - 1u))] = it;
         }
     }
@@ -325,7 +284,7 @@ K_roots(IceParams ice, KInput in, TraceOutputs out, AttFill af, const RootItem *
         if (active) {
             const RootItem it = rootq[w];
             pair = it.pair; g1 = it.g1; g2 = it.g2;
-            valid = it.valid != 0;
+            valid = (it.valid & 1) != 0;
             if (valid) {
                 double x1, y1, z1, x2, y2, z2;
                 load_pair(in, pair, x1, y1, z1, x2, y2, z2);
@@ -391,6 +350,181 @@ K_roots(IceParams ice, KInput in, TraceOutputs out, AttFill af, const RootItem *
                 if (af.dense) for (int j = 0; j < af.F; ++j) af.dense[(2 * pair + 1) * af.F + j] = NAN;
             }
         }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// The same binned pipeline for media with a reflective bottom: the work item is a (pair, mode) with M = 1 + 2 n_reflections
+// modes (k bounces, launch up / down).  K_classify_m / K_hump_m record the number of roots of every mode, K_slots_m turns
+// the counts of a pair into slot offsets (the reference's result order: mode first, then C0 ascending, py:2122-2125) and
+// fills the unused slots, K_roots_m writes every solution to its slot.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(CLASSIFY_THREADS)
+K_classify_m(IceParams ice, KInput in, TraceOutputs out, RmaxTable rmax, int M, int8_t *mode_count, RootItem *rootq,
+             unsigned long long *root_count, HumpItem *humpq, unsigned long long *hump_count)
+{
+    const int64_t t = (int64_t)blockIdx.x * CLASSIFY_THREADS + threadIdx.x;
+    const unsigned lane = threadIdx.x & 31u;
+    const bool in_range = t < in.n_pairs * M;
+    const int64_t p = in_range ? t / M : 0;
+    const int md = in_range ? (int)(t - p * M) : 0;
+    int k, rcase;
+    mode_of(md, k, rcase);
+    int kind = 0, nb = 0;
+    PairGeom g;
+    Bracket br[2];
+    double J1 = 0, J2 = 0, J3 = 0;
+    if (in_range) {
+        double x1, y1, z1, x2, y2, z2;
+        load_pair(in, p, x1, y1, z1, x2, y2, z2);
+        Frame2D f;
+        make_frame(x1, y1, z1, x2, y2, z2, f);
+        const int status = pair_status(ice, f);
+        if (md == 0 && out.status) out.status[p] = status;
+        if (status == 0) {
+            make_pair_geom(ice, f.z1, f.z2, fmax(f.rho, 1e-12), g);
+            Curve cv;
+            cv.ice = &ice; cv.g = &g; cv.k = k; cv.rcase = rcase;
+            bool need_hump;
+            nb = classify_mode(cv, J1, J2, J3, br, need_hump);
+            if (need_hump && md == 0 && rmax.t) {
+                const int i1 = (int)ceil(-f.z1 / rmax.dz), i2 = (int)ceil(-f.z2 / rmax.dz);
+                if (i1 < rmax.n && i2 < rmax.n && i1 >= 0 && i2 >= 0 && f.rho > __ldg(rmax.t + i1 * rmax.n + i2) * (1.0 + 1e-9) + 1e-6) need_hump = false;
+            }
+            kind = nb > 0 ? 1 : (need_hump ? 2 : 0);
+        }
+        if (kind != 2) mode_count[t] = (int8_t)(kind == 1 ? nb : 0);
+    }
+    push_brackets(kind == 1, p, g, br, nb, rootq, root_count, lane, mode_bits(k, rcase, md));
+    const unsigned mh = __ballot_sync(0xffffffffu, kind == 2);
+    if (mh) {
+        const int leader = __ffs(mh) - 1;
+        unsigned long long base = 0;
+        if ((int)lane == leader) base = atomicAdd(hump_count, (unsigned long long)__popc(mh));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (kind == 2) {
+            HumpItem it;
+            it.pair = p; it.g1 = g.g1; it.g2 = g.g2; it.J1 = J1; it.J2 = J2; it.J3 = J3; it.mode = mode_bits(k, rcase, md); it.pad = 0;
+            humpq[base + __popc(mh & ((1u << lane) - 1u))] = it;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(HUMP_THREADS, 4)
+K_hump_m(IceParams ice, KInput in, int M, int8_t *mode_count, const HumpItem *humpq, const unsigned long long *hump_count, RootItem *rootq,
+         unsigned long long *root_count)
+{
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned long long n = *hump_count;
+    const unsigned long long stride = (unsigned long long)gridDim.x * HUMP_THREADS;
+    for (unsigned long long w0 = (unsigned long long)blockIdx.x * HUMP_THREADS + (threadIdx.x & ~31u); w0 < n; w0 += stride) {
+        const unsigned long long w = w0 + lane;
+        const bool active = w < n;
+        PairGeom g;
+        Bracket br[2];
+        int nb = 0, mode = 0;
+        int64_t pair = 0;
+        if (active) {
+            const HumpItem it = humpq[w];
+            pair = it.pair; mode = it.mode;
+            double x1, y1, z1, x2, y2, z2;
+            load_pair(in, pair, x1, y1, z1, x2, y2, z2);
+            Frame2D f;
+            make_frame(x1, y1, z1, x2, y2, z2, f);
+            make_pair_geom_g(ice, f.z1, f.z2, fmax(f.rho, 1e-12), it.g1, it.g2, g);
+            Curve cv;
+            cv.ice = &ice; cv.g = &g; cv.k = (mode >> 8) & 0xff; cv.rcase = (mode >> 16) & 0xff;
+            nb = hump_search(cv, it.J1, it.J2, it.J3, br);
+            mode_count[pair * M + ((mode >> 24) & 0xff)] = (int8_t)nb;
+        }
+        push_brackets(active && nb > 0, pair, g, br, nb, rootq, root_count, lane, mode);
+    }
+}
+
+// counts of the modes of a pair -> slot offsets (in place), n_sol, and the fill of the unused slots (padded layout)
+__global__ void __launch_bounds__(256)
+K_slots_m(KInput in, TraceOutputs out, AttFill af, int M, int S, int K1, int8_t *mode_count)
+{
+    const int64_t p = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (p >= in.n_pairs) return;
+    int n = 0;
+    for (int md = 0; md < M; ++md) { const int c = mode_count[p * M + md]; mode_count[p * M + md] = (int8_t)n; n += c; }
+    if (out.n_sol) out.n_sol[p] = n;
+    for (int sl = n; sl < S; ++sl) {
+        fill_empty_slot(out, p * S + sl, K1);
+        if (af.sparse) for (int j = 0; j < af.Fs; ++j) af.sparse[(p * S + sl) * af.Fs + j] = NAN;
+        if (af.dense) for (int j = 0; j < af.F; ++j) af.dense[(p * S + sl) * af.F + j] = NAN;
+    }
+}
+
+__global__ void __launch_bounds__(ROOTS_THREADS)
+K_roots_m(IceParams ice, KInput in, TraceOutputs out, AttFill af, int M, int S, int K1, const int8_t *slot_base, const RootItem *rootq,
+          const unsigned long long *root_count, SolRec *worklist, unsigned long long *work_count)
+{
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned long long n = *root_count;
+    const unsigned long long stride = (unsigned long long)gridDim.x * ROOTS_THREADS;
+    for (unsigned long long w0 = (unsigned long long)blockIdx.x * ROOTS_THREADS + (threadIdx.x & ~31u); w0 < n; w0 += stride) {
+        const unsigned long long w = w0 + lane;
+        const bool active = w < n;
+        bool valid = false, keep = true;
+        int64_t pair = 0;
+        int k = 0, rcase = 1, md = 0;
+        Root root;
+        root.v = 0; root.piece = 0; root.beta = 0;
+        double g1 = 0, g2 = 0;
+        if (active) {
+            const RootItem it = rootq[w];
+            pair = it.pair; g1 = it.g1; g2 = it.g2;
+            valid = (it.valid & 1) != 0;
+            k = (it.valid >> 8) & 0xff; rcase = (it.valid >> 16) & 0xff; md = (it.valid >> 24) & 0xff;
+            if (valid) {
+                double x1, y1, z1, x2, y2, z2;
+                load_pair(in, pair, x1, y1, z1, x2, y2, z2);
+                Frame2D f;
+                make_frame(x1, y1, z1, x2, y2, z2, f);
+                PairGeom g;
+                make_pair_geom_g(ice, f.z1, f.z2, fmax(f.rho, 1e-12), g1, g2, g);
+                Curve cv;
+                cv.ice = &ice; cv.g = &g; cv.k = k; cv.rcase = rcase;
+                Bracket b;
+                b.a = it.a; b.ga = it.ga; b.b = it.b; b.gb = it.gb; b.piece = it.piece;
+                root = solve_bracket(cv, b);
+            }
+        }
+        // the two roots of a mode sit in adjacent lanes: C0 ascending = beta descending (py:1547)
+        const double beta_other = __shfl_xor_sync(0xffffffffu, valid ? root.beta : -1.0, 1);
+        int rank = lane & 1;
+        if (valid) rank = (root.beta > beta_other) ? 0 : ((root.beta < beta_other) ? 1 : (int)(lane & 1u));
+        int64_t row = 0;
+        double viewing = NAN;
+        if (valid) {
+            const int slot = slot_base[pair * M + md] + rank;
+            row = pair * S + slot;
+            double x1, y1, z1, x2, y2, z2;
+            load_pair(in, pair, x1, y1, z1, x2, y2, z2);
+            Frame2D f;
+            make_frame(x1, y1, z1, x2, y2, z2, f);
+            PairGeom g;
+            make_pair_geom_g(ice, f.z1, f.z2, fmax(f.rho, 1e-12), g1, g2, g);
+            SolutionProps pr;
+            solution_props(ice, g, f.x1y, k, rcase, root, pr);
+            write_solution(out, row, K1, f, k, rcase, pr);
+            if (in.sx) {
+                const ShowerCut sc = load_cut(in, pair);
+                double lx, lz;
+                launch_2d(f, pr, lx, lz);
+                viewing = viewing_angle_of(sc, f.ex, f.ey, lx, lz);
+                keep = passes_cut(sc, viewing, f.swap ? g.n2 : g.n1);
+            }
+            if (out.viewing_angle) out.viewing_angle[row] = viewing;
+            if (worklist && keep) {
+                SolRec rec;
+                make_solrec(ice, g, pair, slot, row, k, rcase, root, rec);
+                worklist[atomicAdd(work_count, 1ull)] = rec;
+            }
+        }
+        warp_fill_nan_slot(valid && !keep, row, af, lane);
     }
 }
 
@@ -957,21 +1091,6 @@ K_att_expand(AttTables tb, const SolRec *worklist, const unsigned long long *wor
     }
 }
 
-// fills the attenuation slots of pairs that have fewer than S solutions with NaN
-__global__ void K_att_fill(const int32_t *n_sol, int64_t n_pairs, int S, int Fs, int F, double *att_sparse, double *att_dense)
-{
-    const int64_t total = n_pairs * S;
-    for (int64_t q = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); q < total;
-         q += (int64_t)gridDim.x * (blockDim.x >> 5)) {
-        const int64_t p = q / S;
-        const int s = (int)(q - p * S);
-        if (s < n_sol[p]) continue;
-        const int lane = threadIdx.x & 31;
-        if (att_sparse) for (int j = lane; j < Fs; j += 32) att_sparse[q * Fs + j] = NAN;
-        if (att_dense) for (int j = lane; j < F; j += 32) att_dense[q * F + j] = NAN;
-    }
-}
-
 // ---------------------------------------------------------------------------------------------------------------
 // compact (per-solution, CSR) output for host calls: exclusive scan of n_sol, then a gather of the existing rows
 // ---------------------------------------------------------------------------------------------------------------
@@ -1218,7 +1337,7 @@ struct Lane {               // one pipeline lane (stream + scratch) for host-mem
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t kev[3] = {nullptr, nullptr, nullptr};   // after K_classify, after K_hump, after the main attenuation kernel
-    DevBuf in, out, work, fallback, sparse_tmp, rootq, humpq, packed, pack_sums, pack_off;
+    DevBuf in, out, work, fallback, sparse_tmp, rootq, humpq, packed, pack_sums, pack_off, modes;
     bool timed = false;
 };
 
@@ -1234,6 +1353,7 @@ struct nrmc_rt_s {
     bool have_sp1 = false;
     int grid_att = 0, grid_sp1 = 0;      // resident blocks (occupancy x SMs) of the persistent attenuation kernels
     int grid_hump = 0, grid_roots = 0;   // the same for the persistent solver kernels
+    int grid_hump_m = 0, grid_roots_m = 0;
     int64_t chunk_pairs = 0;             // 0: automatic; > 0: pairs per chunk (nrmc_rt_set_chunk_pairs)
     size_t smem_att = 0, smem_sp1 = 0;
     DevBuf d_tables, d_gl3, d_sp1;
@@ -1306,10 +1426,14 @@ int nrmc_rt_create(const nrmc_rt_config *cfg, nrmc_rt_t *out)
         h->grid_hump = std::max(1, nb) * h->n_sm;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, K_roots<false>, ROOTS_THREADS, 0) != cudaSuccess) { delete h; return NRMC_ERR_CUDA; }
         h->grid_roots = std::max(1, nb) * h->n_sm;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, K_hump_m, HUMP_THREADS, 0) != cudaSuccess) { delete h; return NRMC_ERR_CUDA; }
+        h->grid_hump_m = std::max(1, nb) * h->n_sm;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, K_roots_m, ROOTS_THREADS, 0) != cudaSuccess) { delete h; return NRMC_ERR_CUDA; }
+        h->grid_roots_m = std::max(1, nb) * h->n_sm;
     }
     h->rmax.t = nullptr; h->rmax.n = 0; h->rmax.dz = RMAX_DZ;
-    if (n_refl == 0) {
-        // R_max on a depth grid: lets K_classify discard pairs far in the shadow zone without a maximum search
+    {
+        // R_max on a depth grid (used for the mode without bottom reflection): lets K_classify discard pairs far in the shadow zone without a maximum search
         if (h->d_rmax.reserve((size_t)RMAX_N * RMAX_N * sizeof(double)) != cudaSuccess) { delete h; return NRMC_ERR_CUDA; }
         K_rmax_table<<<(RMAX_N * RMAX_N + 127) / 128, 128>>>(ice, RMAX_N, RMAX_DZ, (double *)h->d_rmax.p);
         // R_max is monotone in both depths: a running maximum over the shallower corners keeps the table an upper bound
@@ -1348,7 +1472,7 @@ void nrmc_rt_destroy(nrmc_rt_t h)
         for (int e = 0; e < 3; ++e) if (h->lanes[l].kev[e]) cudaEventDestroy(h->lanes[l].kev[e]);
         h->lanes[l].in.release(); h->lanes[l].out.release(); h->lanes[l].work.release();
         h->lanes[l].fallback.release(); h->lanes[l].sparse_tmp.release(); h->lanes[l].rootq.release(); h->lanes[l].humpq.release();
-        h->lanes[l].packed.release(); h->lanes[l].pack_sums.release(); h->lanes[l].pack_off.release();
+        h->lanes[l].packed.release(); h->lanes[l].pack_sums.release(); h->lanes[l].pack_off.release(); h->lanes[l].modes.release();
     }
     h->d_tables.release(); h->d_gl3.release(); h->d_sp1.release(); h->d_count.release(); h->d_ant.release(); h->d_rmax.release();
     delete h;
@@ -1582,19 +1706,31 @@ static int launch_chunk(nrmc_rt_s *h, Lane &ln, int lane_id, const KInput &kin, 
             K_roots<false><<<h->grid_roots, ROOTS_THREADS, 0, ln.stream>>>(h->ice, kin, to, af, (const RootItem *)ln.rootq.p, d_roots, wl, d_count, work_cap);
         *n_launches += 3;
     } else {
-        const int64_t blocks = (kin.n_pairs + SOLVE_THREADS - 1) / SOLVE_THREADS;
-        K_solve<<<(unsigned)blocks, SOLVE_THREADS, 0, ln.stream>>>(h->ice, kin, to, wl, d_count, att_sparse, att_dense, h->tb.Fs, h->tb.F);
-        ++*n_launches;
-        if (ln.timed) { cudaEventRecord(ln.kev[0], ln.stream); cudaEventRecord(ln.kev[1], ln.stream); }
+        // bottom reflections: the same pipeline over (pair, mode) work items
+        const int M = 1 + 2 * h->ice.n_refl;
+        unsigned long long *d_roots = cnt + CNT_ROOTS, *d_humps = cnt + CNT_HUMPS;
+        CK(ln.rootq.reserve((size_t)kin.n_pairs * M * 2 * sizeof(RootItem)));
+        CK(ln.humpq.reserve((size_t)kin.n_pairs * M * sizeof(HumpItem)));
+        CK(ln.modes.reserve((size_t)kin.n_pairs * M));
+        int8_t *modes = (int8_t *)ln.modes.p;
+        AttFill af;
+        af.sparse = att_sparse; af.dense = att_dense; af.Fs = h->tb.Fs; af.F = h->tb.F;
+        const int64_t items = kin.n_pairs * M;
+        K_classify_m<<<(unsigned)((items + CLASSIFY_THREADS - 1) / CLASSIFY_THREADS), CLASSIFY_THREADS, 0, ln.stream>>>(
+            h->ice, kin, to, h->rmax, M, modes, (RootItem *)ln.rootq.p, d_roots, (HumpItem *)ln.humpq.p, d_humps);
+        if (ln.timed) cudaEventRecord(ln.kev[0], ln.stream);
+        K_hump_m<<<h->grid_hump_m, HUMP_THREADS, 0, ln.stream>>>(h->ice, kin, M, modes, (const HumpItem *)ln.humpq.p, d_humps,
+                                                                 (RootItem *)ln.rootq.p, d_roots);
+        K_slots_m<<<(unsigned)((kin.n_pairs + 255) / 256), 256, 0, ln.stream>>>(kin, to, af, M, h->S, h->K1, modes);
+        if (ln.timed) cudaEventRecord(ln.kev[1], ln.stream);
+        K_roots_m<<<h->grid_roots_m, ROOTS_THREADS, 0, ln.stream>>>(h->ice, kin, to, af, M, h->S, h->K1, modes, (const RootItem *)ln.rootq.p,
+                                                                   d_roots, wl, d_count);
+        *n_launches += 4;
     }
     if (ln.timed) cudaEventRecord(ln.ev[1], ln.stream);
     if (want_att) {
         const AttTables &tb = h->tb;
         const int nseg_max = h->ice.n_refl + 1;
-        if (h->ice.n_refl > 0) {     // the binned solver writes the NaN rows itself
-            K_att_fill<<<h->n_sm * 8, 256, 0, ln.stream>>>(to.n_sol, kin.n_pairs, h->S, tb.Fs, tb.F, att_sparse, att_dense);
-            ++*n_launches;
-        }
         if (h->have_sp1) {
             // SP1 moment kernel -> sparse factors; rare out-of-band solutions -> generic kernel; dense = interp(sparse)
             unsigned long long *d_fb = cnt + CNT_FALLBACK;
@@ -1640,7 +1776,7 @@ static void accumulate_lane_times(Lane &ln, float *ms)
     float t = 0;
     cudaEventElapsedTime(&t, ln.ev[0], ln.ev[1]); ms[0] += t;
     cudaEventElapsedTime(&t, ln.ev[1], ln.ev[2]); ms[1] += t;
-    cudaEventElapsedTime(&t, ln.ev[0], ln.kev[0]); ms[2] += t;    // K_classify (or the generic K_solve)
+    cudaEventElapsedTime(&t, ln.ev[0], ln.kev[0]); ms[2] += t;    // K_classify / K_classify_m
     cudaEventElapsedTime(&t, ln.kev[0], ln.kev[1]); ms[3] += t;   // K_hump
     cudaEventElapsedTime(&t, ln.kev[1], ln.ev[1]); ms[4] += t;    // K_roots
     cudaEventElapsedTime(&t, ln.ev[1], ln.kev[2]); ms[5] += t;    // main attenuation kernel (+ NaN fill for bottom reflections)
@@ -1705,7 +1841,7 @@ extern "C" int nrmc_rt_trace(nrmc_rt_t h, const nrmc_rt_input *in, const nrmc_rt
         ln.timed = false;
         cudaEvent_t e0 = ln.ev[3], e1 = ln.ev[4];
         if (stats) cudaEventRecord(e0, user);
-        int64_t chunk = std::min<int64_t>(N, h->chunk_pairs > 0 ? h->chunk_pairs : (int64_t)1 << 24);     // bounds the queue / work-list scratch
+        int64_t chunk = std::min<int64_t>(N, h->chunk_pairs > 0 ? h->chunk_pairs : ((int64_t)1 << 24) / (1 + 2 * h->ice.n_refl));     // bounds the queue / work-list scratch
         if (in->outer && chunk < N) chunk = std::max<int64_t>(in->n_antennas, (chunk / in->n_antennas) * in->n_antennas);
         float ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         int rc = NRMC_OK, n_chunks = 0;
@@ -1794,7 +1930,7 @@ extern "C" int nrmc_rt_trace(nrmc_rt_t h, const nrmc_rt_input *in, const nrmc_rt
     const bool direct = compact && h->ice.n_refl == 0;   // the binned solver assigns compact rows itself; otherwise scan + gather
     if (compact && !direct) per_pair = 2 * per_pair + 16;      // second (packed) copy of every array + offsets
     per_pair += h->S * sizeof(SolRec) + 48;
-    if (h->ice.n_refl == 0) per_pair += 2 * sizeof(RootItem) + sizeof(HumpItem);
+    per_pair += (size_t)(1 + 2 * h->ice.n_refl) * (2 * sizeof(RootItem) + sizeof(HumpItem) + 1);
     int64_t chunk = (int64_t)((size_t)1536 * 1024 * 1024 / per_pair);   // ~1.5 GB of device scratch per lane
     chunk = std::max<int64_t>(chunk, 1024);
     if (h->chunk_pairs > 0) chunk = h->chunk_pairs;
