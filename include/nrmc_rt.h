@@ -100,9 +100,11 @@ typedef struct {
     double *attenuation_sparse;/* [N,S,Fs] attenuation factors at the Fs integration frequencies       */
     double *attenuation;       /* [N,S,F]  get_attenuation(iS, frequency, max_detector_freq)           */
     double *viewing_angle;     /* [N,S]    angle(shower direction, launch vector) (simulation.py:191); NaN without sx/sy/sz */
-    /* Compact (per-solution) layout, NRMC_MEMORY_HOST only.  compact != 0: every [N,S,...] array above is written as
+    /* Compact (per-solution) layout.  compact != 0: every [N,S,...] array above is written as
      * [n_rows,...] with one row per EXISTING solution: the rows of pair i are sol_offset[i] .. sol_offset[i+1]-1, in slot
      * order (CSR; sol_offset[N] = n_rows = sum of n_sol).  Empty slots are neither stored nor copied over PCIe.
+     * Device-resident calls: sol_offset is a device array too; rows beyond row_capacity are dropped and reported as
+     * NRMC_ERR_CAPACITY when the call synchronises (stats != NULL).
      * row_capacity = rows the per-solution arrays can hold (N*S always suffices); NRMC_ERR_CAPACITY if exceeded. */
     int32_t compact;
     int32_t reserved;

@@ -329,7 +329,7 @@ class ray_tracing(ray_tracing_base):
         Device-resident variant: `v` (3, Nv) and `a` (3, Na) are contiguous float64 CUDA torch tensors (SoA); the results
         are CUDA torch tensors, the kernels are enqueued on torch's current stream.  Used by bench.py for the
         HBM-resident number and by callers that keep the next stage on the GPU.
-        compact=True (media without bottom reflections): per-solution rows as in `trace_batch`; the per-slot tensors keep
+        compact=True: per-solution rows as in `trace_batch`; the per-slot tensors keep
         their capacity (`row_capacity`, default N*S) and only the first `res["sol_offset"][N]` rows are defined -- reading
         that number is the caller's synchronisation point (`res.n_rows()`).
         """

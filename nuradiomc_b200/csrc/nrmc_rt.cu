@@ -450,6 +450,7 @@ K_slots_m(KInput in, TraceOutputs out, AttFill af, int M, int S, int K1, int8_t 
     int n = 0;
     for (int md = 0; md < M; ++md) { const int c = mode_count[p * M + md]; mode_count[p * M + md] = (int8_t)n; n += c; }
     if (out.n_sol) out.n_sol[p] = n;
+    if (out.row_offset) return;          // compact layout: unused slots have no rows
     for (int sl = n; sl < S; ++sl) {
         fill_empty_slot(out, p * S + sl, K1);
         if (af.sparse) for (int j = 0; j < af.Fs; ++j) af.sparse[(p * S + sl) * af.Fs + j] = NAN;
@@ -500,7 +501,11 @@ K_roots_m(IceParams ice, KInput in, TraceOutputs out, AttFill af, int M, int S, 
         double viewing = NAN;
         if (valid) {
             const int slot = slot_base[pair * M + md] + rank;
-            row = pair * S + slot;
+            row = row_of(out, pair, slot, S);
+            if (out.row_offset && row >= out.row_limit) valid = false;       // caller's compact arrays are full
+        }
+        if (valid) {
+            const int slot = slot_base[pair * M + md] + rank;
             double x1, y1, z1, x2, y2, z2;
             load_pair(in, pair, x1, y1, z1, x2, y2, z2);
             Frame2D f;
@@ -1722,6 +1727,17 @@ static int launch_chunk(nrmc_rt_s *h, Lane &ln, int lane_id, const KInput &kin, 
         K_hump_m<<<h->grid_hump_m, HUMP_THREADS, 0, ln.stream>>>(h->ice, kin, M, modes, (const HumpItem *)ln.humpq.p, d_humps,
                                                                  (RootItem *)ln.rootq.p, d_roots);
         K_slots_m<<<(unsigned)((kin.n_pairs + 255) / 256), 256, 0, ln.stream>>>(kin, to, af, M, h->S, h->K1, modes);
+        if (cc.on) {
+            const int nblk = (int)((kin.n_pairs + PACK_PAIRS - 1) / PACK_PAIRS);
+            CK(ln.pack_sums.reserve((size_t)(nblk + 2) * sizeof(unsigned long long)));
+            unsigned long long *sums = (unsigned long long *)ln.pack_sums.p;
+            PackArrays none;
+            none.n = 0;
+            K_pack_count<<<nblk, PACK_THREADS, 0, ln.stream>>>(to.n_sol, kin.n_pairs, sums);
+            K_pack_scan<<<1, 1024, 0, ln.stream>>>(sums, nblk, cc.base_dev);
+            K_pack<<<nblk, PACK_THREADS, 0, ln.stream>>>(to.n_sol, kin.n_pairs, h->S, sums, cc.base_host, cc.base_dev ? 1 : 0, cc.sol_offset, none);
+            *n_launches += 3;
+        }
         if (ln.timed) cudaEventRecord(ln.kev[1], ln.stream);
         K_roots_m<<<h->grid_roots_m, ROOTS_THREADS, 0, ln.stream>>>(h->ice, kin, to, af, M, h->S, h->K1, modes, (const RootItem *)ln.rootq.p,
                                                                    d_roots, wl, d_count);
@@ -1821,10 +1837,6 @@ extern "C" int nrmc_rt_trace(nrmc_rt_t h, const nrmc_rt_input *in, const nrmc_rt
     if (want_att && h->ice.att_model == 0) { h->err = "attenuation requested but no attenuation model configured"; return NRMC_ERR_UNSUPPORTED; }
     if (want_att && !h->have_freq) { h->err = "attenuation requested before nrmc_rt_set_frequencies"; return NRMC_ERR_NO_FREQUENCIES; }
     const bool compact = out->compact != 0;
-    if (compact && in->memory != NRMC_MEMORY_HOST && h->ice.n_refl > 0) {
-        h->err = "device-resident calls offer the compact output layout only without bottom reflections";
-        return NRMC_ERR_UNSUPPORTED;
-    }
     if (compact && (!out->sol_offset || out->row_capacity < 0)) { h->err = "compact output needs sol_offset[N+1] and row_capacity"; return NRMC_ERR_INVALID_ARGUMENT; }
     CK(cudaSetDevice(h->cfg.device));
     const int S = h->S, K1 = h->K1, Fs = h->tb.Fs, F = h->tb.F;
@@ -1927,8 +1939,7 @@ extern "C" int nrmc_rt_trace(nrmc_rt_t h, const nrmc_rt_input *in, const nrmc_rt
     for (int i = 0; i < N_OUT; ++i) { want[i] = out_ptr(out, i) != nullptr; }
     const bool need_nsol_dev = want_att || want[0] || compact;
     for (int i = 0; i < N_OUT; ++i) if (want[i] || (i == 0 && need_nsol_dev)) per_pair += elem[i] + 16;
-    const bool direct = compact && h->ice.n_refl == 0;   // the binned solver assigns compact rows itself; otherwise scan + gather
-    if (compact && !direct) per_pair = 2 * per_pair + 16;      // second (packed) copy of every array + offsets
+    const bool direct = compact;      // the binned solver assigns the compact rows itself (scan of n_sol before K_roots)
     per_pair += h->S * sizeof(SolRec) + 48;
     per_pair += (size_t)(1 + 2 * h->ice.n_refl) * (2 * sizeof(RootItem) + sizeof(HumpItem) + 1);
     int64_t chunk = (int64_t)((size_t)1536 * 1024 * 1024 / per_pair);   // ~1.5 GB of device scratch per lane
@@ -2052,48 +2063,6 @@ extern "C" int nrmc_rt_trace(nrmc_rt_t h, const nrmc_rt_input *in, const nrmc_rt
                 CK(cudaMemcpyAsync((unsigned char *)out_ptr(out, i) + (size_t)p0 * elem[i], dout + off[i], bytes, cudaMemcpyDeviceToHost, ln.stream));
                 d2h += bytes;
             }
-        } else {
-            // per-solution rows: scan n_sol, gather the existing rows into a second device block, copy only those
-            const int nblk = (int)((np + PACK_PAIRS - 1) / PACK_PAIRS);
-            CK(ln.packed.reserve(total));
-            CK(ln.pack_sums.reserve((size_t)(nblk + 2) * sizeof(unsigned long long)));
-            CK(ln.pack_off.reserve((size_t)np * sizeof(int64_t)));
-            unsigned char *dpk = (unsigned char *)ln.packed.p;
-            PackArrays pa;
-            pa.n = 0;
-            for (int i = 2; i < N_OUT; ++i) {
-                if (!want[i]) continue;
-                pa.src[pa.n] = dout + off[i]; pa.dst[pa.n] = dpk + off[i]; pa.row_bytes[pa.n] = (int32_t)(elem[i] / S); ++pa.n;
-            }
-            unsigned long long *sums = (unsigned long long *)ln.pack_sums.p;
-            K_pack_count<<<nblk, PACK_THREADS, 0, ln.stream>>>(to.n_sol, np, sums);
-            K_pack_scan<<<1, 1024, 0, ln.stream>>>(sums, nblk, nullptr);
-            K_pack<<<nblk, PACK_THREADS, 0, ln.stream>>>(to.n_sol, np, S, sums, row_base, 0, (int64_t *)ln.pack_off.p, pa);
-            n_launches += 3;
-            CK(cudaGetLastError());
-            unsigned long long rows = 0;
-            CK(cudaMemcpyAsync(&rows, sums + nblk, sizeof(rows), cudaMemcpyDeviceToHost, ln.stream));
-            CK(cudaStreamSynchronize(ln.stream));      // the row count sizes the copies; the other lane's copies keep the link busy meanwhile
-            d2h += sizeof(rows);
-            if (row_base + (int64_t)rows > out->row_capacity) {
-                h->err = "compact output: row_capacity exceeded";
-                for (int l = 0; l < 2; ++l) cudaStreamSynchronize(h->lanes[l].stream);
-                return NRMC_ERR_CAPACITY;
-            }
-            for (int i = 0; i < 2; ++i) {
-                if (!want[i]) continue;
-                CK(cudaMemcpyAsync((unsigned char *)out_ptr(out, i) + (size_t)p0 * elem[i], dout + off[i], (size_t)np * elem[i], cudaMemcpyDeviceToHost, ln.stream));
-                d2h += (size_t)np * elem[i];
-            }
-            CK(cudaMemcpyAsync(out->sol_offset + p0, ln.pack_off.p, (size_t)np * sizeof(int64_t), cudaMemcpyDeviceToHost, ln.stream));
-            d2h += (size_t)np * sizeof(int64_t);
-            for (int i = 2; i < N_OUT; ++i) {
-                if (!want[i] || rows == 0) continue;
-                const size_t rb = elem[i] / S;
-                CK(cudaMemcpyAsync((unsigned char *)out_ptr(out, i) + (size_t)row_base * rb, dpk + off[i], (size_t)rows * rb, cudaMemcpyDeviceToHost, ln.stream));
-                d2h += (size_t)rows * rb;
-            }
-            row_base += (int64_t)rows;
         }
     }
     for (int l = 0; l < 2; ++l) {

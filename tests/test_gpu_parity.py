@@ -297,28 +297,26 @@ def test_compact_layout_equals_padded_layout(make, ice, n_refl, model, zmin, rma
     assert cmp_.solutions(7) == pad.solutions(7)
     with pytest.raises(RuntimeError, match="capacity"):
         rt.trace_batch(V, A, outer=True, compact=True, row_capacity=10)
-    if n_refl == 0:      # device-resident compact layout (the binned solver assigns the rows itself), several chunks
-        import torch
-        dv = torch.tensor(np.ascontiguousarray(V.T), device="cuda:0")
-        da = torch.tensor(np.ascontiguousarray(A.T), device="cuda:0")
-        for chunk in (0, 1500):
-            rt.set_chunk_pairs(chunk)
-            dev = rt.trace_batch_device(dv, da, outer=True, frequency=ff, attenuation="both", compact=True)
-            n_rows = dev.n_rows()
-            assert n_rows == filled.sum()
-            for k in cmp_:
-                got = dev[k].cpu().numpy()
-                np.testing.assert_array_equal(got if k in ("n_sol", "status", "sol_offset") else got[:n_rows], cmp_[k], err_msg=f"device {k}")
-            only_dense = rt.trace_batch_device(dv, da, outer=True, frequency=ff, attenuation="dense", compact=True)
-            np.testing.assert_array_equal(only_dense["attenuation"][:n_rows].cpu().numpy(), cmp_["attenuation"])
-            with pytest.raises(RuntimeError, match="capacity"):
-                rt.trace_batch_device(dv, da, outer=True, compact=True, row_capacity=10, sync_stats=True)
-        rt.set_chunk_pairs(0)
-    else:
-        import torch
-        with pytest.raises(RuntimeError, match="bottom reflections"):
-            rt.trace_batch_device(torch.zeros((3, 4), dtype=torch.float64, device="cuda:0") - 50.,
-                                  torch.zeros((3, 4), dtype=torch.float64, device="cuda:0") - 10., compact=True)
+    # device-resident compact layout (the binned solver assigns the rows itself), several chunks
+    import torch
+    dv = torch.tensor(np.ascontiguousarray(V.T), device="cuda:0")
+    da = torch.tensor(np.ascontiguousarray(A.T), device="cuda:0")
+    for chunk in (0, 1500):
+        rt.set_chunk_pairs(chunk)
+        dev = rt.trace_batch_device(dv, da, outer=True, frequency=ff, attenuation="both", compact=True)
+        n_rows = dev.n_rows()
+        assert n_rows == filled.sum()
+        for k in cmp_:
+            got = dev[k].cpu().numpy()
+            np.testing.assert_array_equal(got if k in ("n_sol", "status", "sol_offset") else got[:n_rows], cmp_[k], err_msg=f"device {k}")
+        only_dense = rt.trace_batch_device(dv, da, outer=True, frequency=ff, attenuation="dense", compact=True)
+        np.testing.assert_array_equal(only_dense["attenuation"][:n_rows].cpu().numpy(), cmp_["attenuation"])
+        with pytest.raises(RuntimeError, match="capacity"):
+            rt.trace_batch_device(dv, da, outer=True, compact=True, row_capacity=10, sync_stats=True)
+        host_chunked = rt.trace_batch(V, A, outer=True, frequency=ff, attenuation="both", compact=True)
+        for k in cmp_:
+            np.testing.assert_array_equal(host_chunked[k], cmp_[k], err_msg=f"host chunk {chunk} {k}")
+    rt.set_chunk_pairs(0)
     empty = rt.trace_batch(np.zeros((0, 3)), np.zeros((0, 3)), compact=True)
     assert list(empty["sol_offset"]) == [0] and empty["C0"].shape[0] == 0
 
