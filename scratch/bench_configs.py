@@ -9,7 +9,10 @@ from conftest import cylinder
 from test_gpu_parity import RNOG
 prop = propagation.get_propagation_module("analytic")
 ff512 = np.fft.rfftfreq(1022, 0.2)
+from conftest import t05_points
 cfgs = {
+    "cfg1": dict(ice="southpole_simple", att="SP1", nr=0, V=t05_points(0, -3000.), A=np.array([[0, 0, -100.]]),
+                 kw=dict(frequency=np.linspace(0, 0.5, 129), attenuation="dense"), nfreq=100),
     "cfg2": dict(ice="southpole_2015", att=None, nr=0, V=cylinder(2, 1_000_000, 4000, -2700),
                  A=np.array([[10, 10, -190.], [10, -10, -190.], [-10, -10, -190.], [-10, 10, -190.]]), kw={}),
     "cfg3 (2e5 of the 1e6 vertices)": dict(ice="greenland_simple", att="GL1", nr=0, V=cylinder(3, 200_000, 4000, -2700), A=RNOG,
@@ -21,7 +24,7 @@ cfgs = {
                  kw=dict(frequency=ff512, max_detector_freq=1.2, attenuation="sparse")),
 }
 for name, c in cfgs.items():
-    rt = prop(medium.get_ice_model(c["ice"]), attenuation_model=c["att"], n_reflections=c["nr"], n_frequencies_integration=25)
+    rt = prop(medium.get_ice_model(c["ice"]), attenuation_model=c["att"], n_reflections=c["nr"], n_frequencies_integration=c.get("nfreq", 25))
     dv = torch.tensor(np.ascontiguousarray(c["V"].T), device="cuda:0"); da = torch.tensor(np.ascontiguousarray(c["A"].T), device="cuda:0")
     out = None
     for _ in range(3):
