@@ -93,7 +93,7 @@ __device__ __forceinline__ double expm1_c(double x)        // accurate for x -> 
 #define NRMC_GL1_SPP 32       // sub-panels per panel for the rational GL1 model where a frequency comes within 60 m of the pole of
                               // 1/(A(z) - s_f) or crosses the 1 m floor along the path; worst dense-bin deviation on wide random
                               // geometry (scratch/stress_att.py): 8 -> 1.2e-4, 16 -> 1.0e-4, 32 -> 5e-5; cost is linear in it
-#define NRMC_GL1_SPP_EASY 4   // everywhere else the integrand is smooth (2 already give 4e-6)
+#define NRMC_GL1_SPP_EASY 2   // everywhere else the integrand is smooth (two sub-panels: 4e-6)
 #endif
 #define NRMC_MAX_SEG (NRMC_MAX_REFLECTIONS + 1)
 

@@ -826,8 +826,23 @@ K_att(IceParams ice, KInput in, AttTables tb, const SolRec *worklist, const unsi
         // quadrature: each half-warp integrates one 16-node slot per pass; slot sums are added to their panel.
         // Phase 0: all frequencies below j_hard on the plan's sub-panels; phase 1 (GL1 only): the hard ones on the fine ones.
         for (int phase = 0; phase < 2 && need_loop; ++phase) {
-            const int j_begin = phase == 0 ? 0 : j_hard, j_end = phase == 0 ? j_hard : tb.Fs;
+            // phase 0: every frequency on the plan's sub-panels.  Phase 1 (GL1): the frequencies from j_hard on are redone on
+            // the fine sub-panels -- unless the coarse exponent already exceeds 30: such a factor (< 1e-13) stays invisible
+            // even if the coarse quadrature is off by a third, while a visible factor (I < 16) never passes the test.
+            const int j_begin = phase == 0 ? 0 : j_hard, j_end = tb.Fs;
             if (j_begin >= j_end) continue;
+            if (phase == 1) {
+                bool redo = false;
+                const int m0 = plan_total_mult(plan, 0), m1 = plan_total_mult(plan, 1), m2 = plan_total_mult(plan, 2);
+                for (int j = j_hard + lane; j < tb.Fs; j += 32) {
+                    const bool r = m0 * H[j] + m1 * H[tb.Fs_pad + j] + m2 * H[2 * tb.Fs_pad + j] < 30.0;
+                    fac[j] = r ? 1.0 : 0.0;                  // fac is free until the factors are formed
+                    if (r) { H[j] = 0.0; H[tb.Fs_pad + j] = 0.0; H[2 * tb.Fs_pad + j] = 0.0; }
+                    redo = redo || r;
+                }
+                __syncwarp();
+                if (!__any_sync(0xffffffffu, redo)) continue;
+            }
             if (phase == 1) {
                 plan.spp = (plan.spp / NRMC_GL1_SPP_EASY) * NRMC_GL1_SPP;
                 plan.n_slots = plan.na * plan.spp;
@@ -847,6 +862,7 @@ K_att(IceParams ice, KInput in, AttTables tb, const SolRec *worklist, const unsi
             const int panel_other = __shfl_xor_sync(0xffffffffu, live ? panel : -1, 16);
             const bool merge = (panel_other == panel);       // both half-warps work on the same panel
             for (int j = j_begin; j < j_end; ++j) {
+                if (phase == 1 && fac[j] == 0.0) continue;       // warp-uniform
                 double term = live ? wds * att_inv_length(ice.att_model, nd, s_fa[j], s_fb[j]) : 0.0;
                 term += __shfl_xor_sync(0xffffffffu, term, 8);
                 term += __shfl_xor_sync(0xffffffffu, term, 4);
