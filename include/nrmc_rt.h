@@ -165,8 +165,29 @@ typedef struct {
     double reflection_coefficient;     /* medium.reflection_coefficient (medium_base.py:61) */
     double reflection_phase_shift;     /* medium.reflection_phase_shift [rad] */
     double *r_theta, *r_phi;           /* [n_rows] complex, or NULL */
+    const double *focusing;            /* [n_rows] focusing factor on eTheta, ePhi (py:3012-3015: spec[1:] *= focusing), or NULL */
 } nrmc_rt_effects;
 int nrmc_rt_apply_propagation_effects(nrmc_rt_t h, const nrmc_rt_effects *fx, void *stream);
+
+/* Signal focusing of every solution (ray_tracing.get_focusing, analyticraytracing.py:2778-2888, numerical branch; the
+ * reference's analytic branch raises AttributeError at :831 and is not reproduced).  The reference re-traces the pair with the
+ * receiver moved by dz = -1 cm and differences the launch angle; here d(launch angle)/d(receiver depth) is the exact
+ * derivative from the closed-form dR/dbeta (the dz -> 0 limit; 2e-3 from the 1 cm difference quotient, inside the 3e-3 noise of
+ * the reference's own root finding):
+ *   focusing = min(limit, sqrt(D / sin(rec) |d launch / dz|) sqrt(D sin(launch) / rho)) * sqrt(n_emitter / n_receiver).
+ * `in` as in nrmc_rt_trace (memory must be NRMC_MEMORY_DEVICE); the solutions are read from a result of nrmc_rt_trace over the
+ * same input: padded [N,S] arrays (sol_offset NULL) or compact rows.  The receiver is the antenna (the reference's X2). */
+typedef struct {
+    const int32_t *n_sol;              /* [N] */
+    const double *C0;                  /* [N,S] or [n_rows] */
+    const int8_t *reflection;          /* [N,S] or [n_rows]; NULL: no bottom reflections */
+    const int8_t *reflection_case;     /* [N,S] or [n_rows]; NULL: case 1 */
+    const double *path_length;         /* [N,S] or [n_rows] */
+    const int64_t *sol_offset;         /* [N+1] compact layout, or NULL */
+    double limit;                      /* config['propagation']['focusing_limit'] (default 2) */
+    double *focusing;                  /* out: [N,S] (NaN in empty slots) or [n_rows] */
+} nrmc_rt_focusing;
+int nrmc_rt_focusing_factor(nrmc_rt_t h, const nrmc_rt_input *in, const nrmc_rt_focusing *fo, void *stream);
 
 /* Pairs per internal chunk (device scratch and the host-call pipeline are sized per chunk).  0 = automatic (2^24 pairs for
  * device-resident calls, ~1.5 GB of scratch per stream for host calls).  A tuning / testing knob: results do not depend on it. */

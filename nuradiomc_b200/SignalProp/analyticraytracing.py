@@ -187,6 +187,7 @@ class ray_tracing(ray_tracing_base):
         self._x2 = None
         self._cache = None          # results of the current pair (arrays with leading dimension S)
         self._att_cache = {}
+        self._foc_cache = {}
         self._batch = None          # (lookup dict, BatchResult) from prepare_batch
         self._batch_index = None
 
@@ -379,11 +380,69 @@ class ray_tracing(ray_tracing_base):
         res.frequencies_sparse = h.sparse if frequency is not None else None
         return res
 
-    def apply_propagation_effects_batch(self, spectra, reflection_angle=None, reflection=None, attenuation=None,
-                                        attenuation_sparse=None, return_coefficients=False):
+    def focusing_batch(self, X1, X2, result, outer=False, limit=None):
         """
-        Batched `apply_propagation_effects` (reference :2937-3033, in-ice branch; focusing / birefringence are out of
-        scope): one row per ray-tracing solution.
+        Focusing factor of every solution of a batch result (`get_focusing`, reference :2778-2888, numerical branch) in one
+        kernel: the derivative of the launch angle with respect to the receiver depth is exact (closed-form dR/dbeta) where
+        the reference differences two traces 1 cm apart.  X2 are the receivers.  `result`: what `trace_batch` /
+        `trace_batch_device` returned for the same points (padded or compact; needs n_sol, C0, path_length and, with
+        bottom reflections, reflection / reflection_case).  Host result -> numpy array, device result -> CUDA tensor
+        (X1, X2 then as in `trace_batch_device`: (3, N) tensors); shape (N, S) or (rows,).
+        limit: maximum amplification, default config['propagation']['focusing_limit'] (2).
+        """
+        import torch
+        h = self._h()
+        dev = torch.device("cuda", self._device)
+        if limit is None:
+            limit = float(self._config['propagation'].get('focusing_limit', 2))
+        on_host = isinstance(result["C0"], np.ndarray)
+        if on_host:
+            X1 = np.asarray(X1, dtype=np.float64).reshape(-1, 3)
+            X2 = np.asarray(X2, dtype=np.float64).reshape(-1, 3)
+            if not outer and X2.shape[0] == 1 and X1.shape[0] != 1:
+                X2 = np.repeat(X2, X1.shape[0], axis=0)
+            v = torch.as_tensor(np.ascontiguousarray(X1.T)).to(dev)
+            a = torch.as_tensor(np.ascontiguousarray(X2.T)).to(dev)
+        else:
+            v, a = X1, X2
+            assert v.is_cuda and a.is_cuda and v.dtype == torch.float64 and a.dtype == torch.float64
+            assert v.dim() == 2 and v.shape[0] == 3 and a.dim() == 2 and a.shape[0] == 3 and v.is_contiguous() and a.is_contiguous()
+        Nv, Na = v.shape[1], a.shape[1]
+        if not outer and Nv != Na:
+            raise ValueError("X1 and X2 must have the same number of points unless outer=True")
+
+        def dev_tensor(name, required=True):
+            x = result.get(name)
+            if x is None:
+                if required:
+                    raise ValueError(f"focusing_batch needs the output '{name}' of the trace")
+                return None
+            if isinstance(x, np.ndarray):
+                return torch.as_tensor(np.ascontiguousarray(x)).to(dev)
+            return x.contiguous()
+        compact = bool(getattr(result, "compact", False))
+        need_modes = self._n_reflections > 0
+        t = {k: dev_tensor(k) for k in ("n_sol", "C0", "path_length")}
+        t["reflection"], t["reflection_case"] = dev_tensor("reflection", need_modes), dev_tensor("reflection_case", need_modes)
+        t["sol_offset"] = dev_tensor("sol_offset") if compact else None
+        foc = torch.empty_like(t["C0"])
+        fo = _lib.Focusing()
+        for k in ("n_sol", "C0", "path_length", "reflection", "reflection_case", "sol_offset"):
+            setattr(fo, k, t[k].data_ptr() if t[k] is not None else None)
+        fo.limit, fo.focusing = float(limit), foc.data_ptr()
+        inp = _lib.Input()
+        inp.n_vertices, inp.vx, inp.vy, inp.vz = Nv, v[0].data_ptr(), v[1].data_ptr(), v[2].data_ptr()
+        inp.n_antennas, inp.ax, inp.ay, inp.az = Na, a[0].data_ptr(), a[1].data_ptr(), a[2].data_ptr()
+        inp.outer, inp.memory = int(bool(outer)), _lib.MEMORY_DEVICE
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _lib.check(_lib.load().nrmc_rt_focusing_factor(h.ptr, C.byref(inp), C.byref(fo), C.c_void_p(stream)), h.ptr, "focusing_factor")
+        return foc.cpu().numpy() if on_host else foc
+
+    def apply_propagation_effects_batch(self, spectra, reflection_angle=None, reflection=None, attenuation=None,
+                                        attenuation_sparse=None, return_coefficients=False, focusing=None):
+        """
+        Batched `apply_propagation_effects` (reference :2937-3033, in-ice branch; birefringence is out of scope): one row
+        per ray-tracing solution.  focusing: (R,) factors of `focusing_batch` on eTheta and ePhi (:3012-3015), optional.
 
         spectra: (R, 3, F) complex128 -- eR, eTheta, ePhi spectra; a CUDA torch tensor is modified in place (and
         returned), a numpy array is copied to the device and the result is returned as a new numpy array.
@@ -412,6 +471,9 @@ class ray_tracing(ray_tracing_base):
         refl = dev_tensor(reflection, torch.int8)
         att = dev_tensor(attenuation, torch.float64)
         att_sp = dev_tensor(attenuation_sparse, torch.float64)
+        foc = dev_tensor(focusing, torch.float64)
+        if foc is not None and tuple(foc.shape) != (spec.shape[0],):
+            raise ValueError("focusing must have one factor per row")
         K1 = self._n_reflections + 1
         if ang is not None and tuple(ang.shape) != (R, K1):
             raise ValueError(f"reflection_angle must have the shape ({R}, {K1})")
@@ -424,6 +486,7 @@ class ray_tracing(ray_tracing_base):
         fx.attenuation_sparse = att_sp.data_ptr() if att_sp is not None else None
         fx.reflection_angle = ang.data_ptr() if ang is not None else None
         fx.reflection = refl.data_ptr() if refl is not None else None
+        fx.focusing = foc.data_ptr() if foc is not None else None
         rc, ph = getattr(self._medium, "reflection_coefficient", None), getattr(self._medium, "reflection_phase_shift", None)
         fx.reflection_coefficient = 1.0 if rc is None else float(rc)
         fx.reflection_phase_shift = 0.0 if ph is None else float(ph)
@@ -448,8 +511,8 @@ class ray_tracing(ray_tracing_base):
         """
         self._check(i_solution)
         self._need_cache()
-        if self._config['propagation'].get('focusing', False) or self._config['propagation'].get('birefringence', False):
-            raise NotImplementedError("focusing and birefringence are outside the scope of nuradiomc_b200 (SURVEY.md section 8a)")
+        if self._config['propagation'].get('birefringence', False):
+            raise NotImplementedError("birefringence is outside the scope of nuradiomc_b200 (SURVEY.md section 8a)")
         if self._X2[2] > 0 or self._X1[2] > 0:
             raise NotImplementedError("air/ice transmission is experimental in the reference (:2971) and not provided")
         spec = np.array(efield.get_frequency_spectrum(), dtype=np.complex128)
@@ -459,9 +522,12 @@ class ray_tracing(ray_tracing_base):
             max_freq = np.max(ff) if self._max_detector_frequency is None else self._max_detector_frequency
             att = self.get_attenuation(i_solution, ff, max_freq)[None, :]
         k = self._results[i_solution]['reflection']
+        foc = None
+        if self._config['propagation'].get('focusing', False):     # :3012-3015
+            foc = np.array([self.get_focusing(i_solution, limit=float(self._config['propagation']['focusing_limit']))])
         out, r_t, r_p = self.apply_propagation_effects_batch(
             spec[None], reflection_angle=np.ascontiguousarray(self._cache["reflection_angle"][i_solution][None, :]),
-            reflection=np.array([k], np.int8), attenuation=att, return_coefficients=True)
+            reflection=np.array([k], np.int8), attenuation=att, return_coefficients=True, focusing=foc)
         if not np.all(np.isnan(self._cache["reflection_angle"][i_solution][:k + 1])):
             try:    # the reference stores the coefficients on the field object (:2993-2994)
                 try:
@@ -506,6 +572,7 @@ class ray_tracing(ray_tracing_base):
         self._swap = None
         self._cache = None
         self._att_cache = {}
+        self._foc_cache = {}
         self._batch_index = None
 
     def set_start_and_end_point(self, x1, x2):
@@ -624,6 +691,30 @@ class ray_tracing(ray_tracing_base):
             self._att_cache[key] = res["attenuation"][0]
         return np.array(self._att_cache[key][iS])
 
+    def get_focusing(self, iS, dz=-1. * units.cm, limit=2., analytic=False):
+        """
+        gain of the signal at the receiver due to the focusing effect (reference :2778-2888).  `dz` is accepted for
+        compatibility: the kernel differentiates exactly (the dz -> 0 limit of the reference's difference quotient).
+        `analytic=True` raises AttributeError in the reference (:831, `self.n`); both values give the same result here.
+        """
+        self._check(iS)
+        self._need_cache()
+        if self._X1[2] > 0 or self._X2[2] > 0:
+            raise NotImplementedError("air/ice transmission is experimental in the reference (:2877-2886) and not provided")
+        key = float(limit)
+        if key not in self._foc_cache:
+            n, S = len(self._results), self.get_number_of_raytracing_solutions()
+
+            def slots(name, dtype, fill):      # one padded [1, S] row (the cache holds n rows after set_solution)
+                a = np.full((1, S), fill, dtype=dtype)
+                a[0, :n] = self._cache[name][:n]
+                return a
+            res = {"n_sol": np.array([n], np.int32), "C0": slots("C0", np.float64, np.nan),
+                   "path_length": slots("path_length", np.float64, np.nan), "reflection": slots("reflection", np.int8, 0),
+                   "reflection_case": slots("reflection_case", np.int8, 0)}
+            self._foc_cache[key] = self.focusing_batch(self._X1[None, :], self._X2[None, :], res, limit=limit)[0]
+        return float(self._foc_cache[key][iS])
+
     def get_path(self, iS, n_points=1000):
         """not on the hot path (path sampling is plotting support) -- not provided"""
         raise NotImplementedError("get_path (path sampling for plotting) is outside the scope of nuradiomc_b200")
@@ -639,15 +730,16 @@ class ray_tracing(ray_tracing_base):
         ]
 
     def get_raytracing_output(self, i_solution):
-        if self._config['propagation']['focusing']:
-            raise NotImplementedError("focusing is outside the scope of nuradiomc_b200 (SURVEY.md section 8a)")
+        focusing = 1
+        if self._config['propagation']['focusing']:     # :2913-2916
+            focusing = self.get_focusing(i_solution, limit=float(self._config['propagation']['focusing_limit']))
         return {
             'ray_tracing_C0': self.get_results()[i_solution]['C0'],
             'ray_tracing_C1': self.get_results()[i_solution]['C1'],
             'ray_tracing_reflection': self.get_results()[i_solution]['reflection'],
             'ray_tracing_reflection_case': self.get_results()[i_solution]['reflection_case'],
             'ray_tracing_solution_type': self.get_solution_type(i_solution),
-            'focusing_factor': 1
+            'focusing_factor': focusing
         }
 
     def set_config(self, config):

@@ -45,12 +45,17 @@ class Effects(C.Structure):
     _fields_ = [("n_rows", C.c_int64), ("n_freq", C.c_int32), ("reserved", C.c_int32), ("spectrum", C.c_void_p),
                 ("attenuation", C.c_void_p), ("attenuation_sparse", C.c_void_p), ("reflection_angle", C.c_void_p),
                 ("reflection", C.c_void_p), ("reflection_coefficient", C.c_double), ("reflection_phase_shift", C.c_double),
-                ("r_theta", C.c_void_p), ("r_phi", C.c_void_p)]
+                ("r_theta", C.c_void_p), ("r_phi", C.c_void_p), ("focusing", C.c_void_p)]
+
+
+class Focusing(C.Structure):
+    _fields_ = [("n_sol", C.c_void_p), ("C0", C.c_void_p), ("reflection", C.c_void_p), ("reflection_case", C.c_void_p),
+                ("path_length", C.c_void_p), ("sol_offset", C.c_void_p), ("limit", C.c_double), ("focusing", C.c_void_p)]
 
 
 EXPORTS = ("nrmc_rt_create", "nrmc_rt_destroy", "nrmc_rt_last_error", "nrmc_rt_max_solutions", "nrmc_rt_set_frequencies",
            "nrmc_rt_get_sparse_frequencies", "nrmc_rt_trace", "nrmc_rt_set_chunk_pairs", "nrmc_rt_host_alloc", "nrmc_rt_host_free",
-           "nrmc_rt_attenuation_length", "nrmc_rt_apply_propagation_effects", "nrmc_rt_measure_fp64_peak", "nrmc_rt_device_count", "nrmc_rt_version")
+           "nrmc_rt_attenuation_length", "nrmc_rt_apply_propagation_effects", "nrmc_rt_focusing_factor", "nrmc_rt_measure_fp64_peak", "nrmc_rt_device_count", "nrmc_rt_version")
 
 _lib = None
 
@@ -88,6 +93,8 @@ def load():
     lib.nrmc_rt_attenuation_length.restype = C.c_int
     lib.nrmc_rt_apply_propagation_effects.argtypes = [C.c_void_p, C.POINTER(Effects), C.c_void_p]
     lib.nrmc_rt_apply_propagation_effects.restype = C.c_int
+    lib.nrmc_rt_focusing_factor.argtypes = [C.c_void_p, C.POINTER(Input), C.POINTER(Focusing), C.c_void_p]
+    lib.nrmc_rt_focusing_factor.restype = C.c_int
     lib.nrmc_rt_measure_fp64_peak.argtypes = [C.c_int32, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     lib.nrmc_rt_measure_fp64_peak.restype = C.c_int
     lib.nrmc_rt_device_count.argtypes = []

@@ -508,6 +508,39 @@ NRMC_HD void solution_props(const IceParams &ice, const PairGeom &g, double x1y,
 
 
 // ---------------------------------------------------------------------------------------------------------------
+// Signal focusing (ray_tracing.get_focusing, py:2778-2888).  The reference re-traces the pair with the receiver moved by
+// dz = -1 cm and forms  sqrt(D / sin(rec) |d launch angle / dz|) * sqrt(D sin(launch) / rho), limits it, and multiplies by
+// sqrt(n_emitter / n_receiver).  Here the derivative is exact: on R(beta; z_e, z_r) = rho,
+//   d beta / d z_r = -(dR/dz_r) / (dR/dbeta),  |dR/dz_r| = tan(theta_r) = beta / s_r,  |d launch / d beta| = 1 / s_e,
+// so |d launch / d z_r| = beta / (s_r s_e |dR/dbeta|), with dR/dbeta = (dR/dt) / (dbeta/dt) from the same closed form the
+// Newton solver uses.  s_2 / (dbeta/dt) is formed analytically: it stays finite when the apex approaches the shallower
+// point (s_2 -> 0).  The branch (arrival before / after the turning point) is the one whose range reproduces rho.
+// D: path length of the solution.  Symmetric in emitter / receiver up to the index factors, so `swap` only selects them.
+// ---------------------------------------------------------------------------------------------------------------
+NRMC_HD double focusing_factor(const IceParams &ice, const PairGeom &g, bool swap, int k, int rcase, double beta,
+                                double path_length, double limit)
+{
+    Curve cv;
+    cv.ice = &ice; cv.g = &g; cv.k = k; cv.rcase = rcase;
+    const bool band = beta > ice.ns && g.s2max > 0.0;
+    const double nX = band ? g.n2 : ice.ns;
+    const double t = t_of_beta(nX, fmin(beta, nX));
+    double d0, d1;
+    const double r0 = curve_gd(cv, band ? 1 : 0, t, d0);      // arrival before the turning point
+    const double r1 = curve_gd(cv, band ? 2 : 3, t, d1);      // after
+    const double dg = fabs(r0) <= fabs(r1) ? d0 : d1;
+    RayState r;
+    ray_state(ice, g, band, t, r);
+    const double q = 1.0 / (1.0 + t * t);
+    const double s2_over_bp = band ? 0.5 / q : r.s2 / fmax(2.0 * r.ss * q, 1e-300);   // s_2 / (dbeta/dt)
+    const double W = r.s1 * s2_over_bp * fabs(dg);            // s_e s_r |dR/dbeta|
+    const double n_e = swap ? g.n2 : g.n1, n_r = swap ? g.n1 : g.n2;
+    double f = sqrt(path_length * n_r / W) * sqrt(path_length * beta / (n_e * g.rho));
+    if (!(f <= limit)) f = limit;                             // also the caustic (W -> 0) and 0/0
+    return f * sqrt(n_e / n_r);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // one (vertex, antenna) pair: geometry -> modes -> roots -> properties -> SoA outputs          (py:2057-2146)
 // ---------------------------------------------------------------------------------------------------------------
 struct TraceOutputs {          // all [N,S] pair-major, S = 2 + 4 n_refl; any pointer may be null (skipped)

@@ -1274,6 +1274,7 @@ K_apply_effects(nrmc_rt_effects fx, AttTables tb, int K1, double n_surface)
                 const cplx b = {amp * cos(ph), amp * sin(ph)};
                 ct = cmul(ct, b); cp = cmul(cp, b);
             }
+            if (fx.focusing) { const double fc = fx.focusing[row]; ct.re *= fc; ct.im *= fc; cp.re *= fc; cp.im *= fc; }   // py:3012-3015
             s_c[0] = ct; s_c[1] = cp;
         }
         __syncthreads();
@@ -1298,6 +1299,30 @@ K_apply_effects(nrmc_rt_effects fx, AttTables tb, int K1, double n_surface)
         }
         __syncthreads();
     }
+}
+
+// Focusing factor of every solution of a trace result (py:2778-2888): thread per pair, exact d(launch angle)/d(receiver depth)
+__global__ void __launch_bounds__(128)
+K_focusing(IceParams ice, KInput in, nrmc_rt_focusing fo, int S)
+{
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= in.n_pairs) return;
+    const int n = fo.n_sol[p];
+    const int64_t row0 = fo.sol_offset ? fo.sol_offset[p] : p * S;
+    if (n > 0) {
+        double x1, y1, z1, x2, y2, z2;
+        load_pair(in, p, x1, y1, z1, x2, y2, z2);
+        Frame2D f;
+        make_frame(x1, y1, z1, x2, y2, z2, f);
+        PairGeom g;
+        make_pair_geom(ice, f.z1, f.z2, fmax(f.rho, 1e-12), g);
+        for (int s = 0; s < n && s < S; ++s) {
+            const int64_t q = row0 + s;
+            const int k = fo.reflection ? fo.reflection[q] : 0, rcase = fo.reflection_case ? fo.reflection_case[q] : 1;
+            fo.focusing[q] = focusing_factor(ice, g, f.swap, k, rcase > 0 ? rcase : 1, 1.0 / fo.C0[q], fo.path_length[q], fo.limit);
+        }
+    }
+    if (!fo.sol_offset) for (int s = n < 0 ? 0 : n; s < S; ++s) fo.focusing[row0 + s] = NAN;
 }
 
 __global__ void K_att_length(IceParams ice, Gl3Table gl3, const double *z, const double *f, int64_t n, double *out)
@@ -2118,6 +2143,26 @@ extern "C" int nrmc_rt_apply_propagation_effects(nrmc_rt_t h, const nrmc_rt_effe
     const double n_surface = h->ice.n_ice - h->ice.dn * exp(-0.01 * h->ice.inv_z0);    // n(z = -1 cm), py:2990
     const int64_t blocks = std::min<int64_t>(fx->n_rows, (int64_t)h->n_sm * 16);
     K_apply_effects<<<(unsigned)blocks, FX_THREADS, 0, (cudaStream_t)stream>>>(*fx, h->tb, h->K1, n_surface);
+    CK(cudaGetLastError());
+    return NRMC_OK;
+}
+
+extern "C" int nrmc_rt_focusing_factor(nrmc_rt_t h, const nrmc_rt_input *in, const nrmc_rt_focusing *fo, void *stream)
+{
+    if (!h || !in || !fo) return NRMC_ERR_INVALID_ARGUMENT;
+    if (in->memory != NRMC_MEMORY_DEVICE) { h->err = "nrmc_rt_focusing_factor takes device pointers"; return NRMC_ERR_INVALID_ARGUMENT; }
+    if (in->n_vertices < 0 || in->n_antennas < 0 || (!in->outer && in->n_antennas != in->n_vertices)) return NRMC_ERR_INVALID_ARGUMENT;
+    const int64_t N = in->outer ? in->n_vertices * in->n_antennas : in->n_vertices;
+    if (N == 0) return NRMC_OK;
+    if (!in->vx || !in->vy || !in->vz || !in->ax || !in->ay || !in->az || !fo->n_sol || !fo->C0 || !fo->path_length || !fo->focusing ||
+        !(fo->limit > 0.0))
+        return NRMC_ERR_INVALID_ARGUMENT;
+    CK(cudaSetDevice(h->cfg.device));
+    KInput kin;
+    kin.vx = in->vx; kin.vy = in->vy; kin.vz = in->vz; kin.ax = in->ax; kin.ay = in->ay; kin.az = in->az;
+    kin.n_pairs = N; kin.n_antennas = in->outer ? in->n_antennas : 1; kin.outer = in->outer;
+    kin.sx = kin.sy = kin.sz = nullptr; kin.delta_C_cut = 0.0;
+    K_focusing<<<(unsigned)((N + 127) / 128), 128, 0, (cudaStream_t)stream>>>(h->ice, kin, *fo, h->S);
     CK(cudaGetLastError());
     return NRMC_OK;
 }

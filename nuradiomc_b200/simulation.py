@@ -43,12 +43,13 @@ def cherenkov_mask(result, medium, vertices, n_channels, delta_C_cut):
         return np.abs(result["viewing_angle"] - cherenkov[:, None]) <= delta_C_cut
 
 
-def raytracing_datasets(result, n_showers, n_channels, keep=None):
+def raytracing_datasets(result, n_showers, n_channels, keep=None, focusing=None):
     """
     The per-station ray-tracing datasets of the HDF5 output file, shapes as output_writer_hdf5.py:267-294 builds them
     per shower and stacks them: travel_times, travel_distances (nSh, nCh, nS); launch_vectors, receive_vectors
     (nSh, nCh, nS, 3); the propagator's output parameters (nSh, nCh, nS).  Entries without solution are NaN
     (:272-275).  keep: optional (N, S) mask (e.g. `cherenkov_mask`): solutions the simulation skipped are NaN as well.
+    focusing: optional (N, S) factors of `ray_tracing.focusing_batch` (config['propagation']['focusing']); 1 otherwise.
     """
     if getattr(result, "compact", False):
         raise ValueError("raytracing_datasets needs the padded layout (compact=False)")
@@ -71,7 +72,8 @@ def raytracing_datasets(result, n_showers, n_channels, keep=None):
         "ray_tracing_reflection": grid(result["reflection"]),
         "ray_tracing_reflection_case": grid(result["reflection_case"]),
         "ray_tracing_solution_type": grid(result["solution_type"]),
-        "focusing_factor": grid(np.ones_like(result["C0"])),       # get_raytracing_output: 1 unless focusing is enabled
+        # get_raytracing_output (analyticraytracing.py:2905-2935): 1 unless focusing is enabled
+        "focusing_factor": grid(np.ones_like(result["C0"]) if focusing is None else focusing),
     }
     return ds
 

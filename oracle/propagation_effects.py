@@ -1,7 +1,7 @@
 """
 TEST INFRASTRUCTURE -- numpy restatement of the reference's propagation effects, the step after the ray trace:
-ray_tracing.apply_propagation_effects (NuRadioMC/SignalProp/analyticraytracing.py:2937-3033, in-ice branch, focusing and
-birefringence off) and the Fresnel reflection coefficients (NuRadioReco/utilities/geometryUtilities.py:211-263).
+ray_tracing.apply_propagation_effects (NuRadioMC/SignalProp/analyticraytracing.py:2937-3033, in-ice branch, birefringence
+off; the focusing factor is an input, oracle/focusing.py) and the Fresnel reflection coefficients (NuRadioReco/utilities/geometryUtilities.py:211-263).
 Pinned by tests/golden/propagation_effects.npz (the reference's own functions, run by tests/golden/make_golden.py effects).
 Only tests/ may import this module.
 """
@@ -23,7 +23,7 @@ def fresnel_r_s(zenith, n_2, n_1):
 
 
 def apply_propagation_effects(spec, attenuation, reflection_angles, n_bottom_reflections, n_surface,
-                              reflection_coefficient=None, reflection_phase_shift=None):
+                              reflection_coefficient=None, reflection_phase_shift=None, focusing=None):
     """
     spec: (3, F) complex (eR, eTheta, ePhi); attenuation: (F,) or None; reflection_angles: per path segment, NaN = None.
     Returns (spec, r_theta, r_phi) as the reference leaves them (analyticraytracing.py:2963-3010).
@@ -44,4 +44,6 @@ def apply_propagation_effects(spec, attenuation, reflection_angles, n_bottom_ref
         c = reflection_coefficient ** k * np.exp(1j * ((k * reflection_phase_shift) % (2 * np.pi)))
         spec[1] *= c
         spec[2] *= c
+    if focusing is not None:                                             # :3012-3015
+        spec[1:] *= focusing
     return spec, r_theta, r_phi

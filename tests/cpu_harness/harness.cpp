@@ -17,3 +17,26 @@ extern "C" int harness_trace(double n_ice, double dn, double z0, double zr, int 
         trace_pair(ice, X1[3 * i], X1[3 * i + 1], X1[3 * i + 2], X2[3 * i], X2[3 * i + 1], X2[3 * i + 2], i, o, nullptr);
     return 0;
 }
+
+// focusing factor of every solution of a padded [N,S] result (same device function as K_focusing)
+extern "C" int harness_focusing(double n_ice, double dn, double z0, double zr, int n_refl, int64_t N, const double *X1,
+                                const double *X2, const int32_t *n_sol, const double *C0, const int8_t *reflection,
+                                const int8_t *reflection_case, const double *path_length, double limit, double *focusing)
+{
+    IceParams ice;
+    ice.n_ice = n_ice; ice.dn = dn; ice.z0 = z0; ice.inv_z0 = 1.0 / z0; ice.ns = n_ice - dn;
+    ice.n_refl = n_refl; ice.zr = n_refl > 0 ? zr : -1e30;
+    ice.gr = n_refl > 0 ? dn * exp(zr / z0) : 0.0; ice.nr = n_ice - ice.gr; ice.att_model = 0;
+    const int S = 2 + 4 * n_refl;
+    for (int64_t i = 0; i < N; ++i) {
+        Frame2D f;
+        make_frame(X1[3 * i], X1[3 * i + 1], X1[3 * i + 2], X2[3 * i], X2[3 * i + 1], X2[3 * i + 2], f);
+        PairGeom g;
+        make_pair_geom(ice, f.z1, f.z2, fmax(f.rho, 1e-12), g);
+        for (int s = 0; s < S; ++s) {
+            const int64_t q = i * S + s;
+            focusing[q] = s < n_sol[i] ? focusing_factor(ice, g, f.swap, reflection[q], reflection_case[q], 1.0 / C0[q], path_length[q], limit) : NAN;
+        }
+    }
+    return 0;
+}

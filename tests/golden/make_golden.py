@@ -197,8 +197,56 @@ def make_effects_golden():
     print("propagation_effects: solutions", int(out["sp_n_sol"].sum()), int(out["mb_n_sol"].sum()))
 
 
+def _focusing_work(args):
+    ice, n_refl, X1, X2, limit = args
+    import ref_harness as rh
+    r = rh.make_tracer(ice, n_reflections=n_refl)
+    # get_focusing builds its second tracer without compile_numba=False (analyticraytracing.py:2834-2835), which would switch
+    # the whole module to the numba functions; give it the plain one it would otherwise create
+    r._r1 = rh.make_tracer(ice, n_reflections=n_refl)
+    S = r.get_number_of_raytracing_solutions()
+    foc = np.full((len(X1), S), np.nan)
+    n_sol = np.zeros(len(X1), np.int32)
+    n_sol_displaced = np.zeros(len(X1), np.int32)
+    C0 = np.full((len(X1), S), np.nan)
+    for i in range(len(X1)):
+        r.set_start_and_end_point(X1[i], X2[i])
+        r.find_solutions()
+        n_sol[i] = r.get_number_of_solutions()
+        for iS in range(n_sol[i]):
+            C0[i, iS] = r.get_results()[iS]["C0"]
+            foc[i, iS] = r.get_focusing(iS, limit=limit)
+        n_sol_displaced[i] = r._r1.get_number_of_solutions() if n_sol[i] else 0
+    return foc, n_sol, n_sol_displaced, C0
+
+
+def make_focusing_golden():
+    """fixtures of ray_tracing.get_focusing (analyticraytracing.py:2778-2888, numerical branch, dz = -1 cm): the reference's
+    own values; `n_sol_displaced` is the solution count of its second trace (receiver moved by dz) -- where it differs from
+    n_sol the reference returns 1 or pairs unrelated rays (:2840,:2863)."""
+    out = {}
+    pool = Pool(8)
+    V, A = pairs(cylinder(51, 150, 4000., -2700.), np.array([[10, 10, -190.], [0, 0, -2.]]))
+    Vs = cylinder(52, 60, 2000., -300.)       # emitters above the receiver: the reference swaps the points (:2072-2077)
+    X1 = np.concatenate([V, Vs])
+    X2 = np.concatenate([A, np.repeat([[0, 0, -800.]], len(Vs), 0)])
+    Vm, Am = pairs(cylinder(53, 60, 1000., -500.), np.array([[3, 3, -5.], [-3, 0, -1.]]))
+    for tag, ice, n_refl, P1, P2, limit in (("sp", "southpole_2015", 0, X1, X2, 2.0), ("sp_nolimit", "southpole_2015", 0, X1[:120], X2[:120], 1e9),
+                                            ("mb", "mooresbay_simple", 1, Vm, Am, 2.0)):
+        N = len(P1)
+        chunk = max(1, N // 32)
+        parts = pool.map(_focusing_work, [(ice, n_refl, P1[lo:lo + chunk], P2[lo:lo + chunk], limit) for lo in range(0, N, chunk)])
+        foc, n_sol, n_disp, C0 = (np.concatenate([p[k] for p in parts]) for k in range(4))
+        out.update({f"{tag}_X1": P1, f"{tag}_X2": P2, f"{tag}_focusing": foc, f"{tag}_n_sol": n_sol, f"{tag}_n_sol_displaced": n_disp,
+                    f"{tag}_C0": C0, f"{tag}_limit": np.array(limit), f"{tag}_ice": ice, f"{tag}_n_reflections": n_refl})
+        print(f"focusing {tag}: N={N} solutions={int(n_sol.sum())} displaced-count-differs={int((n_sol != n_disp).sum())}", flush=True)
+    np.savez_compressed(os.path.join(HERE, "focusing.npz"), **out)
+
+
 if __name__ == "__main__":
     if sys.argv[1:] == ["effects"]:
         make_effects_golden()
+    elif sys.argv[1:] == ["focusing"]:
+        make_focusing_golden()
     else:
         main(sys.argv[1:])

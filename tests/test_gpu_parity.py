@@ -443,6 +443,87 @@ def test_propagation_effects_kernel(make, oracle_mod, tag, ice, att, n_refl):
             rt.apply_propagation_effects_batch(spec_in, attenuation_sparse=res["attenuation_sparse"])
 
 
+@pytest.mark.parametrize("tag", ["sp", "sp_nolimit", "mb"])
+def test_focusing_kernel(make, oracle_mod, tag):
+    """K_focusing (get_focusing, analyticraytracing.py:2778-2888) through the C ABI: against the reference's own values
+    (tests/golden/focusing.npz, 5e-3 = the reference's root-finding noise on its 1 cm difference quotient), against the oracle
+    restatement (same quotient on the oracle's traces: 2e-3, its truncation error), padded == compact == device-resident,
+    and the scalar API"""
+    import torch
+    from oracle.focusing import get_focusing
+    g = load_golden("focusing")
+    ice, n_refl, limit = str(g[f"{tag}_ice"]), int(g[f"{tag}_n_reflections"]), float(g[f"{tag}_limit"])
+    X1, X2, ref = g[f"{tag}_X1"], g[f"{tag}_X2"], g[f"{tag}_focusing"]
+    rt = make(ice, n_reflections=n_refl)
+    res = rt.trace_batch(X1, X2)
+    f = rt.focusing_batch(X1, X2, res, limit=limit)
+    S = res["C0"].shape[1]
+    filled = np.arange(S)[None, :] < res["n_sol"][:, None]
+    assert f.shape == res["C0"].shape and np.isnan(f[~filled]).all() and np.isfinite(f[filled]).all()
+    n_of = lambda z: rt._medium.get_index_of_refraction(np.array([0, 0, 1.])[None, :] * np.asarray(z)[:, None])
+    assert (f[filled] <= (limit * np.sqrt(n_of(X1[:, 2]) / n_of(X2[:, 2])))[:, None].repeat(S, 1)[filled] * (1 + 1e-12)).all()
+    ok = filled & (res["n_sol"] == g[f"{tag}_n_sol"])[:, None] & (g[f"{tag}_n_sol"] == g[f"{tag}_n_sol_displaced"])[:, None]
+    assert ok.sum() >= 0.98 * np.isfinite(ref).sum()
+    np.testing.assert_allclose(f[ok], ref[ok], rtol=5e-3)
+    o = oracle_mod.Oracle(ice, n_reflections=n_refl)
+    fo, comparable = get_focusing(o, X1, X2, limit=limit)
+    sel = comparable & filled
+    near_limit = np.isclose(np.maximum(fo, f), (limit * np.sqrt(n_of(X1[:, 2]) / n_of(X2[:, 2])))[:, None], rtol=1e-2)
+    sel &= ~near_limit                       # either side may clip first within the quotient's truncation error
+    assert sel.sum() > 0.8 * filled.sum()
+    np.testing.assert_allclose(f[sel], fo[sel], rtol=2e-3)
+    # compact rows and device-resident tensors give the same numbers
+    resc = rt.trace_batch(X1, X2, compact=True)
+    fc = rt.focusing_batch(X1, X2, resc, limit=limit)
+    np.testing.assert_array_equal(fc, f[filled])
+    v = torch.as_tensor(np.ascontiguousarray(X1.T)).cuda()
+    a = torch.as_tensor(np.ascontiguousarray(X2.T)).cuda()
+    resd = rt.trace_batch_device(v, a, compact=True)
+    fd = rt.focusing_batch(v, a, resd, limit=limit)
+    np.testing.assert_array_equal(fd[:resd.n_rows()].cpu().numpy(), fc)
+    # scalar API (default limit 2) and the HDF5 output parameter (:2905-2935)
+    i = int(np.nonzero(res["n_sol"] == res["n_sol"].max())[0][0])
+    rt.set_start_and_end_point(X1[i], X2[i])
+    rt.find_solutions()
+    f2 = rt.focusing_batch(X1[i:i + 1], X2[i:i + 1], {k: res[k][i:i + 1] for k in res}, limit=2.0)[0]
+    for iS in range(rt.get_number_of_solutions()):
+        assert rt.get_focusing(iS) == f2[iS]
+        assert rt.get_raytracing_output(iS)["focusing_factor"] == 1
+    rt.set_config({"propagation": {"attenuate_ice": False, "focusing": True, "focusing_limit": 1.5, "birefringence": False}})
+    f15 = rt.focusing_batch(X1[i:i + 1], X2[i:i + 1], {k: res[k][i:i + 1] for k in res})[0]
+    assert rt.get_raytracing_output(0)["focusing_factor"] == f15[0]
+    with pytest.raises(IndexError):
+        rt.get_focusing(rt.get_number_of_solutions())
+
+
+def test_propagation_effects_with_focusing(make, oracle_mod):
+    """config['propagation']['focusing']: eTheta and ePhi scaled by get_focusing, eR untouched (analyticraytracing.py:3012-3015)"""
+    from oracle import propagation_effects as pe
+    g = load_golden("propagation_effects")
+    ff, X1, X2 = g["sp_frequencies"], g["sp_X1"], g["sp_X2"]
+    cfg = {"propagation": {"attenuate_ice": True, "focusing": True, "focusing_limit": 2, "birefringence": False}}
+    rt = make("southpole_2015", attenuation_model="SP1", n_frequencies_integration=12, config=cfg)
+    res = rt.trace_batch(X1, X2, frequency=ff, max_detector_freq=float(ff.max()), attenuation="dense", compact=True)
+    foc = rt.focusing_batch(X1, X2, res)
+    S = g["sp_spec_in"].shape[1]
+    spec_in = g["sp_spec_in"][np.arange(S)[None, :] < res["n_sol"][:, None]]
+    out = rt.apply_propagation_effects_batch(spec_in, reflection_angle=res["reflection_angle"], reflection=res["reflection"],
+                                             attenuation=res["attenuation"], focusing=foc)
+    n_ice, dn, z0, _ = oracle_mod.ICE_MODELS["southpole_2015"]
+    for r in range(len(spec_in)):
+        exp, _, _ = pe.apply_propagation_effects(spec_in[r], res["attenuation"][r], res["reflection_angle"][r, :1], 0,
+                                                 n_ice - dn * np.exp(-0.01 / z0), focusing=foc[r])
+        np.testing.assert_allclose(out[r], exp, rtol=1e-12, atol=1e-14)
+    i = int(np.nonzero(res["n_sol"] == 2)[0][0])
+    rt.set_start_and_end_point(X1[i], X2[i])
+    rt.find_solutions()
+    r0 = int(res["sol_offset"][i])
+    for iS in range(2):
+        fld = _Field(spec_in[r0 + iS], ff, 2.0)
+        rt.apply_propagation_effects(fld, iS)
+        np.testing.assert_allclose(fld.spec, out[r0 + iS], rtol=1e-12, atol=1e-14)
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # the callers either side of the path (SURVEY.md 8(f) N2-N4)
 # ---------------------------------------------------------------------------------------------------------------

@@ -45,6 +45,20 @@ def harness(oracle_mod):
                         p(X1), p(X2), *[p(out[k]) for k in ("n_sol", "status", "type", "reflection", "reflection_case", "C0", "C1",
                                                            "path_length", "travel_time", "launch", "receive", "reflection_angle")])
         return out
+
+    def focusing(ice, n_refl, X1, X2, res, limit):
+        n_ice, dn, z0, zr = oracle_mod.ICE_MODELS[ice]
+        if zr is None:
+            n_refl = 0
+        X1 = np.ascontiguousarray(np.atleast_2d(X1), float)
+        X2 = np.ascontiguousarray(np.atleast_2d(X2), float)
+        p = lambda a: np.ascontiguousarray(a).ctypes.data_as(C.c_void_p)
+        out = np.zeros_like(res["C0"])
+        H.harness_focusing(C.c_double(n_ice), C.c_double(dn), C.c_double(z0), C.c_double(zr or 0.), C.c_int(n_refl), C.c_int64(len(X1)),
+                           p(X1), p(X2), p(res["n_sol"]), p(res["C0"]), p(res["reflection"]), p(res["reflection_case"]),
+                           p(res["path_length"]), C.c_double(limit), p(out))
+        return out
+    run.focusing = focusing
     return run
 
 
@@ -179,3 +193,39 @@ def test_wide_geometry_stress_counts(harness, oracle_mod):
             for c in ora["C0"][i][:ora["n_sol"][i]]:
                 assert np.nanmin(np.abs(out["C0"][i] - c)) < 1e-6 * c
         _assert_parity(out, ora, exact_count=False)
+
+
+@pytest.mark.parametrize("tag", ["sp", "sp_nolimit", "mb"])
+def test_focusing_vs_reference_and_own_difference_quotient(harness, tag):
+    """focusing_factor (nrmc_math.cuh; exact d launch / d z_receiver from the closed-form dR/dbeta) against
+    (a) the reference's get_focusing (tests/golden/focusing.npz): 5e-3 = the reference's own root-finding noise on its 1 cm
+        difference quotient (see test_oracle_golden.py::test_focusing_restatement_vs_reference);
+    (b) the difference quotient of the kernel maths' own traces (roots to 1e-16), which converges linearly in dz to the exact
+        derivative: 2e-3 at the reference's 1 cm, 2e-4 at 1 mm."""
+    g = load_golden("focusing")
+    ice, n_refl, limit = str(g[f"{tag}_ice"]), int(g[f"{tag}_n_reflections"]), float(g[f"{tag}_limit"])
+    X1, X2, ref = g[f"{tag}_X1"], g[f"{tag}_X2"], g[f"{tag}_focusing"]
+    a = harness(ice, n_refl, X1, X2)
+    f = harness.focusing(ice, n_refl, X1, X2, a, limit)
+    S = a["C0"].shape[1]
+    filled = np.arange(S)[None, :] < a["n_sol"][:, None]
+    assert np.isnan(f[~filled]).all() and np.isfinite(f[filled]).all()
+    ok = filled & (a["n_sol"] == g[f"{tag}_n_sol"])[:, None] & (g[f"{tag}_n_sol"] == g[f"{tag}_n_sol_displaced"])[:, None]
+    assert ok.sum() >= 0.98 * np.isfinite(ref).sum()
+    np.testing.assert_allclose(f[ok], ref[ok], rtol=5e-3)
+    n_ice, dn, z0, _ = __import__("oracle.oracle", fromlist=["x"]).ICE_MODELS[ice]
+    n_of = lambda z: n_ice - dn * np.exp(z / z0)
+    for dz, tol in ((-1e-2, 3e-3), (-1e-3, 3e-4)):
+        X2b = X2.copy()
+        X2b[:, 2] += dz
+        b = harness(ice, n_refl, X1, X2b)
+        same = filled & (a["n_sol"] == b["n_sol"])[:, None] & (a["reflection"] == b["reflection"]) & (a["reflection_case"] == b["reflection_case"])
+        with np.errstate(invalid="ignore", divide="ignore"):
+            la, lb = np.arccos(a["launch"][..., 2]), np.arccos(b["launch"][..., 2])
+            D, rho = a["path_length"], np.linalg.norm((X2 - X1)[:, :2], axis=1)[:, None]
+            fd = np.sqrt(D / np.sin(np.arccos(-a["receive"][..., 2])) * np.abs((lb - la) / dz)) * np.sqrt(D * np.sin(la) / rho)
+        fd = np.minimum(fd, limit) * np.sqrt(n_of(X1[:, 2]) / n_of(X2[:, 2]))[:, None]
+        clipped = np.isclose(np.maximum(fd, f), limit * np.sqrt(n_of(X1[:, 2]) / n_of(X2[:, 2]))[:, None], rtol=1e-2)   # near the limit either may clip first
+        sel = same & ~clipped
+        assert sel.sum() > 0.8 * filled.sum()
+        np.testing.assert_allclose(f[sel], fd[sel], rtol=tol)
