@@ -156,12 +156,74 @@ struct Curve {                // one (reflection, case) mode of one pair
     int k, rcase;
 };
 
-#ifndef NRMC_RSQRT
-#if defined(__CUDA_ARCH__)
-#define NRMC_RSQRT(x) rsqrt(x)
-#else
-#define NRMC_RSQRT(x) (1.0 / sqrt(x))
+// Reciprocal, reciprocal square root and logarithm of the solver's inner loop.  On the device they are the fast paths only:
+// CUDA's 1/x, rsqrt and log guard every call with an exponent-range test, a convergence barrier and a slow-path call, and
+// log materialises its polynomial with two UMOVs per coefficient; the arguments here are positive normal numbers (sums of
+// squares, the k factors of the range function), so the hardware seed (MUFU.RCP64H / RSQ64H, 2^-23) plus Newton steps is all
+// that is needed, and log keeps its coefficients in constant memory (fdlibm's reduction and degree-14 odd polynomial,
+// < 1 ulp).  Zero, inf and NaN (a horizontal ray in numerically homogeneous ice) give the IEEE results (inf, 0, NaN), so
+// they propagate as before; denormals count as zero.  NRMC_STOCK_MATH: CUDA's functions everywhere (A/B builds).
+#if defined(__CUDACC__)
+__constant__ double c_logc[9] = {1.479819860511658591e-01, 1.531383769920937332e-01, 1.818357216161805012e-01, 2.222219843214978396e-01,
+                                 2.857142874366239149e-01, 3.999999999940941908e-01, 6.666666666666735130e-01,
+                                 6.93147180369123816490e-01, 1.90821492927058770002e-10};   // Lg7 .. Lg1, ln2_hi, ln2_lo
 #endif
+#if defined(__CUDA_ARCH__) && !defined(NRMC_STOCK_MATH)
+__device__ __forceinline__ bool nrmc_is_normal(double x)            // finite, non-zero, not denormal (either sign)
+{
+    return (unsigned)((__double2hiint(x) & 0x7ff00000) - 0x00100000) < 0x7fe00000u;
+}
+__device__ __forceinline__ double nrmc_rcp(double x)
+{
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));           // 0 -> inf, inf -> 0, NaN -> NaN: returned as they are
+    if (nrmc_is_normal(x)) {
+        double e = fma(-x, y, 1.0);
+        y = fma(y, e, y);
+        e = fma(-x, y, 1.0);
+        y = fma(y, e, y);
+    }
+    return y;
+}
+__device__ __forceinline__ double nrmc_rsqrt(double x)
+{
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));         // 0 -> inf, inf -> 0, negative / NaN -> NaN
+    if (nrmc_is_normal(x) && x > 0.0) {
+        double e = fma(-(x * y), y, 1.0);                           // 1 - x y^2
+        y = fma(fma(0.375, e, 0.5) * e, y, y);                      // third order: y (1 + e/2 + 3 e^2/8)
+        e = fma(-(x * y), y, 1.0);
+        y = fma(0.5 * e, y, y);
+    }
+    return y;
+}
+__device__ __forceinline__ double nrmc_log(double x)
+{
+    int hi = __double2hiint(x);
+    if ((unsigned)(hi - 0x00100000) >= 0x7fe00000u)                 // not a positive normal number
+        return (x != x || x < 0.0) ? NAN : (x > 1.0 ? INFINITY : -INFINITY);   // (denormals count as 0)
+    hi += 0x3ff00000 - 0x3fe6a09e;                                  // mantissa into [sqrt(1/2), sqrt(2))
+    const double dk = (double)((hi >> 20) - 0x3ff);
+    const double m = __hiloint2double((hi & 0x000fffff) + 0x3fe6a09e, __double2loint(x));
+    const double f = m - 1.0;
+    const double s = f * nrmc_rcp(2.0 + f);
+    const double z = s * s, w = z * z;
+    const double t1 = w * fma(w, fma(w, c_logc[1], c_logc[3]), c_logc[5]);
+    const double t2 = z * fma(w, fma(w, fma(w, c_logc[0], c_logc[2]), c_logc[4]), c_logc[6]);
+    const double hfsq = 0.5 * f * f;
+    return fma(dk, c_logc[7], -((hfsq - fma(s, hfsq + (t2 + t1), dk * c_logc[8])) - f));
+}
+#define NRMC_RCP(x) nrmc_rcp(x)
+#define NRMC_RSQRT(x) nrmc_rsqrt(x)
+#define NRMC_LOG(x) nrmc_log(x)
+#elif defined(__CUDA_ARCH__)
+#define NRMC_RCP(x) (1.0 / (x))
+#define NRMC_RSQRT(x) rsqrt(x)
+#define NRMC_LOG(x) log(x)
+#else
+#define NRMC_RCP(x) (1.0 / (x))
+#define NRMC_RSQRT(x) (1.0 / sqrt(x))
+#define NRMC_LOG(x) log(x)
 #endif
 
 // g = R - rho on piece p in {0,1,2,3} at parameter t and (WITH_D) dg/dt, in ONE pass.  With h = sigma sigma',
@@ -177,7 +239,7 @@ NRMC_HD double curve_eval(const Curve &cv, int p, double t, double &dg)
     const PairGeom &g = *cv.g;
     const bool band = (p == 1 || p == 2), turned = (p >= 2);
     const PieceConsts pc = piece_consts(ice, g, band);
-    const double q = 1.0 / (1.0 + t * t);
+    const double q = NRMC_RCP(1.0 + t * t);
     const double beta = pc.nX * (2.0 * t) * q;
     const double sig = pc.nX * ((1.0 - t) * (1.0 + t)) * q;
     const double sg2 = sig * sig;
@@ -201,7 +263,7 @@ NRMC_HD double curve_eval(const Curve &cv, int p, double t, double &dg)
     double P, lin, dlnP = 0.0;
     if (cv.k == 0) {
         const double Kx = turned ? KT : 1.0;
-        const double iv = 1.0 / (k1 * k2 * Kx);
+        const double iv = NRMC_RCP(k1 * k2 * Kx);
         P = (turned ? KT * KT * KT : k2 * k2) * iv;
         lin = turned ? -g.z1 - g.z2 : g.z2 - g.z1;
         if (WITH_D) dlnP = ((turned ? 2.0 * dKT * k1 * k2 - dk2 * k1 * KT : dk2 * k1) - dk1 * k2 * Kx) * iv;
@@ -221,7 +283,7 @@ NRMC_HD double curve_eval(const Curve &cv, int p, double t, double &dg)
             dlnP = m.a1 * dk1 / k1 + m.a2 * dk2 / k2 + m.ar * dkr / kr + (m.aT ? m.aT * dKT / KT : 0.0);
         }
     }
-    const double Bk = lin - ice.z0 * log(P);
+    const double Bk = lin - ice.z0 * NRMC_LOG(P);
     double R = A * Bk;
     if (WITH_D) dg = (bp - A * drc) * irc * Bk - A * ice.z0 * dlnP;
     if (!(R == R)) { R = 1e300; if (WITH_D) dg = 0.0; }   // horizontal ray in (numerically) homogeneous ice: infinite range
@@ -250,6 +312,9 @@ NRMC_HD double guess_t(const IceParams &ice, const PairGeom &g, int p)
 // derivative, kept inside the bracket (bisection when a step leaves it).  x0: starting point (NaN: secant point).
 // Stops on |g| <= 1e-10 m or when the Newton step is below 1e-9 relative (the step is then applied unevaluated:
 // quadratic convergence puts the result at ~1e-16).
+// (Tried: the zero of the inverse cubic Hermite interpolant through the last two points instead of the Newton step from the
+// second evaluation on -- 3.60 -> 3.33 evaluations per root on the cfg5 geometry, the slowest lane of a warp 5.56 -> 5.09 --
+// but the three extra live doubles and the longer loop body cost more on the B200 than the evaluations saved: 15.4 vs 15.1 ms.)
 NRMC_HD double solve_piece(const Curve &cv, int p, double a, double ga, double b, double gb, double x0)
 {
     const double gtol = 1e-10;
@@ -263,7 +328,7 @@ NRMC_HD double solve_piece(const Curve &cv, int p, double a, double ga, double b
         if (fabs(gx) <= gtol) break;
         if ((gx > 0) == (gb > 0)) { b = x; gb = gx; } else { a = x; ga = gx; }
         lo = fmin(a, b); hi = fmax(a, b);
-        double xn = x - gx / dg;
+        double xn = x - gx * NRMC_RCP(dg);
         if (!(xn > lo && xn < hi)) xn = 0.5 * (a + b);
         else if (fabs(xn - x) <= 1e-9 * (fabs(x) + 1e-3)) { x = xn; break; }
         if (hi - lo <= 4e-16 * (fabs(lo) + fabs(hi))) { x = xn; break; }
@@ -462,11 +527,11 @@ NRMC_HD void solution_props(const IceParams &ice, const PairGeom &g, double x1y,
     const double A = r.beta / r.rc;
     o.C0 = 1.0 / r.beta;
     // C_1 = y1 - y(z1; C_1 = 0),  y = z0 beta/sqrt(c) ln(gamma / (2 k1))       (py:487-491,118-125)
-    o.C1 = x1y - ice.z0 * A * log(g.g1 / (2.0 * r.k1_1));
+    o.C1 = x1y - ice.z0 * A * NRMC_LOG(g.g1 / (2.0 * r.k1_1));
     // solution type on the UNREFLECTED geometry (py:2146 -> :1386-1398): direct iff rho < y_turn - y1
     if (k == 0) o.type = turned ? (r.reflected ? 3 : 2) : 1;
     else {
-        double T1 = A * (-g.z1 - ice.z0 * log(r.KT / r.k1_1));
+        double T1 = A * (-g.z1 - ice.z0 * NRMC_LOG(r.KT / r.k1_1));
         o.type = (g.rho < T1) ? 1 : (r.reflected ? 3 : 2);
     }
     // launch: theta1 with sin = beta/n1, downward start (case 2, k>0) -> pi - theta1   (py:1161-1196)
@@ -487,7 +552,7 @@ NRMC_HD void solution_props(const IceParams &ice, const PairGeom &g, double x1y,
     num *= ipow(k2_T, m.aT);
     double ssum = m.a1 * r.s1 + m.a2 * r.s2 + m.aT * sT;
     if (m.ar != 0) { den *= ipow(k2_r, -m.ar); ssum += m.ar * r.sr; }
-    double lk2 = log(num / den);
+    double lk2 = NRMC_LOG(num / den);
     double sumU = g.rho / A;
     o.path_length = ice.n_ice / r.rc * sumU + ice.z0 * lk2;
     o.travel_time = (ice.n_ice * ice.n_ice / r.rc * sumU + ice.z0 * (ssum + ice.n_ice * lk2)) / NRMC_SPEED_OF_LIGHT;
@@ -603,7 +668,7 @@ NRMC_HD void make_solrec(const IceParams &ice, const PairGeom &g, int64_t pair, 
     const double sig = (band ? g.n2 : ice.ns) * ((1.0 - root.v) * (1.0 + root.v)) * q;
     const double c = (band ? g.c0_band : g.c0_sub) + sig * sig;
     r.delta = c / (ice.n_ice + r.beta);
-    r.zv = ice.z0 * log(r.delta / ice.dn);
+    r.zv = ice.z0 * NRMC_LOG(r.delta / ice.dn);
     r.z1 = g.z1; r.z2 = g.z2;
 }
 

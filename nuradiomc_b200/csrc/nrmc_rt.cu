@@ -264,8 +264,11 @@ K_hump(IceParams ice, KInput in, TraceOutputs out, AttFill af, const HumpItem *h
 }
 
 #define ROOTS_THREADS 128
+#ifndef ROOTS_MIN_BLOCKS
+#define ROOTS_MIN_BLOCKS 7      // 72 registers, no spills: 28 warps per SM (6: 78 registers; 8: 64 registers with spills)
+#endif
 template <bool CUT>
-__global__ void __launch_bounds__(ROOTS_THREADS)
+__global__ void __launch_bounds__(ROOTS_THREADS, ROOTS_MIN_BLOCKS)
 K_roots(IceParams ice, KInput in, TraceOutputs out, AttFill af, const RootItem *rootq, const unsigned long long *root_count, SolRec *worklist,
         unsigned long long *work_count, unsigned long long work_cap)
 {
@@ -991,6 +994,10 @@ __device__ __forceinline__ void sp1_node(const IceParams &ice, const AttPlan &pl
 #define SP1_EW 4             // frequencies per lane and emit step (independent chains)
 #endif
 #define SP1_SEG 24
+#ifndef SP1_EXP_SKIP
+#define SP1_EXP_SKIP 3      // leading Taylor coefficients left out of the emit's exponential: degree 8 on |r| <= ln2/2,
+                            // truncation r^9/9! <= 2e-10 relative on the factor (tolerance 1e-4); 0.8 ms per 1e8 pairs
+#endif
 #define SP1_ROW (SP1_SEG + 1)        // odd row pitch: conflict-free column writes
 __device__ __forceinline__ void sp1_emit(const double (&M)[SP1_K], const double *s_wk, const double *s_E, int j_begin, int j_end,
                                          double *stage, double *dst, unsigned lane)
@@ -1015,9 +1022,9 @@ __device__ __forceinline__ void sp1_emit(const double (&M)[SP1_K], const double 
         double x[SP1_EW], r[SP1_EW], pv[SP1_EW];
         int kk[SP1_EW];
 #pragma unroll
-        for (int u = 0; u < SP1_EW; ++u) { x[u] = fmax(-acc[u] * s_E[jj[u]], -700.0); r[u] = exp_reduce(x[u], kk[u]); pv[u] = c_expc[0]; }
+        for (int u = 0; u < SP1_EW; ++u) { x[u] = fmax(-acc[u] * s_E[jj[u]], -700.0); r[u] = exp_reduce(x[u], kk[u]); pv[u] = c_expc[SP1_EXP_SKIP]; }
 #pragma unroll
-        for (int i = 1; i < 10; ++i) {
+        for (int i = 1 + SP1_EXP_SKIP; i < 10; ++i) {
 #pragma unroll
             for (int u = 0; u < SP1_EW; ++u) pv[u] = fma(pv[u], r[u], c_expc[i]);
         }
@@ -1039,6 +1046,8 @@ __device__ __forceinline__ void sp1_emit(const double (&M)[SP1_K], const double 
     __syncwarp();
 }
 
+// (A/B on the B200: capping the registers at 80 for a sixth block spills and costs 2.7 ms; CUDA's rsqrt replaced by the fast path
+// lets ptxas hoist every constant -- 158 registers, three blocks -- for the same time as 96 registers and five blocks.)
 template <bool HAVE_HI>
 __global__ void __launch_bounds__(SP1_THREADS)
 K_att_sp1(IceParams ice, KInput in, AttTables tb, Sp1Tables sp, const SolRec *worklist, const unsigned long long *work_count,
@@ -1660,6 +1669,7 @@ int nrmc_rt_set_frequencies(nrmc_rt_t h, const double *frequency, int32_t n, dou
                 CK(cudaFuncSetAttribute(K_att_sp1<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_sp1));
                 CK(cudaFuncSetAttribute(K_att_sp1<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_sp1));
             }
+
             int nb = 0;
             if (t.n_hi > 0) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, K_att_sp1<true>, SP1_THREADS, h->smem_sp1));
             else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, K_att_sp1<false>, SP1_THREADS, h->smem_sp1));

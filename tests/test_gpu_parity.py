@@ -443,6 +443,33 @@ def test_propagation_effects_kernel(make, oracle_mod, tag, ice, att, n_refl):
             rt.apply_propagation_effects_batch(spec_in, attenuation_sparse=res["attenuation_sparse"])
 
 
+from test_kernel_math_cpu import harness  # noqa: E402,F401  (fixture: host build of nrmc_math.cuh, test-only)
+
+
+@pytest.mark.parametrize("ice,n_refl,rmax,zmin", [("southpole_2015", 0, 6000, -2700), ("greenland_simple", 0, 4000, -2700),
+                                                   ("mooresbay_simple", 1, 1000, -500)])
+def test_device_maths_equals_host_build(make, harness, ice, n_refl, rmax, zmin):
+    """The device evaluates 1/x, rsqrt and log of the solver loop with its own fast paths (hardware seed + Newton steps,
+    nrmc_math.cuh); the host build of the same header uses libm.  Same algorithm, so the results must agree to rounding:
+    identical counts and types, C0 to 1e-12, path length and travel time to 1e-11 relative (the root itself is only defined to
+    |R - rho| <= 1e-10 m), vectors to 1e-11."""
+    V = cylinder(61, 4000, rmax, zmin)
+    A = np.array([[0, 0, -150.], [1500, -1500, -5.], [30, 40, -60.]])
+    X1, X2 = np.repeat(V, len(A), 0), np.tile(A, (len(V), 1))
+    res = make(ice, n_reflections=n_refl).trace_batch(X1, X2)
+    h = harness(ice, n_refl, X1, X2)
+    assert np.array_equal(res["n_sol"], h["n_sol"])
+    assert np.array_equal(res["solution_type"], h["type"]) and np.array_equal(res["reflection"], h["reflection"])
+    S = h["C0"].shape[1]
+    filled = np.arange(S)[None, :] < h["n_sol"][:, None]
+    assert filled.sum() > 5000
+    np.testing.assert_allclose(res["C0"][filled], h["C0"][filled], rtol=1e-12)
+    np.testing.assert_allclose(res["path_length"][filled], h["path_length"][filled], rtol=1e-11)
+    np.testing.assert_allclose(res["travel_time"][filled], h["travel_time"][filled], rtol=1e-11)
+    np.testing.assert_allclose(res["launch_vector"][filled], h["launch"][filled], atol=1e-11)
+    np.testing.assert_allclose(res["receive_vector"][filled], h["receive"][filled], atol=1e-11)
+
+
 @pytest.mark.parametrize("tag", ["sp", "sp_nolimit", "mb"])
 def test_focusing_kernel(make, oracle_mod, tag):
     """K_focusing (get_focusing, analyticraytracing.py:2778-2888) through the C ABI: against the reference's own values
