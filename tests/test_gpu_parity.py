@@ -576,11 +576,15 @@ def test_viewing_angle_cut(make, ice, att, n_refl, rmax, zmin):
     n_vertex = np.repeat(rt._medium.get_index_of_refraction(V), len(A))
     keep = np.abs(va - np.arccos(1. / n_vertex)[:, None]) <= cut
     margin = np.abs(np.abs(va - np.arccos(1. / n_vertex)[:, None]) - cut) > 1e-9
+    # the cut is a second instantiation of the solver kernel (K_roots<true>): same source, but ptxas may contract and order the
+    # arithmetic differently, so floating-point outputs agree to rounding (1e-13), integers exactly
     for k in plain:
         if k.startswith("attenuation"):
             sel = filled & keep & margin
-            np.testing.assert_array_equal(res[k][sel], plain[k][sel], err_msg=k)
+            np.testing.assert_allclose(res[k][sel], plain[k][sel], rtol=1e-12, atol=1e-300, err_msg=k)
             assert np.isnan(res[k][filled & ~keep & margin]).all(), k
+        elif np.issubdtype(np.asarray(plain[k]).dtype, np.floating):
+            np.testing.assert_allclose(res[k], plain[k], rtol=1e-13, atol=1e-13, equal_nan=True, err_msg=k)
         else:
             np.testing.assert_array_equal(res[k], plain[k], err_msg=k)
     assert 0.05 < keep[filled].mean() < 0.95
