@@ -143,3 +143,29 @@ def test_shard_bounds():
             assert max(sizes) - min(sizes) <= 1
     idx = np.concatenate([shard_vertices(101, 4, r, permutation_seed=3) for r in range(4)])
     assert np.array_equal(np.sort(idx), np.arange(101))
+
+
+def test_ctypes_structures_match_the_header(tmp_path):
+    """the ctypes mirrors in nuradiomc_b200/_lib.py have the size and field offsets of the structs in include/nrmc_rt.h
+    (compiled with gcc: a drift between the two is an ABI bug no parity test would localise)"""
+    import ctypes as C
+    import subprocess
+    from nuradiomc_b200 import _lib
+    pairs = {"nrmc_rt_config": _lib.Config, "nrmc_rt_input": _lib.Input, "nrmc_rt_output": _lib.Output,
+             "nrmc_rt_stats": _lib.Stats, "nrmc_rt_effects": _lib.Effects, "nrmc_rt_focusing": _lib.Focusing}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "nrmc_rt.h"', 'int main(void) {']
+    for cname, cls in pairs.items():
+        lines.append(f'printf("{cname} size %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'printf("{cname} {fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ['return 0; }']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.check_call(["/usr/bin/gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)])
+    out = subprocess.check_output([str(exe)], text=True).split("\n")
+    got = {tuple(l.split()[:2]): int(l.split()[2]) for l in out if l.strip()}
+    for cname, cls in pairs.items():
+        assert got[(cname, "size")] == C.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert got[(cname, fname)] == getattr(cls, fname).offset, (cname, fname)
