@@ -920,13 +920,22 @@ K_att(IceParams ice, KInput in, AttTables tb, const SolRec *worklist, const unsi
 // shared memory by TMA.  Solutions whose slopes leave the band where the SP1_K-term series is accurate to 1e-9, or that
 // could touch the 1 m floor of attenuation.py:252-255, are handed to the generic kernel (fallback list).
 // ---------------------------------------------------------------------------------------------------------------
+#ifndef SP1_CHEB
+#define SP1_CHEB 1            // 1: Chebyshev moments (8 per band), 0: monomial moments (10 per band) -- same truncation, 2e-7
+#endif
+#if SP1_CHEB
+#define SP1_K 8
+#else
 #define SP1_K 10
+#endif
 #define SP1_NQ 12             // Gauss-Legendre nodes per panel: <= 6e-6 on the factor (16: 1e-8; 10: 9e-5) -- scratch/attconv.cpp
 struct Sp1Tables {
-    const double *wk;         // [Fs_pad][SP1_K]  w_j^k / k!
+    const double *wk;         // [Fs_pad][SP1_K]  expansion coefficients of exp((p - p_ref) w_j) in the moment basis:
+                              //                  Chebyshev: eps_k I_k(r w_j) (modified Bessel), monomial: w_j^k / k!
     const double *E;          // [Fs_pad]         exp(p_ref(band_j) * w_j)
     const int32_t *band;      // [Fs_pad]         0: f < 1 GHz, 1: f >= 1 GHz (attenuation.py:180-185)
     double pref_lo, pref_hi;
+    double inv_r_lo, inv_r_hi; // 1 / (half-width of the slope band the series covers): x = (p - p_ref) / r in [-1, 1]
     double wabs_lo, wabs_hi;  // max |ln f| per band (series radius)
     double wmin_lo, wmax_lo, wmin_hi, wmax_hi;
     int32_t n_lo, n_hi;
@@ -973,6 +982,24 @@ __device__ __forceinline__ void sp1_node(const IceParams &ice, const AttPlan &pl
     const double b2 = fma(t, fma(t, c_sp1[12], c_sp1[11]), c_sp1[10]);
     const double p1 = (b1 - b0) * c_sp1[13], p2 = (b2 - b1) * c_sp1[14];
     const double c = wds * exp_c_neg(b1);              // b1 = ln(1/L at 1 GHz) <= -5.5 for any temperature
+#if SP1_CHEB
+    // M_k += c T_k(x), x = (p - p_ref) / r: three-term recurrence, one FMA and one add per moment.  exp(d w) = sum_k eps_k
+    // I_k(r w) T_k(d / r) converges like I_K(0.9) instead of 0.9^K / K!: 8 moments do what 10 monomial ones did.
+    {
+        const double x = (p1 - sp.pref_lo) * sp.inv_r_lo, x2 = x + x;
+        double t0 = c, t1 = c * x;
+        Mlo[0] += t0; Mlo[1] += t1;
+#pragma unroll
+        for (int k = 2; k < SP1_K; ++k) { const double t2 = fma(x2, t1, -t0); Mlo[k] += t2; t0 = t1; t1 = t2; }
+    }
+    if (HAVE_HI) {
+        const double x = (p2 - sp.pref_hi) * sp.inv_r_hi, x2 = x + x;
+        double t0 = c, t1 = c * x;
+        Mhi[0] += t0; Mhi[1] += t1;
+#pragma unroll
+        for (int k = 2; k < SP1_K; ++k) { const double t2 = fma(x2, t1, -t0); Mhi[k] += t2; t0 = t1; t1 = t2; }
+    }
+#else
     const double dlo = p1 - sp.pref_lo;
     double tk = c;
 #pragma unroll
@@ -983,6 +1010,7 @@ __device__ __forceinline__ void sp1_node(const IceParams &ice, const AttPlan &pl
 #pragma unroll
         for (int k = 0; k < SP1_K; ++k) { Mhi[k] += tk; tk *= dhi; }
     }
+#endif
 }
 
 // Factors exp(-E_j sum_k M_k wk[j][k]) of the integration frequencies [j_begin, j_end) (at most SP1_SEG of them) for the 32
@@ -1626,10 +1654,28 @@ int nrmc_rt_set_frequencies(nrmc_rt_t h, const double *frequency, int32_t n, dou
             const int b = sp[j] < 1.0 ? 0 : 1;
             band[j] = b;
             E[j] = exp((b ? t.pref_hi : t.pref_lo) * w);
-            double term = 1.0;
-            for (int k = 0; k < SP1_K; ++k) { wk[(size_t)j * SP1_K + k] = term; term *= w / (k + 1); }
             if (b) { ++t.n_hi; t.wabs_hi = std::max(t.wabs_hi, fabs(w)); t.wmin_hi = std::min(t.wmin_hi, w); t.wmax_hi = std::max(t.wmax_hi, w); }
             else { ++t.n_lo; t.wabs_lo = std::max(t.wabs_lo, fabs(w)); t.wmin_lo = std::min(t.wmin_lo, w); t.wmax_lo = std::max(t.wmax_lo, w); }
+        }
+        // the series covers slopes within r of p_ref, r chosen so that |r w| <= 0.9 for every frequency of the band
+        const double r_lo = t.n_lo ? 0.9 / std::max(t.wabs_lo, 1e-300) : INFINITY, r_hi = t.n_hi ? 0.9 / std::max(t.wabs_hi, 1e-300) : INFINITY;
+        t.inv_r_lo = 1.0 / r_lo; t.inv_r_hi = 1.0 / r_hi;
+        for (int j = 0; j < Fs; ++j) {
+            const double w = log(sp[j]);
+#if SP1_CHEB
+            // exp(d w) = I_0(z) + 2 sum_k I_k(z) T_k(d / r), z = r w, |z| <= 0.9; I_k(z) = sum_m (z/2)^(2m+k) / (m! (m+k)!), I_k(-z) = (-1)^k I_k(z)
+            const double z = w == 0.0 ? 0.0 : (band[j] ? r_hi : r_lo) * w, hz = 0.5 * fabs(z);
+            for (int k = 0; k < SP1_K; ++k) {
+                double term = 1.0;
+                for (int i = 1; i <= k; ++i) term *= hz / i;                 // (z/2)^k / k!
+                double sum = 0.0;
+                for (int m = 0; m < 40; ++m) { sum += term; term *= hz * hz / ((m + 1.0) * (m + 1.0 + k)); }
+                wk[(size_t)j * SP1_K + k] = (k == 0 ? 1.0 : 2.0) * ((z < 0.0 && (k & 1)) ? -sum : sum);
+            }
+#else
+            double term = 1.0;
+            for (int k = 0; k < SP1_K; ++k) { wk[(size_t)j * SP1_K + k] = term; term *= w / (k + 1); }
+#endif
         }
         {
             // SP1 coefficients (attenuation.py:176-178): b_i(T) = c0 + c1 T + c2 T^2
@@ -1642,7 +1688,6 @@ int nrmc_rt_set_frequencies(nrmc_rt_t h, const double *frequency, int32_t n, dou
                 t.qtv[i] = q[2] != 0.0 ? -q[1] / (2.0 * q[2]) : 0.0;
             };
             const double inf = INFINITY;
-            const double r_lo = t.n_lo ? 0.9 / std::max(t.wabs_lo, 1e-300) : inf, r_hi = t.n_hi ? 0.9 / std::max(t.wabs_hi, 1e-300) : inf;
             set(0, P1, t.pref_lo - r_lo, t.pref_lo + r_lo);
             set(1, P2, t.pref_hi - r_hi, t.pref_hi + r_hi);
             const double wl[4] = {t.wmin_lo, t.wmax_lo, t.wmin_hi, t.wmax_hi};
