@@ -936,6 +936,7 @@ struct Sp1Tables {
     const int32_t *band;      // [Fs_pad]         0: f < 1 GHz, 1: f >= 1 GHz (attenuation.py:180-185)
     double pref_lo, pref_hi;
     double inv_r_lo, inv_r_hi; // 1 / (half-width of the slope band the series covers): x = (p - p_ref) / r in [-1, 1]
+    double xlo[3], xhi[3];    // x as a quadratic in the ice temperature T: x = xlo[0] + xlo[1] T + xlo[2] T^2
     double wabs_lo, wabs_hi;  // max |ln f| per band (series radius)
     double wmin_lo, wmax_lo, wmin_hi, wmax_hi;
     int32_t n_lo, n_hi;
@@ -977,29 +978,31 @@ __device__ __forceinline__ void sp1_node(const IceParams &ice, const AttPlan &pl
     const double wds = wscale * u * n * rsqrt(plan.delta * em * (n + plan.beta));
     const double a = fabs(z);
     const double t = fma(fma(fma(c_sp1[0], a, c_sp1[1]), a, c_sp1[2]), a, c_sp1[3]);
-    const double b0 = fma(t, fma(t, c_sp1[6], c_sp1[5]), c_sp1[4]);
     const double b1 = fma(t, fma(t, c_sp1[9], c_sp1[8]), c_sp1[7]);
-    const double b2 = fma(t, fma(t, c_sp1[12], c_sp1[11]), c_sp1[10]);
-    const double p1 = (b1 - b0) * c_sp1[13], p2 = (b2 - b1) * c_sp1[14];
     const double c = wds * exp_c_neg(b1);              // b1 = ln(1/L at 1 GHz) <= -5.5 for any temperature
 #if SP1_CHEB
     // M_k += c T_k(x), x = (p - p_ref) / r: three-term recurrence, one FMA and one add per moment.  exp(d w) = sum_k eps_k
     // I_k(r w) T_k(d / r) converges like I_K(0.9) instead of 0.9^K / K!: 8 moments do what 10 monomial ones did.
+    // The slopes are quadratics in the ice temperature ((b1 - b0) / ln 1e4, (b2 - b1) / ln 3.16, attenuation.py:176-185), and so
+    // is x: its three coefficients come from the host.
     {
-        const double x = (p1 - sp.pref_lo) * sp.inv_r_lo, x2 = x + x;
+        const double x = fma(t, fma(t, sp.xlo[2], sp.xlo[1]), sp.xlo[0]), x2 = x + x;
         double t0 = c, t1 = c * x;
         Mlo[0] += t0; Mlo[1] += t1;
 #pragma unroll
         for (int k = 2; k < SP1_K; ++k) { const double t2 = fma(x2, t1, -t0); Mlo[k] += t2; t0 = t1; t1 = t2; }
     }
     if (HAVE_HI) {
-        const double x = (p2 - sp.pref_hi) * sp.inv_r_hi, x2 = x + x;
+        const double x = fma(t, fma(t, sp.xhi[2], sp.xhi[1]), sp.xhi[0]), x2 = x + x;
         double t0 = c, t1 = c * x;
         Mhi[0] += t0; Mhi[1] += t1;
 #pragma unroll
         for (int k = 2; k < SP1_K; ++k) { const double t2 = fma(x2, t1, -t0); Mhi[k] += t2; t0 = t1; t1 = t2; }
     }
 #else
+    const double b0 = fma(t, fma(t, c_sp1[6], c_sp1[5]), c_sp1[4]);
+    const double b2 = fma(t, fma(t, c_sp1[12], c_sp1[11]), c_sp1[10]);
+    const double p1 = (b1 - b0) * c_sp1[13], p2 = (b2 - b1) * c_sp1[14];
     const double dlo = p1 - sp.pref_lo;
     double tk = c;
 #pragma unroll
@@ -1683,6 +1686,10 @@ int nrmc_rt_set_frequencies(nrmc_rt_t h, const double *frequency, int32_t n, dou
             const double s1 = 1.0 / 9.210340371976182, s2 = 1.0 / 1.1505720275988207;
             double P1[3], P2[3];
             for (int m = 0; m < 3; ++m) { P1[m] = (B1[m] - B0[m]) * s1; P2[m] = (B2[m] - B1[m]) * s2; }
+            for (int m = 0; m < 3; ++m) {
+                t.xlo[m] = (P1[m] - (m == 0 ? t.pref_lo : 0.0)) * t.inv_r_lo;
+                t.xhi[m] = (P2[m] - (m == 0 ? t.pref_hi : 0.0)) * t.inv_r_hi;
+            }
             auto set = [&](int i, const double *q, double lo, double hi) {
                 t.qc[i] = q[0]; t.qb[i] = q[1]; t.qa[i] = q[2]; t.qlo[i] = lo; t.qhi[i] = hi;
                 t.qtv[i] = q[2] != 0.0 ? -q[1] / (2.0 * q[2]) : 0.0;
