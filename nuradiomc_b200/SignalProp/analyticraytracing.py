@@ -549,6 +549,11 @@ class ray_tracing(ray_tracing_base):
         X1 = np.asarray(X1, dtype=np.float64).reshape(-1, 3)
         X2 = np.asarray(X2, dtype=np.float64).reshape(-1, 3)
         res = self.trace_batch(X1, X2, outer=outer, **kwargs)
+        if self._config['propagation'].get('focusing', False) and not kwargs.get("compact", False):
+            # the loop will ask for get_focusing / get_raytracing_output of every solution (:2913-2916, :3012-3015): one launch now
+            limit = float(self._config['propagation'].get('focusing_limit', 2))
+            res["focusing_factor"] = self.focusing_batch(X1, X2, res, outer=outer, limit=limit)
+            res.focusing_limit = limit
         lookup = {}
         if outer:
             na = X2.shape[0]
@@ -617,6 +622,8 @@ class ray_tracing(ray_tracing_base):
         self._results = [{'type': int(self._cache["solution_type"][s]), 'C0': float(self._cache["C0"][s]),
                           'C1': float(self._cache["C1"][s]), 'reflection': int(self._cache["reflection"][s]),
                           'reflection_case': int(self._cache["reflection_case"][s])} for s in range(n)]
+        if "focusing_factor" in src:     # pre-traced with focusing on: get_focusing(limit = the configured one) is a lookup
+            self._foc_cache[float(getattr(src, "focusing_limit", 2.))] = np.array(src["focusing_factor"][idx])
 
     def _check(self, iS):
         n = self.get_number_of_solutions()

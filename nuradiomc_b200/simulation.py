@@ -24,7 +24,10 @@ def pretrace_event_group(propagator, vertices, channel_positions, shower_axes=No
     vertices: (nSh, 3) shower vertices; channel_positions: (nCh, 3) absolute antenna positions;
     shower_axes: (nSh, 3) shower axes as stored on the showers (the loop uses the propagation direction, -axis,
     simulation.py:175); delta_C_cut: config['speedup']['delta_C_cut'] [rad].
-    Returns the BatchResult (shower-major: pair = i_shower * nCh + i_channel).
+    Returns the BatchResult (shower-major: pair = i_shower * nCh + i_channel).  With config['propagation']['focusing'] on,
+    the result also holds "focusing_factor" (N, S) (`ray_tracing.focusing_batch`), so that the loop's get_focusing /
+    get_raytracing_output calls (analyticraytracing.py:2913-2916, :3012-3015) launch nothing either; pass it to
+    `raytracing_datasets(..., focusing=res["focusing_factor"])` for the HDF5 output.
     """
     kw = {}
     if shower_axes is not None:

@@ -521,6 +521,16 @@ def test_focusing_kernel(make, oracle_mod, tag):
     assert rt.get_raytracing_output(0)["focusing_factor"] == f15[0]
     with pytest.raises(IndexError):
         rt.get_focusing(rt.get_number_of_solutions())
+    # pre-traced event group with focusing on: the scalar loop's get_focusing / get_raytracing_output are look-ups
+    rt2 = make(ice, n_reflections=n_refl, config={"propagation": {"attenuate_ice": False, "focusing": True, "focusing_limit": 1.5,
+                                                                  "birefringence": False}})
+    pre = rt2.prepare_batch(X1[i:i + 4], X2[i:i + 4])
+    np.testing.assert_array_equal(pre["focusing_factor"][0], f15)
+    rt2.set_start_and_end_point(X1[i], X2[i])
+    rt2.find_solutions()
+    assert 1.5 in rt2._foc_cache
+    for iS in range(rt2.get_number_of_solutions()):
+        assert rt2.get_raytracing_output(iS)["focusing_factor"] == f15[iS]
 
 
 def test_propagation_effects_with_focusing(make, oracle_mod):
