@@ -14,6 +14,7 @@
 // fails with NRMC_ERR_NO_DEVICE / NRMC_ERR_CUDA if the device path is unavailable.
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -754,7 +755,6 @@ K_att(IceParams ice, KInput in, AttTables tb, const SolRec *worklist, const unsi
     const int q = lane & 15, half = lane >> 4;
     const double xq = c_glx[q], wq = c_glw[q];
     const unsigned long long n_front = work_count[0], n_work = n_front + work_count[WL_BACK];
-    const int S = 2 + 4 * ice.n_refl;
     for (unsigned long long w = (unsigned long long)blockIdx.x * ATT_WARPS + warp; w < n_work;
          w += (unsigned long long)gridDim.x * ATT_WARPS) {
         const SolRec rec = worklist_get(worklist, work_cap, n_front, w);
@@ -1130,6 +1130,104 @@ K_att_sp1(IceParams ice, KInput in, AttTables tb, Sp1Tables sp, const SolRec *wo
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// GL1 fast path (no bottom reflections): one THREAD per solution, like the SP1 kernel.  1/L = 1 / max(A(z) - s_f, 1 m) is
+// rational in the frequency, so there is no moment form; but the warp-per-solution kernel spends two thirds of its instructions
+// on the shuffle reductions of its (node, frequency) terms, and a thread that owns a solution needs none.  The frequencies are
+// taken GL1_FC at a time (accumulators in registers), the node geometry is re-evaluated per group.
+// Quadrature: A(z) falls with depth below ~1 km, so a frequency's pole (A = s_f) is approached at the DEEP end of the path:
+// the up-going leg [u_2, u_1] is cut into three sub-panels shrinking by 0.4 towards u_1 (16 nodes each), the leg after the
+// turning point is one panel.  On wide random geometry and on cfg3 this is as accurate as the generic kernel's fine sub-panels
+// (CPU emulation of both schemes against the reference integrand at quad(epsrel=1e-11), scratch/gl1_emul.cpp: dense bins
+// 1.5e-5 / 4.8e-5 / 1.9e-7, identical to the generic kernel's figures)
+// for every frequency that stays 10 m away from the pole along the path.  A solution with a frequency inside those 10 m whose
+// factor is still visible (exponent < 30) goes to the generic kernel through the fall-back list: 3-6 % of the solutions.
+// ---------------------------------------------------------------------------------------------------------------
+#define GL1_FC 13
+#define GL1_ROW GL1_FC              // odd row pitch: conflict-free column writes
+#define GL1_MARGIN 10.0
+__global__ void __launch_bounds__(SP1_THREADS)
+K_att_gl1(IceParams ice, KInput in, AttTables tb, const SolRec *worklist, const unsigned long long *work_count, unsigned long long work_cap,
+          int sparse_is_tmp, double *att_sparse, SolRec *fallback, unsigned long long *fallback_count)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *s_fa = reinterpret_cast<double *>(smem_raw);
+    double *stage = s_fa + tb.Fs_pad + (threadIdx.x >> 5) * (32 * GL1_ROW);
+    for (int j = threadIdx.x; j < tb.Fs_pad; j += SP1_THREADS) s_fa[j] = tb.fa[j];
+    __syncthreads();
+    const unsigned lane = threadIdx.x & 31u;
+    const Gl3Table no_table = {nullptr, 0};
+    const unsigned long long n_front = work_count[0], n_work = n_front + work_count[WL_BACK];
+    const unsigned long long stride = (unsigned long long)gridDim.x * SP1_THREADS;
+    const int n_groups = (tb.Fs + GL1_FC - 1) / GL1_FC, group = (tb.Fs + n_groups - 1) / n_groups;
+    for (unsigned long long w0 = (unsigned long long)blockIdx.x * SP1_THREADS + (threadIdx.x & ~31u); w0 < n_work; w0 += stride) {
+        const unsigned long long w = w0 + lane;
+        const bool active = w < n_work;
+        SolRec rec;
+        AttPlan plan;
+        int j_hard = tb.Fs, n_slots = 0;
+        bool leg0 = false, to_generic = false;
+        double *dst = nullptr;
+        if (active) {
+            rec = worklist_get(worklist, work_cap, n_front, w);
+            if (sparse_is_tmp) rec.row = (int64_t)(w < n_front ? w : work_cap - 1ull - (w - n_front));   // scratch rows: work-list position
+            att_plan_rec(ice, rec, plan);
+            leg0 = plan.turned && plan.u2 > plan.uT;                   // [u_T, u_2], run through twice
+            n_slots = (leg0 ? 1 : 0) + (plan.u1 > plan.u2 ? 3 : 0);    // [u_2, u_1] in three graded sub-panels
+            AttNode a_deep, a_top;
+            att_node(NRMC_ATT_GL1, rec.z1, no_table, a_deep);
+            att_node(NRMC_ATT_GL1, plan.turned ? fmin(rec.zv, 0.0) : rec.z2, no_table, a_top);
+            const double a_min = fmin(a_deep.p0, a_top.p0);
+            for (int j = tb.Fs - 1; j >= 0 && s_fa[j] > a_min - GL1_MARGIN; --j) j_hard = j;    // s_f ascends with the frequency
+            dst = att_sparse + rec.row * (int64_t)tb.Fs;
+        }
+        for (int gi = 0; gi < n_groups; ++gi) {
+            const int jb = gi * group, je = min(jb + group, tb.Fs);
+            double acc[GL1_FC];
+#pragma unroll
+            for (int u = 0; u < GL1_FC; ++u) acc[u] = 0.0;
+#pragma unroll 1
+            for (int sl = 0; sl < n_slots; ++sl) {
+                double lo, hi, mult;
+                if (leg0 && sl == 0) { lo = plan.uT; hi = plan.u2; mult = 2.0; }
+                else {
+                    const int k = sl - (leg0 ? 1 : 0);
+                    const double w0u = (plan.u1 - plan.u2) * (1.0 / 1.56);      // widths w, 0.4 w, 0.16 w
+                    lo = plan.u2 + w0u * (k == 0 ? 0.0 : (k == 1 ? 1.0 : 1.4));
+                    hi = k == 2 ? plan.u1 : plan.u2 + w0u * (k == 0 ? 1.0 : 1.4);
+                    mult = 1.0;
+                }
+#pragma unroll 1
+                for (int q = 0; q < NRMC_NQ; ++q) {
+                    double z, wds;
+                    att_node_geometry(ice, plan, lo, hi, c_glx[q], c_glw[q], z, wds);
+                    AttNode nd;
+                    att_node(NRMC_ATT_GL1, z, no_table, nd);
+                    const double wm = wds * mult;
+#pragma unroll
+                    for (int u = 0; u < GL1_FC; ++u)
+                        acc[u] = fma(wm, NRMC_RCP(fmax(nd.p0 - s_fa[min(jb + u, tb.Fs_pad - 1)], 1.0)), acc[u]);   // attenuation.py:196, :252-255
+                }
+            }
+            double *mine = stage + lane * GL1_ROW;
+#pragma unroll
+            for (int u = 0; u < GL1_FC; ++u) {
+                if (jb + u < je && jb + u >= j_hard && acc[u] < 30.0) to_generic = true;
+                mine[u] = exp_c_neg(-acc[u]);
+            }
+            __syncwarp();
+            const int len = je - jb;
+#pragma unroll 4
+            for (int r = 0; r < 32; ++r) {
+                double *row = reinterpret_cast<double *>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(dst), r));
+                if (row != nullptr && (int)lane < len) __stcs(row + jb + lane, stage[r * GL1_ROW + lane]);
+            }
+            __syncwarp();
+        }
+        if (active && to_generic) fallback[atomicAdd(fallback_count, 1ull)] = rec;     // the generic kernel redoes these rows
+    }
+}
+
 // dense expansion for single-segment paths: np.interp of the sparse factors onto the output grid (py:1077-1078).
 // One warp per work-list record; sparse_is_tmp: the sparse factors sit in scratch rows indexed by the work-list position.
 __global__ void __launch_bounds__(256)
@@ -1436,12 +1534,12 @@ struct nrmc_rt_s {
     std::vector<double> freq_out, freq_sparse;
     AttTables tb;
     Sp1Tables sp1;
-    bool have_sp1 = false;
-    int grid_att = 0, grid_sp1 = 0;      // resident blocks (occupancy x SMs) of the persistent attenuation kernels
+    bool have_sp1 = false, have_gl1 = false;
+    int grid_att = 0, grid_sp1 = 0, grid_gl1 = 0;      // resident blocks (occupancy x SMs) of the persistent attenuation kernels
     int grid_hump = 0, grid_roots = 0;   // the same for the persistent solver kernels
     int grid_hump_m = 0, grid_roots_m = 0;
     int64_t chunk_pairs = 0;             // 0: automatic; > 0: pairs per chunk (nrmc_rt_set_chunk_pairs)
-    size_t smem_att = 0, smem_sp1 = 0;
+    size_t smem_att = 0, smem_sp1 = 0, smem_gl1 = 0;
     DevBuf d_tables, d_gl3, d_sp1;
     bool have_freq = false;
     Lane lanes[2];
@@ -1641,6 +1739,14 @@ int nrmc_rt_set_frequencies(nrmc_rt_t h, const double *frequency, int32_t n, dou
         if (h->ice.att_model == NRMC_ATT_GL3) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, K_att<true>, ATT_THREADS, h->smem_att));
         else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, K_att<false>, ATT_THREADS, h->smem_att));
         h->grid_att = std::max(1, nb) * h->n_sm;
+    }
+    h->have_gl1 = false;
+    if (h->ice.att_model == NRMC_ATT_GL1 && h->ice.n_refl == 0 && !getenv("NRMC_GL1_GENERIC")) {     // (the variable: A/B and tests)
+        h->smem_gl1 = (size_t)Fs_pad * 8 + (size_t)(SP1_THREADS / 32) * 32 * GL1_ROW * sizeof(double);
+        int nb = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, K_att_gl1, SP1_THREADS, h->smem_gl1));
+        h->grid_gl1 = std::max(1, nb) * h->n_sm;
+        h->have_gl1 = true;
     }
     h->have_sp1 = false;
     if (h->ice.att_model == NRMC_ATT_SP1 && h->ice.n_refl == 0) {
@@ -1850,8 +1956,9 @@ static int launch_chunk(nrmc_rt_s *h, Lane &ln, int lane_id, const KInput &kin, 
     if (want_att) {
         const AttTables &tb = h->tb;
         const int nseg_max = h->ice.n_refl + 1;
-        if (h->have_sp1) {
-            // SP1 moment kernel -> sparse factors; rare out-of-band solutions -> generic kernel; dense = interp(sparse)
+        if (h->have_sp1 || h->have_gl1) {
+            // thread-per-solution kernel (SP1 moments / GL1) -> sparse factors; the solutions it hands back -> generic kernel;
+            // dense = interp(sparse)
             unsigned long long *d_fb = cnt + CNT_FALLBACK;
             CK(ln.fallback.reserve((size_t)kin.n_pairs * h->S * sizeof(SolRec)));
             double *sparse = att_sparse;
@@ -1860,7 +1967,10 @@ static int launch_chunk(nrmc_rt_s *h, Lane &ln, int lane_id, const KInput &kin, 
                 CK(ln.sparse_tmp.reserve((size_t)kin.n_pairs * h->S * tb.Fs * sizeof(double)));
                 sparse = (double *)ln.sparse_tmp.p;
             }
-            if (h->sp1.n_hi > 0)
+            if (h->have_gl1)
+                K_att_gl1<<<h->grid_gl1, SP1_THREADS, h->smem_gl1, ln.stream>>>(h->ice, kin, tb, wl, d_count, work_cap, sparse_is_tmp, sparse,
+                                                                                (SolRec *)ln.fallback.p, d_fb);
+            else if (h->sp1.n_hi > 0)
                 K_att_sp1<true><<<h->grid_sp1, SP1_THREADS, h->smem_sp1, ln.stream>>>(h->ice, kin, tb, h->sp1, wl, d_count, work_cap, sparse_is_tmp,
                                                                                       sparse, (SolRec *)ln.fallback.p, d_fb);
             else

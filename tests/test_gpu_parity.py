@@ -443,6 +443,36 @@ def test_propagation_effects_kernel(make, oracle_mod, tag, ice, att, n_refl):
             rt.apply_propagation_effects_batch(spec_in, attenuation_sparse=res["attenuation_sparse"])
 
 
+def test_gl1_thread_per_solution_kernel_equals_generic_kernel(make, oracle_mod, monkeypatch):
+    """K_att_gl1 (thread per solution, graded sub-panels towards the deep end of the path, solutions with a visible frequency
+    within 10 m of the pole handed to the generic kernel) against the generic warp-per-solution kernel (NRMC_GL1_GENERIC=1) and
+    the tight oracle, on the cfg3 set-up and on wide random geometry: 1e-4 relative on factors above 1e-3, 2e-7 absolute below"""
+    ff = np.fft.rfftfreq(1022, 0.2)
+    V = cylinder(63, 1500, 4000, -2700)
+    A = RNOG[[0, 8, 13, 21]]
+    X1, X2 = np.repeat(V, len(A), 0), np.tile(A, (len(V), 1))
+    rng = np.random.default_rng(64)
+    n = 3000
+    ze, zr = -np.exp(rng.uniform(np.log(0.5), np.log(2900.), n)), -np.exp(rng.uniform(np.log(0.5), np.log(2900.), n))
+    rho, phi = np.exp(rng.uniform(np.log(0.1), np.log(9000.), n)), rng.uniform(0, 2 * np.pi, n)
+    W1, W2 = np.stack([rho * np.cos(phi), rho * np.sin(phi), ze], 1), np.stack([np.zeros(n), np.zeros(n), zr], 1)
+    for P1, P2, fmax, nf in ((X1, X2, 1.2, 25), (W1, W2, None, 20), (W1, W2, 0.8, 20)):
+        fast = make("greenland_simple", attenuation_model="GL1", n_frequencies_integration=nf).trace_batch(
+            P1, P2, frequency=ff, max_detector_freq=fmax, attenuation="both")
+        monkeypatch.setenv("NRMC_GL1_GENERIC", "1")
+        generic = make("greenland_simple", attenuation_model="GL1", n_frequencies_integration=nf).trace_batch(
+            P1, P2, frequency=ff, max_detector_freq=fmax, attenuation="both")
+        monkeypatch.delenv("NRMC_GL1_GENERIC")
+        assert np.array_equal(fast["n_sol"], generic["n_sol"])
+        for k in ("attenuation_sparse", "attenuation"):
+            assert np.array_equal(np.isnan(fast[k]), np.isnan(generic[k]))
+            assert_attenuation_parity(fast[k], generic[k], atol=2e-7)
+        ora = oracle_mod.Oracle("greenland_simple", attenuation_model="GL1", n_freq=nf, tight=True).trace(P1[:2000], P2[:2000], ff, fmax)
+        same = fast["n_sol"][:2000] == ora["n_sol"]
+        assert_attenuation_parity(fast["attenuation"][:2000][same], ora["attenuation"][same], atol=2e-7)
+        assert_attenuation_parity(fast["attenuation_sparse"][:2000][same], ora["attenuation_sparse"][same], atol=2e-7)
+
+
 from test_kernel_math_cpu import harness  # noqa: E402,F401  (fixture: host build of nrmc_math.cuh, test-only)
 
 
