@@ -112,6 +112,21 @@ DEFAULT_OUTPUTS = ("n_sol", "status", "solution_type", "reflection", "reflection
                    "travel_time", "launch_vector", "receive_vector", "reflection_angle")
 
 
+def _pair_lookup(X1, X2, outer):
+    """{48-byte key of (x1, x2): pair index} for `prepare_batch`: the key is what `find_solutions` forms from the current points
+    (x1.tobytes() + x2.tobytes()).  Built without a Python loop over the pairs (an event group has 1e5 of them); for duplicate
+    pairs the last index wins, as in a loop."""
+    X1 = np.ascontiguousarray(X1, dtype=np.float64).reshape(-1, 3)
+    X2 = np.ascontiguousarray(X2, dtype=np.float64).reshape(-1, 3)
+    if outer:
+        pairs = np.concatenate([np.repeat(X1, X2.shape[0], axis=0), np.tile(X2, (X1.shape[0], 1))], axis=1)
+    else:
+        X2b = X2 if X2.shape[0] == X1.shape[0] else np.repeat(X2, X1.shape[0], axis=0)
+        pairs = np.concatenate([X1, X2b], axis=1)
+    keys = np.ascontiguousarray(pairs).view(np.dtype((np.void, 48))).ravel().tolist()
+    return dict(zip(keys, range(len(keys))))
+
+
 class BatchResult(dict):
     """SoA results of `trace_batch`: arrays keyed by the field names of nrmc_rt_output, plus `.stats`,
     `.frequencies_sparse`."""
@@ -554,17 +569,7 @@ class ray_tracing(ray_tracing_base):
             limit = float(self._config['propagation'].get('focusing_limit', 2))
             res["focusing_factor"] = self.focusing_batch(X1, X2, res, outer=outer, limit=limit)
             res.focusing_limit = limit
-        lookup = {}
-        if outer:
-            na = X2.shape[0]
-            for i in range(X1.shape[0]):
-                for j in range(na):
-                    lookup[X1[i].tobytes() + X2[j].tobytes()] = i * na + j
-        else:
-            X2b = X2 if X2.shape[0] == X1.shape[0] else np.repeat(X2, X1.shape[0], axis=0)
-            for i in range(X1.shape[0]):
-                lookup[X1[i].tobytes() + X2b[i].tobytes()] = i
-        self._batch = (lookup, res)
+        self._batch = (_pair_lookup(X1, X2, outer), res)
         return res
 
     # ------------------------------------------------------------------------------------------------------

@@ -169,3 +169,23 @@ def test_ctypes_structures_match_the_header(tmp_path):
         assert got[(cname, "size")] == C.sizeof(cls), cname
         for fname, _ in cls._fields_:
             assert got[(cname, fname)] == getattr(cls, fname).offset, (cname, fname)
+
+
+def test_pair_lookup_of_prepare_batch():
+    """the vectorised key table of prepare_batch equals the per-pair construction find_solutions relies on"""
+    from nuradiomc_b200.SignalProp.analyticraytracing import _pair_lookup
+    rng = np.random.default_rng(5)
+    X1, X2 = rng.normal(size=(40, 3)), rng.normal(size=(7, 3))
+    X1[3] = X1[1]                                       # duplicate vertex: the later pair wins, as in a loop
+    X1[5, 2] = -0.0                                     # -0.0 and 0.0 are different keys, as with tobytes()
+    ref = {}
+    for i in range(len(X1)):
+        for j in range(len(X2)):
+            ref[X1[i].tobytes() + X2[j].tobytes()] = i * len(X2) + j
+    assert _pair_lookup(X1, X2, True) == ref
+    ref = {X1[i].tobytes() + X2[0].tobytes(): i for i in range(len(X1))}
+    assert _pair_lookup(X1, X2[:1], False) == ref
+    Y2 = rng.normal(size=(40, 3))
+    ref = {X1[i].tobytes() + Y2[i].tobytes(): i for i in range(len(X1))}
+    got = _pair_lookup(X1, Y2, False)
+    assert got == ref and all(isinstance(k, bytes) and len(k) == 48 for k in got)
