@@ -110,6 +110,11 @@ typedef struct {
     int32_t reserved;
     int64_t *sol_offset;       /* [N+1]    compact only (required then)                                */
     int64_t row_capacity;
+    /* Device-resident compact calls only: row of this call's first solution.  The per-solution arrays are then addressed as
+     * array[row_base + local row] and sol_offset holds those global rows -- the caller passes the BASE pointers of arrays that
+     * several calls (or several GPUs, through peer mappings: nrmc_rt_peer_open) fill side by side, each in its own segment
+     * [row_base, row_base + row_capacity).  0 for a stand-alone call. */
+    int64_t row_base;
 } nrmc_rt_output;
 
 typedef struct {
@@ -192,6 +197,21 @@ int nrmc_rt_focusing_factor(nrmc_rt_t h, const nrmc_rt_input *in, const nrmc_rt_
 /* Pairs per internal chunk (device scratch and the host-call pipeline are sized per chunk).  0 = automatic (2^24 pairs for
  * device-resident calls, ~1.5 GB of scratch per stream for host calls).  A tuning / testing knob: results do not depend on it. */
 int nrmc_rt_set_chunk_pairs(nrmc_rt_t h, int64_t pairs);
+
+/* Result gather over NVLink peer memory (replaces the reference's file-level merge of per-job outputs,
+ * NuRadioMC/utilities/merge_hdf5.py / runner.py:42-99, for one process per GPU on an NVSwitch node).  The gathering rank allocates the
+ * arrays with nrmc_rt_peer_alloc and hands the 64-byte handles to the other processes (any transport: torch.distributed, MPI, a
+ * file); they map them with nrmc_rt_peer_open and pass the mapped BASE pointers, their own row_base and their own slice of the
+ * per-pair arrays as the outputs of a device-resident compact nrmc_rt_trace: the kernels then store every result row straight
+ * into the gathering GPU's HBM while they compute (no staging copy, no host involvement, no collective call).  The writer
+ * synchronises its stream, then any inter-process barrier makes the rows visible to the owner. */
+#define NRMC_PEER_HANDLE_BYTES 64
+int nrmc_rt_peer_alloc(int32_t device, uint64_t bytes, void **dev_ptr, unsigned char *handle /* [64] out */);
+int nrmc_rt_peer_open(int32_t device, const unsigned char *handle /* [64] */, void **dev_ptr);
+int nrmc_rt_peer_close(void *dev_ptr);
+int nrmc_rt_peer_free(void *dev_ptr);
+/* cudaMemcpyAsync between any two device / peer-mapped / pinned pointers on `stream` (the per-pair arrays of a gather) */
+int nrmc_rt_copy_async(void *dst, const void *src, uint64_t bytes, void *stream);
 
 /* pinned host memory for fast NRMC_MEMORY_HOST transfers */
 int nrmc_rt_host_alloc(void **ptr, uint64_t bytes);

@@ -133,12 +133,14 @@ class BatchResult(dict):
     stats = None
     frequencies_sparse = None
     compact = False
+    row_base = 0
+    freq_key = None
     _keep = None
     _full = None
 
     def n_rows(self):
         """number of per-solution rows of a compact result (synchronises a device-resident result)"""
-        return int(self["sol_offset"][-1])
+        return int(self["sol_offset"][-1]) - int(getattr(self, "row_base", 0))
 
     def rows(self, i):
         """index of the per-slot arrays for the solutions of pair i: (i, slice) padded, slice of rows compact"""
@@ -222,10 +224,15 @@ class ray_tracing(ray_tracing_base):
         h = self._h()
         _lib.check(_lib.load().nrmc_rt_set_chunk_pairs(h.ptr, int(pairs)), h.ptr, "set_chunk_pairs")
 
+    @staticmethod
+    def _freq_key(frequency, max_detector_freq):
+        frequency = np.ascontiguousarray(frequency, dtype=np.float64)
+        return (frequency.tobytes(), None if max_detector_freq is None else float(max_detector_freq))
+
     def _set_frequencies(self, frequency, max_detector_freq):
         h = self._h()
         frequency = np.ascontiguousarray(frequency, dtype=np.float64)
-        key = (frequency.tobytes(), None if max_detector_freq is None else float(max_detector_freq))
+        key = self._freq_key(frequency, max_detector_freq)
         if h.freq_key != key:
             lib = _lib.load()
             fmax = float("nan") if max_detector_freq is None else float(max_detector_freq)
@@ -330,6 +337,7 @@ class ray_tracing(ray_tracing_base):
         _lib.check(_lib.load().nrmc_rt_trace(h.ptr, C.byref(inp), C.byref(o), None, C.byref(st)), h.ptr, "trace")
         res.stats = _stats_dict(st)
         res.frequencies_sparse = h.sparse if frequency is not None else None
+        res.freq_key = None if frequency is None else self._freq_key(frequency, max_detector_freq)
         res.compact = bool(compact)
         if compact:     # expose the filled rows; the capacity-sized buffers are kept for reuse through `out=`
             res._full = full
@@ -340,7 +348,8 @@ class ray_tracing(ray_tracing_base):
         return res
 
     def trace_batch_device(self, v, a, frequency=None, max_detector_freq=None, outer=False, outputs=None,
-                           attenuation="sparse", out=None, sync_stats=False, compact=False, row_capacity=None):
+                           attenuation="sparse", out=None, sync_stats=False, compact=False, row_capacity=None,
+                           out_ptrs=None, row_base=0):
         """
         Device-resident variant: `v` (3, Nv) and `a` (3, Na) are contiguous float64 CUDA torch tensors (SoA); the results
         are CUDA torch tensors, the kernels are enqueued on torch's current stream.  Used by bench.py for the
@@ -348,6 +357,9 @@ class ray_tracing(ray_tracing_base):
         compact=True: per-solution rows as in `trace_batch`; the per-slot tensors keep
         their capacity (`row_capacity`, default N*S) and only the first `res["sol_offset"][N]` rows are defined -- reading
         that number is the caller's synchronisation point (`res.n_rows()`).
+        out_ptrs / row_base (compact only): {output name: raw device pointer} of per-solution arrays that live elsewhere --
+        typically the gathering GPU's arrays mapped through NVLink (`nuradiomc_b200.distributed.P2PGather`) -- addressed as
+        array[row_base + local row]; those outputs are not allocated here and do not appear in the result dict.
         """
         import torch
         assert v.is_cuda and a.is_cuda and v.dtype == torch.float64 and a.dtype == torch.float64
@@ -371,9 +383,21 @@ class ray_tracing(ray_tracing_base):
         rows = N * S if row_capacity is None else int(row_capacity)
         if compact and "n_sol" not in names:
             names.insert(0, "n_sol")
+        out_ptrs = dict(out_ptrs or {})
+        if out_ptrs and not compact:
+            raise ValueError("out_ptrs / row_base need the compact layout")
+        for name in list(out_ptrs):
+            if name not in names:
+                names.append(name)
         for name in names:
             dtype, trail = _OUT_SPECS[name]
             per_slot = len(trail(S, K1, Fs, F)) > 0
+            if name in out_ptrs:
+                if not per_slot:
+                    raise ValueError("per-pair outputs stay local (the kernels read them back); gather them with a copy")
+                setattr(o, name, int(out_ptrs[name]))
+                res.pop(name, None)
+                continue
             shape = ((rows,) + trail(S, K1, Fs, F)[1:]) if (compact and per_slot) else (N,) + trail(S, K1, Fs, F)
             if not (name in res and tuple(res[name].shape) == shape):
                 res[name] = torch.empty(shape, dtype=tdt[dtype], device=v.device)
@@ -381,8 +405,9 @@ class ray_tracing(ray_tracing_base):
         if compact:
             if not ("sol_offset" in res and tuple(res["sol_offset"].shape) == (N + 1,)):
                 res["sol_offset"] = torch.empty(N + 1, dtype=torch.int64, device=v.device)
-            o.compact, o.sol_offset, o.row_capacity = 1, res["sol_offset"].data_ptr(), rows
+            o.compact, o.sol_offset, o.row_capacity, o.row_base = 1, res["sol_offset"].data_ptr(), rows, int(row_base)
         res.compact = bool(compact)
+        res.row_base = int(row_base)
         inp = _lib.Input()
         inp.n_vertices, inp.vx, inp.vy, inp.vz = Nv, v[0].data_ptr(), v[1].data_ptr(), v[2].data_ptr()
         inp.n_antennas, inp.ax, inp.ay, inp.az = Na, a[0].data_ptr(), a[1].data_ptr(), a[2].data_ptr()
@@ -561,10 +586,12 @@ class ray_tracing(ray_tracing_base):
         NuRadioMC/simulation/simulation.py:155-210).  Afterwards `set_start_and_end_point(x1, x2)` +
         `find_solutions()` on one of these pairs is a cache lookup instead of a kernel launch.
         """
+        if kwargs.get("compact", False):
+            raise ValueError("prepare_batch serves the scalar API from the padded layout: compact=True is not supported")
         X1 = np.asarray(X1, dtype=np.float64).reshape(-1, 3)
         X2 = np.asarray(X2, dtype=np.float64).reshape(-1, 3)
         res = self.trace_batch(X1, X2, outer=outer, **kwargs)
-        if self._config['propagation'].get('focusing', False) and not kwargs.get("compact", False):
+        if self._config['propagation'].get('focusing', False):
             # the loop will ask for get_focusing / get_raytracing_output of every solution (:2913-2916, :3012-3015): one launch now
             limit = float(self._config['propagation'].get('focusing_limit', 2))
             res["focusing_factor"] = self.focusing_batch(X1, X2, res, outer=outer, limit=limit)
@@ -696,12 +723,27 @@ class ray_tracing(ray_tracing_base):
         """fraction of the signal that reaches the observer per frequency (:2744-2776)"""
         self._check(iS)
         frequency = np.asarray(frequency, dtype=np.float64)
-        key = (frequency.tobytes(), max_detector_freq)
+        key = self._freq_key(frequency, max_detector_freq)
         if key not in self._att_cache:
-            res = self.trace_batch(self._X1[None, :], self._X2[None, :], frequency=frequency,
-                                   max_detector_freq=max_detector_freq, outputs=("n_sol",), attenuation="dense")
-            self._att_cache[key] = res["attenuation"][0]
-        return np.array(self._att_cache[key][iS])
+            src, idx = None, 0
+            if self._batch is not None and self._batch_index is not None and self._batch[1].freq_key == key \
+                    and "attenuation" in self._batch[1]:
+                src, idx = self._batch[1], self._batch_index      # pre-traced with the same frequencies: a lookup
+            else:
+                src = self.trace_batch(self._X1[None, :], self._X2[None, :], frequency=frequency, max_detector_freq=max_detector_freq,
+                                       outputs=("n_sol", "C0", "reflection", "reflection_case"), attenuation="dense")
+            # rows in the trace's slot order, with the identity of each slot: _results may hold a subset in another order
+            # (set_solution after a viewing-angle cut), and the reference looks the solution up by its C0 / reflection / case
+            n = int(src["n_sol"][idx])
+            self._att_cache[key] = (np.array(src["attenuation"][idx][:n]), np.array(src["C0"][idx][:n]),
+                                    np.array(src["reflection"][idx][:n]), np.array(src["reflection_case"][idx][:n]))
+        att, C0s, refl, case = self._att_cache[key]
+        r = self._results[iS]
+        cand = [s for s in range(len(C0s)) if int(refl[s]) == int(r['reflection']) and abs(C0s[s] - r['C0']) <= 1e-6 * abs(r['C0'])
+                and (int(r['reflection']) == 0 or int(r.get('reflection_case', case[s])) in (0, int(case[s])))]
+        if not cand:
+            raise AttributeError("the ray-tracing solution (C0 = {}) does not belong to this pair of points".format(r['C0']))
+        return np.array(att[cand[0]])
 
     def get_focusing(self, iS, dz=-1. * units.cm, limit=2., analytic=False):
         """

@@ -32,7 +32,8 @@ OUTPUT_FIELDS = ("n_sol", "status", "solution_type", "reflection", "reflection_c
 
 class Output(C.Structure):
     _fields_ = [(k, C.c_void_p) for k in OUTPUT_FIELDS] + [("compact", C.c_int32), ("reserved", C.c_int32),
-                                                          ("sol_offset", C.c_void_p), ("row_capacity", C.c_int64)]
+                                                          ("sol_offset", C.c_void_p), ("row_capacity", C.c_int64),
+                                                          ("row_base", C.c_int64)]
 
 
 class Stats(C.Structure):
@@ -55,6 +56,7 @@ class Focusing(C.Structure):
 
 EXPORTS = ("nrmc_rt_create", "nrmc_rt_destroy", "nrmc_rt_last_error", "nrmc_rt_max_solutions", "nrmc_rt_set_frequencies",
            "nrmc_rt_get_sparse_frequencies", "nrmc_rt_trace", "nrmc_rt_set_chunk_pairs", "nrmc_rt_host_alloc", "nrmc_rt_host_free",
+           "nrmc_rt_peer_alloc", "nrmc_rt_peer_open", "nrmc_rt_peer_close", "nrmc_rt_peer_free", "nrmc_rt_copy_async",
            "nrmc_rt_attenuation_length", "nrmc_rt_apply_propagation_effects", "nrmc_rt_focusing_factor", "nrmc_rt_measure_fp64_peak", "nrmc_rt_device_count", "nrmc_rt_version")
 
 _lib = None
@@ -89,6 +91,16 @@ def load():
     lib.nrmc_rt_host_alloc.restype = C.c_int
     lib.nrmc_rt_host_free.argtypes = [C.c_void_p]
     lib.nrmc_rt_host_free.restype = C.c_int
+    lib.nrmc_rt_peer_alloc.argtypes = [C.c_int32, C.c_uint64, C.POINTER(C.c_void_p), C.c_char_p]
+    lib.nrmc_rt_peer_alloc.restype = C.c_int
+    lib.nrmc_rt_peer_open.argtypes = [C.c_int32, C.c_char_p, C.POINTER(C.c_void_p)]
+    lib.nrmc_rt_peer_open.restype = C.c_int
+    lib.nrmc_rt_peer_close.argtypes = [C.c_void_p]
+    lib.nrmc_rt_peer_close.restype = C.c_int
+    lib.nrmc_rt_peer_free.argtypes = [C.c_void_p]
+    lib.nrmc_rt_peer_free.restype = C.c_int
+    lib.nrmc_rt_copy_async.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
+    lib.nrmc_rt_copy_async.restype = C.c_int
     lib.nrmc_rt_attenuation_length.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
     lib.nrmc_rt_attenuation_length.restype = C.c_int
     lib.nrmc_rt_apply_propagation_effects.argtypes = [C.c_void_p, C.POINTER(Effects), C.c_void_p]

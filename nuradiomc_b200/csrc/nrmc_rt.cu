@@ -64,34 +64,112 @@ __device__ __forceinline__ void load_pair(const KInput &in, int64_t p, double &x
 // (direct rays) from the front, two-panel paths (refracted / reflected) from the back, so that the warps of the
 // thread-per-solution kernel are homogeneous.  counts[0] = front entries, counts[WL_BACK] = back entries.
 // Per-lane counter block (16 x u64): [0] work front, [1] work back, [2] fallback front, [3] fallback back (unused, 0),
-// [4] root queue, [5] hump queue.
+// [4] root queue (entries), [5] hump queue.
 #define CNT_WORK 0
 #define CNT_FALLBACK 2
 #define CNT_ROOTS 4
 #define CNT_HUMPS 5
 #define CNT_STRIDE 16
-#define CNT_ROWBASE 32          // running row base of a compact device-resident call (not per lane, not reset per chunk)
+#define N_LANES 3               // two pipeline lanes of the host-memory calls + the lane of device-resident calls
+#define DEV_LANE 2
+#define CNT_ROWBASE (N_LANES * CNT_STRIDE)   // running row base of a compact device-resident call (not reset per chunk)
 #define WL_BACK 1
-__device__ __forceinline__ SolRec worklist_get(const SolRec *wl, unsigned long long cap, unsigned long long n_front, unsigned long long w)
+#define FULL_MASK 0xffffffffu
+
+// Work list in HBM, structure of arrays: the thread-per-solution kernels read entry w with lane w, so every field is one
+// contiguous 256-byte (4-byte fields: 128-byte) access per warp.  (Round 1 kept 64-byte records: every 8-byte field access
+// of a warp touched 32 sectors, two thirds of the L2 traffic of K_roots was "excessive" in ncu's terms.)
+struct WorkList {
+    double *beta, *delta, *zv, *z1, *z2;
+    int64_t *row;
+    int32_t *meta;              // slot | piece << 8 | k << 16 | rcase << 24
+    unsigned long long cap;
+};
+#define WORKLIST_BYTES_PER_ENTRY 52
+static WorkList carve_worklist(void *p, unsigned long long cap)
 {
-    return w < n_front ? wl[w] : wl[cap - 1ull - (w - n_front)];
+    WorkList w;
+    const unsigned long long c = (cap + 1ull) & ~1ull;          // keeps every array 16-byte aligned
+    double *d = (double *)p;
+    w.beta = d; w.delta = d + c; w.zv = d + 2 * c; w.z1 = d + 3 * c; w.z2 = d + 4 * c;
+    w.row = (int64_t *)(d + 5 * c);
+    w.meta = (int32_t *)(d + 6 * c);
+    w.cap = cap;
+    return w;
+}
+static size_t worklist_bytes(unsigned long long cap) { return (size_t)((cap + 1ull) & ~1ull) * WORKLIST_BYTES_PER_ENTRY + 64; }
+
+__device__ __forceinline__ unsigned long long worklist_index(const WorkList &wl, unsigned long long n_front, unsigned long long w)
+{
+    return w < n_front ? w : wl.cap - 1ull - (w - n_front);
+}
+__device__ __forceinline__ SolRec worklist_load(const WorkList &wl, unsigned long long i)
+{
+    SolRec r;
+    r.pair = 0;
+    r.beta = wl.beta[i]; r.delta = wl.delta[i]; r.zv = wl.zv[i]; r.z1 = wl.z1[i]; r.z2 = wl.z2[i];
+    r.row = wl.row[i];
+    const int32_t m = wl.meta[i];
+    r.slot = m & 0xff; r.piece = (uint8_t)((m >> 8) & 0xff); r.k = (uint8_t)((m >> 16) & 0xff); r.rcase = (uint8_t)((m >> 24) & 0xff); r.pad = 0;
+    return r;
+}
+__device__ __forceinline__ void worklist_store(const WorkList &wl, unsigned long long i, const SolRec &r)
+{
+    wl.beta[i] = r.beta; wl.delta[i] = r.delta; wl.zv[i] = r.zv; wl.z1[i] = r.z1; wl.z2[i] = r.z2;
+    wl.row[i] = r.row;
+    wl.meta[i] = (r.slot & 0xff) | ((int32_t)r.piece << 8) | ((int32_t)r.k << 16) | ((int32_t)r.rcase << 24);
+}
+__device__ __forceinline__ SolRec worklist_get(const WorkList &wl, unsigned long long n_front, unsigned long long w)
+{
+    return worklist_load(wl, worklist_index(wl, n_front, w));
 }
 
 #define N_OUT 15            // output arrays of nrmc_rt_output (out_ptr)
 // ---------------------------------------------------------------------------------------------------------------
 // Binned solver for media without bottom reflections (one mode per pair).  Pairs differ wildly in the work they need
 // (shadow zone: a maximum search; lit zone: two root solves), so a thread-per-pair kernel runs with half-empty warps.
-// Here the work is split at the points where it diverges and re-packed through queues in HBM (64-byte items, a few
-// GB/s -- HBM is idle in this workload):
-//   K_classify  thread per pair:  frame, gamma(z1), gamma(z2), the three junction values -> two bracket items
-//                                 (root queue), or one hump item (curve entirely below rho), or "no solution"
-//   K_hump      thread per hump item: maximum search with the closed-form derivative -> two bracket items or "no solution"
-//   K_roots     thread per bracket item: safeguarded Newton, closed-form properties, SoA stores, SolRec for K_att.
-//               The two brackets of a pair sit in adjacent lanes; one shuffle orders them by C0 (py:1547).
-// Queue appends are warp-aggregated (ballot + one atomic per warp).
+// Here the work is split at the points where it diverges and re-packed through queues in HBM (HBM is idle in this workload):
+//   K_classify  thread per pair:  frame, gamma(z1), gamma(z2), the three junction values -> one root-queue ENTRY (two brackets),
+//                                 or one hump item (curve entirely below rho), or "no solution"
+//   K_hump      thread per hump item: maximum search with the closed-form derivative -> one root-queue entry or "no solution"
+//   K_roots     thread per bracket (two lanes per entry): safeguarded Newton, closed-form properties, SoA stores, work-list
+//               record for the attenuation kernels.  One shuffle orders the two roots of a pair by C0 (py:1547).
+// Queue appends are warp-aggregated (ballot + one atomic per warp).  The queues are structures of arrays indexed by the
+// entry, the two brackets of an entry packed as double2: every queue access of a warp is one contiguous run of sectors.
 // ---------------------------------------------------------------------------------------------------------------
-struct RootItem { int64_t pair; double g1, g2, a, ga, b, gb; int32_t piece, valid; };   // 64 bytes; valid: bit 0, mode bits above
-struct HumpItem { int64_t pair; double g1, g2, J1, J2, J3; int32_t mode, pad; };        // 56 bytes
+struct RootQ {
+    int64_t *pair;              // [cap]
+    double *g1, *g2;            // [cap] gamma at the two depths (the only transcendentals of the pair geometry)
+    double2 *a, *ga, *b, *gb;   // [cap] bracket end points and values; .x: first bracket, .y: second
+    int32_t *meta;              // [cap] bits 0-1 piece of bracket 0, 2-3 piece of bracket 1, 4: bracket 1 exists,
+                                //       8-15 k bounces, 16-23 launch case, 24-31 mode index (mode_bits)
+};
+#define ROOTQ_BYTES_PER_ENTRY 92
+static RootQ carve_rootq(void *p, size_t cap)
+{
+    RootQ q;
+    const size_t c = (cap + 3) & ~(size_t)3;
+    double *d = (double *)p;
+    q.pair = (int64_t *)d; q.g1 = d + c; q.g2 = d + 2 * c;
+    q.a = (double2 *)(d + 3 * c); q.ga = (double2 *)(d + 5 * c); q.b = (double2 *)(d + 7 * c); q.gb = (double2 *)(d + 9 * c);
+    q.meta = (int32_t *)(d + 11 * c);
+    return q;
+}
+static size_t rootq_bytes(size_t cap) { return ((cap + 3) & ~(size_t)3) * ROOTQ_BYTES_PER_ENTRY + 64; }
+
+struct HumpQ { int64_t *pair; double *g1, *g2, *J1, *J2, *J3; int32_t *mode; };
+#define HUMPQ_BYTES_PER_ENTRY 52
+static HumpQ carve_humpq(void *p, size_t cap)
+{
+    HumpQ q;
+    const size_t c = (cap + 3) & ~(size_t)3;
+    double *d = (double *)p;
+    q.pair = (int64_t *)d; q.g1 = d + c; q.g2 = d + 2 * c; q.J1 = d + 3 * c; q.J2 = d + 4 * c; q.J3 = d + 5 * c;
+    q.mode = (int32_t *)(d + 6 * c);
+    return q;
+}
+static size_t humpq_bytes(size_t cap) { return ((cap + 3) & ~(size_t)3) * HUMPQ_BYTES_PER_ENTRY + 64; }
+
 // mode of a work item for media with bottom reflections: k bounces (bits 8-15), launch case (16-23), mode index (24-31)
 __device__ __forceinline__ int mode_bits(int k, int rcase, int md) { return (k << 8) | (rcase << 16) | (md << 24); }
 __device__ __forceinline__ void mode_of(int md, int &k, int &rcase) { k = md == 0 ? 0 : (md - 1) / 2 + 1; rcase = md == 0 ? 1 : (md - 1) % 2 + 1; }
@@ -115,24 +193,39 @@ __global__ void K_rmax_table(IceParams ice, int n, double dz, double *table)
     table[i2 * n + i1] = r;
 }
 
-__device__ __forceinline__ void push_brackets(bool have, int64_t pair, const PairGeom &g, const Bracket *br, int nb, RootItem *rootq,
+__global__ void K_set_u64(unsigned long long *p, unsigned long long v) { *p = v; }
+
+__device__ __forceinline__ void push_brackets(bool have, int64_t pair, const PairGeom &g, const Bracket *br, int nb, const RootQ &q,
                                               unsigned long long *root_count, unsigned lane, int mode = 0)
 {
-    const unsigned m = __ballot_sync(0xffffffffu, have);
+    const unsigned m = __ballot_sync(FULL_MASK, have);
     if (m == 0) return;
     const int leader = __ffs(m) - 1;
     unsigned long long base = 0;
-    if ((int)lane == leader) base = atomicAdd(root_count, 2ull * __popc(m));
-    base = __shfl_sync(0xffffffffu, base, leader);
+    if ((int)lane == leader) base = atomicAdd(root_count, (unsigned long long)__popc(m));
+    base = __shfl_sync(FULL_MASK, base, leader);
     if (have) {
-        RootItem *dst = rootq + base + 2ull * __popc(m & ((1u << lane) - 1u));
-        for (int j = 0; j < 2; ++j) {
-            RootItem it;
-            const Bracket &b = br[j < nb ? j : 0];
-            it.pair = pair; it.g1 = g.g1; it.g2 = g.g2; it.a = b.a; it.ga = b.ga; it.b = b.b; it.gb = b.gb;
-            it.piece = b.piece; it.valid = (j < nb ? 1 : 0) | mode;
-            dst[j] = it;
-        }
+        const unsigned long long e = base + __popc(m & ((1u << lane) - 1u));
+        const Bracket &b0 = br[0], &b1 = br[nb > 1 ? 1 : 0];
+        q.pair[e] = pair; q.g1[e] = g.g1; q.g2[e] = g.g2;
+        q.a[e] = make_double2(b0.a, b1.a); q.ga[e] = make_double2(b0.ga, b1.ga);
+        q.b[e] = make_double2(b0.b, b1.b); q.gb[e] = make_double2(b0.gb, b1.gb);
+        q.meta[e] = (b0.piece & 3) | ((b1.piece & 3) << 2) | ((nb > 1 ? 1 : 0) << 4) | mode;
+    }
+}
+
+__device__ __forceinline__ void push_hump(bool have, int64_t pair, const PairGeom &g, double J1, double J2, double J3, int mode, const HumpQ &q,
+                                          unsigned long long *hump_count, unsigned lane)
+{
+    const unsigned mh = __ballot_sync(FULL_MASK, have);
+    if (mh == 0) return;
+    const int leader = __ffs(mh) - 1;
+    unsigned long long base = 0;
+    if ((int)lane == leader) base = atomicAdd(hump_count, (unsigned long long)__popc(mh));
+    base = __shfl_sync(FULL_MASK, base, leader);
+    if (have) {
+        const unsigned long long e = base + __popc(mh & ((1u << lane) - 1u));
+        q.pair[e] = pair; q.g1[e] = g.g1; q.g2[e] = g.g2; q.J1[e] = J1; q.J2[e] = J2; q.J3[e] = J3; q.mode[e] = mode;
     }
 }
 
@@ -143,11 +236,11 @@ struct AttFill { double *sparse, *dense; int32_t Fs, F; };
 __device__ __forceinline__ void warp_fill_nan_rows(bool mine, int64_t pair, const AttFill &af, unsigned lane)
 {
     if (!af.sparse && !af.dense) return;
-    unsigned m = __ballot_sync(0xffffffffu, mine);
+    unsigned m = __ballot_sync(FULL_MASK, mine);
     while (m) {
         const int l = __ffs(m) - 1;
         m &= m - 1;
-        const int64_t pr = __shfl_sync(0xffffffffu, pair, l);
+        const int64_t pr = __shfl_sync(FULL_MASK, pair, l);
         // both slots of the pair: 2 Fs doubles = Fs 16-byte stores (the pair's rows start on a 16-byte boundary), streaming
         const double2 nan2 = make_double2(NAN, NAN);
         if (af.sparse) { double2 *d = reinterpret_cast<double2 *>(af.sparse + pr * 2 * af.Fs); for (int j = lane; j < af.Fs; j += 32) __stcs(d + j, nan2); }
@@ -158,11 +251,11 @@ __device__ __forceinline__ void warp_fill_nan_rows(bool mine, int64_t pair, cons
 __device__ __forceinline__ void warp_fill_nan_slot(bool mine, int64_t q, const AttFill &af, unsigned lane)
 {
     if (!af.sparse && !af.dense) return;
-    unsigned m = __ballot_sync(0xffffffffu, mine);
+    unsigned m = __ballot_sync(FULL_MASK, mine);
     while (m) {
         const int l = __ffs(m) - 1;
         m &= m - 1;
-        const int64_t qq = __shfl_sync(0xffffffffu, q, l);
+        const int64_t qq = __shfl_sync(FULL_MASK, q, l);
         if (af.sparse) { double *d = af.sparse + qq * af.Fs; for (int j = lane; j < af.Fs; j += 32) __stcs(d + j, NAN); }
         if (af.dense) { double *d = af.dense + qq * af.F; for (int j = lane; j < af.F; j += 32) __stcs(d + j, NAN); }
     }
@@ -179,8 +272,8 @@ __device__ __forceinline__ void write_no_solution(const TraceOutputs &out, int64
 
 #define CLASSIFY_THREADS 256
 __global__ void __launch_bounds__(CLASSIFY_THREADS)
-K_classify(IceParams ice, KInput in, TraceOutputs out, AttFill af, RmaxTable rmax, RootItem *rootq, unsigned long long *root_count,
-           HumpItem *humpq, unsigned long long *hump_count)
+K_classify(IceParams ice, KInput in, TraceOutputs out, AttFill af, RmaxTable rmax, RootQ rootq, unsigned long long *root_count,
+           HumpQ humpq, unsigned long long *hump_count)
 {
     const int64_t p = (int64_t)blockIdx.x * CLASSIFY_THREADS + threadIdx.x;
     const unsigned lane = threadIdx.x & 31u;
@@ -216,23 +309,12 @@ K_classify(IceParams ice, KInput in, TraceOutputs out, AttFill af, RmaxTable rma
     }
     if (!out.row_offset) warp_fill_nan_rows(p < in.n_pairs && kind == 0, p, af, lane);
     push_brackets(kind == 1, p, g, br, nb, rootq, root_count, lane);
-    const unsigned mh = __ballot_sync(0xffffffffu, kind == 2);
-    if (mh) {
-        const int leader = __ffs(mh) - 1;
-        unsigned long long base = 0;
-        if ((int)lane == leader) base = atomicAdd(hump_count, (unsigned long long)__popc(mh));
-        base = __shfl_sync(0xffffffffu, base, leader);
-        if (kind == 2) {
-            HumpItem it;
-            it.pair = p; it.g1 = g.g1; it.g2 = g.g2; it.J1 = J1; it.J2 = J2; it.J3 = J3; it.mode = 0; it.pad = 0;
-            humpq[base + __popc(mh & ((1u << lane) - 1u))] = it;
-        }
-    }
+    push_hump(kind == 2, p, g, J1, J2, J3, 0, humpq, hump_count, lane);
 }
 
 #define HUMP_THREADS 128
 __global__ void __launch_bounds__(HUMP_THREADS, 4)
-K_hump(IceParams ice, KInput in, TraceOutputs out, AttFill af, const HumpItem *humpq, const unsigned long long *hump_count, RootItem *rootq,
+K_hump(IceParams ice, KInput in, TraceOutputs out, AttFill af, HumpQ humpq, const unsigned long long *hump_count, RootQ rootq,
        unsigned long long *root_count)
 {
     const unsigned lane = threadIdx.x & 31u;
@@ -246,16 +328,15 @@ K_hump(IceParams ice, KInput in, TraceOutputs out, AttFill af, const HumpItem *h
         int nb = 0;
         int64_t pair = 0;
         if (active) {
-            const HumpItem it = humpq[w];
-            pair = it.pair;
+            pair = humpq.pair[w];
             double x1, y1, z1, x2, y2, z2;
             load_pair(in, pair, x1, y1, z1, x2, y2, z2);
             Frame2D f;
             make_frame(x1, y1, z1, x2, y2, z2, f);
-            make_pair_geom_g(ice, f.z1, f.z2, fmax(f.rho, 1e-12), it.g1, it.g2, g);
+            make_pair_geom_g(ice, f.z1, f.z2, fmax(f.rho, 1e-12), humpq.g1[w], humpq.g2[w], g);
             Curve cv;
             cv.ice = &ice; cv.g = &g; cv.k = 0; cv.rcase = 1;
-            nb = hump_search(cv, it.J1, it.J2, it.J3, br);
+            nb = hump_search(cv, humpq.J1[w], humpq.J2[w], humpq.J3[w], br);
             if (nb == 0) write_no_solution(out, pair, 0);
             else { if (out.n_sol) out.n_sol[pair] = nb; if (out.status) out.status[pair] = 0; }
         }
@@ -264,95 +345,145 @@ K_hump(IceParams ice, KInput in, TraceOutputs out, AttFill af, const HumpItem *h
     }
 }
 
+// bracket j of root-queue entry e (lane pairs read the two halves of the same double2: one contiguous run per warp)
+__device__ __forceinline__ Bracket rootq_bracket(const RootQ &q, unsigned long long w, int meta)
+{
+    Bracket b;
+    b.a = reinterpret_cast<const double *>(q.a)[w]; b.ga = reinterpret_cast<const double *>(q.ga)[w];
+    b.b = reinterpret_cast<const double *>(q.b)[w]; b.gb = reinterpret_cast<const double *>(q.gb)[w];
+    b.piece = (meta >> (2 * (int)(w & 1ull))) & 3;
+    return b;
+}
+
+// launch / receive vectors of the solutions of a warp.  When the rows of the warp's solutions form one contiguous range (the
+// rule: consecutive queue entries are consecutive pairs with solutions) the 3-vectors are transposed through shared memory
+// and written as three fully coalesced runs; lanes storing their own 24-byte rows touch three times as many sectors.
+__device__ __forceinline__ void warp_store_vec3(double *dst, bool valid, int64_t row, bool dense, int64_t row_min, int n_valid, double vx,
+                                                double vy, double vz, double *stage, unsigned lane)
+{
+    if (!dst) return;
+    if (dense) {
+        if (valid) { double *s = stage + 3 * (int)(row - row_min); s[0] = vx; s[1] = vy; s[2] = vz; }
+        __syncwarp();
+        double *d = dst + 3 * row_min;
+        for (int i = lane; i < 3 * n_valid; i += 32) d[i] = stage[i];
+        __syncwarp();
+    } else if (valid) {
+        dst[3 * row] = vx; dst[3 * row + 1] = vy; dst[3 * row + 2] = vz;
+    }
+}
+
 #define ROOTS_THREADS 128
 #ifndef ROOTS_MIN_BLOCKS
-#define ROOTS_MIN_BLOCKS 7      // 72 registers, no spills: 28 warps per SM (6: 78 registers; 8: 64 registers with spills)
+#define ROOTS_MIN_BLOCKS 7      // 72 registers: 28 warps per SM
 #endif
 template <bool CUT>
 __global__ void __launch_bounds__(ROOTS_THREADS, ROOTS_MIN_BLOCKS)
-K_roots(IceParams ice, KInput in, TraceOutputs out, AttFill af, const RootItem *rootq, const unsigned long long *root_count, SolRec *worklist,
-        unsigned long long *work_count, unsigned long long work_cap)
+K_roots(IceParams ice, KInput in, TraceOutputs out, AttFill af, RootQ rootq, const unsigned long long *root_count, WorkList worklist,
+        unsigned long long *work_count)
 {
+    __shared__ double s_stage[ROOTS_THREADS / 32][96];
     const unsigned lane = threadIdx.x & 31u;
-    const unsigned long long n = *root_count;     // even: items are pushed in pairs at even offsets
+    double *stage = s_stage[threadIdx.x >> 5];
+    const unsigned long long n = 2ull * *root_count;     // two lanes per entry
     const unsigned long long stride = (unsigned long long)gridDim.x * ROOTS_THREADS;
     for (unsigned long long w0 = (unsigned long long)blockIdx.x * ROOTS_THREADS + (threadIdx.x & ~31u); w0 < n; w0 += stride) {
         const unsigned long long w = w0 + lane;
         const bool active = w < n;
         bool valid = false;
         int64_t pair = 0;
-        Root root;
-        root.v = 0; root.piece = 0; root.beta = 0;
-        double g1 = 0, g2 = 0, viewing = NAN;
+        double viewing = NAN;
         bool keep = true;      // passes the viewing-angle cut (always, when no shower axes were given)
+        // everything the stores need, computed once, before the two roots of the pair are ordered
+        SolutionProps pr;
+        SolRec rec;
+        double ex = 1.0, ey = 0.0;
+        bool swap = false;
+        pr.C0 = pr.C1 = pr.path_length = pr.travel_time = pr.refl_angle = NAN;
+        pr.sin_l = pr.cos_l = pr.sin_r = pr.cos_r = 0.0; pr.type = 0; pr.refl_mask = 0; pr.n_segments = 1;
+        rec.beta = rec.delta = rec.zv = rec.z1 = rec.z2 = 0.0; rec.piece = 0; rec.k = 0; rec.rcase = 1; rec.pad = 0; rec.slot = 0; rec.row = 0; rec.pair = 0;
         if (active) {
-            const RootItem it = rootq[w];
-            pair = it.pair; g1 = it.g1; g2 = it.g2;
-            valid = (it.valid & 1) != 0;
+            const unsigned long long e = w >> 1;
+            const int meta = rootq.meta[e];
+            pair = rootq.pair[e];
+            valid = (w & 1ull) == 0 || ((meta >> 4) & 1) != 0;
             if (valid) {
                 double x1, y1, z1, x2, y2, z2;
                 load_pair(in, pair, x1, y1, z1, x2, y2, z2);
                 Frame2D f;
                 make_frame(x1, y1, z1, x2, y2, z2, f);
                 PairGeom g;
-                make_pair_geom_g(ice, f.z1, f.z2, fmax(f.rho, 1e-12), g1, g2, g);
+                make_pair_geom_g(ice, f.z1, f.z2, fmax(f.rho, 1e-12), rootq.g1[e], rootq.g2[e], g);
                 Curve cv;
                 cv.ice = &ice; cv.g = &g; cv.k = 0; cv.rcase = 1;
-                Bracket b;
-                b.a = it.a; b.ga = it.ga; b.b = it.b; b.gb = it.gb; b.piece = it.piece;
-                root = solve_bracket(cv, b);
+                const Bracket b = rootq_bracket(rootq, w, meta);
+                const Root root = solve_bracket(cv, b);
+                solution_props(ice, g, f.x1y, 0, 1, root, pr);
+                make_solrec(ice, g, pair, 0, 0, 0, 1, root, rec);
+                ex = f.ex; ey = f.ey; swap = f.swap;
                 if (CUT) {
                     // launch direction from Snell's invariant: sin = beta / n, cos = s / n at the emitter (py:1161-1199, :2583-2590)
                     const ShowerCut sc = load_cut(in, pair);
-                    const double nl = f.swap ? g.n2 : g.n1;
-                    const double sl = sqrt(fmax((nl - root.beta) * (nl + root.beta), 0.0));
-                    const double lx = f.swap ? -root.beta / nl : root.beta / nl;
-                    const double lz = f.swap ? (root.piece >= 2 ? sl / nl : -sl / nl) : sl / nl;
-                    viewing = viewing_angle_of(sc, f.ex, f.ey, lx, lz);
-                    keep = passes_cut(sc, viewing, nl);
+                    viewing = viewing_angle_of(sc, ex, ey, swap ? -pr.sin_r : pr.sin_l, swap ? pr.cos_r : pr.cos_l);
+                    keep = passes_cut(sc, viewing, swap ? g.n2 : g.n1);
                 }
             }
         }
         // order the two roots of the pair by ascending C0 = descending beta (py:1547); the partner sits in lane ^ 1
-        const double beta_other = __shfl_xor_sync(0xffffffffu, valid ? root.beta : -1.0, 1);
+        const double beta_other = __shfl_xor_sync(FULL_MASK, valid ? rec.beta : -1.0, 1);
         int slot = lane & 1;
-        if (valid) slot = (root.beta > beta_other) ? 0 : ((root.beta < beta_other) ? 1 : (int)(lane & 1u));
-        const int64_t row = valid ? row_of(out, pair, slot, 2) : 0;
+        if (valid) slot = (rec.beta > beta_other) ? 0 : ((rec.beta < beta_other) ? 1 : (int)(lane & 1u));
+        int64_t row = valid ? row_of(out, pair, slot, 2) : 0;
         if (out.row_offset && row >= out.row_limit) valid = false;      // caller's compact arrays are full: drop (reported as NRMC_ERR_CAPACITY)
         // work-list slot of this solution (front: one quadrature panel, back: two), one atomic per warp and list end
-        SolRec *rec_dst = nullptr;
-        if (worklist) {
-            const bool two_panel = root.piece >= 2;
-            const unsigned mf = __ballot_sync(0xffffffffu, valid && keep && !two_panel), mb = __ballot_sync(0xffffffffu, valid && keep && two_panel);
+        if (worklist.beta) {
+            const bool two_panel = rec.piece >= 2;
+            const unsigned mf = __ballot_sync(FULL_MASK, valid && keep && !two_panel), mb = __ballot_sync(FULL_MASK, valid && keep && two_panel);
             unsigned long long bf = 0, bb = 0;
-            if (mf) { const int l = __ffs(mf) - 1; if ((int)lane == l) bf = atomicAdd(work_count, (unsigned long long)__popc(mf)); bf = __shfl_sync(0xffffffffu, bf, l); }
-            if (mb) { const int l = __ffs(mb) - 1; if ((int)lane == l) bb = atomicAdd(work_count + WL_BACK, (unsigned long long)__popc(mb)); bb = __shfl_sync(0xffffffffu, bb, l); }
+            if (mf) { const int l = __ffs(mf) - 1; if ((int)lane == l) bf = atomicAdd(work_count, (unsigned long long)__popc(mf)); bf = __shfl_sync(FULL_MASK, bf, l); }
+            if (mb) { const int l = __ffs(mb) - 1; if ((int)lane == l) bb = atomicAdd(work_count + WL_BACK, (unsigned long long)__popc(mb)); bb = __shfl_sync(FULL_MASK, bb, l); }
             const unsigned below = (1u << lane) - 1u;
-            if (valid && keep) rec_dst = two_panel ? worklist + (work_cap - 1ull - (bb + __popc(mb & below))) : worklist + (bf + __popc(mf & below));
+            if (valid && keep) {
+                rec.slot = slot; rec.row = row;
+                worklist_store(worklist, two_panel ? worklist.cap - 1ull - (bb + __popc(mb & below)) : bf + __popc(mf & below), rec);
+            }
         }
         if (CUT) warp_fill_nan_slot(valid && !keep, row, af, lane);     // cut solutions: NaN attenuation rows
-        if (active) {
-            if (valid) {
-                double x1, y1, z1, x2, y2, z2;
-                load_pair(in, pair, x1, y1, z1, x2, y2, z2);
-                Frame2D f;
-                make_frame(x1, y1, z1, x2, y2, z2, f);
-                PairGeom g;
-                make_pair_geom_g(ice, f.z1, f.z2, fmax(f.rho, 1e-12), g1, g2, g);
-                if (rec_dst) {
-                    SolRec rec;
-                    make_solrec(ice, g, pair, slot, row, 0, 1, root, rec);
-                    *rec_dst = rec;
-                }
-                SolutionProps pr;
-                solution_props(ice, g, f.x1y, 0, 1, root, pr);
-                write_solution(out, row, 1, f, 0, 1, pr);
-                if (out.viewing_angle) out.viewing_angle[row] = viewing;
-            } else if (!out.row_offset) {
-                fill_empty_slot(out, 2 * pair + 1, 1);    // single root (tangency at the surface): second slot stays empty
-                if (af.sparse) for (int j = 0; j < af.Fs; ++j) af.sparse[(2 * pair + 1) * af.Fs + j] = NAN;
-                if (af.dense) for (int j = 0; j < af.F; ++j) af.dense[(2 * pair + 1) * af.F + j] = NAN;
-            }
+        // are the rows of this warp's solutions one contiguous range?
+        const unsigned mv = __ballot_sync(FULL_MASK, valid);
+        bool dense = false;
+        int64_t row_min = 0;
+        const int n_valid = __popc(mv);
+        if (mv) {
+            const int64_t row_ref = __shfl_sync(FULL_MASK, row, __ffs(mv) - 1);
+            const int64_t dd = row - row_ref;
+            const int d = valid ? (int)(dd < -64 ? -64 : (dd > 64 ? 64 : dd)) : 0;
+            const int dmin = __reduce_min_sync(FULL_MASK, d), dmax = __reduce_max_sync(FULL_MASK, d);
+            dense = (dmax - dmin + 1 == n_valid);
+            row_min = row_ref + dmin;
+        }
+        if (valid) {
+            if (out.type) out.type[row] = (int8_t)pr.type;
+            if (out.reflection) out.reflection[row] = 0;
+            if (out.reflection_case) out.reflection_case[row] = 1;
+            if (out.C0) out.C0[row] = pr.C0;
+            if (out.C1) out.C1[row] = pr.C1;
+            if (out.path_length) out.path_length[row] = pr.path_length;
+            if (out.travel_time) out.travel_time[row] = pr.travel_time;
+            if (out.reflection_angle) out.reflection_angle[row] = (pr.refl_mask & 1u) ? pr.refl_angle : NAN;
+            if (out.viewing_angle) out.viewing_angle[row] = viewing;
+        }
+        {
+            // 2-D vectors -> 3-D: R^T [vx,0,vz] = [vx ex, vx ey, vz]; roles exchanged when swapped (py:2583-2590,2617-2623)
+            double lx = pr.sin_l, lz = pr.cos_l, rx = -pr.sin_r, rz = pr.cos_r;
+            if (swap) { const double tx = lx, tz = lz; lx = rx; lz = rz; rx = tx; rz = tz; }
+            warp_store_vec3(out.launch, valid, row, dense, row_min, n_valid, lx * ex, lx * ey, lz, stage, lane);
+            warp_store_vec3(out.receive, valid, row, dense, row_min, n_valid, rx * ex, rx * ey, rz, stage, lane);
+        }
+        if (active && !valid && !out.row_offset && (w & 1ull)) {
+            fill_empty_slot(out, 2 * pair + 1, 1);    // single root (tangency at the surface): second slot stays empty
+            if (af.sparse) for (int j = 0; j < af.Fs; ++j) af.sparse[(2 * pair + 1) * af.Fs + j] = NAN;
+            if (af.dense) for (int j = 0; j < af.F; ++j) af.dense[(2 * pair + 1) * af.F + j] = NAN;
         }
     }
 }
@@ -364,8 +495,8 @@ K_roots(IceParams ice, KInput in, TraceOutputs out, AttFill af, const RootItem *
 // fills the unused slots, K_roots_m writes every solution to its slot.
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(CLASSIFY_THREADS)
-K_classify_m(IceParams ice, KInput in, TraceOutputs out, RmaxTable rmax, int M, int8_t *mode_count, RootItem *rootq,
-             unsigned long long *root_count, HumpItem *humpq, unsigned long long *hump_count)
+K_classify_m(IceParams ice, KInput in, TraceOutputs out, RmaxTable rmax, int M, int8_t *mode_count, RootQ rootq,
+             unsigned long long *root_count, HumpQ humpq, unsigned long long *hump_count)
 {
     const int64_t t = (int64_t)blockIdx.x * CLASSIFY_THREADS + threadIdx.x;
     const unsigned lane = threadIdx.x & 31u;
@@ -400,22 +531,11 @@ K_classify_m(IceParams ice, KInput in, TraceOutputs out, RmaxTable rmax, int M, 
         if (kind != 2) mode_count[t] = (int8_t)(kind == 1 ? nb : 0);
     }
     push_brackets(kind == 1, p, g, br, nb, rootq, root_count, lane, mode_bits(k, rcase, md));
-    const unsigned mh = __ballot_sync(0xffffffffu, kind == 2);
-    if (mh) {
-        const int leader = __ffs(mh) - 1;
-        unsigned long long base = 0;
-        if ((int)lane == leader) base = atomicAdd(hump_count, (unsigned long long)__popc(mh));
-        base = __shfl_sync(0xffffffffu, base, leader);
-        if (kind == 2) {
-            HumpItem it;
-            it.pair = p; it.g1 = g.g1; it.g2 = g.g2; it.J1 = J1; it.J2 = J2; it.J3 = J3; it.mode = mode_bits(k, rcase, md); it.pad = 0;
-            humpq[base + __popc(mh & ((1u << lane) - 1u))] = it;
-        }
-    }
+    push_hump(kind == 2, p, g, J1, J2, J3, mode_bits(k, rcase, md), humpq, hump_count, lane);
 }
 
 __global__ void __launch_bounds__(HUMP_THREADS, 4)
-K_hump_m(IceParams ice, KInput in, int M, int8_t *mode_count, const HumpItem *humpq, const unsigned long long *hump_count, RootItem *rootq,
+K_hump_m(IceParams ice, KInput in, int M, int8_t *mode_count, HumpQ humpq, const unsigned long long *hump_count, RootQ rootq,
          unsigned long long *root_count)
 {
     const unsigned lane = threadIdx.x & 31u;
@@ -429,19 +549,18 @@ K_hump_m(IceParams ice, KInput in, int M, int8_t *mode_count, const HumpItem *hu
         int nb = 0, mode = 0;
         int64_t pair = 0;
         if (active) {
-            const HumpItem it = humpq[w];
-            pair = it.pair; mode = it.mode;
+            pair = humpq.pair[w]; mode = humpq.mode[w];
             double x1, y1, z1, x2, y2, z2;
             load_pair(in, pair, x1, y1, z1, x2, y2, z2);
             Frame2D f;
             make_frame(x1, y1, z1, x2, y2, z2, f);
-            make_pair_geom_g(ice, f.z1, f.z2, fmax(f.rho, 1e-12), it.g1, it.g2, g);
+            make_pair_geom_g(ice, f.z1, f.z2, fmax(f.rho, 1e-12), humpq.g1[w], humpq.g2[w], g);
             Curve cv;
             cv.ice = &ice; cv.g = &g; cv.k = (mode >> 8) & 0xff; cv.rcase = (mode >> 16) & 0xff;
-            nb = hump_search(cv, it.J1, it.J2, it.J3, br);
+            nb = hump_search(cv, humpq.J1[w], humpq.J2[w], humpq.J3[w], br);
             mode_count[pair * M + ((mode >> 24) & 0xff)] = (int8_t)nb;
         }
-        push_brackets(active && nb > 0, pair, g, br, nb, rootq, root_count, lane, mode);
+        push_brackets(active && nb > 0, pair, g, br, nb, rootq, root_count, lane, mode & ~0xff);
     }
 }
 
@@ -463,11 +582,11 @@ K_slots_m(KInput in, TraceOutputs out, AttFill af, int M, int S, int K1, int8_t 
 }
 
 __global__ void __launch_bounds__(ROOTS_THREADS)
-K_roots_m(IceParams ice, KInput in, TraceOutputs out, AttFill af, int M, int S, int K1, const int8_t *slot_base, const RootItem *rootq,
-          const unsigned long long *root_count, SolRec *worklist, unsigned long long *work_count)
+K_roots_m(IceParams ice, KInput in, TraceOutputs out, AttFill af, int M, int S, int K1, const int8_t *slot_base, RootQ rootq,
+          const unsigned long long *root_count, WorkList worklist, unsigned long long *work_count)
 {
     const unsigned lane = threadIdx.x & 31u;
-    const unsigned long long n = *root_count;
+    const unsigned long long n = 2ull * *root_count;
     const unsigned long long stride = (unsigned long long)gridDim.x * ROOTS_THREADS;
     for (unsigned long long w0 = (unsigned long long)blockIdx.x * ROOTS_THREADS + (threadIdx.x & ~31u); w0 < n; w0 += stride) {
         const unsigned long long w = w0 + lane;
@@ -475,62 +594,55 @@ K_roots_m(IceParams ice, KInput in, TraceOutputs out, AttFill af, int M, int S, 
         bool valid = false, keep = true;
         int64_t pair = 0;
         int k = 0, rcase = 1, md = 0;
-        Root root;
-        root.v = 0; root.piece = 0; root.beta = 0;
-        double g1 = 0, g2 = 0;
+        double viewing = NAN;
+        SolutionProps pr;
+        SolRec rec;
+        Frame2D f;
+        f.ex = 1.0; f.ey = 0.0; f.swap = false; f.z1 = f.z2 = f.rho = f.x1y = 0.0;
+        rec.beta = 0.0;
         if (active) {
-            const RootItem it = rootq[w];
-            pair = it.pair; g1 = it.g1; g2 = it.g2;
-            valid = (it.valid & 1) != 0;
-            k = (it.valid >> 8) & 0xff; rcase = (it.valid >> 16) & 0xff; md = (it.valid >> 24) & 0xff;
+            const unsigned long long e = w >> 1;
+            const int meta = rootq.meta[e];
+            pair = rootq.pair[e];
+            valid = (w & 1ull) == 0 || ((meta >> 4) & 1) != 0;
+            k = (meta >> 8) & 0xff; rcase = (meta >> 16) & 0xff; md = (meta >> 24) & 0xff;
             if (valid) {
                 double x1, y1, z1, x2, y2, z2;
                 load_pair(in, pair, x1, y1, z1, x2, y2, z2);
-                Frame2D f;
                 make_frame(x1, y1, z1, x2, y2, z2, f);
                 PairGeom g;
-                make_pair_geom_g(ice, f.z1, f.z2, fmax(f.rho, 1e-12), g1, g2, g);
+                make_pair_geom_g(ice, f.z1, f.z2, fmax(f.rho, 1e-12), rootq.g1[e], rootq.g2[e], g);
                 Curve cv;
                 cv.ice = &ice; cv.g = &g; cv.k = k; cv.rcase = rcase;
-                Bracket b;
-                b.a = it.a; b.ga = it.ga; b.b = it.b; b.gb = it.gb; b.piece = it.piece;
-                root = solve_bracket(cv, b);
+                const Bracket b = rootq_bracket(rootq, w, meta);
+                const Root root = solve_bracket(cv, b);
+                solution_props(ice, g, f.x1y, k, rcase, root, pr);
+                make_solrec(ice, g, pair, 0, 0, k, rcase, root, rec);
+                if (in.sx) {
+                    const ShowerCut sc = load_cut(in, pair);
+                    double lx, lz;
+                    launch_2d(f, pr, lx, lz);
+                    viewing = viewing_angle_of(sc, f.ex, f.ey, lx, lz);
+                    keep = passes_cut(sc, viewing, f.swap ? g.n2 : g.n1);
+                }
             }
         }
         // the two roots of a mode sit in adjacent lanes: C0 ascending = beta descending (py:1547)
-        const double beta_other = __shfl_xor_sync(0xffffffffu, valid ? root.beta : -1.0, 1);
+        const double beta_other = __shfl_xor_sync(FULL_MASK, valid ? rec.beta : -1.0, 1);
         int rank = lane & 1;
-        if (valid) rank = (root.beta > beta_other) ? 0 : ((root.beta < beta_other) ? 1 : (int)(lane & 1u));
+        if (valid) rank = (rec.beta > beta_other) ? 0 : ((rec.beta < beta_other) ? 1 : (int)(lane & 1u));
         int64_t row = 0;
-        double viewing = NAN;
         if (valid) {
             const int slot = slot_base[pair * M + md] + rank;
             row = row_of(out, pair, slot, S);
             if (out.row_offset && row >= out.row_limit) valid = false;       // caller's compact arrays are full
-        }
-        if (valid) {
-            const int slot = slot_base[pair * M + md] + rank;
-            double x1, y1, z1, x2, y2, z2;
-            load_pair(in, pair, x1, y1, z1, x2, y2, z2);
-            Frame2D f;
-            make_frame(x1, y1, z1, x2, y2, z2, f);
-            PairGeom g;
-            make_pair_geom_g(ice, f.z1, f.z2, fmax(f.rho, 1e-12), g1, g2, g);
-            SolutionProps pr;
-            solution_props(ice, g, f.x1y, k, rcase, root, pr);
-            write_solution(out, row, K1, f, k, rcase, pr);
-            if (in.sx) {
-                const ShowerCut sc = load_cut(in, pair);
-                double lx, lz;
-                launch_2d(f, pr, lx, lz);
-                viewing = viewing_angle_of(sc, f.ex, f.ey, lx, lz);
-                keep = passes_cut(sc, viewing, f.swap ? g.n2 : g.n1);
-            }
-            if (out.viewing_angle) out.viewing_angle[row] = viewing;
-            if (worklist && keep) {
-                SolRec rec;
-                make_solrec(ice, g, pair, slot, row, k, rcase, root, rec);
-                worklist[atomicAdd(work_count, 1ull)] = rec;
+            if (valid) {
+                write_solution(out, row, K1, f, k, rcase, pr);
+                if (out.viewing_angle) out.viewing_angle[row] = viewing;
+                if (worklist.beta && keep) {
+                    rec.slot = slot; rec.row = row;
+                    worklist_store(worklist, atomicAdd(work_count, 1ull), rec);
+                }
             }
         }
         warp_fill_nan_slot(valid && !keep, row, af, lane);
@@ -733,8 +845,8 @@ __device__ __forceinline__ double k_deepest(const IceParams &ice, const SolRec &
 // dynamic shared memory (doubles): fa[Fs_pad] fb[Fs_pad] it[F_pad] | ii[F_pad] (int32) | per warp: H[3][Fs_pad] fac[nseg][Fs_pad]
 template <bool GL3>
 __global__ void __launch_bounds__(ATT_THREADS)
-K_att(IceParams ice, KInput in, AttTables tb, const SolRec *worklist, const unsigned long long *work_count, unsigned long long work_cap,
-      int nseg_max, double *att_sparse, double *att_dense)
+K_att(IceParams ice, KInput in, AttTables tb, WorkList worklist, const unsigned long long *work_count, int nseg_max, double *att_sparse,
+      double *att_dense)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t bar;
@@ -757,7 +869,7 @@ K_att(IceParams ice, KInput in, AttTables tb, const SolRec *worklist, const unsi
     const unsigned long long n_front = work_count[0], n_work = n_front + work_count[WL_BACK];
     for (unsigned long long w = (unsigned long long)blockIdx.x * ATT_WARPS + warp; w < n_work;
          w += (unsigned long long)gridDim.x * ATT_WARPS) {
-        const SolRec rec = worklist_get(worklist, work_cap, n_front, w);
+        const SolRec rec = worklist_get(worklist, n_front, w);
         AttPlan plan;
         att_plan_rec(ice, rec, plan);
         // GL1: frequencies [j_hard, Fs) come close to the pole of 1/max(A(z) - s_f, 1) or cross its 1 m floor somewhere on the
@@ -901,8 +1013,8 @@ K_att(IceParams ice, KInput in, AttTables tb, const SolRec *worklist, const unsi
                 if (i0 >= 0) {
                     const double t = s_it[b];
                     for (int s = 0; s < plan.nseg; ++s) {
-                        const double f0 = fac[s * tb.Fs_pad + i0], f1 = fac[s * tb.Fs_pad + i0 + 1];
-                        val *= (f1 - f0) * t + f0;
+                        const double f0 = fac[s * tb.Fs_pad + i0];
+                        val *= t != 0.0 ? (fac[s * tb.Fs_pad + i0 + 1] - f0) * t + f0 : f0;     // t == 0: no right neighbour needed (Fs == 1, np.interp ends)
                     }
                 }
                 dst[b] = val;
@@ -1081,8 +1193,8 @@ __device__ __forceinline__ void sp1_emit(const double (&M)[SP1_K], const double 
 // lets ptxas hoist every constant -- 158 registers, three blocks -- for the same time as 96 registers and five blocks.)
 template <bool HAVE_HI>
 __global__ void __launch_bounds__(SP1_THREADS)
-K_att_sp1(IceParams ice, KInput in, AttTables tb, Sp1Tables sp, const SolRec *worklist, const unsigned long long *work_count,
-          unsigned long long work_cap, int sparse_is_tmp, double *att_sparse, SolRec *fallback, unsigned long long *fallback_count)
+K_att_sp1(IceParams ice, KInput in, AttTables tb, Sp1Tables sp, WorkList worklist, const unsigned long long *work_count, int sparse_is_tmp,
+          double *att_sparse, WorkList fallback, unsigned long long *fallback_count)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t bar;
@@ -1101,8 +1213,8 @@ K_att_sp1(IceParams ice, KInput in, AttTables tb, Sp1Tables sp, const SolRec *wo
         for (int k = 0; k < SP1_K; ++k) { Mlo[k] = 0.0; Mhi[k] = 0.0; }
         double *dst = nullptr;
         if (w < n_work) {
-            SolRec rec = worklist_get(worklist, work_cap, n_front, w);
-            if (sparse_is_tmp) rec.row = (int64_t)(w < n_front ? w : work_cap - 1ull - (w - n_front));   // scratch rows: work-list position
+            SolRec rec = worklist_get(worklist, n_front, w);
+            if (sparse_is_tmp) rec.row = (int64_t)worklist_index(worklist, n_front, w);   // scratch rows: work-list position
             AttPlan plan;
             att_plan_rec(ice, rec, plan);
             const bool ok = sp1_path_ok(sp, plan.turned ? fmin(rec.zv, 0.0) : rec.z2, rec.z1);
@@ -1121,7 +1233,7 @@ K_att_sp1(IceParams ice, KInput in, AttTables tb, Sp1Tables sp, const SolRec *wo
                 }
             }
             if (ok) dst = att_sparse + rec.row * (int64_t)tb.Fs;
-            else fallback[atomicAdd(fallback_count, 1ull)] = rec;          // out of the series' band: generic kernel
+            else worklist_store(fallback, atomicAdd(fallback_count, 1ull), rec);          // out of the series' band: generic kernel
         }
         const int n_lo = HAVE_HI ? sp.n_lo : tb.Fs;
         for (int jb = 0; jb < n_lo; jb += SP1_SEG) sp1_emit(Mlo, s_wk, s_E, jb, min(jb + SP1_SEG, n_lo), stage, dst, lane);
@@ -1147,8 +1259,8 @@ K_att_sp1(IceParams ice, KInput in, AttTables tb, Sp1Tables sp, const SolRec *wo
 #define GL1_ROW GL1_FC              // odd row pitch: conflict-free column writes
 #define GL1_MARGIN 10.0
 __global__ void __launch_bounds__(SP1_THREADS)
-K_att_gl1(IceParams ice, KInput in, AttTables tb, const SolRec *worklist, const unsigned long long *work_count, unsigned long long work_cap,
-          int sparse_is_tmp, double *att_sparse, SolRec *fallback, unsigned long long *fallback_count)
+K_att_gl1(IceParams ice, KInput in, AttTables tb, WorkList worklist, const unsigned long long *work_count, int sparse_is_tmp,
+          double *att_sparse, WorkList fallback, unsigned long long *fallback_count)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *s_fa = reinterpret_cast<double *>(smem_raw);
@@ -1169,8 +1281,8 @@ K_att_gl1(IceParams ice, KInput in, AttTables tb, const SolRec *worklist, const 
         bool leg0 = false, to_generic = false;
         double *dst = nullptr;
         if (active) {
-            rec = worklist_get(worklist, work_cap, n_front, w);
-            if (sparse_is_tmp) rec.row = (int64_t)(w < n_front ? w : work_cap - 1ull - (w - n_front));   // scratch rows: work-list position
+            rec = worklist_get(worklist, n_front, w);
+            if (sparse_is_tmp) rec.row = (int64_t)worklist_index(worklist, n_front, w);   // scratch rows: work-list position
             att_plan_rec(ice, rec, plan);
             leg0 = plan.turned && plan.u2 > plan.uT;                   // [u_T, u_2], run through twice
             n_slots = (leg0 ? 1 : 0) + (plan.u1 > plan.u2 ? 3 : 0);    // [u_2, u_1] in three graded sub-panels
@@ -1224,27 +1336,28 @@ K_att_gl1(IceParams ice, KInput in, AttTables tb, const SolRec *worklist, const 
             }
             __syncwarp();
         }
-        if (active && to_generic) fallback[atomicAdd(fallback_count, 1ull)] = rec;     // the generic kernel redoes these rows
+        if (active && to_generic) worklist_store(fallback, atomicAdd(fallback_count, 1ull), rec);     // the generic kernel redoes these rows
     }
 }
 
 // dense expansion for single-segment paths: np.interp of the sparse factors onto the output grid (py:1077-1078).
 // One warp per work-list record; sparse_is_tmp: the sparse factors sit in scratch rows indexed by the work-list position.
 __global__ void __launch_bounds__(256)
-K_att_expand(AttTables tb, const SolRec *worklist, const unsigned long long *work_count, unsigned long long work_cap, int sparse_is_tmp,
-             const double *att_sparse, double *att_dense)
+K_att_expand(AttTables tb, WorkList worklist, const unsigned long long *work_count, int sparse_is_tmp, const double *att_sparse,
+             double *att_dense)
 {
     const int lane = threadIdx.x & 31;
     const unsigned long long n_front = work_count[0], n_work = n_front + work_count[WL_BACK];
     for (unsigned long long w = (unsigned long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w < n_work;
          w += (unsigned long long)gridDim.x * (blockDim.x >> 5)) {
-        const int64_t row = worklist_get(worklist, work_cap, n_front, w).row;
-        const double *src = att_sparse + (sparse_is_tmp ? (int64_t)(w < n_front ? w : work_cap - 1ull - (w - n_front)) : row) * tb.Fs;
+        const unsigned long long wi = worklist_index(worklist, n_front, w);
+        const int64_t row = worklist.row[wi];
+        const double *src = att_sparse + (sparse_is_tmp ? (int64_t)wi : row) * tb.Fs;
         double *dst = att_dense + row * tb.F;
         for (int b = lane; b < tb.F; b += 32) {
             const int i0 = __ldg(tb.ii + b);
             double val = 1.0;
-            if (i0 >= 0) { const double f0 = src[i0], f1 = src[i0 + 1]; val = (f1 - f0) * __ldg(tb.it + b) + f0; }
+            if (i0 >= 0) { const double f0 = src[i0], t = __ldg(tb.it + b); val = t != 0.0 ? (src[i0 + 1] - f0) * t + f0 : f0; }
             dst[b] = val;
         }
     }
@@ -1392,7 +1505,7 @@ K_apply_effects(nrmc_rt_effects fx, AttTables tb, int K1, double n_surface)
     __shared__ cplx s_c[2];      // total factor on eTheta and ePhi
     for (int64_t row = blockIdx.x; row < fx.n_rows; row += gridDim.x) {
         if (threadIdx.x == 0) {
-            cplx ct = {1.0, 0.0}, cp = {1.0, 0.0};
+            cplx ct = {1.0, 0.0}, cp = {1.0, 0.0}, last_p = {1.0, 0.0}, last_s = {1.0, 0.0};
             if (fx.reflection_angle) {
                 for (int s = 0; s < K1; ++s) {
                     const double a = fx.reflection_angle[row * K1 + s];
@@ -1400,11 +1513,13 @@ K_apply_effects(nrmc_rt_effects fx, AttTables tb, int K1, double n_surface)
                         cplx rp, rs;
                         fresnel_r(a, 1.0 / n_surface, rp, rs);
                         ct = cmul(ct, rp); cp = cmul(cp, rs);
+                        last_p = rp; last_s = rs;
                     }
                 }
             }
-            if (fx.r_theta) { fx.r_theta[2 * row] = ct.re; fx.r_theta[2 * row + 1] = ct.im; }
-            if (fx.r_phi) { fx.r_phi[2 * row] = cp.re; fx.r_phi[2 * row + 1] = cp.im; }
+            // the field object keeps the coefficients of the last surface reflection (py:2993-2994 overwrite them per segment)
+            if (fx.r_theta) { fx.r_theta[2 * row] = last_p.re; fx.r_theta[2 * row + 1] = last_p.im; }
+            if (fx.r_phi) { fx.r_phi[2 * row] = last_s.re; fx.r_phi[2 * row + 1] = last_s.im; }
             const int k = fx.reflection ? fx.reflection[row] : 0;
             if (k > 0) {   // analyticraytracing.py:3002-3010
                 const double amp = pow(fx.reflection_coefficient, (double)k);
@@ -1425,8 +1540,8 @@ K_apply_effects(nrmc_rt_effects fx, AttTables tb, int K1, double n_surface)
                 const int i0 = __ldg(tb.ii + b);
                 if (i0 >= 0) {
                     const double *src = fx.attenuation_sparse + row * tb.Fs;
-                    const double f0 = src[i0], f1 = src[i0 + 1];
-                    att = (f1 - f0) * __ldg(tb.it + b) + f0;
+                    const double f0 = src[i0], t = __ldg(tb.it + b);
+                    att = t != 0.0 ? (src[i0 + 1] - f0) * t + f0 : f0;      // a single integration frequency has no right neighbour
                 }
             }
             cplx e0 = spec[b], e1 = spec[fx.n_freq + b], e2 = spec[2 * fx.n_freq + b];
@@ -1517,7 +1632,8 @@ struct DevBuf {
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
-struct Lane {               // one pipeline lane (stream + scratch) for host-memory calls
+struct Lane {               // one pipeline lane (scratch + timing events); lanes 0/1 own a stream (host-memory calls), lane DEV_LANE
+                            // serves device-resident calls on the CALLER's stream (passed per call, never stored)
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t kev[3] = {nullptr, nullptr, nullptr};   // after K_classify, after K_hump, after the main attenuation kernel
@@ -1542,8 +1658,10 @@ struct nrmc_rt_s {
     size_t smem_att = 0, smem_sp1 = 0, smem_gl1 = 0;
     DevBuf d_tables, d_gl3, d_sp1;
     bool have_freq = false;
-    Lane lanes[2];
-    DevBuf d_count;       // work-list counters (one per lane)
+    Lane lanes[N_LANES];
+    cudaEvent_t dev_done = nullptr;   // recorded on the caller's stream after every device-resident call: the next call (possibly on
+    bool dev_pending = false;         // another stream) and nrmc_rt_set_frequencies order themselves behind it
+    DevBuf d_count;       // work-list counters (one block per lane) + the running row base
     DevBuf d_rmax;        // R_max table of the shadow-zone test
     RmaxTable rmax;
     DevBuf d_ant;         // antenna table for outer-product host calls
@@ -1598,12 +1716,13 @@ int nrmc_rt_create(const nrmc_rt_config *cfg, nrmc_rt_t *out)
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess) { delete h; return NRMC_ERR_NO_DEVICE; }
     h->n_sm = prop.multiProcessorCount;
-    for (int l = 0; l < 2; ++l) {
-        if (cudaStreamCreateWithFlags(&h->lanes[l].stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return NRMC_ERR_CUDA; }
+    for (int l = 0; l < N_LANES; ++l) {
+        if (l != DEV_LANE && cudaStreamCreateWithFlags(&h->lanes[l].stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return NRMC_ERR_CUDA; }
         for (int e = 0; e < 6; ++e) cudaEventCreate(&h->lanes[l].ev[e]);
         for (int e = 0; e < 3; ++e) cudaEventCreate(&h->lanes[l].kev[e]);
     }
-    if (h->d_count.reserve(512) != cudaSuccess) { delete h; return NRMC_ERR_CUDA; }
+    if (cudaEventCreateWithFlags(&h->dev_done, cudaEventDisableTiming) != cudaSuccess) { delete h; return NRMC_ERR_CUDA; }
+    if (h->d_count.reserve((CNT_ROWBASE + 16) * sizeof(unsigned long long)) != cudaSuccess) { delete h; return NRMC_ERR_CUDA; }
     {
         int nb = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, K_hump, HUMP_THREADS, 0) != cudaSuccess) { delete h; return NRMC_ERR_CUDA; }
@@ -1650,7 +1769,9 @@ void nrmc_rt_destroy(nrmc_rt_t h)
 {
     if (!h) return;
     cudaSetDevice(h->cfg.device);
-    for (int l = 0; l < 2; ++l) {
+    if (h->dev_pending) cudaEventSynchronize(h->dev_done);
+    if (h->dev_done) cudaEventDestroy(h->dev_done);
+    for (int l = 0; l < N_LANES; ++l) {
         if (h->lanes[l].stream) { cudaStreamSynchronize(h->lanes[l].stream); cudaStreamDestroy(h->lanes[l].stream); }
         for (int e = 0; e < 6; ++e) if (h->lanes[l].ev[e]) cudaEventDestroy(h->lanes[l].ev[e]);
         for (int e = 0; e < 3; ++e) if (h->lanes[l].kev[e]) cudaEventDestroy(h->lanes[l].kev[e]);
@@ -1670,6 +1791,8 @@ int nrmc_rt_set_frequencies(nrmc_rt_t h, const double *frequency, int32_t n, dou
     if (!h || !frequency || n <= 0) return NRMC_ERR_INVALID_ARGUMENT;
     if (h->ice.att_model == 0) { h->err = "no attenuation model configured"; return NRMC_ERR_UNSUPPORTED; }
     cudaSetDevice(h->cfg.device);
+    // the tables are rewritten in place: wait for device-resident calls still reading them on the caller's stream
+    if (h->dev_pending) { CK(cudaEventSynchronize(h->dev_done)); h->dev_pending = false; }
     // --- __get_frequencies_for_attenuation, analyticraytracing.py:885-931 ---
     const int n_int = h->cfg.n_frequencies_integration > 0 ? h->cfg.n_frequencies_integration : 100;
     int n_nonnull = 0;
@@ -1702,7 +1825,7 @@ int nrmc_rt_set_frequencies(nrmc_rt_t h, const double *frequency, int32_t n, dou
     for (int b = 0; b < n; ++b) {
         const double x = frequency[b];
         if (!(x > 0)) { ii[b] = -1; continue; }
-        if (Fs == 1) { ii[b] = 0; it[b] = 0.0; continue; }   // handled below: i0+1 must stay in range
+        if (Fs == 1) { ii[b] = 0; it[b] = 0.0; continue; }   // np.interp on one point: the value itself (the kernels do not touch i0+1 when t == 0)
         if (x <= sp[0]) { ii[b] = 0; it[b] = 0.0; }
         else if (x >= sp[Fs - 1]) { ii[b] = Fs - 2; it[b] = 1.0; }
         else {
@@ -1712,7 +1835,7 @@ int nrmc_rt_set_frequencies(nrmc_rt_t h, const double *frequency, int32_t n, dou
             it[b] = (x - sp[lo]) / (sp[hi] - sp[lo]);
         }
     }
-    if (Fs == 1) { fa.resize(2, fa[0]); fb.resize(2, fb[0]); }   // Fs_pad == 2: duplicate so that i0+1 is valid
+    if (Fs == 1) { fa[1] = fa[0]; fb[1] = fb[0]; }               // Fs_pad == 2: the padding entry repeats the frequency
     const size_t bytes = (size_t)Fs_pad * 16 + (size_t)F_pad * 12 + 64;
     CK(h->d_tables.reserve(bytes));
     unsigned char *base = (unsigned char *)h->d_tables.p;
@@ -1860,6 +1983,40 @@ int nrmc_rt_host_alloc(void **ptr, uint64_t bytes)
 }
 int nrmc_rt_host_free(void *ptr) { return cudaFreeHost(ptr) == cudaSuccess ? NRMC_OK : NRMC_ERR_CUDA; }
 
+// ---- result gather over NVLink peer memory: CUDA IPC handles of plain cudaMalloc blocks --------------------------------------
+int nrmc_rt_peer_alloc(int32_t device, uint64_t bytes, void **dev_ptr, unsigned char *handle)
+{
+    if (!dev_ptr || !handle || bytes == 0) return NRMC_ERR_INVALID_ARGUMENT;
+    static_assert(sizeof(cudaIpcMemHandle_t) == NRMC_PEER_HANDLE_BYTES, "handle size");
+    if (cudaSetDevice(device) != cudaSuccess) return NRMC_ERR_NO_DEVICE;
+    void *p = nullptr;
+    if (cudaMalloc(&p, bytes) != cudaSuccess) { cudaGetLastError(); return NRMC_ERR_CUDA; }
+    cudaIpcMemHandle_t hd;
+    if (cudaIpcGetMemHandle(&hd, p) != cudaSuccess) { cudaGetLastError(); cudaFree(p); return NRMC_ERR_CUDA; }
+    memcpy(handle, &hd, sizeof(hd));
+    *dev_ptr = p;
+    return NRMC_OK;
+}
+int nrmc_rt_peer_open(int32_t device, const unsigned char *handle, void **dev_ptr)
+{
+    if (!dev_ptr || !handle) return NRMC_ERR_INVALID_ARGUMENT;
+    if (cudaSetDevice(device) != cudaSuccess) return NRMC_ERR_NO_DEVICE;
+    cudaIpcMemHandle_t hd;
+    memcpy(&hd, handle, sizeof(hd));
+    void *p = nullptr;
+    if (cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); return NRMC_ERR_CUDA; }
+    *dev_ptr = p;
+    return NRMC_OK;
+}
+int nrmc_rt_peer_close(void *dev_ptr) { return cudaIpcCloseMemHandle(dev_ptr) == cudaSuccess ? NRMC_OK : NRMC_ERR_CUDA; }
+int nrmc_rt_peer_free(void *dev_ptr) { return cudaFree(dev_ptr) == cudaSuccess ? NRMC_OK : NRMC_ERR_CUDA; }
+int nrmc_rt_copy_async(void *dst, const void *src, uint64_t bytes, void *stream)
+{
+    if (bytes == 0) return NRMC_OK;
+    if (!dst || !src) return NRMC_ERR_INVALID_ARGUMENT;
+    return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, (cudaStream_t)stream) == cudaSuccess ? NRMC_OK : NRMC_ERR_CUDA;
+}
+
 }  // extern "C"
 
 // enqueue the kernels for one chunk of pairs whose inputs/outputs are device resident
@@ -1872,7 +2029,7 @@ struct CompactCtx {
     int64_t row_limit = 0;                  // rows the caller's per-slot arrays hold
 };
 
-static int launch_chunk(nrmc_rt_s *h, Lane &ln, int lane_id, const KInput &kin, const TraceOutputs &to_in, double *att_sparse,
+static int launch_chunk(nrmc_rt_s *h, Lane &ln, int lane_id, cudaStream_t st, const KInput &kin, const TraceOutputs &to_in, double *att_sparse,
                         double *att_dense, int *n_launches, const CompactCtx &cc = CompactCtx())
 {
     TraceOutputs to = to_in;
@@ -1882,77 +2039,64 @@ static int launch_chunk(nrmc_rt_s *h, Lane &ln, int lane_id, const KInput &kin, 
     unsigned long long *cnt = (unsigned long long *)h->d_count.p + CNT_STRIDE * lane_id;
     unsigned long long *d_count = cnt + CNT_WORK;
     const unsigned long long work_cap = (unsigned long long)kin.n_pairs * h->S;
-    SolRec *wl = nullptr;
+    WorkList wl;
+    memset(&wl, 0, sizeof(wl));
     if (want_att) {
-        CK(ln.work.reserve((size_t)work_cap * sizeof(SolRec)));
-        wl = (SolRec *)ln.work.p;
+        CK(ln.work.reserve(worklist_bytes(work_cap)));
+        wl = carve_worklist(ln.work.p, work_cap);
     }
-    CK(cudaMemsetAsync(cnt, 0, CNT_STRIDE * sizeof(unsigned long long), ln.stream));
-    if (ln.timed) cudaEventRecord(ln.ev[0], ln.stream);
+    CK(cudaMemsetAsync(cnt, 0, CNT_STRIDE * sizeof(unsigned long long), st));
+    if (ln.timed) cudaEventRecord(ln.ev[0], st);
+    const int M = 1 + 2 * h->ice.n_refl;
+    unsigned long long *d_roots = cnt + CNT_ROOTS, *d_humps = cnt + CNT_HUMPS;
+    CK(ln.rootq.reserve(rootq_bytes((size_t)kin.n_pairs * M)));
+    CK(ln.humpq.reserve(humpq_bytes((size_t)kin.n_pairs * M)));
+    const RootQ rootq = carve_rootq(ln.rootq.p, (size_t)kin.n_pairs * M);
+    const HumpQ humpq = carve_humpq(ln.humpq.p, (size_t)kin.n_pairs * M);
+    AttFill af;
+    af.sparse = att_sparse; af.dense = att_dense; af.Fs = h->tb.Fs; af.F = h->tb.F;
+    auto row_scan = [&]() -> int {
+        // compact layout: exclusive scan of n_sol -> row of every pair's first solution (global rows)
+        const int nblk = (int)((kin.n_pairs + PACK_PAIRS - 1) / PACK_PAIRS);
+        CK(ln.pack_sums.reserve((size_t)(nblk + 2) * sizeof(unsigned long long)));
+        unsigned long long *sums = (unsigned long long *)ln.pack_sums.p;
+        PackArrays none;
+        none.n = 0;
+        K_pack_count<<<nblk, PACK_THREADS, 0, st>>>(to.n_sol, kin.n_pairs, sums);
+        K_pack_scan<<<1, 1024, 0, st>>>(sums, nblk, cc.base_dev);
+        K_pack<<<nblk, PACK_THREADS, 0, st>>>(to.n_sol, kin.n_pairs, h->S, sums, cc.base_host, cc.base_dev ? 1 : 0, cc.sol_offset, none);
+        *n_launches += 3;
+        return NRMC_OK;
+    };
     if (h->ice.n_refl == 0) {
-        // binned solver: classify -> hump search -> roots, re-packed through queues (counters [4+lane], [6+lane])
-        unsigned long long *d_roots = cnt + CNT_ROOTS, *d_humps = cnt + CNT_HUMPS;
-        CK(ln.rootq.reserve((size_t)kin.n_pairs * 2 * sizeof(RootItem)));
-        CK(ln.humpq.reserve((size_t)kin.n_pairs * sizeof(HumpItem)));
+        // binned solver: classify -> hump search -> roots, re-packed through queues
         const int64_t blocks = (kin.n_pairs + CLASSIFY_THREADS - 1) / CLASSIFY_THREADS;
-        AttFill af;
-        af.sparse = att_sparse; af.dense = att_dense; af.Fs = h->tb.Fs; af.F = h->tb.F;
-        K_classify<<<(unsigned)blocks, CLASSIFY_THREADS, 0, ln.stream>>>(h->ice, kin, to, af, h->rmax, (RootItem *)ln.rootq.p, d_roots,
-                                                                         (HumpItem *)ln.humpq.p, d_humps);
-        if (ln.timed) cudaEventRecord(ln.kev[0], ln.stream);
-        K_hump<<<h->grid_hump, HUMP_THREADS, 0, ln.stream>>>(h->ice, kin, to, af, (const HumpItem *)ln.humpq.p, d_humps,
-                                                             (RootItem *)ln.rootq.p, d_roots);
-        if (cc.on) {
-            const int nblk = (int)((kin.n_pairs + PACK_PAIRS - 1) / PACK_PAIRS);
-            CK(ln.pack_sums.reserve((size_t)(nblk + 2) * sizeof(unsigned long long)));
-            unsigned long long *sums = (unsigned long long *)ln.pack_sums.p;
-            PackArrays none;
-            none.n = 0;
-            K_pack_count<<<nblk, PACK_THREADS, 0, ln.stream>>>(to.n_sol, kin.n_pairs, sums);
-            K_pack_scan<<<1, 1024, 0, ln.stream>>>(sums, nblk, cc.base_dev);
-            K_pack<<<nblk, PACK_THREADS, 0, ln.stream>>>(to.n_sol, kin.n_pairs, h->S, sums, cc.base_host, cc.base_dev ? 1 : 0, cc.sol_offset, none);
-            *n_launches += 3;
-        }
-        if (ln.timed) cudaEventRecord(ln.kev[1], ln.stream);
+        K_classify<<<(unsigned)blocks, CLASSIFY_THREADS, 0, st>>>(h->ice, kin, to, af, h->rmax, rootq, d_roots, humpq, d_humps);
+        if (ln.timed) cudaEventRecord(ln.kev[0], st);
+        K_hump<<<h->grid_hump, HUMP_THREADS, 0, st>>>(h->ice, kin, to, af, humpq, d_humps, rootq, d_roots);
+        if (cc.on) { const int rc = row_scan(); if (rc != NRMC_OK) return rc; }
+        if (ln.timed) cudaEventRecord(ln.kev[1], st);
         if (kin.sx)
-            K_roots<true><<<h->grid_roots, ROOTS_THREADS, 0, ln.stream>>>(h->ice, kin, to, af, (const RootItem *)ln.rootq.p, d_roots, wl, d_count, work_cap);
+            K_roots<true><<<h->grid_roots, ROOTS_THREADS, 0, st>>>(h->ice, kin, to, af, rootq, d_roots, wl, d_count);
         else
-            K_roots<false><<<h->grid_roots, ROOTS_THREADS, 0, ln.stream>>>(h->ice, kin, to, af, (const RootItem *)ln.rootq.p, d_roots, wl, d_count, work_cap);
+            K_roots<false><<<h->grid_roots, ROOTS_THREADS, 0, st>>>(h->ice, kin, to, af, rootq, d_roots, wl, d_count);
         *n_launches += 3;
     } else {
         // bottom reflections: the same pipeline over (pair, mode) work items
-        const int M = 1 + 2 * h->ice.n_refl;
-        unsigned long long *d_roots = cnt + CNT_ROOTS, *d_humps = cnt + CNT_HUMPS;
-        CK(ln.rootq.reserve((size_t)kin.n_pairs * M * 2 * sizeof(RootItem)));
-        CK(ln.humpq.reserve((size_t)kin.n_pairs * M * sizeof(HumpItem)));
         CK(ln.modes.reserve((size_t)kin.n_pairs * M));
         int8_t *modes = (int8_t *)ln.modes.p;
-        AttFill af;
-        af.sparse = att_sparse; af.dense = att_dense; af.Fs = h->tb.Fs; af.F = h->tb.F;
         const int64_t items = kin.n_pairs * M;
-        K_classify_m<<<(unsigned)((items + CLASSIFY_THREADS - 1) / CLASSIFY_THREADS), CLASSIFY_THREADS, 0, ln.stream>>>(
-            h->ice, kin, to, h->rmax, M, modes, (RootItem *)ln.rootq.p, d_roots, (HumpItem *)ln.humpq.p, d_humps);
-        if (ln.timed) cudaEventRecord(ln.kev[0], ln.stream);
-        K_hump_m<<<h->grid_hump_m, HUMP_THREADS, 0, ln.stream>>>(h->ice, kin, M, modes, (const HumpItem *)ln.humpq.p, d_humps,
-                                                                 (RootItem *)ln.rootq.p, d_roots);
-        K_slots_m<<<(unsigned)((kin.n_pairs + 255) / 256), 256, 0, ln.stream>>>(kin, to, af, M, h->S, h->K1, modes);
-        if (cc.on) {
-            const int nblk = (int)((kin.n_pairs + PACK_PAIRS - 1) / PACK_PAIRS);
-            CK(ln.pack_sums.reserve((size_t)(nblk + 2) * sizeof(unsigned long long)));
-            unsigned long long *sums = (unsigned long long *)ln.pack_sums.p;
-            PackArrays none;
-            none.n = 0;
-            K_pack_count<<<nblk, PACK_THREADS, 0, ln.stream>>>(to.n_sol, kin.n_pairs, sums);
-            K_pack_scan<<<1, 1024, 0, ln.stream>>>(sums, nblk, cc.base_dev);
-            K_pack<<<nblk, PACK_THREADS, 0, ln.stream>>>(to.n_sol, kin.n_pairs, h->S, sums, cc.base_host, cc.base_dev ? 1 : 0, cc.sol_offset, none);
-            *n_launches += 3;
-        }
-        if (ln.timed) cudaEventRecord(ln.kev[1], ln.stream);
-        K_roots_m<<<h->grid_roots_m, ROOTS_THREADS, 0, ln.stream>>>(h->ice, kin, to, af, M, h->S, h->K1, modes, (const RootItem *)ln.rootq.p,
-                                                                   d_roots, wl, d_count);
+        K_classify_m<<<(unsigned)((items + CLASSIFY_THREADS - 1) / CLASSIFY_THREADS), CLASSIFY_THREADS, 0, st>>>(
+            h->ice, kin, to, h->rmax, M, modes, rootq, d_roots, humpq, d_humps);
+        if (ln.timed) cudaEventRecord(ln.kev[0], st);
+        K_hump_m<<<h->grid_hump_m, HUMP_THREADS, 0, st>>>(h->ice, kin, M, modes, humpq, d_humps, rootq, d_roots);
+        K_slots_m<<<(unsigned)((kin.n_pairs + 255) / 256), 256, 0, st>>>(kin, to, af, M, h->S, h->K1, modes);
+        if (cc.on) { const int rc = row_scan(); if (rc != NRMC_OK) return rc; }
+        if (ln.timed) cudaEventRecord(ln.kev[1], st);
+        K_roots_m<<<h->grid_roots_m, ROOTS_THREADS, 0, st>>>(h->ice, kin, to, af, M, h->S, h->K1, modes, rootq, d_roots, wl, d_count);
         *n_launches += 4;
     }
-    if (ln.timed) cudaEventRecord(ln.ev[1], ln.stream);
+    if (ln.timed) cudaEventRecord(ln.ev[1], st);
     if (want_att) {
         const AttTables &tb = h->tb;
         const int nseg_max = h->ice.n_refl + 1;
@@ -1960,7 +2104,8 @@ static int launch_chunk(nrmc_rt_s *h, Lane &ln, int lane_id, const KInput &kin, 
             // thread-per-solution kernel (SP1 moments / GL1) -> sparse factors; the solutions it hands back -> generic kernel;
             // dense = interp(sparse)
             unsigned long long *d_fb = cnt + CNT_FALLBACK;
-            CK(ln.fallback.reserve((size_t)kin.n_pairs * h->S * sizeof(SolRec)));
+            CK(ln.fallback.reserve(worklist_bytes(work_cap)));
+            const WorkList fb = carve_worklist(ln.fallback.p, work_cap);
             double *sparse = att_sparse;
             const int sparse_is_tmp = sparse ? 0 : 1;
             if (!sparse) {
@@ -1968,32 +2113,28 @@ static int launch_chunk(nrmc_rt_s *h, Lane &ln, int lane_id, const KInput &kin, 
                 sparse = (double *)ln.sparse_tmp.p;
             }
             if (h->have_gl1)
-                K_att_gl1<<<h->grid_gl1, SP1_THREADS, h->smem_gl1, ln.stream>>>(h->ice, kin, tb, wl, d_count, work_cap, sparse_is_tmp, sparse,
-                                                                                (SolRec *)ln.fallback.p, d_fb);
+                K_att_gl1<<<h->grid_gl1, SP1_THREADS, h->smem_gl1, st>>>(h->ice, kin, tb, wl, d_count, sparse_is_tmp, sparse, fb, d_fb);
             else if (h->sp1.n_hi > 0)
-                K_att_sp1<true><<<h->grid_sp1, SP1_THREADS, h->smem_sp1, ln.stream>>>(h->ice, kin, tb, h->sp1, wl, d_count, work_cap, sparse_is_tmp,
-                                                                                      sparse, (SolRec *)ln.fallback.p, d_fb);
+                K_att_sp1<true><<<h->grid_sp1, SP1_THREADS, h->smem_sp1, st>>>(h->ice, kin, tb, h->sp1, wl, d_count, sparse_is_tmp, sparse, fb, d_fb);
             else
-                K_att_sp1<false><<<h->grid_sp1, SP1_THREADS, h->smem_sp1, ln.stream>>>(h->ice, kin, tb, h->sp1, wl, d_count, work_cap, sparse_is_tmp,
-                                                                                       sparse, (SolRec *)ln.fallback.p, d_fb);
-            if (ln.timed) cudaEventRecord(ln.kev[2], ln.stream);
-            K_att<false><<<h->grid_att, ATT_THREADS, h->smem_att, ln.stream>>>(h->ice, kin, tb, (const SolRec *)ln.fallback.p, d_fb, work_cap,
-                                                                               nseg_max, sparse, nullptr);
+                K_att_sp1<false><<<h->grid_sp1, SP1_THREADS, h->smem_sp1, st>>>(h->ice, kin, tb, h->sp1, wl, d_count, sparse_is_tmp, sparse, fb, d_fb);
+            if (ln.timed) cudaEventRecord(ln.kev[2], st);
+            K_att<false><<<h->grid_att, ATT_THREADS, h->smem_att, st>>>(h->ice, kin, tb, fb, d_fb, nseg_max, sparse, nullptr);
             *n_launches += 2;
             if (att_dense) {
-                K_att_expand<<<h->n_sm * 8, 256, 0, ln.stream>>>(tb, wl, d_count, work_cap, sparse_is_tmp, sparse, att_dense);
+                K_att_expand<<<h->n_sm * 8, 256, 0, st>>>(tb, wl, d_count, sparse_is_tmp, sparse, att_dense);
                 ++*n_launches;
             }
         } else {
             if (h->ice.att_model == NRMC_ATT_GL3)
-                K_att<true><<<h->grid_att, ATT_THREADS, h->smem_att, ln.stream>>>(h->ice, kin, tb, wl, d_count, work_cap, nseg_max, att_sparse, att_dense);
+                K_att<true><<<h->grid_att, ATT_THREADS, h->smem_att, st>>>(h->ice, kin, tb, wl, d_count, nseg_max, att_sparse, att_dense);
             else
-                K_att<false><<<h->grid_att, ATT_THREADS, h->smem_att, ln.stream>>>(h->ice, kin, tb, wl, d_count, work_cap, nseg_max, att_sparse, att_dense);
+                K_att<false><<<h->grid_att, ATT_THREADS, h->smem_att, st>>>(h->ice, kin, tb, wl, d_count, nseg_max, att_sparse, att_dense);
             ++*n_launches;
-            if (ln.timed) cudaEventRecord(ln.kev[2], ln.stream);
+            if (ln.timed) cudaEventRecord(ln.kev[2], st);
         }
-    } else if (ln.timed) cudaEventRecord(ln.kev[2], ln.stream);
-    if (ln.timed) cudaEventRecord(ln.ev[2], ln.stream);
+    } else if (ln.timed) cudaEventRecord(ln.kev[2], st);
+    if (ln.timed) cudaEventRecord(ln.ev[2], st);
     CK(cudaGetLastError());
     return NRMC_OK;
 }
@@ -2059,10 +2200,11 @@ extern "C" int nrmc_rt_trace(nrmc_rt_t h, const nrmc_rt_input *in, const nrmc_rt
 
     if (in->memory == NRMC_MEMORY_DEVICE) {
         // device-resident: the caller's pointers are used directly; chunked only to bound the work-list scratch
-        Lane &ln = h->lanes[0];
+        // (own scratch lane: a host-memory call that follows on the library's streams shares nothing with it; a second
+        //  device-resident call, possibly on another stream, is ordered behind this one through dev_done)
+        Lane &ln = h->lanes[DEV_LANE];
         cudaStream_t user = (cudaStream_t)stream;
-        cudaStream_t saved = ln.stream;
-        ln.stream = user;
+        if (h->dev_pending) CK(cudaStreamWaitEvent(user, h->dev_done, 0));
         ln.timed = false;
         cudaEvent_t e0 = ln.ev[3], e1 = ln.ev[4];
         if (stats) cudaEventRecord(e0, user);
@@ -2071,7 +2213,7 @@ extern "C" int nrmc_rt_trace(nrmc_rt_t h, const nrmc_rt_input *in, const nrmc_rt
         float ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         int rc = NRMC_OK, n_chunks = 0;
         unsigned long long *row_base_dev = (unsigned long long *)h->d_count.p + CNT_ROWBASE;
-        if (compact) CK(cudaMemsetAsync(row_base_dev, 0, sizeof(unsigned long long), user));
+        if (compact) K_set_u64<<<1, 1, 0, user>>>(row_base_dev, (unsigned long long)out->row_base);   // first row of this call's solutions
         for (int64_t p0 = 0; p0 < N && rc == NRMC_OK; p0 += chunk, ++n_chunks) {
             const int64_t np = std::min(chunk, N - p0);
             const int64_t ps = compact ? 0 : p0 * S;        // first row of the chunk in the per-slot arrays (compact: rows are global)
@@ -2113,14 +2255,14 @@ extern "C" int nrmc_rt_trace(nrmc_rt_t h, const nrmc_rt_input *in, const nrmc_rt
             }
             ln.timed = (stats != nullptr);
             CompactCtx cc;
-            if (compact) { cc.on = true; cc.sol_offset = out->sol_offset + p0; cc.base_dev = row_base_dev; cc.row_limit = out->row_capacity; }
-            rc = launch_chunk(h, ln, 0, kin, to, out->attenuation_sparse ? out->attenuation_sparse + ps * Fs : nullptr,
+            if (compact) { cc.on = true; cc.sol_offset = out->sol_offset + p0; cc.base_dev = row_base_dev; cc.row_limit = out->row_base + out->row_capacity; }
+            rc = launch_chunk(h, ln, DEV_LANE, user, kin, to, out->attenuation_sparse ? out->attenuation_sparse + ps * Fs : nullptr,
                               out->attenuation ? out->attenuation + ps * F : nullptr, &n_launches, cc);
             if (rc == NRMC_OK && stats) {
                 accumulate_lane_times(ln, ms);
                 if (want_att) {
                     unsigned long long cnt2[2] = {0, 0};
-                    cudaMemcpy(cnt2, h->d_count.p, sizeof(cnt2), cudaMemcpyDeviceToHost);
+                    cudaMemcpy(cnt2, (unsigned long long *)h->d_count.p + CNT_STRIDE * DEV_LANE, sizeof(cnt2), cudaMemcpyDeviceToHost);
                     stats->n_solutions += (int64_t)(cnt2[0] + cnt2[WL_BACK]);
                 }
             }
@@ -2136,11 +2278,13 @@ extern "C" int nrmc_rt_trace(nrmc_rt_t h, const nrmc_rt_input *in, const nrmc_rt
             if (compact) {
                 unsigned long long rows = 0;
                 cudaMemcpy(&rows, row_base_dev, sizeof(rows), cudaMemcpyDeviceToHost);
+                rows -= (unsigned long long)out->row_base;
                 if ((int64_t)rows > out->row_capacity) { h->err = "compact output: row_capacity exceeded"; rc = NRMC_ERR_CAPACITY; }
                 if (!want_att) stats->n_solutions = (int64_t)rows;
             }
         }
-        ln.stream = saved;
+        cudaEventRecord(h->dev_done, user);
+        h->dev_pending = true;
         ln.timed = false;
         return rc;
     }
@@ -2153,8 +2297,8 @@ extern "C" int nrmc_rt_trace(nrmc_rt_t h, const nrmc_rt_input *in, const nrmc_rt
     const bool need_nsol_dev = want_att || want[0] || compact;
     for (int i = 0; i < N_OUT; ++i) if (want[i] || (i == 0 && need_nsol_dev)) per_pair += elem[i] + 16;
     const bool direct = compact;      // the binned solver assigns the compact rows itself (scan of n_sol before K_roots)
-    per_pair += h->S * sizeof(SolRec) + 48;
-    per_pair += (size_t)(1 + 2 * h->ice.n_refl) * (2 * sizeof(RootItem) + sizeof(HumpItem) + 1);
+    per_pair += (size_t)h->S * 2 * WORKLIST_BYTES_PER_ENTRY + 48;
+    per_pair += (size_t)(1 + 2 * h->ice.n_refl) * (ROOTQ_BYTES_PER_ENTRY + HUMPQ_BYTES_PER_ENTRY + 1);
     int64_t chunk = (int64_t)((size_t)1536 * 1024 * 1024 / per_pair);   // ~1.5 GB of device scratch per lane
     chunk = std::max<int64_t>(chunk, 1024);
     if (h->chunk_pairs > 0) chunk = h->chunk_pairs;
@@ -2242,7 +2386,7 @@ extern "C" int nrmc_rt_trace(nrmc_rt_t h, const nrmc_rt_input *in, const nrmc_rt
             cc.on = true; cc.sol_offset = (int64_t *)ln.pack_off.p; cc.base_host = row_base;
             cc.row_limit = std::min<int64_t>(out->row_capacity, row_base + np * S);
         }
-        int rc = launch_chunk(h, ln, lid, kin, to, (double *)dps(12), (double *)dps(13), &n_launches, cc);
+        int rc = launch_chunk(h, ln, lid, ln.stream, kin, to, (double *)dps(12), (double *)dps(13), &n_launches, cc);
         if (rc != NRMC_OK) return rc;
         if (direct) {
             const int nblk = (int)((np + PACK_PAIRS - 1) / PACK_PAIRS);

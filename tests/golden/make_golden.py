@@ -87,6 +87,15 @@ def cases():
     V, A = pairs(cylinder(7, 24, 3000., -2700.), RNOG[[0, 13]])
     c["greenland_GL3"] = dict(ice="greenland_simple", att="GL3", n_refl=0, n_freq=15, X1=V, X2=A,
                               freqs=np.fft.rfftfreq(256, 0.5), fmax=None)
+    # round 2: >= 1e3 pairs of the two attenuation benchmarks (cfg3: all 24 RNO-G channels; cfg5: 5 of the 25 stations x 4 depths)
+    V, A = pairs(cylinder(33, 42, 4000., -2700.), RNOG)
+    c["greenland_cfg3_large"] = dict(ice="greenland_simple", att="GL1", n_refl=0, n_freq=25, X1=V, X2=A,
+                                     freqs=np.fft.rfftfreq(1022, 0.2), fmax=1.2)
+    g5 = np.array([[x, y, z] for x, y in ((0., 0.), (1500., -1500.), (-3000., 3000.), (3000., 0.), (-1500., -3000.))
+                   for z in (-145., -150., -155., -160.)])
+    V, A = pairs(cylinder(55, 50, 6000., -2700.), g5)
+    c["sp2015_cfg5_large"] = dict(ice="southpole_2015", att="SP1", n_refl=0, n_freq=25, X1=V, X2=A,
+                                  freqs=np.fft.rfftfreq(1022, 0.2), fmax=1.2)
     V, A = pairs(cylinder(8, 10, 800., -550.), np.array([[3, 3, -5.]]))
     c["mooresbay_GL3"] = dict(ice="mooresbay_simple", att="GL3", n_refl=1, n_freq=10, X1=V, X2=A,
                               freqs=np.fft.rfftfreq(128, 0.5), fmax=None)

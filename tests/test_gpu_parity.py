@@ -54,7 +54,7 @@ def test_T06_golden_through_kernel(make):
 
 @pytest.mark.parametrize("name", ["sp_simple_T05", "sp2015_cfg2", "mooresbay_cfg4", "mooresbay_T06", "sp1_cfg1",
                                   "greenland_cfg3", "mooresbay_cfg4_MB1", "sp2015_cfg5_SP1", "greenland_GL2", "greenland_GL3",
-                                  "mooresbay_GL3"])
+                                  "mooresbay_GL3", "greenland_cfg3_large", "sp2015_cfg5_large"])
 def test_python_reference_fixtures(make, name):
     """fixtures produced by the reference's own Python path (tests/golden/make_golden.py)"""
     g = load_golden(name)
@@ -870,3 +870,107 @@ def test_wide_geometry_stress_and_far_field_hump(make, oracle_mod):
         bad = np.nonzero(res["n_sol"] != ora["n_sol"])[0]
         assert len(bad) <= 2 and (res["n_sol"][bad] > ora["n_sol"][bad]).all()     # only roots the oracle's scan window misses
         assert_parity(res, ora, exact_count=False)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# regressions of the round-1 review
+# ---------------------------------------------------------------------------------------------------------------
+def test_get_attenuation_after_set_solution_subset(make):
+    """set_solution with the first solution masked out (what the viewing-angle cut leaves in the HDF5 datasets): get_attenuation /
+    the vectors of solution 0 must be those of the solution that was injected, not of the trace's slot 0"""
+    ff = np.fft.rfftfreq(256, 0.5)
+    rt = make("southpole_2015", attenuation_model="SP1", n_frequencies_integration=20)
+    x1, x2 = np.array([400., 300., -900.]), np.array([10., 10., -190.])
+    full = rt.trace_batch(x1[None], x2[None], frequency=ff, max_detector_freq=0.8)
+    assert full["n_sol"][0] == 2 and not np.allclose(full["attenuation"][0, 0], full["attenuation"][0, 1])
+    fresh = make("southpole_2015", attenuation_model="SP1", n_frequencies_integration=20)
+    fresh.set_start_and_end_point(x1, x2)
+    fresh.set_solution({"ray_tracing_C0": np.array([np.nan, full["C0"][0, 1]]), "ray_tracing_C1": np.array([np.nan, full["C1"][0, 1]]),
+                        "ray_tracing_solution_type": np.array([0, full["solution_type"][0, 1]]),
+                        "ray_tracing_reflection": np.array([0, 0]), "ray_tracing_reflection_case": np.array([0, 1])})
+    assert fresh.get_number_of_solutions() == 1
+    np.testing.assert_array_equal(fresh.get_attenuation(0, ff, 0.8), full["attenuation"][0, 1])
+    np.testing.assert_array_equal(fresh.get_launch_vector(0), full["launch_vector"][0, 1])
+    assert fresh.get_travel_time(0) == full["travel_time"][0, 1]
+    # both injected, in reversed order
+    fresh.set_start_and_end_point(x1, x2)
+    fresh.set_solution({"ray_tracing_C0": full["C0"][0, ::-1], "ray_tracing_C1": full["C1"][0, ::-1],
+                        "ray_tracing_solution_type": full["solution_type"][0, ::-1]})
+    np.testing.assert_array_equal(fresh.get_attenuation(0, ff, 0.8), full["attenuation"][0, 1])
+    np.testing.assert_array_equal(fresh.get_attenuation(1, ff, 0.8), full["attenuation"][0, 0])
+
+
+def test_single_frequency_attenuation(make, oracle_mod):
+    """one positive frequency: np.interp on one point returns the value itself (no read of a right neighbour)"""
+    V = cylinder(77, 200, 3000, -2500)
+    X2 = np.repeat([[0., 0., -150.]], len(V), 0)
+    for model, ice, n_refl in (("SP1", "southpole_2015", 0), ("GL1", "greenland_simple", 0), ("MB1", "mooresbay_simple", 1)):
+        if n_refl:
+            V2, X22 = cylinder(78, 100, 800, -500), np.repeat([[3., 3., -5.]], 100, 0)
+        else:
+            V2, X22 = V, X2
+        for ff in (np.array([0.3]), np.array([0., 0.3])):
+            rt = make(ice, attenuation_model=model, n_reflections=n_refl, n_frequencies_integration=25)
+            res = rt.trace_batch(V2, X22, frequency=ff, attenuation="both")
+            ora = oracle_mod.Oracle(ice, attenuation_model=model, n_reflections=n_refl, n_freq=25, tight=True).trace(V2, X22, ff, None)
+            assert np.array_equal(res["n_sol"], ora["n_sol"])
+            assert res["attenuation_sparse"].shape[-1] == 1
+            assert_attenuation_parity(res["attenuation"], ora["attenuation"])
+            filled = np.arange(res["C0"].shape[1])[None, :] < res["n_sol"][:, None]
+            assert np.isfinite(res["attenuation"][filled]).all() and np.isnan(res["attenuation"][~filled]).all()
+            np.testing.assert_array_equal(res["attenuation"][..., -1], res["attenuation_sparse"][..., 0])
+            # and through the effects kernel with the sparse factors (single-segment paths)
+            if n_refl == 0:
+                rows = res["attenuation_sparse"][filled]
+                spec = np.ones((len(rows), 3, len(ff)), complex)
+                out = rt.apply_propagation_effects_batch(spec, attenuation_sparse=rows)
+                np.testing.assert_allclose(out[:, 0, -1].real, rows[:, 0], rtol=1e-15)
+
+
+def test_prepare_batch_serves_attenuation_and_rejects_compact(make):
+    ff = np.fft.rfftfreq(128, 0.5)
+    rt = make("southpole_2015", attenuation_model="SP1", n_frequencies_integration=15)
+    V, A = cylinder(91, 20, 2500, -2000), np.array([[0, 0, -150.], [30, 0, -100.]])
+    with pytest.raises(ValueError):
+        rt.prepare_batch(V, A, outer=True, compact=True)
+    res = rt.prepare_batch(V, A, outer=True, frequency=ff, max_detector_freq=0.7)
+    calls = []
+    orig = rt.trace_batch
+    rt.trace_batch = lambda *a, **k: (calls.append(1), orig(*a, **k))[1]
+    for i, v in enumerate(V):
+        for j, a in enumerate(A):
+            rt.set_start_and_end_point(v, a)
+            rt.find_solutions()
+            for iS in range(rt.get_number_of_solutions()):
+                np.testing.assert_array_equal(rt.get_attenuation(iS, ff, 0.7), res["attenuation"][i * len(A) + j, iS])
+    assert not calls, "the scalar loop after prepare_batch(frequency=...) must not trace again"
+    rt.set_start_and_end_point(V[0], A[0])
+    rt.find_solutions()
+    if rt.get_number_of_solutions():
+        rt.get_attenuation(0, ff, 0.5)            # another max_detector_freq: not in the batch, one trace
+        assert len(calls) == 1
+
+
+def test_device_call_followed_by_host_call_on_one_handle(make):
+    """a device-resident call returns before its kernels ran; a host-memory call (own streams) right behind it, a second device call
+    on another stream and a change of the frequency set must not disturb it (own scratch lane, event ordering)"""
+    import torch
+    ff, ff2 = np.fft.rfftfreq(256, 0.5), np.fft.rfftfreq(64, 1.0)
+    rt = make("southpole_2015", attenuation_model="SP1", n_frequencies_integration=20)
+    V, A = cylinder(92, 30000, 6000, -2700), np.array([[0, 0, -150.], [1500, 0, -160.]])
+    ref = rt.trace_batch(V, A, outer=True, frequency=ff, max_detector_freq=0.8, attenuation="sparse")
+    dv, da = torch.tensor(np.ascontiguousarray(V.T), device="cuda"), torch.tensor(np.ascontiguousarray(A.T), device="cuda")
+    side = torch.cuda.Stream()
+    for _ in range(3):
+        d1 = rt.trace_batch_device(dv, da, outer=True, frequency=ff, max_detector_freq=0.8, attenuation="sparse")
+        with torch.cuda.stream(side):
+            d2 = rt.trace_batch_device(dv, da, outer=True, frequency=ff, max_detector_freq=0.8, attenuation="sparse")
+        h = rt.trace_batch(V[:500], A, outer=True, frequency=ff, max_detector_freq=0.8, attenuation="sparse")
+        small = rt.trace_batch(V[:50], A, outer=True, frequency=ff2, attenuation="sparse")     # rewrites the frequency tables
+        torch.cuda.synchronize()
+        for d in (d1, d2):
+            for k in ("n_sol", "C0", "travel_time", "attenuation_sparse"):
+                np.testing.assert_array_equal(d[k].cpu().numpy(), ref[k], err_msg=k)
+        for k in ("n_sol", "C0", "attenuation_sparse"):
+            np.testing.assert_array_equal(h[k], ref[k][:1000], err_msg=k)
+        assert small["attenuation_sparse"].shape[-1] == len(small.frequencies_sparse)
