@@ -71,6 +71,19 @@ __device__ __forceinline__ double expm1_c_neg(double x)    // -700 < x <= 0
     const double s = __hiloint2double((1023 + k) << 20, 0);
     return fma(s, q, s - 1.0);
 }
+// -700 < x <= 0 guaranteed by the caller (no clamp: FP64 min / max are emulated with six instructions), degree-8 polynomial:
+// truncation r^9 / 9! relative to r, 6e-10 -- the quadrature weights of the attenuation kernels need 1e-7
+__device__ __forceinline__ double expm1_c_small(double x)
+{
+    int k;
+    const double r = exp_reduce(x, k);
+    double p = c_expc[3];
+#pragma unroll
+    for (int i = 4; i < 10; ++i) p = fma(p, r, c_expc[i]);
+    const double q = fma(p * r, r, r);
+    const double s = __hiloint2double((1023 + k) << 20, 0);
+    return fma(s, q, s - 1.0);
+}
 __device__ __forceinline__ double expm1_c(double x)        // accurate for x -> 0: k = 0 returns the polynomial itself
 {
     int k;

@@ -44,8 +44,85 @@
 
 namespace nrmc {
 
+// Reciprocal, reciprocal square root and logarithm of the solver's inner loop.  On the device they are the fast paths only:
+// CUDA's 1/x, rsqrt and log guard every call with an exponent-range test, a convergence barrier and a slow-path call, and
+// log materialises its polynomial with two UMOVs per coefficient; the arguments here are positive normal numbers (sums of
+// squares, the k factors of the range function), so the hardware seed (MUFU.RCP64H / RSQ64H, 2^-23) plus Newton steps is all
+// that is needed, and log keeps its coefficients in constant memory (fdlibm's reduction and degree-14 odd polynomial,
+// < 1 ulp).  Zero, inf and NaN (a horizontal ray in numerically homogeneous ice) give the IEEE results (inf, 0, NaN), so
+// they propagate as before; denormals count as zero.  NRMC_STOCK_MATH: CUDA's functions everywhere (A/B builds).
+#if defined(__CUDACC__)
+__constant__ double c_logc[9] = {1.479819860511658591e-01, 1.531383769920937332e-01, 1.818357216161805012e-01, 2.222219843214978396e-01,
+                                 2.857142874366239149e-01, 3.999999999940941908e-01, 6.666666666666735130e-01,
+                                 6.93147180369123816490e-01, 1.90821492927058770002e-10};   // Lg7 .. Lg1, ln2_hi, ln2_lo
+#endif
+#if defined(__CUDA_ARCH__) && !defined(NRMC_STOCK_MATH)
+__device__ __forceinline__ bool nrmc_is_normal(double x)            // finite, non-zero, not denormal (either sign)
+{
+    return (unsigned)((__double2hiint(x) & 0x7ff00000) - 0x00100000) < 0x7fe00000u;
+}
+__device__ __forceinline__ double nrmc_rcp(double x)
+{
+    double y0;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(x));          // 0 -> inf, inf -> 0, NaN -> NaN: returned as they are
+    // branch-free: the refinement runs on every input and is discarded (two selects) where it would turn inf into NaN --
+    // a divergent branch with its convergence barrier costs more issue slots than the four FMAs
+    double e = fma(-x, y0, 1.0);
+    double y = fma(y0, e, y0);
+    e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    return nrmc_is_normal(x) ? y : y0;
+}
+__device__ __forceinline__ double nrmc_rsqrt(double x)
+{
+    double y0;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(x));        // 0 -> inf, inf -> 0, negative / NaN -> NaN
+    double e = fma(-(x * y0), y0, 1.0);                             // 1 - x y^2
+    double y = fma(fma(0.375, e, 0.5) * e, y0, y0);                 // third order: y (1 + e/2 + 3 e^2/8)
+    e = fma(-(x * y), y, 1.0);
+    y = fma(0.5 * e, y, y);
+    return (unsigned)(__double2hiint(x) - 0x00100000) < 0x7fe00000u ? y : y0;     // positive normal numbers only (branch-free)
+}
+__device__ __forceinline__ double nrmc_log(double x)
+{
+    int hi = __double2hiint(x);
+    if ((unsigned)(hi - 0x00100000) >= 0x7fe00000u)                 // not a positive normal number
+        return (x != x || x < 0.0) ? NAN : (x > 1.0 ? INFINITY : -INFINITY);   // (denormals count as 0)
+    hi += 0x3ff00000 - 0x3fe6a09e;                                  // mantissa into [sqrt(1/2), sqrt(2))
+    const double dk = (double)((hi >> 20) - 0x3ff);
+    const double m = __hiloint2double((hi & 0x000fffff) + 0x3fe6a09e, __double2loint(x));
+    const double f = m - 1.0;
+    const double s = f * nrmc_rcp(2.0 + f);
+    const double z = s * s, w = z * z;
+    const double t1 = w * fma(w, fma(w, c_logc[1], c_logc[3]), c_logc[5]);
+    const double t2 = z * fma(w, fma(w, fma(w, c_logc[0], c_logc[2]), c_logc[4]), c_logc[6]);
+    const double hfsq = 0.5 * f * f;
+    return fma(dk, c_logc[7], -((hfsq - fma(s, hfsq + (t2 + t1), dk * c_logc[8])) - f));
+}
+#define NRMC_RCP(x) nrmc_rcp(x)
+#define NRMC_RSQRT(x) nrmc_rsqrt(x)
+#define NRMC_LOG(x) nrmc_log(x)
+// sqrt(x) for x >= 0 (0 -> 0) through the fast reciprocal square root
+__device__ __forceinline__ double nrmc_sqrt_pos(double x) { const double r = x * nrmc_rsqrt(x); return x > 0.0 ? r : 0.0; }
+#define NRMC_SQRT(x) nrmc_sqrt_pos(x)
+#elif defined(__CUDA_ARCH__)
+#define NRMC_RCP(x) (1.0 / (x))
+#define NRMC_RSQRT(x) rsqrt(x)
+#define NRMC_LOG(x) log(x)
+#define NRMC_SQRT(x) sqrt(x)
+#else
+#define NRMC_RCP(x) (1.0 / (x))
+#define NRMC_RSQRT(x) (1.0 / sqrt(x))
+#define NRMC_LOG(x) log(x)
+#define NRMC_SQRT(x) sqrt(x)
+#endif
+// max / min of two numbers where neither is NaN or the NaN may propagate either way: one compare and a select.  (fmax / fmin
+// canonicalise NaNs: DSETP + two moves + SEL + FSEL + LOP3 on sm_100, where FP64 min / max have no instruction.)
+#define NRMC_MAX(a, b) ((a) > (b) ? (a) : (b))
+#define NRMC_MIN(a, b) ((a) < (b) ? (a) : (b))
+
 struct IceParams {            // medium_base.py:206-252 (+ add_reflective_bottom :47-66)
-    double n_ice, dn, z0, inv_z0;
+    double n_ice, dn, z0, inv_z0, inv_dn;
     double ns;                // n(0) = n_ice - dn
     double zr;                // reflective layer depth (<0) ; valid if n_refl > 0
     double gr, nr;            // gamma(zr), n(zr)
@@ -91,8 +168,8 @@ NRMC_HD void make_pair_geom_g(const IceParams &ice, double z1, double z2, double
     g.Br = (g.g2 - ice.gr) * (ice.nr + g.n2);
     g.c0_sub = ice.dn * (ice.n_ice + ice.ns);
     g.c0_band = g.g2 * (ice.n_ice + g.n2);
-    g.s2max = sqrt(fmax(g.A2, 0.0));
-    g.tmin = ice.ns / (g.n2 + g.s2max);
+    g.s2max = NRMC_SQRT(NRMC_MAX(g.A2, 0.0));
+    g.tmin = ice.ns * NRMC_RCP(g.n2 + g.s2max);
 }
 
 NRMC_HD void make_pair_geom(const IceParams &ice, double z1, double z2, double rho, PairGeom &g)
@@ -130,17 +207,17 @@ struct RayState {
 NRMC_HD void ray_state(const IceParams &ice, const PairGeom &g, bool band, double t, RayState &r)
 {
     const PieceConsts pc = piece_consts(ice, g, band);
-    const double q = 1.0 / (1.0 + t * t);
+    const double q = NRMC_RCP(1.0 + t * t);
     r.beta = pc.nX * (2.0 * t) * q;
     const double sig = pc.nX * ((1.0 - t) * (1.0 + t)) * q;
     const double sg2 = sig * sig;
     const double c = pc.c0 + sg2;
     r.ss = band ? 0.0 : sig;
-    r.s1 = sqrt(pc.O1 + sg2);
-    r.s2 = band ? sig : sqrt(pc.O2 + sg2);
-    r.sr = ice.n_refl > 0 ? sqrt(pc.Or + sg2) : 0.0;
+    r.s1 = NRMC_SQRT(pc.O1 + sg2);
+    r.s2 = band ? sig : NRMC_SQRT(pc.O2 + sg2);
+    r.sr = ice.n_refl > 0 ? NRMC_SQRT(pc.Or + sg2) : 0.0;
     r.reflected = !band;
-    r.rc = sqrt(c);
+    r.rc = NRMC_SQRT(c);
     r.k1_1 = r.rc * r.s1 + (c - ice.n_ice * g.g1);
     r.k1_2 = r.rc * r.s2 + (c - ice.n_ice * g.g2);
     r.k1_r = ice.n_refl > 0 ? r.rc * r.sr + (c - ice.n_ice * ice.gr) : 1.0;
@@ -148,83 +225,13 @@ NRMC_HD void ray_state(const IceParams &ice, const PairGeom &g, bool band, doubl
 }
 
 // parameter t of the ray with invariant beta inside a class with radius nX (beta < nX)
-NRMC_HD double t_of_beta(double nX, double beta) { return beta / (nX + sqrt(fmax((nX - beta) * (nX + beta), 0.0))); }
+NRMC_HD double t_of_beta(double nX, double beta) { return beta * NRMC_RCP(nX + NRMC_SQRT(NRMC_MAX((nX - beta) * (nX + beta), 0.0))); }
 
 struct Curve {                // one (reflection, case) mode of one pair
     const IceParams *ice;
     const PairGeom *g;
     int k, rcase;
 };
-
-// Reciprocal, reciprocal square root and logarithm of the solver's inner loop.  On the device they are the fast paths only:
-// CUDA's 1/x, rsqrt and log guard every call with an exponent-range test, a convergence barrier and a slow-path call, and
-// log materialises its polynomial with two UMOVs per coefficient; the arguments here are positive normal numbers (sums of
-// squares, the k factors of the range function), so the hardware seed (MUFU.RCP64H / RSQ64H, 2^-23) plus Newton steps is all
-// that is needed, and log keeps its coefficients in constant memory (fdlibm's reduction and degree-14 odd polynomial,
-// < 1 ulp).  Zero, inf and NaN (a horizontal ray in numerically homogeneous ice) give the IEEE results (inf, 0, NaN), so
-// they propagate as before; denormals count as zero.  NRMC_STOCK_MATH: CUDA's functions everywhere (A/B builds).
-#if defined(__CUDACC__)
-__constant__ double c_logc[9] = {1.479819860511658591e-01, 1.531383769920937332e-01, 1.818357216161805012e-01, 2.222219843214978396e-01,
-                                 2.857142874366239149e-01, 3.999999999940941908e-01, 6.666666666666735130e-01,
-                                 6.93147180369123816490e-01, 1.90821492927058770002e-10};   // Lg7 .. Lg1, ln2_hi, ln2_lo
-#endif
-#if defined(__CUDA_ARCH__) && !defined(NRMC_STOCK_MATH)
-__device__ __forceinline__ bool nrmc_is_normal(double x)            // finite, non-zero, not denormal (either sign)
-{
-    return (unsigned)((__double2hiint(x) & 0x7ff00000) - 0x00100000) < 0x7fe00000u;
-}
-__device__ __forceinline__ double nrmc_rcp(double x)
-{
-    double y;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));           // 0 -> inf, inf -> 0, NaN -> NaN: returned as they are
-    if (nrmc_is_normal(x)) {
-        double e = fma(-x, y, 1.0);
-        y = fma(y, e, y);
-        e = fma(-x, y, 1.0);
-        y = fma(y, e, y);
-    }
-    return y;
-}
-__device__ __forceinline__ double nrmc_rsqrt(double x)
-{
-    double y;
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));         // 0 -> inf, inf -> 0, negative / NaN -> NaN
-    if (nrmc_is_normal(x) && x > 0.0) {
-        double e = fma(-(x * y), y, 1.0);                           // 1 - x y^2
-        y = fma(fma(0.375, e, 0.5) * e, y, y);                      // third order: y (1 + e/2 + 3 e^2/8)
-        e = fma(-(x * y), y, 1.0);
-        y = fma(0.5 * e, y, y);
-    }
-    return y;
-}
-__device__ __forceinline__ double nrmc_log(double x)
-{
-    int hi = __double2hiint(x);
-    if ((unsigned)(hi - 0x00100000) >= 0x7fe00000u)                 // not a positive normal number
-        return (x != x || x < 0.0) ? NAN : (x > 1.0 ? INFINITY : -INFINITY);   // (denormals count as 0)
-    hi += 0x3ff00000 - 0x3fe6a09e;                                  // mantissa into [sqrt(1/2), sqrt(2))
-    const double dk = (double)((hi >> 20) - 0x3ff);
-    const double m = __hiloint2double((hi & 0x000fffff) + 0x3fe6a09e, __double2loint(x));
-    const double f = m - 1.0;
-    const double s = f * nrmc_rcp(2.0 + f);
-    const double z = s * s, w = z * z;
-    const double t1 = w * fma(w, fma(w, c_logc[1], c_logc[3]), c_logc[5]);
-    const double t2 = z * fma(w, fma(w, fma(w, c_logc[0], c_logc[2]), c_logc[4]), c_logc[6]);
-    const double hfsq = 0.5 * f * f;
-    return fma(dk, c_logc[7], -((hfsq - fma(s, hfsq + (t2 + t1), dk * c_logc[8])) - f));
-}
-#define NRMC_RCP(x) nrmc_rcp(x)
-#define NRMC_RSQRT(x) nrmc_rsqrt(x)
-#define NRMC_LOG(x) nrmc_log(x)
-#elif defined(__CUDA_ARCH__)
-#define NRMC_RCP(x) (1.0 / (x))
-#define NRMC_RSQRT(x) rsqrt(x)
-#define NRMC_LOG(x) log(x)
-#else
-#define NRMC_RCP(x) (1.0 / (x))
-#define NRMC_RSQRT(x) (1.0 / sqrt(x))
-#define NRMC_LOG(x) log(x)
-#endif
 
 // g = R - rho on piece p in {0,1,2,3} at parameter t and (WITH_D) dg/dt, in ONE pass.  With h = sigma sigma',
 //   d k1_i = h (s_i/rc + rc/s_i + 2),  d ln P = sum a_i d k_i / k_i  (one shared reciprocal for k = 0),
@@ -246,7 +253,7 @@ NRMC_HD double curve_eval(const Curve &cv, int p, double t, double &dg)
     const double c = pc.c0 + sg2;
     const double irc = NRMC_RSQRT(c), rc = c * irc;
     const double x1 = pc.O1 + sg2, x2 = pc.O2 + sg2;
-    const double is1 = NRMC_RSQRT(fmax(x1, 1e-300)), is2 = NRMC_RSQRT(fmax(x2, 1e-300));
+    const double is1 = NRMC_RSQRT(NRMC_MAX(x1, 1e-300)), is2 = NRMC_RSQRT(NRMC_MAX(x2, 1e-300));
     const double s1 = x1 * is1, s2 = band ? sig : x2 * is2;
     const double k1 = rc * s1 + (c - ice.n_ice * g.g1), k2 = rc * s2 + (c - ice.n_ice * g.g2);
     const double KT = band ? ice.dn * beta : rc * sig + (c - ice.n_ice * ice.dn);
@@ -269,7 +276,7 @@ NRMC_HD double curve_eval(const Curve &cv, int p, double t, double &dg)
         if (WITH_D) dlnP = ((turned ? 2.0 * dKT * k1 * k2 - dk2 * k1 * KT : dk2 * k1) - dk1 * k2 * Kx) * iv;
     } else {
         const ModeCoeffs m = mode_coeffs(cv.k, cv.rcase, turned);
-        const double xr = pc.Or + sg2, isr = NRMC_RSQRT(fmax(xr, 1e-300)), sr = xr * isr;
+        const double xr = pc.Or + sg2, isr = NRMC_RSQRT(NRMC_MAX(xr, 1e-300)), sr = xr * isr;
         const double kr = rc * sr + (c - ice.n_ice * ice.gr);
         double num = 1.0, den = 1.0;
         if (m.a1 > 0) num *= k1; else den *= k1;            // |a1| == 1
@@ -302,8 +309,8 @@ NRMC_HD double guess_t(const IceParams &ice, const PairGeom &g, int p)
     const double dz = (p == 3) ? -g.z1 - g.z2 : g.z2 - g.z1;
     if (!(dz > 0.0)) return NAN;
     const double dgam = (p == 3) ? (ice.dn - g.g1) + (ice.dn - g.g2) : g.g2 - g.g1;
-    const double nbar = ice.n_ice - ice.z0 * dgam / dz;
-    const double b0 = nbar * g.rho / sqrt(g.rho * g.rho + dz * dz);
+    const double nbar = ice.n_ice - ice.z0 * dgam * NRMC_RCP(dz);
+    const double b0 = nbar * g.rho * NRMC_RSQRT(g.rho * g.rho + dz * dz);
     const double nX = (p == 1) ? g.n2 : ice.ns;
     return (b0 < nX) ? t_of_beta(nX, b0) : NAN;
 }
@@ -318,18 +325,19 @@ NRMC_HD double guess_t(const IceParams &ice, const PairGeom &g, int p)
 NRMC_HD double solve_piece(const Curve &cv, int p, double a, double ga, double b, double gb, double x0)
 {
     const double gtol = 1e-10;
-    double lo = fmin(a, b), hi = fmax(a, b);
+    // the bracket is kept ordered (lo < hi) from the start: no min / max per iteration
+    double lo = a, glo = ga, hi = b, ghi = gb;
+    if (b < a) { lo = b; glo = gb; hi = a; ghi = ga; }
     double x = x0;
-    if (!(x > lo && x < hi)) x = (a * gb - b * ga) / (gb - ga);
-    if (!(x > lo && x < hi)) x = 0.5 * (a + b);
+    if (!(x > lo && x < hi)) x = (lo * ghi - hi * glo) * NRMC_RCP(ghi - glo);
+    if (!(x > lo && x < hi)) x = 0.5 * (lo + hi);
     for (int it = 0; it < 100; ++it) {
         double dg;
         const double gx = curve_gd(cv, p, x, dg);
         if (fabs(gx) <= gtol) break;
-        if ((gx > 0) == (gb > 0)) { b = x; gb = gx; } else { a = x; ga = gx; }
-        lo = fmin(a, b); hi = fmax(a, b);
+        if ((gx > 0) == (ghi > 0)) { hi = x; ghi = gx; } else { lo = x; glo = gx; }
         double xn = x - gx * NRMC_RCP(dg);
-        if (!(xn > lo && xn < hi)) xn = 0.5 * (a + b);
+        if (!(xn > lo && xn < hi)) xn = 0.5 * (lo + hi);
         else if (fabs(xn - x) <= 1e-9 * (fabs(x) + 1e-3)) { x = xn; break; }
         if (hi - lo <= 4e-16 * (fabs(lo) + fabs(hi))) { x = xn; break; }
         x = xn;
@@ -478,7 +486,7 @@ NRMC_HD Root solve_bracket(const Curve &cv, const Bracket &b)
     // the straight-line starting points describe the whole piece; a bracket made by the hump search starts from its secant point
     const bool whole = (b.a == piece_begin(*cv.g, b.piece) && b.b == piece_end(*cv.g, b.piece));
     r.v = solve_piece(cv, b.piece, b.a, b.ga, b.b, b.gb, (cv.k == 0 && whole) ? guess_t(*cv.ice, *cv.g, b.piece) : NAN);
-    const double q = 1.0 / (1.0 + r.v * r.v);
+    const double q = NRMC_RCP(1.0 + r.v * r.v);
     r.beta = ((b.piece == 1 || b.piece == 2) ? cv.g->n2 : cv.ice->ns) * (2.0 * r.v) * q;
     return r;
 }
@@ -524,23 +532,25 @@ NRMC_HD void solution_props(const IceParams &ice, const PairGeom &g, double x1y,
     RayState r;
     ray_state(ice, g, band, root.v, r);
     const ModeCoeffs m = mode_coeffs(k, rcase, turned);
-    const double A = r.beta / r.rc;
-    o.C0 = 1.0 / r.beta;
+    // (reciprocals through the fast path and shared: every true division costs a slow-path branch in the kernel)
+    const double irc = NRMC_RCP(r.rc), in1 = NRMC_RCP(g.n1), in2 = NRMC_RCP(g.n2);
+    const double A = r.beta * irc;
+    o.C0 = NRMC_RCP(r.beta);
     // C_1 = y1 - y(z1; C_1 = 0),  y = z0 beta/sqrt(c) ln(gamma / (2 k1))       (py:487-491,118-125)
-    o.C1 = x1y - ice.z0 * A * NRMC_LOG(g.g1 / (2.0 * r.k1_1));
+    o.C1 = x1y - ice.z0 * A * NRMC_LOG(g.g1 * NRMC_RCP(2.0 * r.k1_1));
     // solution type on the UNREFLECTED geometry (py:2146 -> :1386-1398): direct iff rho < y_turn - y1
     if (k == 0) o.type = turned ? (r.reflected ? 3 : 2) : 1;
     else {
-        double T1 = A * (-g.z1 - ice.z0 * NRMC_LOG(r.KT / r.k1_1));
+        double T1 = A * (-g.z1 - ice.z0 * NRMC_LOG(r.KT * NRMC_RCP(r.k1_1)));
         o.type = (g.rho < T1) ? 1 : (r.reflected ? 3 : 2);
     }
     // launch: theta1 with sin = beta/n1, downward start (case 2, k>0) -> pi - theta1   (py:1161-1196)
-    o.sin_l = r.beta / g.n1;
-    o.cos_l = r.s1 / g.n1;
+    o.sin_l = r.beta * in1;
+    o.cos_l = r.s1 * in1;
     if (k > 0 && rcase == 2) o.cos_l = -o.cos_l;
     // receive: pi - theta2 if the last segment arrives up-going, theta2 otherwise      (py:1198-1199)
-    o.sin_r = r.beta / g.n2;
-    o.cos_r = turned ? r.s2 / g.n2 : -r.s2 / g.n2;
+    o.sin_r = r.beta * in2;
+    o.cos_r = turned ? r.s2 * in2 : -r.s2 * in2;
     // path length / travel time (py:602-783): S(z) = n_ice/rc U(z) + z0 ln k2,  ct(z) = n_ice^2/rc U(z) + z0 (s + n_ice ln k2)
     // summed with the same integer coefficients as the range:  sum a U = rho rc / beta at the root.
     double k2_1 = r.s1 + g.n1, k2_2 = r.s2 + g.n2, k2_r = r.sr + ice.nr;
@@ -552,10 +562,10 @@ NRMC_HD void solution_props(const IceParams &ice, const PairGeom &g, double x1y,
     num *= ipow(k2_T, m.aT);
     double ssum = m.a1 * r.s1 + m.a2 * r.s2 + m.aT * sT;
     if (m.ar != 0) { den *= ipow(k2_r, -m.ar); ssum += m.ar * r.sr; }
-    double lk2 = NRMC_LOG(num / den);
-    double sumU = g.rho / A;
-    o.path_length = ice.n_ice / r.rc * sumU + ice.z0 * lk2;
-    o.travel_time = (ice.n_ice * ice.n_ice / r.rc * sumU + ice.z0 * (ssum + ice.n_ice * lk2)) / NRMC_SPEED_OF_LIGHT;
+    double lk2 = NRMC_LOG(num * NRMC_RCP(den));
+    double nsumU = ice.n_ice * g.rho * o.C0;                  // n_ice / rc * sum a U,  sum a U = rho rc / beta
+    o.path_length = nsumU + ice.z0 * lk2;
+    o.travel_time = (ice.n_ice * nsumU + ice.z0 * (ssum + ice.n_ice * lk2)) * (1.0 / NRMC_SPEED_OF_LIGHT);
     // surface reflection angle per segment (py:1201-1237)
     o.n_segments = k + 1;
     o.refl_mask = 0;
@@ -664,11 +674,11 @@ NRMC_HD void make_solrec(const IceParams &ice, const PairGeom &g, int64_t pair, 
     r.beta = root.beta;
     // c = n_ice^2 - beta^2 = c0 + sigma^2 with sigma from the curve parameter (ray_state)
     const bool band = (root.piece == 1 || root.piece == 2);
-    const double q = 1.0 / (1.0 + root.v * root.v);
+    const double q = NRMC_RCP(1.0 + root.v * root.v);
     const double sig = (band ? g.n2 : ice.ns) * ((1.0 - root.v) * (1.0 + root.v)) * q;
     const double c = (band ? g.c0_band : g.c0_sub) + sig * sig;
-    r.delta = c / (ice.n_ice + r.beta);
-    r.zv = ice.z0 * NRMC_LOG(r.delta / ice.dn);
+    r.delta = c * NRMC_RCP(ice.n_ice + r.beta);
+    r.zv = ice.z0 * NRMC_LOG(r.delta * ice.inv_dn);
     r.z1 = g.z1; r.z2 = g.z2;
 }
 
@@ -684,8 +694,9 @@ NRMC_HD void make_frame(double ax, double ay, double az, double bx, double by, d
     f.swap = bz < az;
     if (f.swap) { double t; t = ax; ax = bx; bx = t; t = ay; ay = by; by = t; t = az; az = bz; bz = t; }
     double dx = bx - ax, dy = by - ay;
-    f.rho = sqrt(dx * dx + dy * dy);
-    if (f.rho > 0) { f.ex = dx / f.rho; f.ey = dy / f.rho; } else { f.ex = 1.0; f.ey = 0.0; }  // atan2(0,0) = 0
+    const double d2 = dx * dx + dy * dy, rs = NRMC_RSQRT(d2);
+    // (horizontal distances below 1e-150 m count as zero; NaN and inf coordinates propagate to rho for pair_status)
+    if (d2 > 1e-300) { f.rho = d2 * rs; f.ex = dx * rs; f.ey = dy * rs; } else { f.rho = d2 == d2 ? 0.0 : d2; f.ex = 1.0; f.ey = 0.0; }  // atan2(0,0) = 0
     f.z1 = az; f.z2 = bz; f.x1y = ax;
 }
 

@@ -123,6 +123,14 @@ __device__ __forceinline__ SolRec worklist_get(const WorkList &wl, unsigned long
 {
     return worklist_load(wl, worklist_index(wl, n_front, w));
 }
+// pull the record a lane will need in its NEXT trip through a persistent loop into L2 (no registers, no shared memory): the loads
+// at the top of the trip then cost an L2 hit instead of a DRAM round trip (20 % of K_att_sp1's stall samples sat on them)
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void worklist_prefetch(const WorkList &wl, unsigned long long i)
+{
+    prefetch_l2(wl.beta + i); prefetch_l2(wl.delta + i); prefetch_l2(wl.zv + i); prefetch_l2(wl.z1 + i); prefetch_l2(wl.z2 + i);
+    prefetch_l2(wl.row + i); prefetch_l2(wl.meta + i);
+}
 
 #define N_OUT 15            // output arrays of nrmc_rt_output (out_ptr)
 // ---------------------------------------------------------------------------------------------------------------
@@ -308,8 +316,37 @@ K_classify(IceParams ice, KInput in, TraceOutputs out, AttFill af, RmaxTable rma
         if (kind == 1) { if (out.n_sol) out.n_sol[p] = nb; if (out.status) out.status[p] = 0; }
     }
     if (!out.row_offset) warp_fill_nan_rows(p < in.n_pairs && kind == 0, p, af, lane);
-    push_brackets(kind == 1, p, g, br, nb, rootq, root_count, lane);
-    push_hump(kind == 2, p, g, J1, J2, J3, 0, humpq, hump_count, lane);
+    // Queue appends aggregated over the BLOCK (one atomic per queue and block): the entries of 256 consecutive pairs stay
+    // contiguous and in pair order, so the 16 entries a warp of K_roots works on are consecutive pairs with solutions --
+    // consecutive output rows -- except where a warp straddles two blocks' runs (1 in 12).  With warp-level appends a quarter
+    // of the warps of K_roots fell off the coalesced store path.
+    __shared__ unsigned s_cnt[2][CLASSIFY_THREADS / 32];
+    __shared__ unsigned long long s_base[2];
+    const unsigned warp = threadIdx.x >> 5;
+    const unsigned mr = __ballot_sync(FULL_MASK, kind == 1), mh = __ballot_sync(FULL_MASK, kind == 2);
+    if (lane == 0) { s_cnt[0][warp] = __popc(mr); s_cnt[1][warp] = __popc(mh); }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+        unsigned total = 0;
+        for (int w = 0; w < CLASSIFY_THREADS / 32; ++w) total += s_cnt[threadIdx.x][w];
+        s_base[threadIdx.x] = total ? atomicAdd(threadIdx.x == 0 ? root_count : hump_count, (unsigned long long)total) : 0ull;
+    }
+    __syncthreads();
+    if (kind == 1 || kind == 2) {
+        const int qi = kind - 1;
+        unsigned before = __popc((qi == 0 ? mr : mh) & ((1u << lane) - 1u));
+        for (unsigned w = 0; w < warp; ++w) before += s_cnt[qi][w];
+        const unsigned long long e = s_base[qi] + before;
+        if (kind == 1) {
+            const Bracket &b0 = br[0], &b1 = br[nb > 1 ? 1 : 0];
+            rootq.pair[e] = p; rootq.g1[e] = g.g1; rootq.g2[e] = g.g2;
+            rootq.a[e] = make_double2(b0.a, b1.a); rootq.ga[e] = make_double2(b0.ga, b1.ga);
+            rootq.b[e] = make_double2(b0.b, b1.b); rootq.gb[e] = make_double2(b0.gb, b1.gb);
+            rootq.meta[e] = (b0.piece & 3) | ((b1.piece & 3) << 2) | ((nb > 1 ? 1 : 0) << 4);
+        } else {
+            humpq.pair[e] = p; humpq.g1[e] = g.g1; humpq.g2[e] = g.g2; humpq.J1[e] = J1; humpq.J2[e] = J2; humpq.J3[e] = J3; humpq.mode[e] = 0;
+        }
+    }
 }
 
 #define HUMP_THREADS 128
@@ -390,6 +427,14 @@ K_roots(IceParams ice, KInput in, TraceOutputs out, AttFill af, RootQ rootq, con
     for (unsigned long long w0 = (unsigned long long)blockIdx.x * ROOTS_THREADS + (threadIdx.x & ~31u); w0 < n; w0 += stride) {
         const unsigned long long w = w0 + lane;
         const bool active = w < n;
+#ifndef ROOTS_NO_PREFETCH
+        if (w + stride < n) {
+            const unsigned long long wn = w + stride, en = wn >> 1;
+            if ((lane & 1u) == 0) { prefetch_l2(rootq.pair + en); prefetch_l2(rootq.g1 + en); prefetch_l2(rootq.g2 + en); prefetch_l2(rootq.meta + en); }
+            prefetch_l2(reinterpret_cast<const double *>(rootq.a) + wn); prefetch_l2(reinterpret_cast<const double *>(rootq.ga) + wn);
+            prefetch_l2(reinterpret_cast<const double *>(rootq.b) + wn); prefetch_l2(reinterpret_cast<const double *>(rootq.gb) + wn);
+        }
+#endif
         bool valid = false;
         int64_t pair = 0;
         double viewing = NAN;
@@ -1025,110 +1070,52 @@ K_att(IceParams ice, KInput in, AttTables tb, WorkList worklist, const unsigned 
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// SP1 fast path (no bottom reflections): 1/L = exp(b1(z) + p(z) ln f) with the slope p(z) confined to a narrow band
-// around a constant p_ref, so  sum_q c_q exp(p_q w) = exp(p_ref w) sum_k (w^k / k!) M_k,  M_k = sum_q c_q (p_q - p_ref)^k:
-// the per-(node, frequency) exponential disappears.  One THREAD per solution: 32 nodes accumulate 2 x SP1_K moments in
-// registers (no reduction at all), then every integration frequency is a SP1_K-term dot product with a table staged in
-// shared memory by TMA.  Solutions whose slopes leave the band where the SP1_K-term series is accurate to 1e-9, or that
-// could touch the 1 m floor of attenuation.py:252-255, are handed to the generic kernel (fallback list).
+// SP1 fast path (no bottom reflections).  1/L(z, f) = exp(b1(T) + p(T) ln f) with b1 and the slope p quadratics in the ice
+// temperature T (attenuation.py:170-192) and T a monotone cubic in depth (:141-142).  For every integration frequency f_j the
+// function g_j(tau) = 1/L(T(tau), f_j) of the normalised temperature tau in [-1, 1] (surface ... SP1_DEPTH_MAX) is entire and varies
+// by a factor e^{+-1.3} at most (b1 is a parabola in T with its maximum at -20 C), so its Chebyshev series converges fast:
+//     int ds / L(z, f_j) = sum_q w_q g_j(tau_q) = sum_k A_jk M_k,      M_k = sum_q w_q T_k(tau_q)        (w_q: ds-weights)
+// with SP1_KT = 12 frequency-INDEPENDENT moments (sum of the dropped coefficients <= 2.2e-7 A_j0 for every f in 1 MHz ... 3 GHz, 7e-6
+// with 10; the host measures it for the frequency set at hand and disables the fast path if it exceeds SP1_TRUNCATION).  The reference's per-(node, frequency)
+// exponential disappears AND so does the per-node exp(b1): a node costs its geometry (one expm1, one rsqrt), a cubic for tau and
+// a three-term recurrence.  (Round 1 expanded in the slope per band, 2 x 8 moments plus one exponential per node: 88 FP64
+// instructions per node, now 60; tests/test_sp1_moment_form.py restates the mathematics on the CPU.)
+// One THREAD per solution: the moments sit in registers (no reduction at all), then every integration frequency is a SP1_KT-term
+// dot product with a table staged in shared memory by TMA.  Paths that reach below SP1_DEPTH_MAX go to the generic kernel
+// (fall-back list).  The 1 m floor of attenuation.py:252-255 cannot be reached where the fast path is enabled: the host checks
+// g_j < 1 on the whole temperature range.
 // ---------------------------------------------------------------------------------------------------------------
-#ifndef SP1_CHEB
-#define SP1_CHEB 1            // 1: Chebyshev moments (8 per band), 0: monomial moments (10 per band) -- same truncation, 2e-7
+#ifndef SP1_KT
+#define SP1_KT 12
 #endif
-#if SP1_CHEB
-#define SP1_K 8
-#else
-#define SP1_K 10
-#endif
+#define SP1_K SP1_KT          // row pitch of the coefficient table
+#define SP1_DEPTH_MAX 2800.0
+#define SP1_TRUNCATION 3e-7
 #define SP1_NQ 12             // Gauss-Legendre nodes per panel: <= 6e-6 on the factor (16: 1e-8; 10: 9e-5) -- scratch/attconv.cpp
 struct Sp1Tables {
-    const double *wk;         // [Fs_pad][SP1_K]  expansion coefficients of exp((p - p_ref) w_j) in the moment basis:
-                              //                  Chebyshev: eps_k I_k(r w_j) (modified Bessel), monomial: w_j^k / k!
-    const double *E;          // [Fs_pad]         exp(p_ref(band_j) * w_j)
-    const int32_t *band;      // [Fs_pad]         0: f < 1 GHz, 1: f >= 1 GHz (attenuation.py:180-185)
-    double pref_lo, pref_hi;
-    double inv_r_lo, inv_r_hi; // 1 / (half-width of the slope band the series covers): x = (p - p_ref) / r in [-1, 1]
-    double xlo[3], xhi[3];    // x as a quadratic in the ice temperature T: x = xlo[0] + xlo[1] T + xlo[2] T^2
-    double wabs_lo, wabs_hi;  // max |ln f| per band (series radius)
-    double wmin_lo, wmax_lo, wmin_hi, wmax_hi;
-    int32_t n_lo, n_hi;
-    // validity of the moment form as six quadratics of the ice temperature T that must stay inside [lo, hi] along the path:
-    // slopes within the series radius (2), exponent below the 1 m floor at the band edges (4); tv = vertex of the quadratic
-    double qa[6], qb[6], qc[6], qlo[6], qhi[6], qtv[6];
+    const double *wk;         // [Fs_pad][SP1_KT]  Chebyshev coefficients A_jk of g_j(tau)
+    double tau[4];            // tau(a) = ((tau[0] a + tau[1]) a + tau[2]) a + tau[3], a = depth [m]
+    double depth_max;
 };
 #define SP1_THREADS 128
 
-// Is the moment form valid along the whole path?  Every condition (slope inside the series radius, exponent below the 1 m
-// floor of attenuation.py:252-255) is a quadratic in the ice temperature T, and T(depth) is monotone, so the extrema over the
-// path are at the shallowest / deepest point or at the quadratic's vertex: checked once per solution instead of per node.
-__device__ __forceinline__ bool sp1_path_ok(const Sp1Tables &sp, double z_top, double z_deep)
-{
-    const double at = fabs(z_top), ad = fabs(z_deep);
-    const double Tl = fma(fma(fma(c_sp1[0], at, c_sp1[1]), at, c_sp1[2]), at, c_sp1[3]);
-    const double Th = fma(fma(fma(c_sp1[0], ad, c_sp1[1]), ad, c_sp1[2]), ad, c_sp1[3]);
-    bool ok = Th >= Tl;
-#pragma unroll
-    for (int i = 0; i < 6; ++i) {
-        const double tv = fmin(fmax(sp.qtv[i], Tl), Th);
-        const double v1 = fma(fma(sp.qa[i], Tl, sp.qb[i]), Tl, sp.qc[i]);
-        const double v2 = fma(fma(sp.qa[i], Th, sp.qb[i]), Th, sp.qc[i]);
-        const double v3 = fma(fma(sp.qa[i], tv, sp.qb[i]), tv, sp.qc[i]);
-        ok = ok && fmin(v1, fmin(v2, v3)) >= sp.qlo[i] && fmax(v1, fmax(v2, v3)) <= sp.qhi[i];
-    }
-    return ok;
-}
-
-// one quadrature node of the SP1 kernel: depth terms and the moment update
-template <bool HAVE_HI>
+// one quadrature node of the SP1 kernel: geometry (attenuation-independent) and the moment update
 __device__ __forceinline__ void sp1_node(const IceParams &ice, const AttPlan &plan, const Sp1Tables &sp, double u, double wscale,
-                                         double (&Mlo)[SP1_K], double (&Mhi)[SP1_K])
+                                         double (&M)[SP1_KT])
 {
     const double uu = u * u;
-    const double z = fmin(plan.zv - uu, 0.0);
-    const double em = -expm1_c_neg(-uu * ice.inv_z0);
+    const double a = fabs(plan.zv - uu);                   // depth of the node (zv - uu <= 0 up to rounding at a virtual apex)
+    const double em = -expm1_c_small(-uu * ice.inv_z0);    // u^2 / z0 <= 3 km / z0: far inside the range of the reduction
     const double n = plan.beta + plan.delta * em;
     const double wds = wscale * u * n * rsqrt(plan.delta * em * (n + plan.beta));
-    const double a = fabs(z);
-    const double t = fma(fma(fma(c_sp1[0], a, c_sp1[1]), a, c_sp1[2]), a, c_sp1[3]);
-    const double b1 = fma(t, fma(t, c_sp1[9], c_sp1[8]), c_sp1[7]);
-    const double c = wds * exp_c_neg(b1);              // b1 = ln(1/L at 1 GHz) <= -5.5 for any temperature
-#if SP1_CHEB
-    // M_k += c T_k(x), x = (p - p_ref) / r: three-term recurrence, one FMA and one add per moment.  exp(d w) = sum_k eps_k
-    // I_k(r w) T_k(d / r) converges like I_K(0.9) instead of 0.9^K / K!: 8 moments do what 10 monomial ones did.
-    // The slopes are quadratics in the ice temperature ((b1 - b0) / ln 1e4, (b2 - b1) / ln 3.16, attenuation.py:176-185), and so
-    // is x: its three coefficients come from the host.
-    {
-        const double x = fma(t, fma(t, sp.xlo[2], sp.xlo[1]), sp.xlo[0]), x2 = x + x;
-        double t0 = c, t1 = c * x;
-        Mlo[0] += t0; Mlo[1] += t1;
+    const double x = fma(fma(fma(sp.tau[0], a, sp.tau[1]), a, sp.tau[2]), a, sp.tau[3]), x2 = x + x;
+    double t0 = wds, t1 = wds * x;
+    M[0] += t0; M[1] += t1;
 #pragma unroll
-        for (int k = 2; k < SP1_K; ++k) { const double t2 = fma(x2, t1, -t0); Mlo[k] += t2; t0 = t1; t1 = t2; }
-    }
-    if (HAVE_HI) {
-        const double x = fma(t, fma(t, sp.xhi[2], sp.xhi[1]), sp.xhi[0]), x2 = x + x;
-        double t0 = c, t1 = c * x;
-        Mhi[0] += t0; Mhi[1] += t1;
-#pragma unroll
-        for (int k = 2; k < SP1_K; ++k) { const double t2 = fma(x2, t1, -t0); Mhi[k] += t2; t0 = t1; t1 = t2; }
-    }
-#else
-    const double b0 = fma(t, fma(t, c_sp1[6], c_sp1[5]), c_sp1[4]);
-    const double b2 = fma(t, fma(t, c_sp1[12], c_sp1[11]), c_sp1[10]);
-    const double p1 = (b1 - b0) * c_sp1[13], p2 = (b2 - b1) * c_sp1[14];
-    const double dlo = p1 - sp.pref_lo;
-    double tk = c;
-#pragma unroll
-    for (int k = 0; k < SP1_K; ++k) { Mlo[k] += tk; tk *= dlo; }
-    if (HAVE_HI) {
-        const double dhi = p2 - sp.pref_hi;
-        tk = c;
-#pragma unroll
-        for (int k = 0; k < SP1_K; ++k) { Mhi[k] += tk; tk *= dhi; }
-    }
-#endif
+    for (int k = 2; k < SP1_KT; ++k) { const double t2 = fma(x2, t1, -t0); M[k] += t2; t0 = t1; t1 = t2; }
 }
 
-// Factors exp(-E_j sum_k M_k wk[j][k]) of the integration frequencies [j_begin, j_end) (at most SP1_SEG of them) for the 32
+// Factors exp(-sum_k M_k A_jk) of the integration frequencies [j_begin, j_end) (at most SP1_SEG of them) for the 32
 // solutions of a warp.  Each lane computes its own solution four frequencies at a time and parks the values in the warp's
 // staging rows in shared memory; the warp then writes row after row with consecutive lanes on consecutive frequencies.
 // (A lane storing its own row directly makes every 8-byte store a separate 32-byte sector write: measured 60 % of the
@@ -1142,8 +1129,8 @@ __device__ __forceinline__ void sp1_node(const IceParams &ice, const AttPlan &pl
                             // truncation r^9/9! <= 2e-10 relative on the factor (tolerance 1e-4); 0.8 ms per 1e8 pairs
 #endif
 #define SP1_ROW (SP1_SEG + 1)        // odd row pitch: conflict-free column writes
-__device__ __forceinline__ void sp1_emit(const double (&M)[SP1_K], const double *s_wk, const double *s_E, int j_begin, int j_end,
-                                         double *stage, double *dst, unsigned lane)
+__device__ __forceinline__ void sp1_emit(const double (&M)[SP1_KT], const double *s_wk, int j_begin, int j_end, double *stage, double *dst,
+                                         unsigned lane)
 {
     double *mine = stage + lane * SP1_ROW;
     for (int j0 = j_begin; j0 < j_end; j0 += SP1_EW) {
@@ -1152,7 +1139,7 @@ __device__ __forceinline__ void sp1_emit(const double (&M)[SP1_K], const double 
 #pragma unroll
         for (int u = 0; u < SP1_EW; ++u) { jj[u] = min(j0 + u, j_end - 1); acc[u] = 0.0; }
 #pragma unroll
-        for (int k = 0; k < SP1_K; k += 2) {
+        for (int k = 0; k + 1 < SP1_KT; k += 2) {
 #pragma unroll
             for (int u = 0; u < SP1_EW; ++u) {
                 const double2 w2 = *reinterpret_cast<const double2 *>(s_wk + jj[u] * SP1_K + k);
@@ -1160,12 +1147,16 @@ __device__ __forceinline__ void sp1_emit(const double (&M)[SP1_K], const double 
                 acc[u] = fma(M[k + 1], w2.y, acc[u]);
             }
         }
+        if (SP1_KT & 1) {
+#pragma unroll
+            for (int u = 0; u < SP1_EW; ++u) acc[u] = fma(M[SP1_KT - 1], s_wk[jj[u] * SP1_K + SP1_KT - 1], acc[u]);
+        }
         // four exponentials as interleaved chains (values first, the shared-memory stores after: a store between them would
         // order the chains, the compiler cannot prove that the staging row does not alias the tables)
         double x[SP1_EW], r[SP1_EW], pv[SP1_EW];
         int kk[SP1_EW];
 #pragma unroll
-        for (int u = 0; u < SP1_EW; ++u) { x[u] = fmax(-acc[u] * s_E[jj[u]], -700.0); r[u] = exp_reduce(x[u], kk[u]); pv[u] = c_expc[SP1_EXP_SKIP]; }
+        for (int u = 0; u < SP1_EW; ++u) { x[u] = fmax(-acc[u], -700.0); r[u] = exp_reduce(x[u], kk[u]); pv[u] = c_expc[SP1_EXP_SKIP]; }
 #pragma unroll
         for (int i = 1 + SP1_EXP_SKIP; i < 10; ++i) {
 #pragma unroll
@@ -1189,9 +1180,6 @@ __device__ __forceinline__ void sp1_emit(const double (&M)[SP1_K], const double 
     __syncwarp();
 }
 
-// (A/B on the B200: capping the registers at 80 for a sixth block spills and costs 2.7 ms; CUDA's rsqrt replaced by the fast path
-// lets ptxas hoist every constant -- 158 registers, three blocks -- for the same time as 96 registers and five blocks.)
-template <bool HAVE_HI>
 __global__ void __launch_bounds__(SP1_THREADS)
 K_att_sp1(IceParams ice, KInput in, AttTables tb, Sp1Tables sp, WorkList worklist, const unsigned long long *work_count, int sparse_is_tmp,
           double *att_sparse, WorkList fallback, unsigned long long *fallback_count)
@@ -1199,25 +1187,26 @@ K_att_sp1(IceParams ice, KInput in, AttTables tb, Sp1Tables sp, WorkList worklis
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t bar;
     double *s_wk = reinterpret_cast<double *>(smem_raw);
-    double *s_E = s_wk + tb.Fs_pad * SP1_K;
-    double *stage = s_E + tb.Fs_pad + (threadIdx.x >> 5) * (32 * SP1_ROW);
-    stage_tables(&bar, s_wk, sp.wk, (uint32_t)tb.Fs_pad * SP1_K * 8u, s_E, sp.E, (uint32_t)tb.Fs_pad * 8u, nullptr, nullptr, 0u,
-                 nullptr, nullptr, 0u);
+    double *stage = s_wk + tb.Fs_pad * SP1_K + (threadIdx.x >> 5) * (32 * SP1_ROW);
+    stage_tables(&bar, s_wk, sp.wk, (uint32_t)tb.Fs_pad * SP1_K * 8u, nullptr, nullptr, 0u, nullptr, nullptr, 0u, nullptr, nullptr, 0u);
     const unsigned lane = threadIdx.x & 31u;
     const unsigned long long n_front = work_count[0], n_work = n_front + work_count[WL_BACK];
     const unsigned long long stride = (unsigned long long)gridDim.x * SP1_THREADS;
     for (unsigned long long w0 = (unsigned long long)blockIdx.x * SP1_THREADS + (threadIdx.x & ~31u); w0 < n_work; w0 += stride) {
         const unsigned long long w = w0 + lane;
-        double Mlo[SP1_K], Mhi[SP1_K];
+#ifndef SP1_NO_PREFETCH
+        if (w + stride < n_work) worklist_prefetch(worklist, worklist_index(worklist, n_front, w + stride));
+#endif
+        double M[SP1_KT];
 #pragma unroll
-        for (int k = 0; k < SP1_K; ++k) { Mlo[k] = 0.0; Mhi[k] = 0.0; }
+        for (int k = 0; k < SP1_KT; ++k) M[k] = 0.0;
         double *dst = nullptr;
         if (w < n_work) {
             SolRec rec = worklist_get(worklist, n_front, w);
             if (sparse_is_tmp) rec.row = (int64_t)worklist_index(worklist, n_front, w);   // scratch rows: work-list position
             AttPlan plan;
             att_plan_rec(ice, rec, plan);
-            const bool ok = sp1_path_ok(sp, plan.turned ? fmin(rec.zv, 0.0) : rec.z2, rec.z1);
+            const bool ok = rec.z1 >= -sp.depth_max;        // the whole path lies inside the temperature range of the series
             // k = 0 paths: panel 0 = [u_T, u_2] twice (after the turning point), panel 1 = [u_2, u_1] once
 #pragma unroll 1
             for (int panel = plan.turned ? 0 : 1; panel < 2 && ok; ++panel) {
@@ -1228,17 +1217,14 @@ K_att_sp1(IceParams ice, KInput in, AttTables tb, Sp1Tables sp, WorkList worklis
 #pragma unroll 1
                 for (int i = 0; i < SP1_NQ / 2; ++i) {                     // the symmetric node pair mid -+ half x_i: two independent chains
                     const double hx = half * c_glx12h[i], ws = scale * c_glw12h[i];
-                    sp1_node<HAVE_HI>(ice, plan, sp, mid - hx, ws, Mlo, Mhi);
-                    sp1_node<HAVE_HI>(ice, plan, sp, mid + hx, ws, Mlo, Mhi);
+                    sp1_node(ice, plan, sp, mid - hx, ws, M);
+                    sp1_node(ice, plan, sp, mid + hx, ws, M);
                 }
             }
             if (ok) dst = att_sparse + rec.row * (int64_t)tb.Fs;
-            else worklist_store(fallback, atomicAdd(fallback_count, 1ull), rec);          // out of the series' band: generic kernel
+            else worklist_store(fallback, atomicAdd(fallback_count, 1ull), rec);          // below the series' depth range: generic kernel
         }
-        const int n_lo = HAVE_HI ? sp.n_lo : tb.Fs;
-        for (int jb = 0; jb < n_lo; jb += SP1_SEG) sp1_emit(Mlo, s_wk, s_E, jb, min(jb + SP1_SEG, n_lo), stage, dst, lane);
-        if (HAVE_HI)
-            for (int jb = n_lo; jb < tb.Fs; jb += SP1_SEG) sp1_emit(Mhi, s_wk, s_E, jb, min(jb + SP1_SEG, tb.Fs), stage, dst, lane);
+        for (int jb = 0; jb < tb.Fs; jb += SP1_SEG) sp1_emit(M, s_wk, jb, min(jb + SP1_SEG, tb.Fs), stage, dst, lane);
     }
 }
 
@@ -1700,7 +1686,7 @@ int nrmc_rt_create(const nrmc_rt_config *cfg, nrmc_rt_t *out)
     nrmc_rt_s *h = new nrmc_rt_s();
     h->cfg = *cfg;
     IceParams &ice = h->ice;
-    ice.n_ice = cfg->n_ice; ice.dn = cfg->delta_n; ice.z0 = cfg->z_0; ice.inv_z0 = 1.0 / cfg->z_0;
+    ice.n_ice = cfg->n_ice; ice.dn = cfg->delta_n; ice.z0 = cfg->z_0; ice.inv_z0 = 1.0 / cfg->z_0; ice.inv_dn = 1.0 / cfg->delta_n;
     ice.ns = cfg->n_ice - cfg->delta_n;
     int n_refl = cfg->n_reflections;
     if (n_refl > 0 && !(cfg->reflection_z == cfg->reflection_z)) n_refl = 0;   // propagation_base_class.py:128-133
@@ -1873,87 +1859,47 @@ int nrmc_rt_set_frequencies(nrmc_rt_t h, const double *frequency, int32_t n, dou
     }
     h->have_sp1 = false;
     if (h->ice.att_model == NRMC_ATT_SP1 && h->ice.n_refl == 0) {
-        // tables of the SP1 moment kernel: w_j^k / k!, exp(p_ref w_j), band flag (attenuation.py:170-192)
+        // tables of the SP1 moment kernel: Chebyshev coefficients in the normalised temperature of 1/L(T, f_j) (attenuation.py:170-192)
         Sp1Tables &t = h->sp1;
-        t.pref_lo = 0.24; t.pref_hi = 1.75;
-        t.wabs_lo = t.wabs_hi = 0.0; t.n_lo = t.n_hi = 0;
-        t.wmin_lo = t.wmin_hi = INFINITY; t.wmax_lo = t.wmax_hi = -INFINITY;
-        const int band_pad = (Fs_pad + 3) & ~3;
-        std::vector<double> wk((size_t)Fs_pad * SP1_K, 0.0), E(Fs_pad, 0.0);
-        std::vector<int32_t> band(band_pad, 0);
-        for (int j = 0; j < Fs; ++j) {
+        const double SB0[3] = {-6.74890, 0.026709, -0.000884}, SB1[3] = {-6.22121, -0.070927, -0.001773}, SB2[3] = {-4.09468, -0.002213, -0.000332};
+        const double TC[4] = {1.83415e-09, -1.59061e-08, 0.00267687, -51.0696};          // temperature profile, attenuation.py:141-142
+        auto temp = [&](double a) { return ((TC[0] * a + TC[1]) * a + TC[2]) * a + TC[3]; };
+        const double T0 = temp(0.0), T1 = temp(SP1_DEPTH_MAX), Tmid = 0.5 * (T0 + T1), Thalf = 0.5 * (T1 - T0);
+        for (int m = 0; m < 4; ++m) t.tau[m] = (TC[m] - (m == 3 ? Tmid : 0.0)) / Thalf;
+        t.depth_max = SP1_DEPTH_MAX;
+        std::vector<double> wk((size_t)Fs_pad * SP1_K, 0.0);
+        bool series_ok = true;
+        const int NC = 64, KX = SP1_KT + 6;
+        for (int j = 0; j < Fs && series_ok; ++j) {
             const double w = log(sp[j]);
-            const int b = sp[j] < 1.0 ? 0 : 1;
-            band[j] = b;
-            E[j] = exp((b ? t.pref_hi : t.pref_lo) * w);
-            if (b) { ++t.n_hi; t.wabs_hi = std::max(t.wabs_hi, fabs(w)); t.wmin_hi = std::min(t.wmin_hi, w); t.wmax_hi = std::max(t.wmax_hi, w); }
-            else { ++t.n_lo; t.wabs_lo = std::max(t.wabs_lo, fabs(w)); t.wmin_lo = std::min(t.wmin_lo, w); t.wmax_lo = std::max(t.wmax_lo, w); }
-        }
-        // the series covers slopes within r of p_ref, r chosen so that |r w| <= 0.9 for every frequency of the band
-        const double r_lo = t.n_lo ? 0.9 / std::max(t.wabs_lo, 1e-300) : INFINITY, r_hi = t.n_hi ? 0.9 / std::max(t.wabs_hi, 1e-300) : INFINITY;
-        t.inv_r_lo = 1.0 / r_lo; t.inv_r_hi = 1.0 / r_hi;
-        for (int j = 0; j < Fs; ++j) {
-            const double w = log(sp[j]);
-#if SP1_CHEB
-            // exp(d w) = I_0(z) + 2 sum_k I_k(z) T_k(d / r), z = r w, |z| <= 0.9; I_k(z) = sum_m (z/2)^(2m+k) / (m! (m+k)!), I_k(-z) = (-1)^k I_k(z)
-            const double z = w == 0.0 ? 0.0 : (band[j] ? r_hi : r_lo) * w, hz = 0.5 * fabs(z);
-            for (int k = 0; k < SP1_K; ++k) {
-                double term = 1.0;
-                for (int i = 1; i <= k; ++i) term *= hz / i;                 // (z/2)^k / k!
+            const bool hi = !(sp[j] < 1.0);                                               // attenuation.py:180-185
+            double coef[KX], g[NC];
+            for (int m = 0; m < NC; ++m) {
+                const double T = Tmid + Thalf * cos(M_PI * (m + 0.5) / NC);
+                const double b0 = SB0[0] + T * (SB0[1] + T * SB0[2]), b1 = SB1[0] + T * (SB1[1] + T * SB1[2]), b2 = SB2[0] + T * (SB2[1] + T * SB2[2]);
+                const double q = b1 + (hi ? (b2 - b1) / 1.1505720275988207 : (b1 - b0) / 9.210340371976182) * w;
+                if (!(q < 0.0)) series_ok = false;                                        // 1 m floor (attenuation.py:252-255) within reach
+                g[m] = exp(q);
+            }
+            for (int k = 0; k < KX; ++k) {
                 double sum = 0.0;
-                for (int m = 0; m < 40; ++m) { sum += term; term *= hz * hz / ((m + 1.0) * (m + 1.0 + k)); }
-                wk[(size_t)j * SP1_K + k] = (k == 0 ? 1.0 : 2.0) * ((z < 0.0 && (k & 1)) ? -sum : sum);
+                for (int m = 0; m < NC; ++m) sum += g[m] * cos(k * M_PI * (m + 0.5) / NC);
+                coef[k] = (k == 0 ? 1.0 : 2.0) * sum / NC;
             }
-#else
-            double term = 1.0;
-            for (int k = 0; k < SP1_K; ++k) { wk[(size_t)j * SP1_K + k] = term; term *= w / (k + 1); }
-#endif
+            double tail = 0.0;
+            for (int k = SP1_KT; k < KX; ++k) tail += fabs(coef[k]);
+            if (!(tail <= SP1_TRUNCATION * fabs(coef[0]))) series_ok = false;            // this frequency set needs more moments
+            for (int k = 0; k < SP1_KT; ++k) wk[(size_t)j * SP1_K + k] = coef[k];
         }
-        {
-            // SP1 coefficients (attenuation.py:176-178): b_i(T) = c0 + c1 T + c2 T^2
-            const double B0[3] = {-6.74890, 0.026709, -0.000884}, B1[3] = {-6.22121, -0.070927, -0.001773}, B2[3] = {-4.09468, -0.002213, -0.000332};
-            const double s1 = 1.0 / 9.210340371976182, s2 = 1.0 / 1.1505720275988207;
-            double P1[3], P2[3];
-            for (int m = 0; m < 3; ++m) { P1[m] = (B1[m] - B0[m]) * s1; P2[m] = (B2[m] - B1[m]) * s2; }
-            for (int m = 0; m < 3; ++m) {
-                t.xlo[m] = (P1[m] - (m == 0 ? t.pref_lo : 0.0)) * t.inv_r_lo;
-                t.xhi[m] = (P2[m] - (m == 0 ? t.pref_hi : 0.0)) * t.inv_r_hi;
-            }
-            auto set = [&](int i, const double *q, double lo, double hi) {
-                t.qc[i] = q[0]; t.qb[i] = q[1]; t.qa[i] = q[2]; t.qlo[i] = lo; t.qhi[i] = hi;
-                t.qtv[i] = q[2] != 0.0 ? -q[1] / (2.0 * q[2]) : 0.0;
-            };
-            const double inf = INFINITY;
-            set(0, P1, t.pref_lo - r_lo, t.pref_lo + r_lo);
-            set(1, P2, t.pref_hi - r_hi, t.pref_hi + r_hi);
-            const double wl[4] = {t.wmin_lo, t.wmax_lo, t.wmin_hi, t.wmax_hi};
-            for (int j = 0; j < 4; ++j) {
-                const double *P = j < 2 ? P1 : P2;
-                const bool used = j < 2 ? t.n_lo > 0 : t.n_hi > 0;
-                double q[3];
-                for (int m = 0; m < 3; ++m) q[m] = B1[m] + (used ? P[m] * wl[j] : 0.0);
-                set(2 + j, q, -inf, -1e-300);      // exponent strictly below 0: 1/L < 1 / m
-            }
-        }
-        bool banded_in_order = true;      // the kernel emits [0, n_lo) from the low-band moments and [n_lo, Fs) from the high-band ones
-        for (int j = 0; j < Fs; ++j) if (band[j] != (j < t.n_lo ? 0 : 1)) banded_in_order = false;
-        const size_t b_wk = wk.size() * 8, b_E = E.size() * 8, b_band = band.size() * 4;
-        CK(h->d_sp1.reserve(b_wk + b_E + b_band + 64));
-        unsigned char *q = (unsigned char *)h->d_sp1.p;
-        CK(cudaMemcpy(q, wk.data(), b_wk, cudaMemcpyHostToDevice));
-        CK(cudaMemcpy(q + b_wk, E.data(), b_E, cudaMemcpyHostToDevice));
-        CK(cudaMemcpy(q + b_wk + b_E, band.data(), b_band, cudaMemcpyHostToDevice));
-        t.wk = (const double *)q; t.E = (const double *)(q + b_wk); t.band = (const int32_t *)(q + b_wk + b_E);
-        h->smem_sp1 = b_wk + b_E + (size_t)(SP1_THREADS / 32) * 32 * SP1_ROW * sizeof(double);
-        if (h->smem_sp1 <= 200 * 1024 && banded_in_order) {
-            if (h->smem_sp1 > 48 * 1024) {
-                CK(cudaFuncSetAttribute(K_att_sp1<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_sp1));
-                CK(cudaFuncSetAttribute(K_att_sp1<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_sp1));
-            }
-
+        const size_t b_wk = wk.size() * 8;
+        CK(h->d_sp1.reserve(b_wk + 64));
+        CK(cudaMemcpy(h->d_sp1.p, wk.data(), b_wk, cudaMemcpyHostToDevice));
+        t.wk = (const double *)h->d_sp1.p;
+        h->smem_sp1 = b_wk + (size_t)(SP1_THREADS / 32) * 32 * SP1_ROW * sizeof(double);
+        if (h->smem_sp1 <= 200 * 1024 && series_ok) {
+            if (h->smem_sp1 > 48 * 1024) CK(cudaFuncSetAttribute(K_att_sp1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_sp1));
             int nb = 0;
-            if (t.n_hi > 0) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, K_att_sp1<true>, SP1_THREADS, h->smem_sp1));
-            else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, K_att_sp1<false>, SP1_THREADS, h->smem_sp1));
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, K_att_sp1, SP1_THREADS, h->smem_sp1));
             h->grid_sp1 = std::max(1, nb) * h->n_sm;
             h->have_sp1 = true;
         }
@@ -2114,10 +2060,8 @@ static int launch_chunk(nrmc_rt_s *h, Lane &ln, int lane_id, cudaStream_t st, co
             }
             if (h->have_gl1)
                 K_att_gl1<<<h->grid_gl1, SP1_THREADS, h->smem_gl1, st>>>(h->ice, kin, tb, wl, d_count, sparse_is_tmp, sparse, fb, d_fb);
-            else if (h->sp1.n_hi > 0)
-                K_att_sp1<true><<<h->grid_sp1, SP1_THREADS, h->smem_sp1, st>>>(h->ice, kin, tb, h->sp1, wl, d_count, sparse_is_tmp, sparse, fb, d_fb);
             else
-                K_att_sp1<false><<<h->grid_sp1, SP1_THREADS, h->smem_sp1, st>>>(h->ice, kin, tb, h->sp1, wl, d_count, sparse_is_tmp, sparse, fb, d_fb);
+                K_att_sp1<<<h->grid_sp1, SP1_THREADS, h->smem_sp1, st>>>(h->ice, kin, tb, h->sp1, wl, d_count, sparse_is_tmp, sparse, fb, d_fb);
             if (ln.timed) cudaEventRecord(ln.kev[2], st);
             K_att<false><<<h->grid_att, ATT_THREADS, h->smem_att, st>>>(h->ice, kin, tb, fb, d_fb, nseg_max, sparse, nullptr);
             *n_launches += 2;

@@ -38,7 +38,7 @@ def apply_propagation_effects(spec, attenuation, reflection_angles, n_bottom_ref
         rt, rp = fresnel_r_p(a, 1.0, n_surface), fresnel_r_s(a, 1.0, n_surface)
         spec[1] *= rt
         spec[2] *= rp
-        r_theta, r_phi = r_theta * rt, r_phi * rp
+        r_theta, r_phi = rt, rp                                          # :2993-2994 overwrite: the field keeps the LAST reflection's
     k = int(n_bottom_reflections)
     if k > 0:                                                            # :3000-3010
         c = reflection_coefficient ** k * np.exp(1j * ((k * reflection_phase_shift) % (2 * np.pi)))

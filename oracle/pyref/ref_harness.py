@@ -29,8 +29,10 @@ _att = None
 _units = None
 
 
-def load_reference():
-    """Import the reference's analytic ray tracer from the scratch copy (plain Python path, no numba, no C++)."""
+def load_reference(patch_f4=True):
+    """Import the reference's analytic ray tracer from the scratch copy (plain Python path, no numba, no C++).
+    patch_f4=False leaves `obj_delta_y_square` untouched (the numba timing variant of ref_bench.py jit-compiles it;
+    only valid without bottom reflections)."""
     global _ray, _medium, _att, _units
     if _ray is not None:
         return _ray, _medium, _att
@@ -61,7 +63,8 @@ def load_reference():
     def _obj_copy(logC0, x1, *a, **k):
         return _orig(logC0, np.array(x1, dtype=float), *a, **k)
 
-    ray.obj_delta_y_square = _obj_copy
+    if patch_f4:
+        ray.obj_delta_y_square = _obj_copy
     _ray, _medium, _att, _units = ray, medium, attenuation, units
     return ray, medium, attenuation
 

@@ -9,7 +9,7 @@ extern "C" int harness_trace(double n_ice, double dn, double z0, double zr, int 
                              double *launch, double *receive, double *reflection_angle)
 {
     IceParams ice;
-    ice.n_ice = n_ice; ice.dn = dn; ice.z0 = z0; ice.inv_z0 = 1.0 / z0; ice.ns = n_ice - dn;
+    ice.n_ice = n_ice; ice.dn = dn; ice.z0 = z0; ice.inv_z0 = 1.0 / z0; ice.inv_dn = 1.0 / dn; ice.ns = n_ice - dn;
     ice.n_refl = n_refl; ice.zr = n_refl > 0 ? zr : -1e30;
     ice.gr = n_refl > 0 ? dn * exp(zr / z0) : 0.0; ice.nr = n_ice - ice.gr; ice.att_model = 0;
     TraceOutputs o = {n_sol, status, type, reflection, reflection_case, C0, C1, path_length, travel_time, launch, receive, reflection_angle};
@@ -24,7 +24,7 @@ extern "C" int harness_focusing(double n_ice, double dn, double z0, double zr, i
                                 const int8_t *reflection_case, const double *path_length, double limit, double *focusing)
 {
     IceParams ice;
-    ice.n_ice = n_ice; ice.dn = dn; ice.z0 = z0; ice.inv_z0 = 1.0 / z0; ice.ns = n_ice - dn;
+    ice.n_ice = n_ice; ice.dn = dn; ice.z0 = z0; ice.inv_z0 = 1.0 / z0; ice.inv_dn = 1.0 / dn; ice.ns = n_ice - dn;
     ice.n_refl = n_refl; ice.zr = n_refl > 0 ? zr : -1e30;
     ice.gr = n_refl > 0 ? dn * exp(zr / z0) : 0.0; ice.nr = n_ice - ice.gr; ice.att_model = 0;
     const int S = 2 + 4 * n_refl;

@@ -425,6 +425,12 @@ def test_propagation_effects_kernel(make, oracle_mod, tag, ice, att, n_refl):
         np.testing.assert_allclose(out[r], exp, rtol=1e-12, atol=1e-14)
         np.testing.assert_allclose([r_t[r], r_p[r]], [et, ep], rtol=1e-12)
         np.testing.assert_allclose(out[r], ref[r], rtol=1e-2, atol=1e-3 * np.abs(ref[r]).max())
+    # the coefficients the reference left on its field objects (the last surface reflection's, py:2993-2994)
+    ref_t, ref_p = g[f"{tag}_r_theta"][filled], g[f"{tag}_r_phi"][filled]
+    has = ~np.isnan(ref_t)
+    assert has.sum() > 0
+    np.testing.assert_allclose(r_t[has], ref_t[has], rtol=1e-9)
+    np.testing.assert_allclose(r_p[has], ref_p[has], rtol=1e-9)
     if n_refl == 0:
         out2 = rt.apply_propagation_effects_batch(spec_in, reflection_angle=res["reflection_angle"], reflection=res["reflection"],
                                                   attenuation_sparse=res["attenuation_sparse"])

@@ -1,73 +1,82 @@
 """
-CPU check of the mathematics behind the SP1 attenuation kernel (K_att_sp1, nuradiomc_b200/csrc/nrmc_rt.cu): the attenuation
-exponent  I(f) = sum_q c_q exp(p_q ln f)  over quadrature nodes q (c_q = ds-weight / L(z_q, 1 GHz), p_q the slope of
-ln(1/L) in ln f at the node's depth, attenuation.py:170-192) is evaluated from 8 frequency-independent Chebyshev moments
-per band,  I(f) = exp(p_ref w) sum_k eps_k I_k(r w) M_k,  M_k = sum_q c_q T_k((p_q - p_ref) / r),  w = ln f,  |r w| <= 0.9.
-Restated here in numpy with the kernel's three-term recurrence and the host code's Bessel series; truncation must stay
-below 2.5e-7 relative (the kernel's own budget; the parity tolerance on the attenuation factor is 1e-4).
+CPU check of the mathematics behind the SP1 attenuation kernel (K_att_sp1, nuradiomc_b200/csrc/nrmc_rt.cu).  The attenuation
+exponent of a path is  I(f) = sum_q w_q / L(z_q, f)  over quadrature nodes q with ds-weights w_q, and for SP1
+1/L(z, f) = exp(b1(T) + p(T) ln f): b1 and the slope p are quadratics in the ice temperature T, T a monotone cubic in depth
+(attenuation.py:141-142, :170-192).  The kernel expands, per integration frequency f_j, g_j(tau) = 1/L(T(tau), f_j) in
+Chebyshev polynomials of the normalised temperature tau in [-1, 1] (surface ... 2800 m):
+    I(f_j) = sum_k A_jk M_k,   M_k = sum_q w_q T_k(tau_q)     (12 frequency-independent moments, three-term recurrence)
+with A_jk from a 64-point Chebyshev-Gauss rule on the host (nrmc_rt_set_frequencies).  Restated here in numpy; the truncation
+must stay below 3e-7 relative (the kernel's budget; the parity tolerance on the attenuation factor is 1e-4).
 """
-import math
-
 import numpy as np
 
-K = 8
+K = 12
+NC = 64
+DEPTH_MAX = 2800.0
+B0, B1, B2 = (-6.74890, 0.026709, -0.000884), (-6.22121, -0.070927, -0.001773), (-4.09468, -0.002213, -0.000332)
+TC = (1.83415e-09, -1.59061e-08, 0.00267687, -51.0696)
 
 
-def bessel_table(z):
-    """eps_k I_k(z), k < K, by the ascending series -- the loop of nrmc_rt_set_frequencies (SP1 tables)"""
-    hz = 0.5 * abs(z)
-    out = np.zeros(K)
-    for k in range(K):
-        term = 1.0
-        for i in range(1, k + 1):
-            term *= hz / i
-        total = 0.0
-        for m in range(40):
-            total += term
-            term *= hz * hz / ((m + 1.0) * (m + 1.0 + k))
-        out[k] = (1.0 if k == 0 else 2.0) * (-total if (z < 0 and k & 1) else total)
-    return out
+def temperature(depth):
+    return ((TC[0] * depth + TC[1]) * depth + TC[2]) * depth + TC[3]
 
 
-def chebyshev_moments(c, x):
-    """M_k = sum_q c_q T_k(x_q) with t_{k+1} = 2 x t_k - t_{k-1}: sp1_node"""
+def inv_length(T, f):
+    """1 / L of attenuation.py:170-192 as a function of the ice temperature (f in GHz)"""
+    b = lambda B: B[0] + B[1] * T + B[2] * T * T
+    w = np.log(f)
+    slope = (b(B2) - b(B1)) / 1.1505720275988207 if f >= 1.0 else (b(B1) - b(B0)) / 9.210340371976182
+    return np.exp(b(B1) + slope * w)
+
+
+def chebyshev_table(f, n_coef):
+    """A_k of g(tau) = 1/L(T(tau), f): the host loop of nrmc_rt_set_frequencies"""
+    T0, T1 = temperature(0.0), temperature(DEPTH_MAX)
+    theta = np.pi * (np.arange(NC) + 0.5) / NC
+    g = inv_length(0.5 * (T0 + T1) + 0.5 * (T1 - T0) * np.cos(theta), f)
+    return np.array([(1.0 if k == 0 else 2.0) * np.sum(g * np.cos(k * theta)) / NC for k in range(n_coef)])
+
+
+def chebyshev_moments(w, tau):
+    """M_k = sum_q w_q T_k(tau_q) with t_{k+1} = 2 tau t_k - t_{k-1}: sp1_node"""
     M = np.zeros(K)
-    t0, t1 = c.copy(), c * x
+    t0, t1 = w.copy(), w * tau
     M[0], M[1] = t0.sum(), t1.sum()
     for k in range(2, K):
-        t0, t1 = t1, 2.0 * x * t1 - t0
+        t0, t1 = t1, 2.0 * tau * t1 - t0
         M[k] = t1.sum()
     return M
 
 
-def test_bessel_series_against_scipy():
-    from scipy.special import iv
-    for z in np.linspace(-0.9, 0.9, 19):
-        ref = np.array([(1 if k == 0 else 2) * iv(k, z) for k in range(K)])
-        np.testing.assert_allclose(bessel_table(z), ref, rtol=1e-14, atol=1e-300)
+def test_attenuation_length_restatement_matches_the_oracle():
+    """the temperature form above is the reference's SP1 model (checked through the C oracle's get_attenuation_length)"""
+    from oracle import oracle
+    oracle.build()
+    o = oracle.Oracle("southpole_2015", attenuation_model="SP1")
+    z = -np.linspace(1.0, 2790.0, 40)
+    for f in (0.005, 0.3, 0.99, 1.0, 1.7, 2.5):
+        L = np.array([o.attenuation_length(zz, f) for zz in z])
+        np.testing.assert_allclose(1.0 / inv_length(temperature(-z), f), L, rtol=1e-12)
 
 
 def test_moment_form_reproduces_the_direct_sum():
-    # SP1 slopes over the temperature range of South Pole ice (attenuation.py:141-142, :176-185)
-    B0, B1, B2 = (-6.74890, 0.026709, -0.000884), (-6.22121, -0.070927, -0.001773), (-4.09468, -0.002213, -0.000332)
-    b = lambda B, T: B[0] + B[1] * T + B[2] * T * T
     rng = np.random.default_rng(3)
-    freqs = np.concatenate([np.linspace(2.5 / 511, 1.2, 25), np.linspace(1.2 + 2.5 / 511, 2.5, 12)])     # cfg3 / cfg5 grid
-    for band, sel, pref in ((0, freqs < 1.0, 0.24), (1, freqs >= 1.0, 1.75)):
-        w = np.log(freqs[sel])
-        r = 0.9 / np.abs(w).max()
+    grids = {"cfg3/cfg5": np.concatenate([np.linspace(2.5 / 511, 1.2, 25), np.linspace(1.2 + 2.5 / 511, 2.5, 12)]),
+             "cfg1": np.linspace(0.5 / 128, 0.5, 100), "1 MHz .. 3 GHz": np.geomspace(1e-3, 3.0, 40)}
+    T0, T1 = temperature(0.0), temperature(DEPTH_MAX)
+    for name, freqs in grids.items():
         worst = 0.0
-        for _ in range(200):
-            depth = np.sort(rng.uniform(0, 2700, 24))
-            T = 1.83415e-09 * depth ** 3 - 1.59061e-08 * depth ** 2 + 0.00267687 * depth - 51.0696
-            p = (b(B1, T) - b(B0, T)) / 9.210340371976182 if band == 0 else (b(B2, T) - b(B1, T)) / 1.1505720275988207   # ln 1e4, ln 3.16
-            x = (p - pref) / r
-            if np.abs(x).max() > 1.0:        # outside the series' band: the kernel hands such paths to the generic kernel
-                continue
-            c = rng.uniform(0.1, 3.0, 24) * np.exp(b(B1, T))
-            M = chebyshev_moments(c, x)
-            for wj in w:
-                direct = np.sum(c * np.exp(p * wj))
-                series = math.exp(pref * wj) * float(bessel_table(r * wj) @ M)
+        for f in freqs:
+            A = chebyshev_table(f, K + 6)
+            assert np.abs(A[K:]).sum() <= 3e-7 * abs(A[0]), (name, f)          # the host's own acceptance test
+            assert inv_length(np.linspace(T0, T1, 200), f).max() < 1.0           # the 1 m floor is out of reach
+            for _ in range(20):
+                depth = rng.uniform(0, DEPTH_MAX, 24)
+                w = rng.uniform(0.1, 30.0, 24)
+                tau = (temperature(depth) - 0.5 * (T0 + T1)) / (0.5 * (T1 - T0))
+                assert np.abs(tau).max() <= 1.0
+                direct = np.sum(w * inv_length(temperature(depth), f))
+                series = float(A[:K] @ chebyshev_moments(w, tau))
                 worst = max(worst, abs(series / direct - 1.0))
-        assert 0 < worst < 2.5e-7, (band, worst)
+        assert 0 < worst < 3e-7, (name, worst)
+        print(name, "worst relative truncation", worst)
