@@ -401,7 +401,12 @@ class ray_tracing(ray_tracing_base):
             shape = ((rows,) + trail(S, K1, Fs, F)[1:]) if (compact and per_slot) else (N,) + trail(S, K1, Fs, F)
             if not (name in res and tuple(res[name].shape) == shape):
                 res[name] = torch.empty(shape, dtype=tdt[dtype], device=v.device)
-            setattr(o, name, res[name].data_ptr())
+            ptr = res[name].data_ptr()
+            if compact and per_slot and row_base:
+                # the kernels address every per-solution array as array[row_base + local row]: arrays that stay local (not in
+                # out_ptrs) are handed over shifted back by row_base rows, so that local row r lands in res[name][r]
+                ptr -= int(row_base) * int(np.prod(shape[1:], dtype=np.int64)) * res[name].element_size()
+            setattr(o, name, ptr)
         if compact:
             if not ("sol_offset" in res and tuple(res["sol_offset"].shape) == (N + 1,)):
                 res["sol_offset"] = torch.empty(N + 1, dtype=torch.int64, device=v.device)

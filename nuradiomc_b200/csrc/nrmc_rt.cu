@@ -12,6 +12,7 @@
 //
 // No tensor cores: nothing here is a contraction.  There is no CPU fallback: every entry point
 // fails with NRMC_ERR_NO_DEVICE / NRMC_ERR_CUDA if the device path is unavailable.
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -427,14 +428,6 @@ K_roots(IceParams ice, KInput in, TraceOutputs out, AttFill af, RootQ rootq, con
     for (unsigned long long w0 = (unsigned long long)blockIdx.x * ROOTS_THREADS + (threadIdx.x & ~31u); w0 < n; w0 += stride) {
         const unsigned long long w = w0 + lane;
         const bool active = w < n;
-#ifndef ROOTS_NO_PREFETCH
-        if (w + stride < n) {
-            const unsigned long long wn = w + stride, en = wn >> 1;
-            if ((lane & 1u) == 0) { prefetch_l2(rootq.pair + en); prefetch_l2(rootq.g1 + en); prefetch_l2(rootq.g2 + en); prefetch_l2(rootq.meta + en); }
-            prefetch_l2(reinterpret_cast<const double *>(rootq.a) + wn); prefetch_l2(reinterpret_cast<const double *>(rootq.ga) + wn);
-            prefetch_l2(reinterpret_cast<const double *>(rootq.b) + wn); prefetch_l2(reinterpret_cast<const double *>(rootq.gb) + wn);
-        }
-#endif
         bool valid = false;
         int64_t pair = 0;
         double viewing = NAN;
@@ -889,12 +882,9 @@ __device__ __forceinline__ double k_deepest(const IceParams &ice, const SolRec &
 // Generic attenuation kernel (all models, any number of bottom reflections): one warp per solution.
 // dynamic shared memory (doubles): fa[Fs_pad] fb[Fs_pad] it[F_pad] | ii[F_pad] (int32) | per warp: H[3][Fs_pad] fac[nseg][Fs_pad]
 template <bool GL3>
-__global__ void __launch_bounds__(ATT_THREADS)
-K_att(IceParams ice, KInput in, AttTables tb, WorkList worklist, const unsigned long long *work_count, int nseg_max, double *att_sparse,
-      double *att_dense)
+__device__ __forceinline__ void att_generic_body(const IceParams &ice, const AttTables &tb, const WorkList &worklist, const unsigned long long *work_count,
+                                                 int nseg_max, double *att_sparse, double *att_dense, unsigned char *smem_raw, uint64_t &bar)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ __align__(8) uint64_t bar;
     const bool dense = att_dense != nullptr;
     const int Fd_pad = dense ? tb.F_pad : 0;
     double *s_fa = reinterpret_cast<double *>(smem_raw);
@@ -1067,6 +1057,52 @@ K_att(IceParams ice, KInput in, AttTables tb, WorkList worklist, const unsigned 
         }
         __syncwarp();
     }
+}
+
+template <bool GL3>
+__global__ void __launch_bounds__(ATT_THREADS)
+K_att(IceParams ice, KInput in, AttTables tb, WorkList worklist, const unsigned long long *work_count, int nseg_max, double *att_sparse,
+      double *att_dense)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t bar;
+    att_generic_body<GL3>(ice, tb, worklist, work_count, nseg_max, att_sparse, att_dense, smem_raw, bar);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Small batches (the scalar API of the reference's production caller, simulation.py:173-210, is a batch of ONE pair): the binned
+// pipeline costs 5-8 launches whose fixed cost dwarfs the arithmetic.  One cooperative launch instead: phase 1 traces a pair per
+// thread (all modes, padded layout, work-list records), a grid-wide barrier, phase 2 integrates the attenuation with the generic
+// warp-per-solution code.  Used for N <= NRMC_SMALL_PAIRS pairs in the padded layout.
+// ---------------------------------------------------------------------------------------------------------------
+#define NRMC_SMALL_PAIRS 2048
+template <bool GL3>
+__global__ void __launch_bounds__(ATT_THREADS)
+K_small(IceParams ice, KInput in, TraceOutputs out, AttFill af, AttTables tb, WorkList worklist, unsigned long long *work_count, int nseg_max,
+        double *att_sparse, double *att_dense)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t bar;
+    const int S = 2 + 4 * ice.n_refl;
+    for (int64_t p = (int64_t)blockIdx.x * ATT_THREADS + threadIdx.x; p < in.n_pairs; p += (int64_t)gridDim.x * ATT_THREADS) {
+        double x1, y1, z1, x2, y2, z2;
+        load_pair(in, p, x1, y1, z1, x2, y2, z2);
+        const ShowerCut sc = load_cut(in, p);
+        SolRec recs[2 + 4 * NRMC_MAX_REFLECTIONS];
+        int n_recs = 0;
+        uint32_t cut_mask = 0;
+        const int n = trace_pair(ice, x1, y1, z1, x2, y2, z2, p, out, worklist.beta ? recs : nullptr, &sc, &n_recs, &cut_mask);
+        for (int sl = 0; sl < S; ++sl) {              // attenuation rows of the empty slots and of the cut solutions: NaN
+            if (sl < n && !((cut_mask >> sl) & 1u)) continue;
+            if (af.sparse) for (int j = 0; j < af.Fs; ++j) af.sparse[(p * S + sl) * af.Fs + j] = NAN;
+            if (af.dense) for (int j = 0; j < af.F; ++j) af.dense[(p * S + sl) * af.F + j] = NAN;
+        }
+        if (worklist.beta) for (int r = 0; r < n_recs; ++r) worklist_store(worklist, atomicAdd(work_count, 1ull), recs[r]);
+    }
+    if (!worklist.beta) return;
+    __threadfence();
+    cooperative_groups::this_grid().sync();
+    att_generic_body<GL3>(ice, tb, worklist, work_count, nseg_max, att_sparse, att_dense, smem_raw, bar);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -1638,6 +1674,9 @@ struct nrmc_rt_s {
     Sp1Tables sp1;
     bool have_sp1 = false, have_gl1 = false;
     int grid_att = 0, grid_sp1 = 0, grid_gl1 = 0;      // resident blocks (occupancy x SMs) of the persistent attenuation kernels
+    int grid_small = 0, grid_small_noatt = 0;          // the same for the cooperative small-batch kernel (with / without the attenuation tables)
+    void *small_host = nullptr;                        // pinned staging block of the small-batch host path (inputs and outputs in ONE copy each)
+    size_t small_host_cap = 0;
     int grid_hump = 0, grid_roots = 0;   // the same for the persistent solver kernels
     int grid_hump_m = 0, grid_roots_m = 0;
     int64_t chunk_pairs = 0;             // 0: automatic; > 0: pairs per chunk (nrmc_rt_set_chunk_pairs)
@@ -1719,6 +1758,8 @@ int nrmc_rt_create(const nrmc_rt_config *cfg, nrmc_rt_t *out)
         h->grid_hump_m = std::max(1, nb) * h->n_sm;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, K_roots_m, ROOTS_THREADS, 0) != cudaSuccess) { delete h; return NRMC_ERR_CUDA; }
         h->grid_roots_m = std::max(1, nb) * h->n_sm;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, K_small<false>, ATT_THREADS, 0) != cudaSuccess) { delete h; return NRMC_ERR_CUDA; }
+        h->grid_small_noatt = std::max(1, nb) * h->n_sm;
     }
     h->rmax.t = nullptr; h->rmax.n = 0; h->rmax.dz = RMAX_DZ;
     {
@@ -1766,6 +1807,7 @@ void nrmc_rt_destroy(nrmc_rt_t h)
         h->lanes[l].packed.release(); h->lanes[l].pack_sums.release(); h->lanes[l].pack_off.release(); h->lanes[l].modes.release();
     }
     h->d_tables.release(); h->d_gl3.release(); h->d_sp1.release(); h->d_count.release(); h->d_ant.release(); h->d_rmax.release();
+    if (h->small_host) cudaFreeHost(h->small_host);
     delete h;
 }
 
@@ -1848,6 +1890,13 @@ int nrmc_rt_set_frequencies(nrmc_rt_t h, const double *frequency, int32_t n, dou
         if (h->ice.att_model == NRMC_ATT_GL3) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, K_att<true>, ATT_THREADS, h->smem_att));
         else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, K_att<false>, ATT_THREADS, h->smem_att));
         h->grid_att = std::max(1, nb) * h->n_sm;
+        if (h->smem_att > 48 * 1024) {
+            CK(cudaFuncSetAttribute(K_small<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_att));
+            CK(cudaFuncSetAttribute(K_small<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_att));
+        }
+        if (h->ice.att_model == NRMC_ATT_GL3) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, K_small<true>, ATT_THREADS, h->smem_att));
+        else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, K_small<false>, ATT_THREADS, h->smem_att));
+        h->grid_small = std::max(1, nb) * h->n_sm;
     }
     h->have_gl1 = false;
     if (h->ice.att_model == NRMC_ATT_GL1 && h->ice.n_refl == 0 && !getenv("NRMC_GL1_GENERIC")) {     // (the variable: A/B and tests)
@@ -2121,6 +2170,122 @@ static void *out_ptr(const nrmc_rt_output *o, int i)
     return nullptr;
 }
 
+// one cooperative launch for a small batch in the padded layout (device pointers; scratch of lane `lane_id`)
+static int launch_small(nrmc_rt_s *h, Lane &ln, int lane_id, cudaStream_t st, const KInput &kin, const TraceOutputs &to, double *att_sparse,
+                        double *att_dense, int *n_launches)
+{
+    const bool want_att = att_sparse || att_dense;
+    unsigned long long *cnt = (unsigned long long *)h->d_count.p + CNT_STRIDE * lane_id;
+    const unsigned long long work_cap = (unsigned long long)kin.n_pairs * h->S;
+    WorkList wl;
+    memset(&wl, 0, sizeof(wl));
+    if (want_att) {
+        CK(ln.work.reserve(worklist_bytes(work_cap)));
+        wl = carve_worklist(ln.work.p, work_cap);
+        CK(cudaMemsetAsync(cnt, 0, CNT_STRIDE * sizeof(unsigned long long), st));
+    }
+    if (ln.timed) cudaEventRecord(ln.ev[0], st);
+    AttFill af;
+    af.sparse = att_sparse; af.dense = att_dense; af.Fs = h->tb.Fs; af.F = h->tb.F;
+    IceParams ice = h->ice;
+    KInput k = kin;
+    TraceOutputs t = to;
+    t.row_offset = nullptr; t.row_limit = 0;
+    AttTables tb = h->tb;
+    unsigned long long *d_count = cnt + CNT_WORK;
+    int nseg_max = h->ice.n_refl + 1;
+    const int64_t want_blocks = std::max<int64_t>((kin.n_pairs + ATT_THREADS - 1) / ATT_THREADS, want_att ? ((int64_t)work_cap + ATT_WARPS - 1) / ATT_WARPS : 1);
+    const int grid = (int)std::min<int64_t>(want_att ? h->grid_small : h->grid_small_noatt, want_blocks);
+    void *args[] = {&ice, &k, &t, &af, &tb, &wl, &d_count, &nseg_max, &att_sparse, &att_dense};
+    const void *fn = h->ice.att_model == NRMC_ATT_GL3 ? (const void *)K_small<true> : (const void *)K_small<false>;
+    CK(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(ATT_THREADS), args, want_att ? h->smem_att : 0, st));
+    ++*n_launches;
+    if (ln.timed) { cudaEventRecord(ln.ev[1], st); cudaEventRecord(ln.kev[0], st); cudaEventRecord(ln.kev[1], st); cudaEventRecord(ln.kev[2], st); cudaEventRecord(ln.ev[2], st); }
+    return NRMC_OK;
+}
+
+static void accumulate_lane_times(Lane &ln, float *ms);
+static void store_times(nrmc_rt_stats *stats, const float *ms);
+static void *out_ptr(const nrmc_rt_output *o, int i);
+
+// Host-memory call on a small batch: ONE pinned staging block carries all inputs to the device in one copy and all outputs back
+// in one copy (a scalar call of the Python class spent 230 us in ~20 separate copies, launches and synchronisations)
+#define NRMC_SMALL_STAGE_MAX ((size_t)8 << 20)
+static int trace_small_host(nrmc_rt_s *h, const nrmc_rt_input *in, const nrmc_rt_output *out, nrmc_rt_stats *stats, int64_t N, const size_t *elem)
+{
+    Lane &ln = h->lanes[0];
+    cudaStream_t st = ln.stream;
+    const int64_t nv = in->n_vertices, na = in->n_antennas;
+    const size_t n_in = (size_t)(3 * nv + 3 * na + (in->sx ? 3 * nv : 0));
+    const size_t in_bytes = (n_in * 8 + 15) & ~(size_t)15;
+    bool want[N_OUT];
+    size_t off[N_OUT], total = 0;
+    for (int i = 0; i < N_OUT; ++i) {
+        want[i] = out_ptr(out, i) != nullptr;
+        off[i] = total;
+        if (want[i]) total += ((size_t)N * elem[i] + 15) & ~(size_t)15;
+    }
+    const bool staged = total <= NRMC_SMALL_STAGE_MAX;
+    const size_t need = in_bytes + (staged ? total : 0);
+    if (need > h->small_host_cap) {
+        if (h->small_host) cudaFreeHost(h->small_host);
+        h->small_host = nullptr; h->small_host_cap = 0;
+        const size_t cap = std::max(need, (size_t)1 << 16);
+        CK(cudaHostAlloc(&h->small_host, cap, cudaHostAllocDefault));
+        h->small_host_cap = cap;
+    }
+    double *hin = (double *)h->small_host;
+    memcpy(hin, in->vx, nv * 8); memcpy(hin + nv, in->vy, nv * 8); memcpy(hin + 2 * nv, in->vz, nv * 8);
+    memcpy(hin + 3 * nv, in->ax, na * 8); memcpy(hin + 3 * nv + na, in->ay, na * 8); memcpy(hin + 3 * nv + 2 * na, in->az, na * 8);
+    if (in->sx) { double *hs = hin + 3 * nv + 3 * na; memcpy(hs, in->sx, nv * 8); memcpy(hs + nv, in->sy, nv * 8); memcpy(hs + 2 * nv, in->sz, nv * 8); }
+    CK(ln.in.reserve(in_bytes));
+    CK(ln.out.reserve(std::max<size_t>(total, 16)));
+    cudaEvent_t e0 = ln.ev[3], e1 = ln.ev[4];
+    if (stats) cudaEventRecord(e0, st);
+    CK(cudaMemcpyAsync(ln.in.p, hin, n_in * 8, cudaMemcpyHostToDevice, st));
+    double *din = (double *)ln.in.p;
+    KInput kin;
+    kin.outer = in->outer; kin.n_antennas = na; kin.n_pairs = N; kin.delta_C_cut = in->delta_C_cut;
+    kin.vx = din; kin.vy = din + nv; kin.vz = din + 2 * nv; kin.ax = din + 3 * nv; kin.ay = din + 3 * nv + na; kin.az = din + 3 * nv + 2 * na;
+    kin.sx = kin.sy = kin.sz = nullptr;
+    if (in->sx) { kin.sx = din + 3 * nv + 3 * na; kin.sy = kin.sx + nv; kin.sz = kin.sx + 2 * nv; }
+    unsigned char *dout = (unsigned char *)ln.out.p;
+    auto dp = [&](int i) -> void * { return want[i] ? (void *)(dout + off[i]) : nullptr; };
+    TraceOutputs to;
+    to.n_sol = (int32_t *)dp(0); to.status = (int32_t *)dp(1); to.type = (int8_t *)dp(2); to.reflection = (int8_t *)dp(3);
+    to.reflection_case = (int8_t *)dp(4); to.C0 = (double *)dp(5); to.C1 = (double *)dp(6); to.path_length = (double *)dp(7);
+    to.travel_time = (double *)dp(8); to.launch = (double *)dp(9); to.receive = (double *)dp(10); to.reflection_angle = (double *)dp(11);
+    to.viewing_angle = (double *)dp(14);
+    to.row_offset = nullptr; to.row_limit = 0;
+    ln.timed = (stats != nullptr);
+    int n_launches = 0;
+    const int rc = launch_small(h, ln, 0, st, kin, to, (double *)dp(12), (double *)dp(13), &n_launches);
+    if (rc != NRMC_OK) { ln.timed = false; return rc; }
+    int64_t d2h = 0;
+    unsigned char *hout = (unsigned char *)h->small_host + in_bytes;
+    if (staged) {
+        if (total) CK(cudaMemcpyAsync(hout, dout, total, cudaMemcpyDeviceToHost, st));
+        d2h = (int64_t)total;
+    } else {
+        for (int i = 0; i < N_OUT; ++i)
+            if (want[i]) { CK(cudaMemcpyAsync(out_ptr(out, i), dout + off[i], (size_t)N * elem[i], cudaMemcpyDeviceToHost, st)); d2h += (int64_t)N * elem[i]; }
+    }
+    if (stats) cudaEventRecord(e1, st);
+    CK(cudaStreamSynchronize(st));
+    if (staged) for (int i = 0; i < N_OUT; ++i) if (want[i]) memcpy(out_ptr(out, i), hout + off[i], (size_t)N * elem[i]);
+    if (stats) {
+        float ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        accumulate_lane_times(ln, ms);
+        cudaEventElapsedTime(&stats->ms_total, e0, e1);
+        store_times(stats, ms);
+        stats->n_pairs = N; stats->n_launches = n_launches; stats->n_chunks = 1;
+        stats->h2d_bytes = (int64_t)n_in * 8; stats->d2h_bytes = d2h;
+        if (out->n_sol) { int64_t n = 0; for (int64_t i = 0; i < N; ++i) n += out->n_sol[i]; stats->n_solutions = n; }
+    }
+    ln.timed = false;
+    return NRMC_OK;
+}
+
 extern "C" int nrmc_rt_trace(nrmc_rt_t h, const nrmc_rt_input *in, const nrmc_rt_output *out, void *stream, nrmc_rt_stats *stats)
 {
     if (!h || !in || !out) return NRMC_ERR_INVALID_ARGUMENT;
@@ -2158,6 +2323,7 @@ extern "C" int nrmc_rt_trace(nrmc_rt_t h, const nrmc_rt_input *in, const nrmc_rt
         int rc = NRMC_OK, n_chunks = 0;
         unsigned long long *row_base_dev = (unsigned long long *)h->d_count.p + CNT_ROWBASE;
         if (compact) K_set_u64<<<1, 1, 0, user>>>(row_base_dev, (unsigned long long)out->row_base);   // first row of this call's solutions
+        const bool small = !compact && h->chunk_pairs == 0 && N <= NRMC_SMALL_PAIRS && !getenv("NRMC_NO_SMALL_PATH");
         for (int64_t p0 = 0; p0 < N && rc == NRMC_OK; p0 += chunk, ++n_chunks) {
             const int64_t np = std::min(chunk, N - p0);
             const int64_t ps = compact ? 0 : p0 * S;        // first row of the chunk in the per-slot arrays (compact: rows are global)
@@ -2200,8 +2366,11 @@ extern "C" int nrmc_rt_trace(nrmc_rt_t h, const nrmc_rt_input *in, const nrmc_rt
             ln.timed = (stats != nullptr);
             CompactCtx cc;
             if (compact) { cc.on = true; cc.sol_offset = out->sol_offset + p0; cc.base_dev = row_base_dev; cc.row_limit = out->row_base + out->row_capacity; }
-            rc = launch_chunk(h, ln, DEV_LANE, user, kin, to, out->attenuation_sparse ? out->attenuation_sparse + ps * Fs : nullptr,
-                              out->attenuation ? out->attenuation + ps * F : nullptr, &n_launches, cc);
+            if (small)
+                rc = launch_small(h, ln, DEV_LANE, user, kin, to, out->attenuation_sparse, out->attenuation, &n_launches);
+            else
+                rc = launch_chunk(h, ln, DEV_LANE, user, kin, to, out->attenuation_sparse ? out->attenuation_sparse + ps * Fs : nullptr,
+                                  out->attenuation ? out->attenuation + ps * F : nullptr, &n_launches, cc);
             if (rc == NRMC_OK && stats) {
                 accumulate_lane_times(ln, ms);
                 if (want_att) {
@@ -2233,6 +2402,8 @@ extern "C" int nrmc_rt_trace(nrmc_rt_t h, const nrmc_rt_input *in, const nrmc_rt
         return rc;
     }
 
+    // ---------------- host memory, small batch in the padded layout: one staged copy each way, one cooperative launch --------
+    if (!compact && h->chunk_pairs == 0 && N <= NRMC_SMALL_PAIRS && !getenv("NRMC_NO_SMALL_PATH")) return trace_small_host(h, in, out, stats, N, elem);
     // ---------------- host memory: chunked, two lanes (streams) so copies of one chunk overlap kernels of the other --------
     const int64_t na = in->n_antennas;
     size_t per_pair = 0;

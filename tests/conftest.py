@@ -10,6 +10,12 @@ if ROOT not in sys.path:
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 
+# The GPU parity tests exist to check the production kernels (binned solver, moment / thread-per-solution attenuation kernels).
+# Batches of <= 2048 pairs in the padded layout would take the fused small-batch launch (K_small) instead; it is switched off for
+# the suite and checked by its own tests (test_small_batch_path_*, which delete the variable again).
+os.environ.setdefault("NRMC_NO_SMALL_PATH", "1")
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 

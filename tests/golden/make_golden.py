@@ -252,8 +252,80 @@ def make_focusing_golden():
     np.savez_compressed(os.path.join(HERE, "focusing.npz"), **out)
 
 
+def _n3_work(args):
+    """the ray-tracing part of the reference's per-(shower, channel) loop (NuRadioMC/simulation/simulation.py:155-210) with the
+    reference propagator, and the per-station HDF5 datasets as output_writer_hdf5.py:267-294 assembles them"""
+    ice, n_refl, V, axes, A, delta_C_cut = args
+    import ref_harness as rh
+    sys.path.insert(0, os.path.join(REPO, "oracle", "pyref", "stubs"))
+    from radiotools import helper as hp
+    r = rh.make_tracer(ice, n_reflections=n_refl)
+    nS = r.get_number_of_raytracing_solutions()
+    nSh, nCh = len(V), len(A)
+    ds = {k: np.full((nSh, nCh, nS), np.nan) for k in ("travel_times", "travel_distances", "ray_tracing_C0", "ray_tracing_C1",
+                                                        "ray_tracing_reflection", "ray_tracing_reflection_case",
+                                                        "ray_tracing_solution_type", "focusing_factor", "viewing_angles")}
+    ds["launch_vectors"] = np.full((nSh, nCh, nS, 3), np.nan)
+    ds["receive_vectors"] = np.full((nSh, nCh, nS, 3), np.nan)
+    n_sol = np.zeros((nSh, nCh), np.int32)
+    medium = r._medium
+    for iSh in range(nSh):
+        x1 = V[iSh]
+        shower_direction = -1 * axes[iSh]                                   # simulation.py:175
+        cherenkov_angle = np.arccos(1. / medium.get_index_of_refraction(x1))
+        for iCh in range(nCh):
+            r.set_start_and_end_point(x1, A[iCh])
+            r.find_solutions()
+            if not r.has_solution():
+                continue
+            n = r.get_number_of_solutions()
+            n_sol[iSh, iCh] = n
+            viewing = np.array([np.arccos(np.clip(np.dot(shower_direction, r.get_launch_vector(iS)) / np.linalg.norm(shower_direction), -1, 1))
+                                for iS in range(n)])                        # hp.get_angle (:191)
+            delta_Cs = viewing - cherenkov_angle
+            if min(np.abs(delta_Cs)) > delta_C_cut:                         # :195-197
+                continue
+            for iS in range(n):
+                if np.abs(delta_Cs[iS]) > delta_C_cut:                      # :204-206
+                    continue
+                ds["travel_distances"][iSh, iCh, iS] = r.get_path_length(iS)
+                ds["travel_times"][iSh, iCh, iS] = r.get_travel_time(iS)
+                ds["viewing_angles"][iSh, iCh, iS] = viewing[iS]
+                ds["launch_vectors"][iSh, iCh, iS] = r.get_launch_vector(iS)
+                zen, az = hp.cartesian_to_spherical(*r.get_receive_vector(iS))      # simulation.py stores zenith / azimuth ...
+                ds["receive_vectors"][iSh, iCh, iS] = hp.spherical_to_cartesian(zen, az)   # ... output_writer_hdf5.py:289-290
+                for key, value in r.get_raytracing_output(iS).items():      # efp.raytracing_solution (output_writer_hdf5.py:283-286)
+                    ds[key][iSh, iCh, iS] = value
+    ds["n_sol"] = n_sol
+    return ds
+
+
+def make_n3_golden():
+    """fixture of the caller either side of the path: the reference's scalar loop + HDF5 dataset layout"""
+    rng = np.random.default_rng(66)
+    out = {}
+    pool = Pool(8)
+    for tag, ice, n_refl, V, A in (
+            ("sp", "southpole_2015", 0, cylinder(61, 48, 3000., -2500.), np.array([[0, 0, -150.], [10, 10, -190.], [-8, 3, -60.], [3, -9, -2.]])),
+            ("mb", "mooresbay_simple", 1, cylinder(62, 24, 800., -500.), np.array([[3, 3, -5.], [-3, 0, -1.], [0, 3, -1.]]))):
+        axes = rng.normal(size=(len(V), 3))
+        axes /= np.linalg.norm(axes, axis=1)[:, None]
+        cut = 40. * np.pi / 180.                                            # config_default.yaml speedup.delta_C_cut
+        chunk = 6
+        parts = pool.map(_n3_work, [(ice, n_refl, V[lo:lo + chunk], axes[lo:lo + chunk], A, cut) for lo in range(0, len(V), chunk)])
+        for k in parts[0]:
+            out[f"{tag}_{k}"] = np.concatenate([p[k] for p in parts], axis=0)
+        out.update({f"{tag}_vertices": V, f"{tag}_shower_axes": axes, f"{tag}_channels": A, f"{tag}_delta_C_cut": np.array(cut),
+                    f"{tag}_ice": ice, f"{tag}_n_reflections": n_refl})
+        kept = int(np.isfinite(out[f"{tag}_travel_times"]).sum())
+        print(f"n3 {tag}: {len(V)} showers x {len(A)} channels, solutions {int(out[f'{tag}_n_sol'].sum())}, kept after the viewing-angle cut {kept}", flush=True)
+    np.savez_compressed(os.path.join(HERE, "simulation_datasets.npz"), **out)
+
+
 if __name__ == "__main__":
-    if sys.argv[1:] == ["effects"]:
+    if sys.argv[1:] == ["n3"]:
+        make_n3_golden()
+    elif sys.argv[1:] == ["effects"]:
         make_effects_golden()
     elif sys.argv[1:] == ["focusing"]:
         make_focusing_golden()

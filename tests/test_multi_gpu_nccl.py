@@ -49,6 +49,14 @@ def _worker(rank, world, port, V, A, ff, ret):
     for _ in range(2):          # twice: the block is reused from step to step
         pg.trace(dv, da, **kw)
         pg.finish()
+    # records only: the factors stay in the HBM of the rank that computed them, in LOCAL rows
+    pr = P2PGather(rt, n_local, names=[k for k in ROW_KEYS if k != "attenuation_sparse"], Fs=Fs)
+    loc = pr.trace(dv, da, **kw)
+    pr.finish()
+    ret[f"local_att_{rank}"] = loc["attenuation_sparse"][:loc.n_rows()].cpu().numpy()
+    if rank == 0:
+        ret["p2p_records"] = {k: v.cpu().numpy() for k, v in pr.compacted().items()}
+    pr.close()
     if rank == 0:
         for k in KEYS:
             ret[k] = full[k].cpu().numpy()
@@ -87,6 +95,11 @@ def test_sharded_trace_and_gather_equal_single_device():
         np.testing.assert_array_equal(g["sol_offset"], onec["sol_offset"], err_msg=tag)
         for k in ROW_KEYS:
             np.testing.assert_array_equal(g[k][:n_rows], onec[k][:n_rows], err_msg=f"{tag} {k}")
+    g = ret["p2p_records"]
+    for k in ROW_KEYS:
+        if k != "attenuation_sparse":
+            np.testing.assert_array_equal(g[k][:n_rows], onec[k][:n_rows], err_msg=f"p2p records {k}")
+    np.testing.assert_array_equal(np.concatenate([ret["local_att_0"], ret["local_att_1"]]), onec["attenuation_sparse"][:n_rows])
     # the un-compacted peer block: rank 1's rows start at its segment base and are addressed by sol_offset / n_sol
     raw, n_pairs0 = ret["p2p_raw"], (5001 // 2 + 1) * 3
     assert raw["sol_offset"][n_pairs0] == ret["row_base"][1]
