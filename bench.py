@@ -306,6 +306,7 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=8.0, help="seconds of CPU work per cpu_baseline entry")
     ap.add_argument("--gather", default="all", choices=["all", "p2p", "nccl", "none"])
     ap.add_argument("--gather-steps", type=int, default=0, help="0: min(steps, 5)")
+    ap.add_argument("--gather-chunks", type=int, default=8, help="chunks per rank of the pipelined p2p-dma gather")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -598,6 +599,8 @@ def run_gathered(args, rt, dv, da, kw, out_local, meas, n_pairs_rank, n_pairs_to
 
     variants = []
     if args.gather in ("all", "p2p"):
+        if world > 1:
+            variants.append(("p2p-dma", "records+sparse", row_names))
         variants.append(("p2p", "records+sparse", row_names))
         if any(n.startswith("attenuation") for n in row_names):
             variants.append(("p2p", "records", [n for n in row_names if not n.startswith("attenuation")]))
@@ -605,16 +608,20 @@ def run_gathered(args, rt, dv, da, kw, out_local, meas, n_pairs_rank, n_pairs_to
         key = f"{kind}:{what}"
         try:
             pg = nd.P2PGather(rt, n_pairs_rank, names=names, Fs=Fs, F=F, rows_per_pair=rows_per_pair + 1024.0 / max(n_pairs_rank, 1))
+            run = (lambda: pg.trace_pushed(dv, da, n_chunks=args.gather_chunks, **kw_g)) if kind == "p2p-dma" else (lambda: pg.trace(dv, da, **kw_g))
             for _ in range(2):
-                pg.trace(dv, da, **kw_g)
+                run()
             pg.finish()
-            ms_dev, ms_host = timed(lambda: pg.trace(dv, da, **kw_g))
+            ms_dev, ms_host = timed(run)
             n_rows = int(meas["n_solutions"])
             nv = torch.tensor([float(pg.nvlink_bytes(n_rows))], device=dev, dtype=torch.float64)
             if world > 1:
                 dist.all_reduce(nv)
             entry = {"value": n_pairs_total / (max(ms_dev, ms_host) * 1e-3), "unit": "pairs/s", "ms_per_step": max(ms_dev, ms_host),
-                     "gather": what, "variant": "p2p: kernels store into rank 0's HBM through NVLink peer mappings (no collective, no staging)",
+                     "gather": what,
+                     "variant": ("p2p-dma: chunk-pipelined -- while chunk c+1 computes, the copy engines push the rows of chunk c into rank 0's "
+                                 "HBM (peer-to-peer cudaMemcpyAsync into the mapped block, %d chunks per rank)" % args.gather_chunks) if kind == "p2p-dma"
+                     else "p2p: kernels store into rank 0's HBM through NVLink peer mappings (no collective, no staging)",
                      "nvlink_bytes_per_step": int(nv.item()), "rank0_block_bytes": pg.block_bytes}
             entry["nvlink_gbs_into_rank0"] = entry["nvlink_bytes_per_step"] / (entry["ms_per_step"] * 1e-3) / 1e9
             # integrity: a checksum of the gathered rows against the sum of the ranks' local checksums
@@ -664,7 +671,7 @@ def run_gathered(args, rt, dv, da, kw, out_local, meas, n_pairs_rank, n_pairs_to
             torch.cuda.empty_cache()
         except Exception as e:
             res[key] = {"error": repr(e)[:400]}
-    ok = [k for k in ("p2p:records+sparse", "nccl:records+sparse", "p2p:records") if k in res and "value" in res[k]]
+    ok = [k for k in ("p2p-dma:records+sparse", "p2p:records+sparse", "nccl:records+sparse", "p2p:records") if k in res and "value" in res[k]]
     full = [k for k in ok if res[k]["gather"] == "records+sparse"] or ok
     if full:
         res["headline"] = max(full, key=lambda k: res[k]["value"])

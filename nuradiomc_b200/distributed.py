@@ -292,6 +292,83 @@ class P2PGather:
                        None, "copy_async")
         return res
 
+    def trace_pushed(self, v, a, n_chunks=4, **kw):
+        """
+        The same gather with the rows moved by the copy engines instead of by the kernels' own stores ("p2p-dma"): the rank's
+        vertices are traced chunk by chunk into local HBM (two alternating buffers); while chunk c+1 computes, the filled rows
+        of chunk c are pushed into this rank's segment of the gathering rank's block by peer-to-peer cudaMemcpyAsync on a
+        second stream (full-line NVLink writes at wire speed; the kernels' own 8-byte row stores reach about half of that).
+        The only host involvement is reading one row count per chunk.  Same layout on the gathering rank as `trace`.
+        """
+        import torch
+        from nuradiomc_b200 import _lib
+        from nuradiomc_b200.SignalProp.analyticraytracing import BatchResult
+        r, dev = self.rank, torch.device("cuda", self.device)
+        outer = kw.get("outer", False)
+        na = a.shape[1] if outer else 1
+        nv = v.shape[1]
+        n_chunks = max(1, min(int(n_chunks), nv))
+        key = (v.data_ptr(), nv, n_chunks)
+        if getattr(self, "_push_key", None) != key:
+            bounds = [shard_bounds(nv, n_chunks, c) for c in range(n_chunks)]
+            self._push_chunks = [(lo, hi, v[:, lo:hi].contiguous()) for lo, hi in bounds]
+            self._push_bufs = [BatchResult(), BatchResult()]
+            self._push_counts = torch.zeros(n_chunks, dtype=torch.int64).pin_memory()
+            self._push_streams = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)]   # two copy engines share the rows
+            self._push_key = key
+        compute = torch.cuda.current_stream(dev)
+        copy, copy2 = self._push_streams
+        cap_chunk = max(self.row_caps[r] // n_chunks + 1024, 1024)
+        ev_done, ev_copied = [None] * n_chunks, [None] * n_chunks
+        state = {"rows": 0, "pairs": 0}
+
+        def push(c):
+            lo, hi, _ = self._push_chunks[c]
+            res = self._push_bufs[c % 2]
+            n_pairs_c = (hi - lo) * na
+            ev_done[c].synchronize()                       # the GPU is already busy with chunk c + 1
+            n = int(self._push_counts[c])
+            row0 = self.row_base[r] + state["rows"]
+            with torch.cuda.stream(copy):
+                copy.wait_event(ev_done[c])
+                copy2.wait_event(ev_done[c])
+                res["sol_offset"][:n_pairs_c].add_(row0)   # global rows of this chunk's pairs
+                cs, cs2 = copy.cuda_stream, copy2.cuda_stream
+                half = n // 2
+                for name in self.names:
+                    off, shape, dt = self.layout[name]
+                    rb = int(np.prod(shape[1:], dtype=np.int64)) * dt.itemsize
+                    dst, src = self.base + off + row0 * rb, res[name].data_ptr()
+                    _lib.check(self.lib.nrmc_rt_copy_async(C.c_void_p(dst), C.c_void_p(src), half * rb, C.c_void_p(cs)), None, "copy_async")
+                    _lib.check(self.lib.nrmc_rt_copy_async(C.c_void_p(dst + half * rb), C.c_void_p(src + half * rb), (n - half) * rb,
+                                                           C.c_void_p(cs2)), None, "copy_async")
+                p0 = self.pair_base[r] + state["pairs"]
+                for name in PER_PAIR:
+                    if name in res:
+                        off, _, dt = self.layout[name]
+                        _lib.check(self.lib.nrmc_rt_copy_async(C.c_void_p(self.base + off + p0 * dt.itemsize), C.c_void_p(res[name].data_ptr()),
+                                                               n_pairs_c * dt.itemsize, C.c_void_p(cs)), None, "copy_async")
+                copy.wait_stream(copy2)
+                ev_copied[c] = torch.cuda.Event()
+                ev_copied[c].record(copy)
+            state["rows"] += n
+            state["pairs"] += n_pairs_c
+        for c in range(n_chunks):
+            lo, hi, vc = self._push_chunks[c]
+            if c >= 2:
+                compute.wait_event(ev_copied[c - 2])       # the buffer is free once its rows have left
+            res = self.rt.trace_batch_device(vc, a, compact=True, out=self._push_bufs[c % 2], row_capacity=cap_chunk, **kw)
+            self._push_bufs[c % 2] = res
+            self._push_counts[c:c + 1].copy_(res["sol_offset"][(hi - lo) * na:(hi - lo) * na + 1], non_blocking=True)
+            ev_done[c] = torch.cuda.Event()
+            ev_done[c].record(compute)
+            if c >= 1:
+                push(c - 1)
+        push(n_chunks - 1)
+        compute.wait_stream(copy)
+        self.n_rows_pushed = state["rows"]
+        return state["rows"]
+
     def finish(self):
         """wait for this rank's stores, then for everybody's: afterwards `arrays` on the gathering rank is complete"""
         import torch

@@ -49,6 +49,14 @@ def _worker(rank, world, port, V, A, ff, ret):
     for _ in range(2):          # twice: the block is reused from step to step
         pg.trace(dv, da, **kw)
         pg.finish()
+    # the same gather with the rows pushed by the copy engines, chunk-pipelined
+    pd = P2PGather(rt, n_local, names=ROW_KEYS, Fs=Fs)
+    for _ in range(2):
+        pd.trace_pushed(dv, da, n_chunks=3, **kw)
+        pd.finish()
+    if rank == 0:
+        ret["p2p_dma"] = {k: v.cpu().numpy() for k, v in pd.compacted().items()}
+    pd.close()
     # records only: the factors stay in the HBM of the rank that computed them, in LOCAL rows
     pr = P2PGather(rt, n_local, names=[k for k in ROW_KEYS if k != "attenuation_sparse"], Fs=Fs)
     loc = pr.trace(dv, da, **kw)
@@ -89,7 +97,7 @@ def test_sharded_trace_and_gather_equal_single_device():
     onec = rt.trace_batch(V, A, outer=True, frequency=ff, max_detector_freq=0.6, attenuation="sparse", compact=True)
     n_rows = int(onec["sol_offset"][-1])
     assert n_rows > 1000
-    for tag in ("nccl", "p2p"):
+    for tag in ("nccl", "p2p", "p2p_dma"):
         g = ret[tag]
         np.testing.assert_array_equal(g["n_sol"], onec["n_sol"], err_msg=tag)
         np.testing.assert_array_equal(g["sol_offset"], onec["sol_offset"], err_msg=tag)
