@@ -63,6 +63,17 @@ __device__ __forceinline__ double exp_c_neg(double x)
     const double p = expm1_poly(r) + 1.0;
     return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
 }
+// x <= 0 of any size, degree-8 polynomial (truncation 2e-10 relative): the factors the thread-per-solution kernels emit
+__device__ __forceinline__ double exp_c_neg8(double x)
+{
+    int k;
+    const double r = exp_reduce(x > -700.0 ? x : -700.0, k);
+    double p = c_expc[3];
+#pragma unroll
+    for (int i = 4; i < 10; ++i) p = fma(p, r, c_expc[i]);
+    const double q = fma(p * r, r, r) + 1.0;
+    return __hiloint2double(__double2hiint(q) + (k << 20), __double2loint(q));
+}
 __device__ __forceinline__ double expm1_c_neg(double x)    // -700 < x <= 0
 {
     int k;
@@ -224,7 +235,7 @@ NRMC_HD void att_node(int model, double z, const Gl3Table &gl3, AttNode &nd)
         break; }
     case 2: {   // GL1 attenuation.py:99-128: 75 MHz length, floored at 100 m
         double L = (((( -3.63912864e-14 * z - 2.21040482e-10) * z - 3.50628312e-07) * z - 9.82378264e-05) * z + 6.87257150e-02) * z + 1.16052586e+03;
-        nd.p0 = fmax(L, 100.0);
+        nd.p0 = L > 100.0 ? L : 100.0;
         break; }
     case 4: {   // GL2 attenuation.py:198-204
         nd.p0 = ((((-4.58987344e-17 * z - 2.89124473e-13) * z - 5.16435542e-10) * z - 2.58901767e-07) * z + 1.58815679e-05) * z + 1.20547286e+00;

@@ -70,6 +70,8 @@ __device__ __forceinline__ void load_pair(const KInput &in, int64_t p, double &x
 #define CNT_FALLBACK 2
 #define CNT_ROOTS 4
 #define CNT_HUMPS 5
+#define CNT_ITEMS 6             // GL1: hard (solution, frequency) items, and those of them that need the fine quadrature
+#define CNT_FINE 7
 #define CNT_STRIDE 16
 #define N_LANES 3               // two pipeline lanes of the host-memory calls + the lane of device-resident calls
 #define DEV_LANE 2
@@ -1265,24 +1267,69 @@ K_att_sp1(IceParams ice, KInput in, AttTables tb, Sp1Tables sp, WorkList worklis
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// GL1 fast path (no bottom reflections): one THREAD per solution, like the SP1 kernel.  1/L = 1 / max(A(z) - s_f, 1 m) is
-// rational in the frequency, so there is no moment form; but the warp-per-solution kernel spends two thirds of its instructions
-// on the shuffle reductions of its (node, frequency) terms, and a thread that owns a solution needs none.  The frequencies are
-// taken GL1_FC at a time (accumulators in registers), the node geometry is re-evaluated per group.
-// Quadrature: A(z) falls with depth below ~1 km, so a frequency's pole (A = s_f) is approached at the DEEP end of the path:
-// the up-going leg [u_2, u_1] is cut into three sub-panels shrinking by 0.4 towards u_1 (16 nodes each), the leg after the
-// turning point is one panel.  On wide random geometry and on cfg3 this is as accurate as the generic kernel's fine sub-panels
-// (CPU emulation of both schemes against the reference integrand at quad(epsrel=1e-11), scratch/gl1_emul.cpp: dense bins
-// 1.5e-5 / 4.8e-5 / 1.9e-7, identical to the generic kernel's figures)
-// for every frequency that stays 10 m away from the pole along the path.  A solution with a frequency inside those 10 m whose
-// factor is still visible (exponent < 30) goes to the generic kernel through the fall-back list: 3-6 % of the solutions.
+// GL1 fast path (no bottom reflections).  1/L = 1 / max(A(z) - s_f, 1 m), A the 75 MHz length (a quintic in depth, attenuation.py:
+// 99-128) and s_f = 0.55 m/MHz (f - 75 MHz) (:195-196): rational in the frequency, so there is no entire-function series as for
+// SP1 -- but for a frequency whose pole A = s_f lies BELOW the values A takes along the path, 1/(A - s_f) is analytic on the
+// path's A-range [A_lo, A_hi] and its Chebyshev series there is a closed form: with x = (A - A_mid) / A_half in [-1, 1] and the
+// pole at -a, a = (A_mid - s_f) / A_half > 1,
+//     1 / (A - s_f) = 1 / (A_half (a + x)) = (1 / A_half) (2 / sqrt(a^2 - 1)) sum'_k (-r)^k T_k(x),   r = a - sqrt(a^2 - 1) < 1,
+// so   int ds / L = (2 / (A_half sqrt(a^2 - 1))) [M_0 / 2 + sum_{k >= 1} (-r)^k M_k],   M_k = sum_q w_q T_k(x_q):
+// GL1_K frequency-independent moments per solution (one thread, 16-node panels, each leg in GL1_SUB sub-panels), then one
+// Horner chain per frequency.  Per (solution, frequency):
+//   easy       A_lo - s_f >= max(1 m, (GL1_XPMIN - 1) A_half): the series (r <= 0.47: r^16 = 6e-6 of the last term);
+//   floor      s_f >= A_hi - 1 m: L = 1 m on the whole path, exponent = path length = M_0, exact;
+//   invisible  the part of the path with A <= s_f + 1 m (L = 1 m) spans at least GL1_IVIS metres of depth (A_lo is reached inside
+//              the path, |dA/dz| <= dadz_max), or path length / max(A_hi - s_f, 1) >= GL1_IVIS: factor < 2.1e-9, written as
+//              exp(-lower bound) (the parity floor for factors below 1e-3 is 1e-7 absolute);
+//   hard       the rest (1.3 % of the items on cfg3, 0.5 per solution): queued as (solution, frequency) ITEMS for K_gl1_item,
+//              which integrates ONE frequency per thread on sub-panels graded towards the deep end of the path (where A falls and
+//              the pole is approached); items whose pole comes within GL1_MARGIN of the path and whose factor is still visible
+//              go on to K_gl1_fine (warp per item, 32 sub-panels per leg).
+// Round 1 integrated every frequency directly (37 x 64 reciprocals per solution, 23.7 kFLOP) and handed every solution with a
+// near-pole frequency to the generic warp-per-solution kernel, which redid ALL its hard frequencies: 5 % of the solutions cost as
+// much as the other 95 %.  scratch/gl1_pole_emul.py: the scheme against the tight oracle on cfg3 and on wide random geometry
+// (easy items: 3.7e-6 / 3.1e-5 worst relative deviation).
 // ---------------------------------------------------------------------------------------------------------------
-#define GL1_FC 13
-#define GL1_ROW GL1_FC              // odd row pitch: conflict-free column writes
+// quadrature node of the u-interval [lo, hi] for the thread-per-solution kernels: as att_node_geometry, with the bounded expm1
+// and the reciprocal square root instead of sqrt + division (the IEEE versions cost two slow-path branches per node)
+__device__ __forceinline__ void node_geometry_fast(const IceParams &ice, const AttPlan &p, double lo, double hi, double x, double w, double &z, double &wds)
+{
+    const double half = 0.5 * (hi - lo);
+    const double u = fma(half, x, 0.5 * (hi + lo));
+    const double uu = u * u;
+    z = NRMC_MIN(p.zv - uu, 0.0);
+    const double em = -expm1_c_small(-uu * ice.inv_z0);
+    const double n = fma(p.delta, em, p.beta);
+    wds = (w * half) * (2.0 * u) * n * rsqrt(p.delta * em * (n + p.beta));
+}
+
+struct Gl1Tables {
+    double zx[4];            // depths in (z_min, 0) where dA/dz = 0: interior extrema of A along a path
+    int32_t nzx, pad;
+    double inv_dadz_max;     // 1 / max |dA/dz| on [z_min, 0]
+    double z_min;            // below this depth A reaches its 100 m floor (attenuation.py:113,124-126): generic kernel
+};
+#define GL1_K 16
+#define GL1_XPMIN 1.3
+#define GL1_SUB 2
+#define GL1_IVIS 20.0
+#define GL1_SEG 13
+#define GL1_ROW GL1_SEG             // odd row pitch: conflict-free column writes
 #define GL1_MARGIN 10.0
-__global__ void __launch_bounds__(SP1_THREADS)
-K_att_gl1(IceParams ice, KInput in, AttTables tb, WorkList worklist, const unsigned long long *work_count, int sparse_is_tmp,
-          double *att_sparse, WorkList fallback, unsigned long long *fallback_count)
+#define GL1_FINE_SPP 32
+
+__device__ __forceinline__ double gl1_A(double z)
+{
+    return (((( -3.63912864e-14 * z - 2.21040482e-10) * z - 3.50628312e-07) * z - 9.82378264e-05) * z + 6.87257150e-02) * z + 1.16052586e+03;
+}
+
+#ifndef GL1_MIN_BLOCKS
+#define GL1_MIN_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(SP1_THREADS, GL1_MIN_BLOCKS)
+K_att_gl1(IceParams ice, AttTables tb, Gl1Tables gt, WorkList worklist, const unsigned long long *work_count, int sparse_is_tmp, double *att_sparse,
+          WorkList fallback, unsigned long long *fallback_count, unsigned long long *items, unsigned long long *item_count,
+          unsigned long long item_cap)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *s_fa = reinterpret_cast<double *>(smem_raw);
@@ -1290,85 +1337,237 @@ K_att_gl1(IceParams ice, KInput in, AttTables tb, WorkList worklist, const unsig
     for (int j = threadIdx.x; j < tb.Fs_pad; j += SP1_THREADS) s_fa[j] = tb.fa[j];
     __syncthreads();
     const unsigned lane = threadIdx.x & 31u;
-    const Gl3Table no_table = {nullptr, 0};
     const unsigned long long n_front = work_count[0], n_work = n_front + work_count[WL_BACK];
     const unsigned long long stride = (unsigned long long)gridDim.x * SP1_THREADS;
-    const int n_groups = (tb.Fs + GL1_FC - 1) / GL1_FC, group = (tb.Fs + n_groups - 1) / n_groups;
     for (unsigned long long w0 = (unsigned long long)blockIdx.x * SP1_THREADS + (threadIdx.x & ~31u); w0 < n_work; w0 += stride) {
         const unsigned long long w = w0 + lane;
-        const bool active = w < n_work;
-        SolRec rec;
-        AttPlan plan;
-        int j_hard = tb.Fs, n_slots = 0;
-        bool leg0 = false, to_generic = false;
+        if (w + stride < n_work) worklist_prefetch(worklist, worklist_index(worklist, n_front, w + stride));
+        double M[GL1_K];
+#pragma unroll
+        for (int k = 0; k < GL1_K; ++k) M[k] = 0.0;
         double *dst = nullptr;
-        if (active) {
-            rec = worklist_get(worklist, n_front, w);
-            if (sparse_is_tmp) rec.row = (int64_t)worklist_index(worklist, n_front, w);   // scratch rows: work-list position
+        double A_lo = 1.0, A_hi = 2.0, A_mid = 1.5, A_half = 0.5, inv_half = 2.0, depth_span = 0.0;
+        unsigned long long wi = 0;
+        SolRec rec;
+        bool active = false, to_generic = false;
+        if (w < n_work) {
+            wi = worklist_index(worklist, n_front, w);
+            rec = worklist_load(worklist, wi);
+            if (sparse_is_tmp) rec.row = (int64_t)wi;               // scratch rows: work-list position
+            AttPlan plan;
             att_plan_rec(ice, rec, plan);
-            leg0 = plan.turned && plan.u2 > plan.uT;                   // [u_T, u_2], run through twice
-            n_slots = (leg0 ? 1 : 0) + (plan.u1 > plan.u2 ? 3 : 0);    // [u_2, u_1] in three graded sub-panels
-            AttNode a_deep, a_top;
-            att_node(NRMC_ATT_GL1, rec.z1, no_table, a_deep);
-            att_node(NRMC_ATT_GL1, plan.turned ? fmin(rec.zv, 0.0) : rec.z2, no_table, a_top);
-            const double a_min = fmin(a_deep.p0, a_top.p0);
-            for (int j = tb.Fs - 1; j >= 0 && s_fa[j] > a_min - GL1_MARGIN; --j) j_hard = j;    // s_f ascends with the frequency
-            dst = att_sparse + rec.row * (int64_t)tb.Fs;
+            active = rec.z1 >= gt.z_min;
+            if (active) {
+                // values A takes along the path: end points and the interior extrema of the quintic
+                const double z_top = plan.turned ? NRMC_MIN(rec.zv, 0.0) : rec.z2;
+                const double Aa = gl1_A(rec.z1), Ab = gl1_A(z_top);
+                A_lo = NRMC_MIN(Aa, Ab); A_hi = NRMC_MAX(Aa, Ab);
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    if (gt.zx[e] > rec.z1 && gt.zx[e] < z_top) { const double Ax = gl1_A(gt.zx[e]); A_lo = NRMC_MIN(A_lo, Ax); A_hi = NRMC_MAX(A_hi, Ax); }
+                A_mid = 0.5 * (A_hi + A_lo);
+                A_half = NRMC_MAX(0.5 * (A_hi - A_lo), 1e-3 * A_mid);
+                inv_half = 1.0 / A_half;
+                depth_span = z_top - rec.z1;
+                // leg 0 = [u_T, u_2] (after the turning point, run through twice), leg 1 = [u_2, u_1]
+#pragma unroll 1
+                for (int leg = plan.turned ? 0 : 1; leg < 2; ++leg) {
+                    const double lo = leg == 0 ? plan.uT : plan.u2, hi = leg == 0 ? plan.u2 : plan.u1;
+                    if (!(hi > lo)) continue;
+                    const double mult = leg == 0 ? 2.0 : 1.0, wsub = (hi - lo) * (1.0 / GL1_SUB);
+#pragma unroll 1
+                    for (int sp = 0; sp < GL1_SUB; ++sp) {
+                        const double a0 = lo + sp * wsub, a1 = sp == GL1_SUB - 1 ? hi : lo + (sp + 1) * wsub;
+#pragma unroll 1
+                        for (int q = 0; q < NRMC_NQ / 2; ++q) {            // the symmetric node pair: two independent chains
+                            double za, wa, zb, wb;
+                            node_geometry_fast(ice, plan, a0, a1, c_glx[q], c_glw[q], za, wa);
+                            node_geometry_fast(ice, plan, a0, a1, c_glx[NRMC_NQ - 1 - q], c_glw[NRMC_NQ - 1 - q], zb, wb);
+                            const double xa = (gl1_A(za) - A_mid) * inv_half, xa2 = xa + xa, xb = (gl1_A(zb) - A_mid) * inv_half, xb2 = xb + xb;
+                            double a_t0 = wa * mult, a_t1 = a_t0 * xa, b_t0 = wb * mult, b_t1 = b_t0 * xb;
+                            M[0] += a_t0 + b_t0; M[1] += a_t1 + b_t1;
+#pragma unroll
+                            for (int k = 2; k < GL1_K; ++k) {
+                                const double a_t2 = fma(xa2, a_t1, -a_t0), b_t2 = fma(xb2, b_t1, -b_t0);
+                                M[k] += a_t2 + b_t2;
+                                a_t0 = a_t1; a_t1 = a_t2; b_t0 = b_t1; b_t1 = b_t2;
+                            }
+                        }
+                    }
+                }
+                dst = att_sparse + rec.row * (int64_t)tb.Fs;
+            } else to_generic = true;
         }
-        for (int gi = 0; gi < n_groups; ++gi) {
-            const int jb = gi * group, je = min(jb + group, tb.Fs);
-            double acc[GL1_FC];
-#pragma unroll
-            for (int u = 0; u < GL1_FC; ++u) acc[u] = 0.0;
-#pragma unroll 1
-            for (int sl = 0; sl < n_slots; ++sl) {
-                double lo, hi, mult;
-                if (leg0 && sl == 0) { lo = plan.uT; hi = plan.u2; mult = 2.0; }
-                else {
-                    const int k = sl - (leg0 ? 1 : 0);
-                    const double w0u = (plan.u1 - plan.u2) * (1.0 / 1.56);      // widths w, 0.4 w, 0.16 w
-                    lo = plan.u2 + w0u * (k == 0 ? 0.0 : (k == 1 ? 1.0 : 1.4));
-                    hi = k == 2 ? plan.u1 : plan.u2 + w0u * (k == 0 ? 1.0 : 1.4);
-                    mult = 1.0;
-                }
-#pragma unroll 1
-                for (int q = 0; q < NRMC_NQ; ++q) {
-                    double z, wds;
-                    att_node_geometry(ice, plan, lo, hi, c_glx[q], c_glw[q], z, wds);
-                    AttNode nd;
-                    att_node(NRMC_ATT_GL1, z, no_table, nd);
-                    const double wm = wds * mult;
-#pragma unroll
-                    for (int u = 0; u < GL1_FC; ++u)
-                        acc[u] = fma(wm, NRMC_RCP(fmax(nd.p0 - s_fa[min(jb + u, tb.Fs_pad - 1)], 1.0)), acc[u]);   // attenuation.py:196, :252-255
-                }
-            }
+        // factors, GL1_SEG frequencies at a time through the warp's staging rows (coalesced row stores, as K_att_sp1)
+        for (int jb = 0; jb < tb.Fs; jb += GL1_SEG) {
+            const int je = min(jb + GL1_SEG, tb.Fs);
             double *mine = stage + lane * GL1_ROW;
+            for (int j = jb; j < je; ++j) {
+                const double s = s_fa[j];
+                double v = NAN;                                       // hard items: K_gl1_item / K_gl1_fine write the factor later
+                if (active) {
+                    const double d = A_lo - s;
+                    if (d >= NRMC_MAX(1.0, (GL1_XPMIN - 1.0) * A_half)) {
+                        const double a = (A_mid - s) * inv_half, a2m1 = fma(a, a, -1.0), isq = rsqrt(a2m1), mr = -NRMC_RCP(fma(a2m1, isq, a));
+                        double acc = M[GL1_K - 1];
 #pragma unroll
-            for (int u = 0; u < GL1_FC; ++u) {
-                if (jb + u < je && jb + u >= j_hard && acc[u] < 30.0) to_generic = true;
-                mine[u] = exp_c_neg(-acc[u]);
+                        for (int k = GL1_K - 2; k >= 1; --k) acc = fma(acc, mr, M[k]);
+                        acc = fma(acc, mr, 0.5 * M[0]);
+                        v = exp_c_neg8(-acc * 2.0 * inv_half * isq);
+                    } else if (s >= A_hi - 1.0) {
+                        v = exp_c_neg8(-M[0]);
+                    } else {
+                        const double lb = NRMC_MAX(NRMC_MIN((s + 1.0 - A_lo) * gt.inv_dadz_max, depth_span), M[0] / NRMC_MAX(A_hi - s, 1.0));
+                        if (lb >= GL1_IVIS) v = exp_c_neg8(-lb);
+                        else if (!to_generic) {
+                            const unsigned long long idx = atomicAdd(item_count, 1ull);
+                            if (idx < item_cap) items[idx] = (wi << 16) | (unsigned long long)j;
+                            else to_generic = true;                   // queue full: the generic kernel redoes the whole row
+                        }
+                    }
+                }
+                mine[j - jb] = v;
             }
             __syncwarp();
             const int len = je - jb;
 #pragma unroll 4
             for (int r = 0; r < 32; ++r) {
-                double *row = reinterpret_cast<double *>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(dst), r));
+                double *row = reinterpret_cast<double *>(__shfl_sync(FULL_MASK, reinterpret_cast<unsigned long long>(dst), r));
                 if (row != nullptr && (int)lane < len) __stcs(row + jb + lane, stage[r * GL1_ROW + lane]);
             }
             __syncwarp();
         }
-        if (active && to_generic) worklist_store(fallback, atomicAdd(fallback_count, 1ull), rec);     // the generic kernel redoes these rows
+        if (w < n_work && to_generic) worklist_store(fallback, atomicAdd(fallback_count, 1ull), rec);
     }
 }
 
-// dense expansion for single-segment paths: np.interp of the sparse factors onto the output grid (py:1077-1078).
-// One warp per work-list record; sparse_is_tmp: the sparse factors sit in scratch rows indexed by the work-list position.
+// one hard (solution, frequency) item per thread: direct quadrature of ds / max(A - s_f, 1) on sub-panels graded towards the deep
+// end of the path (widths w, 0.4 w, 0.16 w on the up-going leg; the leg after the turning point is one panel), 16 nodes each
+__global__ void __launch_bounds__(128)
+K_gl1_item(IceParams ice, AttTables tb, WorkList worklist, int sparse_is_tmp, double *att_sparse, const unsigned long long *items,
+           const unsigned long long *item_count, unsigned long long item_cap, unsigned long long *fine, unsigned long long *fine_count)
+{
+    const unsigned long long n = min(*item_count, item_cap);
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned long long it = items[i], wi = it >> 16;
+        const int j = (int)(it & 0xffffull);
+        const SolRec rec = worklist_load(worklist, wi);
+        const int64_t row = sparse_is_tmp ? (int64_t)wi : rec.row;
+        AttPlan plan;
+        att_plan_rec(ice, rec, plan);
+        const double s = __ldg(tb.fa + j);
+        const bool leg0 = plan.turned && plan.u2 > plan.uT;
+        const int n_slots = (leg0 ? 1 : 0) + (plan.u1 > plan.u2 ? 3 : 0);
+        double acc = 0.0, acc2 = 0.0;
+#pragma unroll 1
+        for (int sl = 0; sl < n_slots; ++sl) {
+            double lo, hi, mult;
+            if (leg0 && sl == 0) { lo = plan.uT; hi = plan.u2; mult = 2.0; }
+            else {
+                const int k = sl - (leg0 ? 1 : 0);
+                const double w0u = (plan.u1 - plan.u2) * (1.0 / 1.56);
+                lo = plan.u2 + w0u * (k == 0 ? 0.0 : (k == 1 ? 1.0 : 1.4));
+                hi = k == 2 ? plan.u1 : plan.u2 + w0u * (k == 0 ? 1.0 : 1.4);
+                mult = 1.0;
+            }
+#pragma unroll 1
+            for (int q = 0; q < NRMC_NQ / 2; ++q) {          // two nodes per trip: independent chains
+                double za, wa, zb, wb;
+                node_geometry_fast(ice, plan, lo, hi, c_glx[q], c_glw[q], za, wa);
+                node_geometry_fast(ice, plan, lo, hi, c_glx[NRMC_NQ - 1 - q], c_glw[NRMC_NQ - 1 - q], zb, wb);
+                const double Aa = NRMC_MAX(gl1_A(za), 100.0), Ab = NRMC_MAX(gl1_A(zb), 100.0);
+                acc = fma(wa * mult, NRMC_RCP(NRMC_MAX(Aa - s, 1.0)), acc);        // attenuation.py:196, :252-255
+                acc2 = fma(wb * mult, NRMC_RCP(NRMC_MAX(Ab - s, 1.0)), acc2);
+            }
+        }
+        const double z_top = plan.turned ? NRMC_MIN(rec.zv, 0.0) : rec.z2;
+        const double a_min = NRMC_MIN(NRMC_MAX(gl1_A(rec.z1), 100.0), NRMC_MAX(gl1_A(z_top), 100.0));
+        acc += acc2;
+        if (s > a_min - GL1_MARGIN && acc < 30.0) fine[atomicAdd(fine_count, 1ull)] = it;      // near the pole and still visible
+        else att_sparse[row * (int64_t)tb.Fs + j] = exp_c_neg(-acc);
+    }
+}
+
+// one near-pole item per WARP.  The pole of 1 / (A - s_f) is approached where A is smallest along the path -- its deep end, or its top
+// for shallow paths (A has a minimum near -500 m) -- and is cut off by the 1 m floor, so the leg that touches that end is divided
+// into GL1_FINE_GRADED sub-panels shrinking by GL1_FINE_RATIO towards it (the innermost ones are centimetres wide: below the scale
+// 1 m / |dA/dz| on which the floored integrand varies), the other leg into GL1_FINE_UNIFORM equal ones; one sub-panel of 16 nodes
+// per lane, one pass.  (First version: 32 - 64 uniform sub-panels per leg, the generic kernel's fine phase: 2 - 4 passes per lane.)
+#define GL1_FINE_GRADED 22
+#define GL1_FINE_UNIFORM 10
+#define GL1_FINE_RATIO 0.6
+__global__ void __launch_bounds__(128)
+K_gl1_fine(IceParams ice, AttTables tb, WorkList worklist, int sparse_is_tmp, double *att_sparse, const unsigned long long *fine,
+           const unsigned long long *fine_count)
+{
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned long long n = *fine_count;
+    const unsigned long long n_warps = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
+    // lane -> position of its sub-panel on the unit interval, graded towards 1:  1 - rho^k ... 1 - rho^(k+1), the last one reaching 1
+    const int kg = (int)lane;
+    const double g_lo = 1.0 - pow(GL1_FINE_RATIO, (double)kg), g_hi = kg == GL1_FINE_GRADED - 1 ? 1.0 : 1.0 - pow(GL1_FINE_RATIO, (double)(kg + 1));
+    for (unsigned long long i = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += n_warps) {
+        const unsigned long long it = fine[i], wi = it >> 16;
+        const int j = (int)(it & 0xffffull);
+        const SolRec rec = worklist_load(worklist, wi);
+        const int64_t row = sparse_is_tmp ? (int64_t)wi : rec.row;
+        AttPlan plan;
+        att_plan_rec(ice, rec, plan);
+        const double s = __ldg(tb.fa + j);
+        const bool leg0 = plan.turned && plan.u2 > plan.uT, leg1 = plan.u1 > plan.u2;
+        const double z_top = plan.turned ? NRMC_MIN(rec.zv, 0.0) : rec.z2;
+        const bool deep_end = gl1_A(rec.z1) <= gl1_A(z_top);          // where A is smallest: u_1 (deep end of leg 1) or the top of the path
+        // graded leg and the end it is graded towards; the top of the path is u_T (start of leg 0) for turned rays, u_2 (start of leg 1) else
+        const int gleg = deep_end ? 1 : (leg0 ? 0 : 1);
+        double a0 = 0.0, a1 = 0.0, mult = 0.0;
+        if ((int)lane < GL1_FINE_GRADED) {
+            if (gleg == 1 ? leg1 : leg0) {
+                const double lo = gleg == 0 ? plan.uT : plan.u2, hi = gleg == 0 ? plan.u2 : plan.u1, wdt = hi - lo;
+                if (deep_end) { a0 = lo + wdt * g_lo; a1 = lo + wdt * g_hi; }      // towards hi
+                else { a0 = hi - wdt * g_hi; a1 = hi - wdt * g_lo; }               // towards lo
+                mult = gleg == 0 ? 2.0 : 1.0;
+            }
+        } else {
+            const int oleg = 1 - gleg, ku = (int)lane - GL1_FINE_GRADED;
+            if (oleg == 1 ? leg1 : leg0) {
+                const double lo = oleg == 0 ? plan.uT : plan.u2, hi = oleg == 0 ? plan.u2 : plan.u1, wsub = (hi - lo) * (1.0 / GL1_FINE_UNIFORM);
+                a0 = lo + ku * wsub; a1 = ku == GL1_FINE_UNIFORM - 1 ? hi : lo + (ku + 1) * wsub;
+                mult = oleg == 0 ? 2.0 : 1.0;
+            }
+        }
+        double acc = 0.0, acc2 = 0.0;
+        if (mult > 0.0 && a1 > a0) {
+#pragma unroll 1
+            for (int q = 0; q < NRMC_NQ / 2; ++q) {
+                double za, wa, zb, wb;
+                node_geometry_fast(ice, plan, a0, a1, c_glx[q], c_glw[q], za, wa);
+                node_geometry_fast(ice, plan, a0, a1, c_glx[NRMC_NQ - 1 - q], c_glw[NRMC_NQ - 1 - q], zb, wb);
+                const double Aa = NRMC_MAX(gl1_A(za), 100.0), Ab = NRMC_MAX(gl1_A(zb), 100.0);
+                acc = fma(wa * mult, NRMC_RCP(NRMC_MAX(Aa - s, 1.0)), acc);
+                acc2 = fma(wb * mult, NRMC_RCP(NRMC_MAX(Ab - s, 1.0)), acc2);
+            }
+        }
+        acc += acc2;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(FULL_MASK, acc, d);
+        if (lane == 0) att_sparse[row * (int64_t)tb.Fs + j] = exp_c_neg(-acc);
+    }
+}
+
+#define EXPAND_F_SMEM 2048          // output bins whose interpolation tables fit the static shared memory of K_att_expand
 __global__ void __launch_bounds__(256)
 K_att_expand(AttTables tb, WorkList worklist, const unsigned long long *work_count, int sparse_is_tmp, const double *att_sparse,
              double *att_dense)
 {
+    // HBM-write bound (4 KB per row at F = 512): the interpolation tables sit in shared memory and every lane has four bins in flight
+    __shared__ double s_it[EXPAND_F_SMEM];
+    __shared__ int32_t s_ii[EXPAND_F_SMEM];
+    const bool in_smem = tb.F <= EXPAND_F_SMEM;
+    if (in_smem) for (int b = threadIdx.x; b < tb.F; b += blockDim.x) { s_it[b] = tb.it[b]; s_ii[b] = tb.ii[b]; }
+    __syncthreads();
     const int lane = threadIdx.x & 31;
+    // (A/B on the B200, 105 GB of rows per cfg3 step: 4 bins in flight per lane 21.4 ms = 4.9 TB/s; 8 or 16 in flight, write-through /
+    //  streaming stores, 16-byte stores: 28 - 31 ms; walking the rows in output order through an inverse map: 23.3 ms)
     const unsigned long long n_front = work_count[0], n_work = n_front + work_count[WL_BACK];
     for (unsigned long long w = (unsigned long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w < n_work;
          w += (unsigned long long)gridDim.x * (blockDim.x >> 5)) {
@@ -1376,12 +1575,24 @@ K_att_expand(AttTables tb, WorkList worklist, const unsigned long long *work_cou
         const int64_t row = worklist.row[wi];
         const double *src = att_sparse + (sparse_is_tmp ? (int64_t)wi : row) * tb.Fs;
         double *dst = att_dense + row * tb.F;
-        for (int b = lane; b < tb.F; b += 32) {
-            const int i0 = __ldg(tb.ii + b);
-            double val = 1.0;
-            if (i0 >= 0) { const double f0 = src[i0], t = __ldg(tb.it + b); val = t != 0.0 ? (src[i0 + 1] - f0) * t + f0 : f0; }
-            dst[b] = val;
+        auto bin = [&](int b) {
+            const int i0 = in_smem ? s_ii[b] : __ldg(tb.ii + b);
+            if (i0 < 0) return 1.0;
+            const double f0 = src[i0], t = in_smem ? s_it[b] : __ldg(tb.it + b);
+            return t != 0.0 ? (src[i0 + 1] - f0) * t + f0 : f0;      // t == 0: no right neighbour needed (Fs == 1, np.interp ends)
+        };
+        int b = lane;
+#ifndef EXPAND_UNROLL
+#define EXPAND_UNROLL 4
+#endif
+        for (; b + 32 * (EXPAND_UNROLL - 1) < tb.F; b += 32 * EXPAND_UNROLL) {
+            double v[EXPAND_UNROLL];
+#pragma unroll
+            for (int u = 0; u < EXPAND_UNROLL; ++u) v[u] = bin(b + 32 * u);
+#pragma unroll
+            for (int u = 0; u < EXPAND_UNROLL; ++u) dst[b + 32 * u] = v[u];
         }
+        for (; b < tb.F; b += 32) dst[b] = bin(b);
     }
 }
 
@@ -1659,7 +1870,7 @@ struct Lane {               // one pipeline lane (scratch + timing events); lane
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t kev[3] = {nullptr, nullptr, nullptr};   // after K_classify, after K_hump, after the main attenuation kernel
-    DevBuf in, out, work, fallback, sparse_tmp, rootq, humpq, packed, pack_sums, pack_off, modes;
+    DevBuf in, out, work, fallback, sparse_tmp, rootq, humpq, packed, pack_sums, pack_off, modes, items;
     bool timed = false;
 };
 
@@ -1674,6 +1885,8 @@ struct nrmc_rt_s {
     Sp1Tables sp1;
     bool have_sp1 = false, have_gl1 = false;
     int grid_att = 0, grid_sp1 = 0, grid_gl1 = 0;      // resident blocks (occupancy x SMs) of the persistent attenuation kernels
+    int grid_gl1_item = 0, grid_gl1_fine = 0;
+    Gl1Tables gl1;
     int grid_small = 0, grid_small_noatt = 0;          // the same for the cooperative small-batch kernel (with / without the attenuation tables)
     void *small_host = nullptr;                        // pinned staging block of the small-batch host path (inputs and outputs in ONE copy each)
     size_t small_host_cap = 0;
@@ -1804,7 +2017,7 @@ void nrmc_rt_destroy(nrmc_rt_t h)
         for (int e = 0; e < 3; ++e) if (h->lanes[l].kev[e]) cudaEventDestroy(h->lanes[l].kev[e]);
         h->lanes[l].in.release(); h->lanes[l].out.release(); h->lanes[l].work.release();
         h->lanes[l].fallback.release(); h->lanes[l].sparse_tmp.release(); h->lanes[l].rootq.release(); h->lanes[l].humpq.release();
-        h->lanes[l].packed.release(); h->lanes[l].pack_sums.release(); h->lanes[l].pack_off.release(); h->lanes[l].modes.release();
+        h->lanes[l].packed.release(); h->lanes[l].pack_sums.release(); h->lanes[l].pack_off.release(); h->lanes[l].modes.release(); h->lanes[l].items.release();
     }
     h->d_tables.release(); h->d_gl3.release(); h->d_sp1.release(); h->d_count.release(); h->d_ant.release(); h->d_rmax.release();
     if (h->small_host) cudaFreeHost(h->small_host);
@@ -1904,6 +2117,27 @@ int nrmc_rt_set_frequencies(nrmc_rt_t h, const double *frequency, int32_t n, dou
         int nb = 0;
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, K_att_gl1, SP1_THREADS, h->smem_gl1));
         h->grid_gl1 = std::max(1, nb) * h->n_sm;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, K_gl1_item, 128, 0));
+        h->grid_gl1_item = std::max(1, nb) * h->n_sm;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, K_gl1_fine, 128, 0));
+        h->grid_gl1_fine = std::max(1, nb) * h->n_sm;
+        {
+            // the 75 MHz length A(z) (attenuation.py:99-128) on a 0.05 m grid: where it reaches its 100 m floor, where it turns, how steep it gets
+            auto A = [](double z) { return (((( -3.63912864e-14 * z - 2.21040482e-10) * z - 3.50628312e-07) * z - 9.82378264e-05) * z + 6.87257150e-02) * z + 1.16052586e+03; };
+            Gl1Tables &g = h->gl1;
+            g.nzx = 0; g.pad = 0; g.z_min = -4000.0;
+            const double dz = 0.05;
+            for (double z = 0.0; z > -4000.0; z -= dz) if (A(z - dz) < 100.0 + 1.0) { g.z_min = z; break; }
+            double smax = 0.0, dprev = 0.0;
+            for (double z = g.z_min; z < 0.0; z += dz) {
+                const double d = (A(z + dz) - A(z)) / dz;
+                smax = std::max(smax, fabs(d));
+                if (z > g.z_min && d * dprev < 0.0 && g.nzx < 4) g.zx[g.nzx++] = z;
+                dprev = d;
+            }
+            for (int e = g.nzx; e < 4; ++e) g.zx[e] = 1.0;
+            g.inv_dadz_max = 1.0 / (1.02 * smax);
+        }
         h->have_gl1 = true;
     }
     h->have_sp1 = false;
@@ -2107,9 +2341,17 @@ static int launch_chunk(nrmc_rt_s *h, Lane &ln, int lane_id, cudaStream_t st, co
                 CK(ln.sparse_tmp.reserve((size_t)kin.n_pairs * h->S * tb.Fs * sizeof(double)));
                 sparse = (double *)ln.sparse_tmp.p;
             }
-            if (h->have_gl1)
-                K_att_gl1<<<h->grid_gl1, SP1_THREADS, h->smem_gl1, st>>>(h->ice, kin, tb, wl, d_count, sparse_is_tmp, sparse, fb, d_fb);
-            else
+            if (h->have_gl1) {
+                // moments + closed-form series; the hard (solution, frequency) items go through two item kernels
+                const unsigned long long item_cap = 2ull * work_cap;
+                CK(ln.items.reserve((size_t)item_cap * 2 * sizeof(unsigned long long)));
+                unsigned long long *items = (unsigned long long *)ln.items.p, *fine = items + item_cap;
+                K_att_gl1<<<h->grid_gl1, SP1_THREADS, h->smem_gl1, st>>>(h->ice, tb, h->gl1, wl, d_count, sparse_is_tmp, sparse, fb, d_fb, items,
+                                                                         cnt + CNT_ITEMS, item_cap);
+                K_gl1_item<<<h->grid_gl1_item, 128, 0, st>>>(h->ice, tb, wl, sparse_is_tmp, sparse, items, cnt + CNT_ITEMS, item_cap, fine, cnt + CNT_FINE);
+                K_gl1_fine<<<h->grid_gl1_fine, 128, 0, st>>>(h->ice, tb, wl, sparse_is_tmp, sparse, fine, cnt + CNT_FINE);
+                *n_launches += 2;
+            } else
                 K_att_sp1<<<h->grid_sp1, SP1_THREADS, h->smem_sp1, st>>>(h->ice, kin, tb, h->sp1, wl, d_count, sparse_is_tmp, sparse, fb, d_fb);
             if (ln.timed) cudaEventRecord(ln.kev[2], st);
             K_att<false><<<h->grid_att, ATT_THREADS, h->smem_att, st>>>(h->ice, kin, tb, fb, d_fb, nseg_max, sparse, nullptr);
