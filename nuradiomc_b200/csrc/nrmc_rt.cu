@@ -1287,7 +1287,7 @@ K_att_sp1(IceParams ice, KInput in, AttTables tb, Sp1Tables sp, WorkList worklis
 //              go on to K_gl1_fine (warp per item, 32 sub-panels per leg).
 // Round 1 integrated every frequency directly (37 x 64 reciprocals per solution, 23.7 kFLOP) and handed every solution with a
 // near-pole frequency to the generic warp-per-solution kernel, which redid ALL its hard frequencies: 5 % of the solutions cost as
-// much as the other 95 %.  scratch/gl1_pole_emul.py: the scheme against the tight oracle on cfg3 and on wide random geometry
+// much as the other 95 %.  scratch/gl1_pole_emul.py: the scheme against the reference integrand at tight quadrature tolerance, on cfg3 and on wide random geometry
 // (easy items: 3.7e-6 / 3.1e-5 worst relative deviation).
 // ---------------------------------------------------------------------------------------------------------------
 // quadrature node of the u-interval [lo, hi] for the thread-per-solution kernels: as att_node_geometry, with the bounded expm1
