@@ -652,7 +652,7 @@ class ray_tracing(ray_tracing_base):
             if idx is not None:
                 src = self._batch[1]
         if src is None:
-            src, idx = self.trace_batch(self._X1[None, :], self._X2[None, :]), 0
+            src, idx = self._trace_one(), 0
         self._batch_index = idx if (self._batch is not None and src is self._batch[1]) else None
         n = int(src["n_sol"][idx])
         self._cache = {k: np.array(src[k][idx]) for k in DEFAULT_OUTPUTS if k in src}
@@ -661,6 +661,33 @@ class ray_tracing(ray_tracing_base):
                           'reflection_case': int(self._cache["reflection_case"][s])} for s in range(n)]
         if "focusing_factor" in src:     # pre-traced with focusing on: get_focusing(limit = the configured one) is a lookup
             self._foc_cache[float(getattr(src, "focusing_limit", 2.))] = np.array(src["focusing_factor"][idx])
+
+    def _trace_one(self):
+        """the current pair through the C ABI with buffers and ctypes structures that are set up once per propagator: the scalar API
+        is a batch of one pair, and at ~70 us of device time per call the Python-side set-up of `trace_batch` (a dozen numpy
+        allocations, three structures) would cost as much again"""
+        ctx = getattr(self, "_one_ctx", None)
+        if ctx is None:
+            S, K1 = self.get_number_of_raytracing_solutions(), self._n_reflections + 1
+            out = {}
+            o = _lib.Output()
+            for name in DEFAULT_OUTPUTS:
+                dtype, trail = _OUT_SPECS[name]
+                out[name] = np.empty((1,) + trail(S, K1, 0, 0), dtype=dtype)
+                setattr(o, name, out[name].ctypes.data)
+            o.compact, o.row_capacity = 0, S
+            pts = np.zeros((6, 1))
+            inp = _lib.Input()
+            inp.n_vertices, inp.vx, inp.vy, inp.vz = 1, pts[0].ctypes.data, pts[1].ctypes.data, pts[2].ctypes.data
+            inp.n_antennas, inp.ax, inp.ay, inp.az = 1, pts[3].ctypes.data, pts[4].ctypes.data, pts[5].ctypes.data
+            inp.outer, inp.memory = 0, _lib.MEMORY_HOST
+            ctx = self._one_ctx = dict(out=out, o=o, pts=pts, inp=inp, fn=_lib.load().nrmc_rt_trace, h=self._h())
+        ctx["pts"][:3, 0] = self._X1
+        ctx["pts"][3:, 0] = self._X2
+        rc = ctx["fn"](ctx["h"].ptr, C.byref(ctx["inp"]), C.byref(ctx["o"]), None, None)
+        if rc < 0:
+            _lib.check(rc, ctx["h"].ptr, "trace")
+        return ctx["out"]
 
     def _check(self, iS):
         n = self.get_number_of_solutions()
