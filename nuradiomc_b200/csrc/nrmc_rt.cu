@@ -72,6 +72,12 @@ __device__ __forceinline__ void load_pair(const KInput &in, int64_t p, double &x
 #define CNT_HUMPS 5
 #define CNT_ITEMS 6             // GL1: hard (solution, frequency) items, and those of them that need the fine quadrature
 #define CNT_FINE 7
+#define CNT_TICKET_ATT 8        // ticket counters of the persistent kernels (dynamic work distribution)
+#define CNT_TICKET_ROOTS 9
+#define CNT_TICKET_HUMP 10
+#define CNT_TICKET_KATT 11
+#define CNT_TICKET_ITEM 12
+#define CNT_TICKET_FINE 13
 #define CNT_STRIDE 16
 #define N_LANES 3               // two pipeline lanes of the host-memory calls + the lane of device-resident calls
 #define DEV_LANE 2
@@ -133,6 +139,14 @@ __device__ __forceinline__ void worklist_prefetch(const WorkList &wl, unsigned l
 {
     prefetch_l2(wl.beta + i); prefetch_l2(wl.delta + i); prefetch_l2(wl.zv + i); prefetch_l2(wl.z1 + i); prefetch_l2(wl.z2 + i);
     prefetch_l2(wl.row + i); prefetch_l2(wl.meta + i);
+}
+
+// next work of a warp of a persistent kernel: one atomic per warp on a ticket counter (zeroed with the counter block of the chunk)
+__device__ __forceinline__ unsigned long long warp_ticket(unsigned long long *ticket, unsigned long long n, unsigned lane)
+{
+    unsigned long long g = 0;
+    if (lane == 0) g = atomicAdd(ticket, n);
+    return __shfl_sync(FULL_MASK, g, 0);
 }
 
 #define N_OUT 15            // output arrays of nrmc_rt_output (out_ptr)
@@ -359,8 +373,11 @@ K_hump(IceParams ice, KInput in, TraceOutputs out, AttFill af, HumpQ humpq, cons
 {
     const unsigned lane = threadIdx.x & 31u;
     const unsigned long long n = *hump_count;
-    const unsigned long long stride = (unsigned long long)gridDim.x * HUMP_THREADS;
-    for (unsigned long long w0 = (unsigned long long)blockIdx.x * HUMP_THREADS + (threadIdx.x & ~31u); w0 < n; w0 += stride) {
+    unsigned long long *ticket = const_cast<unsigned long long *>(hump_count) + (CNT_TICKET_HUMP - CNT_HUMPS);
+    unsigned long long w_next = warp_ticket(ticket, 32ull, lane);
+    while (w_next < n) {
+        const unsigned long long w0 = w_next;
+        w_next = warp_ticket(ticket, 32ull, lane);
         const unsigned long long w = w0 + lane;
         const bool active = w < n;
         PairGeom g;
@@ -426,8 +443,18 @@ K_roots(IceParams ice, KInput in, TraceOutputs out, AttFill af, RootQ rootq, con
     const unsigned lane = threadIdx.x & 31u;
     double *stage = s_stage[threadIdx.x >> 5];
     const unsigned long long n = 2ull * *root_count;     // two lanes per entry
+#ifdef ROOTS_STATIC
     const unsigned long long stride = (unsigned long long)gridDim.x * ROOTS_THREADS;
     for (unsigned long long w0 = (unsigned long long)blockIdx.x * ROOTS_THREADS + (threadIdx.x & ~31u); w0 < n; w0 += stride) {
+#else
+    // warps draw their next 32 brackets from a ticket counter (see K_att_sp1: a static stride leaves the SMs with fewer and
+    // fewer warps towards the end of the launch, the Newton iteration counts differ from warp to warp on top)
+    unsigned long long *ticket = const_cast<unsigned long long *>(root_count) + (CNT_TICKET_ROOTS - CNT_ROOTS);
+    unsigned long long w_next = warp_ticket(ticket, 32ull, lane);
+    while (w_next < n) {
+        const unsigned long long w0 = w_next;
+        w_next = warp_ticket(ticket, 32ull, lane);
+#endif
         const unsigned long long w = w0 + lane;
         const bool active = w < n;
         bool valid = false;
@@ -580,8 +607,11 @@ K_hump_m(IceParams ice, KInput in, int M, int8_t *mode_count, HumpQ humpq, const
 {
     const unsigned lane = threadIdx.x & 31u;
     const unsigned long long n = *hump_count;
-    const unsigned long long stride = (unsigned long long)gridDim.x * HUMP_THREADS;
-    for (unsigned long long w0 = (unsigned long long)blockIdx.x * HUMP_THREADS + (threadIdx.x & ~31u); w0 < n; w0 += stride) {
+    unsigned long long *ticket = const_cast<unsigned long long *>(hump_count) + (CNT_TICKET_HUMP - CNT_HUMPS);
+    unsigned long long w_next = warp_ticket(ticket, 32ull, lane);
+    while (w_next < n) {
+        const unsigned long long w0 = w_next;
+        w_next = warp_ticket(ticket, 32ull, lane);
         const unsigned long long w = w0 + lane;
         const bool active = w < n;
         PairGeom g;
@@ -627,8 +657,11 @@ K_roots_m(IceParams ice, KInput in, TraceOutputs out, AttFill af, int M, int S, 
 {
     const unsigned lane = threadIdx.x & 31u;
     const unsigned long long n = 2ull * *root_count;
-    const unsigned long long stride = (unsigned long long)gridDim.x * ROOTS_THREADS;
-    for (unsigned long long w0 = (unsigned long long)blockIdx.x * ROOTS_THREADS + (threadIdx.x & ~31u); w0 < n; w0 += stride) {
+    unsigned long long *ticket = const_cast<unsigned long long *>(root_count) + (CNT_TICKET_ROOTS - CNT_ROOTS);
+    unsigned long long w_next = warp_ticket(ticket, 32ull, lane);
+    while (w_next < n) {
+        const unsigned long long w0 = w_next;
+        w_next = warp_ticket(ticket, 32ull, lane);
         const unsigned long long w = w0 + lane;
         const bool active = w < n;
         bool valid = false, keep = true;
@@ -885,7 +918,8 @@ __device__ __forceinline__ double k_deepest(const IceParams &ice, const SolRec &
 // dynamic shared memory (doubles): fa[Fs_pad] fb[Fs_pad] it[F_pad] | ii[F_pad] (int32) | per warp: H[3][Fs_pad] fac[nseg][Fs_pad]
 template <bool GL3>
 __device__ __forceinline__ void att_generic_body(const IceParams &ice, const AttTables &tb, const WorkList &worklist, const unsigned long long *work_count,
-                                                 int nseg_max, double *att_sparse, double *att_dense, unsigned char *smem_raw, uint64_t &bar)
+                                                 unsigned long long *ticket, int nseg_max, double *att_sparse, double *att_dense,
+                                                 unsigned char *smem_raw, uint64_t &bar)
 {
     const bool dense = att_dense != nullptr;
     const int Fd_pad = dense ? tb.F_pad : 0;
@@ -904,8 +938,13 @@ __device__ __forceinline__ void att_generic_body(const IceParams &ice, const Att
     const int q = lane & 15, half = lane >> 4;
     const double xq = c_glx[q], wq = c_glw[q];
     const unsigned long long n_front = work_count[0], n_work = n_front + work_count[WL_BACK];
-    for (unsigned long long w = (unsigned long long)blockIdx.x * ATT_WARPS + warp; w < n_work;
-         w += (unsigned long long)gridDim.x * ATT_WARPS) {
+    // one solution per warp: drawn from the ticket counter (persistent grid of K_att), or by a static stride when there is no
+    // counter (K_small: the grid covers the work list, a ticket would only add two atomic round trips to a 0.1 ms launch)
+    const unsigned long long w_stride = (unsigned long long)gridDim.x * ATT_WARPS;
+    unsigned long long w_next = ticket ? warp_ticket(ticket, 1ull, (unsigned)lane) : (unsigned long long)blockIdx.x * ATT_WARPS + warp;
+    while (w_next < n_work) {
+        const unsigned long long w = w_next;
+        w_next = ticket ? warp_ticket(ticket, 1ull, (unsigned)lane) : w + w_stride;
         const SolRec rec = worklist_get(worklist, n_front, w);
         AttPlan plan;
         att_plan_rec(ice, rec, plan);
@@ -1063,12 +1102,12 @@ __device__ __forceinline__ void att_generic_body(const IceParams &ice, const Att
 
 template <bool GL3>
 __global__ void __launch_bounds__(ATT_THREADS)
-K_att(IceParams ice, KInput in, AttTables tb, WorkList worklist, const unsigned long long *work_count, int nseg_max, double *att_sparse,
-      double *att_dense)
+K_att(IceParams ice, KInput in, AttTables tb, WorkList worklist, const unsigned long long *work_count, unsigned long long *ticket, int nseg_max,
+      double *att_sparse, double *att_dense)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t bar;
-    att_generic_body<GL3>(ice, tb, worklist, work_count, nseg_max, att_sparse, att_dense, smem_raw, bar);
+    att_generic_body<GL3>(ice, tb, worklist, work_count, ticket, nseg_max, att_sparse, att_dense, smem_raw, bar);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -1104,7 +1143,7 @@ K_small(IceParams ice, KInput in, TraceOutputs out, AttFill af, AttTables tb, Wo
     if (!worklist.beta) return;
     __threadfence();
     cooperative_groups::this_grid().sync();
-    att_generic_body<GL3>(ice, tb, worklist, work_count, nseg_max, att_sparse, att_dense, smem_raw, bar);
+    att_generic_body<GL3>(ice, tb, worklist, work_count, nullptr, nseg_max, att_sparse, att_dense, smem_raw, bar);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -1218,7 +1257,19 @@ __device__ __forceinline__ void sp1_emit(const double (&M)[SP1_KT], const double
     __syncwarp();
 }
 
+// Work distribution: the warps of the persistent grid draw their next 32 x SP1_CHUNK solutions from a ticket counter.  (A static
+// stride gave every warp the same number of solutions, but the warp schedulers are not fair: ncu showed 20.5 of the 28 resident
+// warps per SM active on average -- warps that ran ahead had finished while the others still had a quarter of their share to do.)
+// Two-panel paths (the back of the work list, twice the nodes) are drawn first, so the tail of the launch consists of cheap ones.
+#ifndef SP1_CHUNK
+#define SP1_CHUNK 1
+#endif
+
+#ifdef SP1_MIN_BLOCKS
+__global__ void __launch_bounds__(SP1_THREADS, SP1_MIN_BLOCKS)
+#else
 __global__ void __launch_bounds__(SP1_THREADS)
+#endif
 K_att_sp1(IceParams ice, KInput in, AttTables tb, Sp1Tables sp, WorkList worklist, const unsigned long long *work_count, int sparse_is_tmp,
           double *att_sparse, WorkList fallback, unsigned long long *fallback_count)
 {
@@ -1229,40 +1280,51 @@ K_att_sp1(IceParams ice, KInput in, AttTables tb, Sp1Tables sp, WorkList worklis
     stage_tables(&bar, s_wk, sp.wk, (uint32_t)tb.Fs_pad * SP1_K * 8u, nullptr, nullptr, 0u, nullptr, nullptr, 0u, nullptr, nullptr, 0u);
     const unsigned lane = threadIdx.x & 31u;
     const unsigned long long n_front = work_count[0], n_work = n_front + work_count[WL_BACK];
-    const unsigned long long stride = (unsigned long long)gridDim.x * SP1_THREADS;
-    for (unsigned long long w0 = (unsigned long long)blockIdx.x * SP1_THREADS + (threadIdx.x & ~31u); w0 < n_work; w0 += stride) {
-        const unsigned long long w = w0 + lane;
-#ifndef SP1_NO_PREFETCH
-        if (w + stride < n_work) worklist_prefetch(worklist, worklist_index(worklist, n_front, w + stride));
-#endif
-        double M[SP1_KT];
+    unsigned long long *ticket = const_cast<unsigned long long *>(work_count) + (CNT_TICKET_ATT - CNT_WORK);
+    unsigned long long g = warp_ticket(ticket, 32ull * SP1_CHUNK, lane);
+    while (g < n_work) {
+        const unsigned long long g_next = warp_ticket(ticket, 32ull * SP1_CHUNK, lane);     // in flight during this chunk
+#pragma unroll 1
+        for (int sub = 0; sub < SP1_CHUNK; ++sub) {
+            const unsigned long long idx = g + 32ull * sub + lane;
+            const bool active = idx < n_work;
+            const unsigned long long w = active ? n_work - 1ull - idx : 0ull;                // back of the list first
+            double M[SP1_KT];
 #pragma unroll
-        for (int k = 0; k < SP1_KT; ++k) M[k] = 0.0;
-        double *dst = nullptr;
-        if (w < n_work) {
-            SolRec rec = worklist_get(worklist, n_front, w);
-            if (sparse_is_tmp) rec.row = (int64_t)worklist_index(worklist, n_front, w);   // scratch rows: work-list position
-            AttPlan plan;
-            att_plan_rec(ice, rec, plan);
-            const bool ok = rec.z1 >= -sp.depth_max;        // the whole path lies inside the temperature range of the series
-            // k = 0 paths: panel 0 = [u_T, u_2] twice (after the turning point), panel 1 = [u_2, u_1] once
+            for (int k = 0; k < SP1_KT; ++k) M[k] = 0.0;
+            double *dst = nullptr;
+            if (active) {
+                SolRec rec = worklist_get(worklist, n_front, w);
+                if (sparse_is_tmp) rec.row = (int64_t)worklist_index(worklist, n_front, w);   // scratch rows: work-list position
+                AttPlan plan;
+                att_plan_rec(ice, rec, plan);
+                const bool ok = rec.z1 >= -sp.depth_max;        // the whole path lies inside the temperature range of the series
+                // k = 0 paths: panel 0 = [u_T, u_2] twice (after the turning point), panel 1 = [u_2, u_1] once
 #pragma unroll 1
-            for (int panel = plan.turned ? 0 : 1; panel < 2 && ok; ++panel) {
-                const double lo = panel == 0 ? plan.uT : plan.u2, hi = panel == 0 ? plan.u2 : plan.u1;
-                if (!(hi > lo)) continue;
-                const double half = 0.5 * (hi - lo), mid = 0.5 * (hi + lo);
-                const double scale = (panel == 0 ? 4.0 : 2.0) * half;      // multiplicity x du/dx x the 2 of ds = 2 u n / ... du
+                for (int panel = plan.turned ? 0 : 1; panel < 2 && ok; ++panel) {
+                    const double lo = panel == 0 ? plan.uT : plan.u2, hi = panel == 0 ? plan.u2 : plan.u1;
+                    if (!(hi > lo)) continue;
+                    const double half = 0.5 * (hi - lo), mid = 0.5 * (hi + lo);
+                    const double scale = (panel == 0 ? 4.0 : 2.0) * half;      // multiplicity x du/dx x the 2 of ds = 2 u n / ... du
 #pragma unroll 1
-                for (int i = 0; i < SP1_NQ / 2; ++i) {                     // the symmetric node pair mid -+ half x_i: two independent chains
-                    const double hx = half * c_glx12h[i], ws = scale * c_glw12h[i];
-                    sp1_node(ice, plan, sp, mid - hx, ws, M);
-                    sp1_node(ice, plan, sp, mid + hx, ws, M);
+                    for (int i = 0; i < SP1_NQ / 2; ++i) {                     // the symmetric node pair mid -+ half x_i: two independent chains
+                        const double hx = half * c_glx12h[i], ws = scale * c_glw12h[i];
+                        sp1_node(ice, plan, sp, mid - hx, ws, M);
+                        sp1_node(ice, plan, sp, mid + hx, ws, M);
+                    }
                 }
+                if (ok) dst = att_sparse + rec.row * (int64_t)tb.Fs;
+                else worklist_store(fallback, atomicAdd(fallback_count, 1ull), rec);          // below the series' depth range: generic kernel
             }
-            if (ok) dst = att_sparse + rec.row * (int64_t)tb.Fs;
-            else worklist_store(fallback, atomicAdd(fallback_count, 1ull), rec);          // below the series' depth range: generic kernel
+#ifndef SP1_NO_PREFETCH
+            {   // the record this lane reads in its next trip -> L2 (the ticket of the next chunk has arrived by now)
+                const unsigned long long nidx = (sub + 1 < SP1_CHUNK ? g + 32ull * (sub + 1) : g_next) + lane;
+                if (nidx < n_work) worklist_prefetch(worklist, worklist_index(worklist, n_front, n_work - 1ull - nidx));
+            }
+#endif
+            for (int jb = 0; jb < tb.Fs; jb += SP1_SEG) sp1_emit(M, s_wk, jb, min(jb + SP1_SEG, tb.Fs), stage, dst, lane);
         }
-        for (int jb = 0; jb < tb.Fs; jb += SP1_SEG) sp1_emit(M, s_wk, jb, min(jb + SP1_SEG, tb.Fs), stage, dst, lane);
+        g = g_next;
     }
 }
 
@@ -1338,10 +1400,13 @@ K_att_gl1(IceParams ice, AttTables tb, Gl1Tables gt, WorkList worklist, const un
     __syncthreads();
     const unsigned lane = threadIdx.x & 31u;
     const unsigned long long n_front = work_count[0], n_work = n_front + work_count[WL_BACK];
-    const unsigned long long stride = (unsigned long long)gridDim.x * SP1_THREADS;
-    for (unsigned long long w0 = (unsigned long long)blockIdx.x * SP1_THREADS + (threadIdx.x & ~31u); w0 < n_work; w0 += stride) {
-        const unsigned long long w = w0 + lane;
-        if (w + stride < n_work) worklist_prefetch(worklist, worklist_index(worklist, n_front, w + stride));
+    // work distribution as K_att_sp1: tickets, two-panel paths (the back of the list) first
+    unsigned long long *ticket = const_cast<unsigned long long *>(work_count) + (CNT_TICKET_ATT - CNT_WORK);
+    unsigned long long g_next = warp_ticket(ticket, 32ull, lane);
+    while (g_next < n_work) {
+        const unsigned long long idx = g_next + lane;
+        g_next = warp_ticket(ticket, 32ull, lane);
+        const unsigned long long w = idx < n_work ? n_work - 1ull - idx : n_work;
         double M[GL1_K];
 #pragma unroll
         for (int k = 0; k < GL1_K; ++k) M[k] = 0.0;
@@ -1398,6 +1463,7 @@ K_att_gl1(IceParams ice, AttTables tb, Gl1Tables gt, WorkList worklist, const un
                 dst = att_sparse + rec.row * (int64_t)tb.Fs;
             } else to_generic = true;
         }
+        if (g_next + lane < n_work) worklist_prefetch(worklist, worklist_index(worklist, n_front, n_work - 1ull - (g_next + lane)));
         // factors, GL1_SEG frequencies at a time through the warp's staging rows (coalesced row stores, as K_att_sp1)
         for (int jb = 0; jb < tb.Fs; jb += GL1_SEG) {
             const int je = min(jb + GL1_SEG, tb.Fs);
@@ -1448,7 +1514,13 @@ K_gl1_item(IceParams ice, AttTables tb, WorkList worklist, int sparse_is_tmp, do
            const unsigned long long *item_count, unsigned long long item_cap, unsigned long long *fine, unsigned long long *fine_count)
 {
     const unsigned long long n = min(*item_count, item_cap);
-    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
+    const unsigned lane = threadIdx.x & 31u;
+    unsigned long long *ticket = const_cast<unsigned long long *>(item_count) + (CNT_TICKET_ITEM - CNT_ITEMS);
+    unsigned long long i_next = warp_ticket(ticket, 32ull, lane);
+    while (i_next < n) {
+        const unsigned long long i = i_next + lane;
+        i_next = warp_ticket(ticket, 32ull, lane);
+        if (i >= n) continue;       // (the lane rejoins the warp at the ticket shuffle)
         const unsigned long long it = items[i], wi = it >> 16;
         const int j = (int)(it & 0xffffull);
         const SolRec rec = worklist_load(worklist, wi);
@@ -1502,11 +1574,14 @@ K_gl1_fine(IceParams ice, AttTables tb, WorkList worklist, int sparse_is_tmp, do
 {
     const unsigned lane = threadIdx.x & 31u;
     const unsigned long long n = *fine_count;
-    const unsigned long long n_warps = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
     // lane -> position of its sub-panel on the unit interval, graded towards 1:  1 - rho^k ... 1 - rho^(k+1), the last one reaching 1
     const int kg = (int)lane;
     const double g_lo = 1.0 - pow(GL1_FINE_RATIO, (double)kg), g_hi = kg == GL1_FINE_GRADED - 1 ? 1.0 : 1.0 - pow(GL1_FINE_RATIO, (double)(kg + 1));
-    for (unsigned long long i = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += n_warps) {
+    unsigned long long *ticket = const_cast<unsigned long long *>(fine_count) + (CNT_TICKET_FINE - CNT_FINE);
+    unsigned long long i_next = warp_ticket(ticket, 1ull, lane);                // one item per warp and ticket
+    while (i_next < n) {
+        const unsigned long long i = i_next;
+        i_next = warp_ticket(ticket, 1ull, lane);
         const unsigned long long it = fine[i], wi = it >> 16;
         const int j = (int)(it & 0xffffull);
         const SolRec rec = worklist_load(worklist, wi);
@@ -2354,7 +2429,7 @@ static int launch_chunk(nrmc_rt_s *h, Lane &ln, int lane_id, cudaStream_t st, co
             } else
                 K_att_sp1<<<h->grid_sp1, SP1_THREADS, h->smem_sp1, st>>>(h->ice, kin, tb, h->sp1, wl, d_count, sparse_is_tmp, sparse, fb, d_fb);
             if (ln.timed) cudaEventRecord(ln.kev[2], st);
-            K_att<false><<<h->grid_att, ATT_THREADS, h->smem_att, st>>>(h->ice, kin, tb, fb, d_fb, nseg_max, sparse, nullptr);
+            K_att<false><<<h->grid_att, ATT_THREADS, h->smem_att, st>>>(h->ice, kin, tb, fb, d_fb, cnt + CNT_TICKET_KATT, nseg_max, sparse, nullptr);
             *n_launches += 2;
             if (att_dense) {
                 K_att_expand<<<h->n_sm * 8, 256, 0, st>>>(tb, wl, d_count, sparse_is_tmp, sparse, att_dense);
@@ -2362,9 +2437,9 @@ static int launch_chunk(nrmc_rt_s *h, Lane &ln, int lane_id, cudaStream_t st, co
             }
         } else {
             if (h->ice.att_model == NRMC_ATT_GL3)
-                K_att<true><<<h->grid_att, ATT_THREADS, h->smem_att, st>>>(h->ice, kin, tb, wl, d_count, nseg_max, att_sparse, att_dense);
+                K_att<true><<<h->grid_att, ATT_THREADS, h->smem_att, st>>>(h->ice, kin, tb, wl, d_count, cnt + CNT_TICKET_KATT, nseg_max, att_sparse, att_dense);
             else
-                K_att<false><<<h->grid_att, ATT_THREADS, h->smem_att, st>>>(h->ice, kin, tb, wl, d_count, nseg_max, att_sparse, att_dense);
+                K_att<false><<<h->grid_att, ATT_THREADS, h->smem_att, st>>>(h->ice, kin, tb, wl, d_count, cnt + CNT_TICKET_KATT, nseg_max, att_sparse, att_dense);
             ++*n_launches;
             if (ln.timed) cudaEventRecord(ln.kev[2], st);
         }

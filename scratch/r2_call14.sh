@@ -1,0 +1,20 @@
+#!/bin/bash
+set -x
+mkdir -p gpurun_out
+nvidia-smi topo -m > gpurun_out/r2p_topo8.txt 2>&1
+for n in 8 4; do
+  timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2957$n bench.py --gpus $n --steps 10 > gpurun_out/r2p_bench_n$n.json 2> gpurun_out/r2p_bench_n$n.err
+  python - <<PY
+import json
+try:
+    d=json.load(open('gpurun_out/r2p_bench_n$n.json'))
+    print('N=$n value %.3e ms %.2f e2e %.3e d2h %.1f probe %.1f' % (d['value'], d['ms_per_step'], d['e2e']['value'], d['e2e']['d2h_gbs'], d['e2e']['d2h_probe_gbs']))
+    g=d.get('gathered',{})
+    for k,v in g.items():
+        if isinstance(v,dict): print('  ', k, v.get('value'), v.get('ms_per_step'), v.get('nvlink_gbs_into_rank0', v.get('nccl_gbs_into_rank0')), v.get('checksum_ok'), v.get('error'))
+    print('  headline', g.get('headline'), d.get('value_gathered'))
+except Exception as e:
+    print('N=$n failed', e)
+PY
+  grep -v "^\[W\|^$\|^\*\*\|OMP_NUM" gpurun_out/r2p_bench_n$n.err | tail -6
+done
