@@ -317,14 +317,25 @@ NRMC_HD double guess_t(const IceParams &ice, const PairGeom &g, int p)
 
 // Bracketed root of g on piece p between a and b (ga, gb of opposite strict sign): Newton steps with the closed-form
 // derivative, kept inside the bracket (bisection when a step leaves it).  x0: starting point (NaN: secant point).
-// Stops on |g| <= 1e-10 m or when the Newton step is below 1e-9 relative (the step is then applied unevaluated:
-// quadratic convergence puts the result at ~1e-16).
+// Stops on |g| <= 1e-10 m or when the Newton step is below 1e-6 relative (the step is then applied unevaluated:
+// quadratic convergence puts the result at ~1e-11; scratch/tolstudy.cpp: against a 1e-9 threshold C0 moves by <= 1.1e-11,
+// the path length by <= 5e-8 m on 4e5 pairs of the cfg5 geometry, for 6 % fewer evaluations).
+// (Tried on the CPU harness, scratch/evalhist.cpp: the refracted rays' mean of 3.5 evaluations -- with 5 % of the solves at 6 - 7,
+// which is what a warp waits for -- comes from the range curve bending over next to the junction t = 1; starting from the root of a
+// parabola with its vertex there, plus a parabolic first step through the junction value, removes the tail (1 % above 4) but
+// raises the mean to 3.85: the curve is close to linear over most of the piece.)
 // (Tried: the zero of the inverse cubic Hermite interpolant through the last two points instead of the Newton step from the
 // second evaluation on -- 3.60 -> 3.33 evaluations per root on the cfg5 geometry, the slowest lane of a warp 5.56 -> 5.09 --
 // but the three extra live doubles and the longer loop body cost more on the B200 than the evaluations saved: 15.4 vs 15.1 ms.)
+#ifndef NRMC_SOLVE_GTOL
+#define NRMC_SOLVE_GTOL 1e-10
+#endif
+#ifndef NRMC_SOLVE_STEP_TOL
+#define NRMC_SOLVE_STEP_TOL 1e-6
+#endif
 NRMC_HD double solve_piece(const Curve &cv, int p, double a, double ga, double b, double gb, double x0)
 {
-    const double gtol = 1e-10;
+    const double gtol = NRMC_SOLVE_GTOL;
     // the bracket is kept ordered (lo < hi) from the start: no min / max per iteration
     double lo = a, glo = ga, hi = b, ghi = gb;
     if (b < a) { lo = b; glo = gb; hi = a; ghi = ga; }
@@ -338,7 +349,7 @@ NRMC_HD double solve_piece(const Curve &cv, int p, double a, double ga, double b
         if ((gx > 0) == (ghi > 0)) { hi = x; ghi = gx; } else { lo = x; glo = gx; }
         double xn = x - gx * NRMC_RCP(dg);
         if (!(xn > lo && xn < hi)) xn = 0.5 * (lo + hi);
-        else if (fabs(xn - x) <= 1e-9 * (fabs(x) + 1e-3)) { x = xn; break; }
+        else if (fabs(xn - x) <= NRMC_SOLVE_STEP_TOL * (fabs(x) + 1e-3)) { x = xn; break; }
         if (hi - lo <= 4e-16 * (fabs(lo) + fabs(hi))) { x = xn; break; }
         x = xn;
     }
@@ -485,7 +496,27 @@ NRMC_HD Root solve_bracket(const Curve &cv, const Bracket &b)
     r.piece = b.piece;
     // the straight-line starting points describe the whole piece; a bracket made by the hump search starts from its secant point
     const bool whole = (b.a == piece_begin(*cv.g, b.piece) && b.b == piece_end(*cv.g, b.piece));
-    r.v = solve_piece(cv, b.piece, b.a, b.ga, b.b, b.gb, (cv.k == 0 && whole) ? guess_t(*cv.ice, *cv.g, b.piece) : NAN);
+    double x0 = (cv.k == 0 && whole) ? guess_t(*cv.ice, *cv.g, b.piece) : NAN;
+#ifndef NRMC_NO_VERTEX_GUESS
+    // Rays that turn (P2 refracted, P3 reflected beyond the straight-line estimate), whole piece, g > 0 at the junction t = 1 (apex
+    // at the receiver / grazing the surface) and g << 0 at the other end: the range curve bends over next to t = 1, the secant
+    // point lands beyond its maximum and the first Newton step is wasted -- 5 % of these solves need 6 - 7 evaluations, and a warp
+    // waits for its slowest lane.  Start from the root of the parabola with its vertex at t = 1 instead: the mean number of
+    // evaluations rises (3.46 -> 3.82, the curve is close to linear further down) but 98.6 % finish within 4 (scratch/evalhist.cpp).
+    if (cv.k == 0 && whole && !(x0 == x0) && b.piece >= 2) {
+        const bool b_is_top = b.b > b.a;
+        const double top = b_is_top ? b.b : b.a, bot = b_is_top ? b.a : b.b, gtop = b_is_top ? b.gb : b.ga, gbot = b_is_top ? b.ga : b.gb;
+        if (gtop > 0.0 && gbot < 0.0) {
+            const double rg = gtop * NRMC_RCP(gtop - gbot), q = NRMC_SQRT(rg);
+#ifdef NRMC_VERTEX_ONLY
+            x0 = top - (top - bot) * q;
+#else
+            x0 = bot + (top - bot) * (1.0 - q) * (1.0 + rg);        // vertex parabola (1 - q) and chord (1 - q^2) blended with weight q
+#endif
+        }
+    }
+#endif
+    r.v = solve_piece(cv, b.piece, b.a, b.ga, b.b, b.gb, x0);
     const double q = NRMC_RCP(1.0 + r.v * r.v);
     r.beta = ((b.piece == 1 || b.piece == 2) ? cv.g->n2 : cv.ice->ns) * (2.0 * r.v) * q;
     return r;

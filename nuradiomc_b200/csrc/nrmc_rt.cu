@@ -78,6 +78,7 @@ __device__ __forceinline__ void load_pair(const KInput &in, int64_t p, double &x
 #define CNT_TICKET_KATT 11
 #define CNT_TICKET_ITEM 12
 #define CNT_TICKET_FINE 13
+#define CNT_WORK_PACKED 14       // K_roots: front | back << 32 (one atomic per warp), split into CNT_WORK / CNT_WORK + WL_BACK afterwards
 #define CNT_STRIDE 16
 #define N_LANES 3               // two pipeline lanes of the host-memory calls + the lane of device-resident calls
 #define DEV_LANE 2
@@ -219,6 +220,11 @@ __global__ void K_rmax_table(IceParams ice, int n, double dz, double *table)
 }
 
 __global__ void K_set_u64(unsigned long long *p, unsigned long long v) { *p = v; }
+__global__ void K_unpack_work(unsigned long long *cnt)
+{
+    const unsigned long long v = cnt[CNT_WORK_PACKED];
+    cnt[CNT_WORK] = v & 0xffffffffull; cnt[CNT_WORK + WL_BACK] = v >> 32;
+}
 
 __device__ __forceinline__ void push_brackets(bool have, int64_t pair, const PairGeom &g, const Bracket *br, int nb, const RootQ &q,
                                               unsigned long long *root_count, unsigned lane, int mode = 0)
@@ -432,7 +438,7 @@ __device__ __forceinline__ void warp_store_vec3(double *dst, bool valid, int64_t
 
 #define ROOTS_THREADS 128
 #ifndef ROOTS_MIN_BLOCKS
-#define ROOTS_MIN_BLOCKS 7      // 72 registers: 28 warps per SM
+#define ROOTS_MIN_BLOCKS 8      // 64 registers: 32 warps per SM (A/B on the B200 with the ticket loop: 7 blocks 10.05, 8 blocks 9.82, 9 blocks 9.81, 10 blocks 9.85 ms per 1e8 pairs)
 #endif
 template <bool CUT>
 __global__ void __launch_bounds__(ROOTS_THREADS, ROOTS_MIN_BLOCKS)
@@ -502,18 +508,17 @@ K_roots(IceParams ice, KInput in, TraceOutputs out, AttFill af, RootQ rootq, con
         if (valid) slot = (rec.beta > beta_other) ? 0 : ((rec.beta < beta_other) ? 1 : (int)(lane & 1u));
         int64_t row = valid ? row_of(out, pair, slot, 2) : 0;
         if (out.row_offset && row >= out.row_limit) valid = false;      // caller's compact arrays are full: drop (reported as NRMC_ERR_CAPACITY)
-        // work-list slot of this solution (front: one quadrature panel, back: two), one atomic per warp and list end
+        // work-list slots of the warp's solutions (front: one quadrature panel, back: two): ONE atomic per warp on a packed counter
+        // (front count in the low, back count in the high 32 bits; K_unpack_work splits it after the launch).  Its value is not
+        // needed before the end of the trip: the round trip to L2 (7 % of the kernel's stall samples when the two bases were
+        // fetched and used on the spot) hides behind the stores of the properties.
+        const bool two_panel = rec.piece >= 2;
+        unsigned mf = 0, mb = 0;
+        unsigned long long wl_base = 0;
         if (worklist.beta) {
-            const bool two_panel = rec.piece >= 2;
-            const unsigned mf = __ballot_sync(FULL_MASK, valid && keep && !two_panel), mb = __ballot_sync(FULL_MASK, valid && keep && two_panel);
-            unsigned long long bf = 0, bb = 0;
-            if (mf) { const int l = __ffs(mf) - 1; if ((int)lane == l) bf = atomicAdd(work_count, (unsigned long long)__popc(mf)); bf = __shfl_sync(FULL_MASK, bf, l); }
-            if (mb) { const int l = __ffs(mb) - 1; if ((int)lane == l) bb = atomicAdd(work_count + WL_BACK, (unsigned long long)__popc(mb)); bb = __shfl_sync(FULL_MASK, bb, l); }
-            const unsigned below = (1u << lane) - 1u;
-            if (valid && keep) {
-                rec.slot = slot; rec.row = row;
-                worklist_store(worklist, two_panel ? worklist.cap - 1ull - (bb + __popc(mb & below)) : bf + __popc(mf & below), rec);
-            }
+            mf = __ballot_sync(FULL_MASK, valid && keep && !two_panel); mb = __ballot_sync(FULL_MASK, valid && keep && two_panel);
+            if ((mf | mb) && (int)lane == __ffs(mf | mb) - 1)
+                wl_base = atomicAdd(work_count + (CNT_WORK_PACKED - CNT_WORK), (unsigned long long)__popc(mf) | ((unsigned long long)__popc(mb) << 32));
         }
         if (CUT) warp_fill_nan_slot(valid && !keep, row, af, lane);     // cut solutions: NaN attenuation rows
         // are the rows of this warp's solutions one contiguous range?
@@ -546,6 +551,15 @@ K_roots(IceParams ice, KInput in, TraceOutputs out, AttFill af, RootQ rootq, con
             if (swap) { const double tx = lx, tz = lz; lx = rx; lz = rz; rx = tx; rz = tz; }
             warp_store_vec3(out.launch, valid, row, dense, row_min, n_valid, lx * ex, lx * ey, lz, stage, lane);
             warp_store_vec3(out.receive, valid, row, dense, row_min, n_valid, rx * ex, rx * ey, rz, stage, lane);
+        }
+        if (mf | mb) {
+            wl_base = __shfl_sync(FULL_MASK, wl_base, __ffs(mf | mb) - 1);
+            const unsigned below = (1u << lane) - 1u;
+            if (valid && keep) {
+                rec.slot = slot; rec.row = row;
+                worklist_store(worklist, two_panel ? worklist.cap - 1ull - ((wl_base >> 32) + __popc(mb & below))
+                                                   : (wl_base & 0xffffffffull) + __popc(mf & below), rec);
+            }
         }
         if (active && !valid && !out.row_offset && (w & 1ull)) {
             fill_empty_slot(out, 2 * pair + 1, 1);    // single root (tangency at the surface): second slot stays empty
@@ -1177,12 +1191,31 @@ struct Sp1Tables {
 #define SP1_THREADS 128
 
 // one quadrature node of the SP1 kernel: geometry (attenuation-independent) and the moment update
-__device__ __forceinline__ void sp1_node(const IceParams &ice, const AttPlan &plan, const Sp1Tables &sp, double u, double wscale,
+// 1 - exp(-y), 0 <= y < 700, with the power of two 2^(i/256) from the shared-memory table: exp(-y) = A (1 + q), A = 2^k 2^(i/256),
+// q = expm1(r) = r + r^2/2 + r^3/6 on |r| <= ln2/512 (truncation r^3/24 <= 1e-10 relative to q: for y -> 0, where k = i = 0 and the
+// result IS -q, that is its relative accuracy; elsewhere 1 - A >= 0.0027 is formed without cancellation).  8 FP64 instructions
+// instead of the 14 of the reduction to |r| <= ln2/2 with a degree-8 polynomial.
+__device__ __forceinline__ double one_minus_exp_neg_tab(double y, const double *s_exp2)
+{
+    const double t = fma(y, -369.3299304675746, 6755399441055744.0);          // -256 / ln 2
+    const int n = __double2loint(t);                                            // <= 0
+    const double r = fma(t - 6755399441055744.0, -0.0027076061740622863, -y);
+    const double q = fma(r * r, fma(r, 0.16666666666666666, 0.5), r);
+    const double T = s_exp2[n & 255];
+    const double A = __hiloint2double(__double2hiint(T) + ((n >> 8) << 20), __double2loint(T));
+    return fma(-A, q, 1.0 - A);
+}
+
+__device__ __forceinline__ void sp1_node(const IceParams &ice, const AttPlan &plan, const Sp1Tables &sp, const double *s_exp2, double u, double wscale,
                                          double (&M)[SP1_KT])
 {
     const double uu = u * u;
     const double a = fabs(plan.zv - uu);                   // depth of the node (zv - uu <= 0 up to rounding at a virtual apex)
+#ifndef SP1_NODE_POLY
+    const double em = one_minus_exp_neg_tab(uu * ice.inv_z0, s_exp2);    // u^2 / z0 <= 3 km / z0
+#else
     const double em = -expm1_c_small(-uu * ice.inv_z0);    // u^2 / z0 <= 3 km / z0: far inside the range of the reduction
+#endif
     const double n = plan.beta + plan.delta * em;
     const double wds = wscale * u * n * rsqrt(plan.delta * em * (n + plan.beta));
     const double x = fma(fma(fma(sp.tau[0], a, sp.tau[1]), a, sp.tau[2]), a, sp.tau[3]), x2 = x + x;
@@ -1198,16 +1231,18 @@ __device__ __forceinline__ void sp1_node(const IceParams &ice, const AttPlan &pl
 // (A lane storing its own row directly makes every 8-byte store a separate 32-byte sector write: measured 60 % of the
 // kernel's time.)
 #ifndef SP1_EW
-#define SP1_EW 4             // frequencies per lane and emit step (independent chains)
+#define SP1_EW 3             // frequencies per lane and emit step (independent chains)
 #endif
+#ifndef SP1_SEG
 #define SP1_SEG 24
+#endif
 #ifndef SP1_EXP_SKIP
 #define SP1_EXP_SKIP 3      // leading Taylor coefficients left out of the emit's exponential: degree 8 on |r| <= ln2/2,
                             // truncation r^9/9! <= 2e-10 relative on the factor (tolerance 1e-4); 0.8 ms per 1e8 pairs
 #endif
 #define SP1_ROW (SP1_SEG + 1)        // odd row pitch: conflict-free column writes
-__device__ __forceinline__ void sp1_emit(const double (&M)[SP1_KT], const double *s_wk, int j_begin, int j_end, double *stage, double *dst,
-                                         unsigned lane)
+__device__ __forceinline__ void sp1_emit(const double (&M)[SP1_KT], const double *s_wk, const double *s_exp2, int j_begin, int j_end,
+                                         double *stage, double *dst, unsigned lane)
 {
     double *mine = stage + lane * SP1_ROW;
     for (int j0 = j_begin; j0 < j_end; j0 += SP1_EW) {
@@ -1232,6 +1267,22 @@ __device__ __forceinline__ void sp1_emit(const double (&M)[SP1_KT], const double
         // order the chains, the compiler cannot prove that the staging row does not alias the tables)
         double x[SP1_EW], r[SP1_EW], pv[SP1_EW];
         int kk[SP1_EW];
+#ifndef SP1_EXP_POLY
+        // exp(x) = 2^k 2^(i/256) e^r, |r| <= ln2/512: the power of two from a 256-entry table in shared memory, e^r = 1 + r + r^2/2
+        // (truncation r^3/6 <= 4.1e-10 relative; the tolerance on the factor is 1e-4): 6 FP64 instructions instead of 13
+#pragma unroll
+        for (int u = 0; u < SP1_EW; ++u) {
+            x[u] = acc[u] < 700.0 ? -acc[u] : -700.0;
+            const double t = fma(x[u], 369.3299304675746, 6755399441055744.0);      // 256 / ln 2
+            kk[u] = __double2loint(t);
+            r[u] = fma(t - 6755399441055744.0, -0.0027076061740622863, x[u]);          // ln 2 / 256
+        }
+#pragma unroll
+        for (int u = 0; u < SP1_EW; ++u) {
+            const double p1 = s_exp2[kk[u] & 255] * fma(r[u], fma(r[u], 0.5, 1.0), 1.0);
+            pv[u] = __hiloint2double(__double2hiint(p1) + ((kk[u] >> 8) << 20), __double2loint(p1));
+        }
+#else
 #pragma unroll
         for (int u = 0; u < SP1_EW; ++u) { x[u] = fmax(-acc[u], -700.0); r[u] = exp_reduce(x[u], kk[u]); pv[u] = c_expc[SP1_EXP_SKIP]; }
 #pragma unroll
@@ -1244,6 +1295,7 @@ __device__ __forceinline__ void sp1_emit(const double (&M)[SP1_KT], const double
             const double p1 = fma(pv[u] * r[u], r[u], r[u]) + 1.0;
             pv[u] = __hiloint2double(__double2hiint(p1) + (kk[u] << 20), __double2loint(p1));
         }
+#endif
 #pragma unroll
         for (int u = 0; u < SP1_EW; ++u) mine[jj[u] - j_begin] = pv[u];
     }
@@ -1275,8 +1327,10 @@ K_att_sp1(IceParams ice, KInput in, AttTables tb, Sp1Tables sp, WorkList worklis
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t bar;
+    __shared__ double s_exp2[256];                          // 2^(i/256) for the emit's exponential
     double *s_wk = reinterpret_cast<double *>(smem_raw);
     double *stage = s_wk + tb.Fs_pad * SP1_K + (threadIdx.x >> 5) * (32 * SP1_ROW);
+    for (int i = threadIdx.x; i < 256; i += SP1_THREADS) s_exp2[i] = exp2((double)i * (1.0 / 256.0));
     stage_tables(&bar, s_wk, sp.wk, (uint32_t)tb.Fs_pad * SP1_K * 8u, nullptr, nullptr, 0u, nullptr, nullptr, 0u, nullptr, nullptr, 0u);
     const unsigned lane = threadIdx.x & 31u;
     const unsigned long long n_front = work_count[0], n_work = n_front + work_count[WL_BACK];
@@ -1309,8 +1363,8 @@ K_att_sp1(IceParams ice, KInput in, AttTables tb, Sp1Tables sp, WorkList worklis
 #pragma unroll 1
                     for (int i = 0; i < SP1_NQ / 2; ++i) {                     // the symmetric node pair mid -+ half x_i: two independent chains
                         const double hx = half * c_glx12h[i], ws = scale * c_glw12h[i];
-                        sp1_node(ice, plan, sp, mid - hx, ws, M);
-                        sp1_node(ice, plan, sp, mid + hx, ws, M);
+                        sp1_node(ice, plan, sp, s_exp2, mid - hx, ws, M);
+                        sp1_node(ice, plan, sp, s_exp2, mid + hx, ws, M);
                     }
                 }
                 if (ok) dst = att_sparse + rec.row * (int64_t)tb.Fs;
@@ -1322,7 +1376,7 @@ K_att_sp1(IceParams ice, KInput in, AttTables tb, Sp1Tables sp, WorkList worklis
                 if (nidx < n_work) worklist_prefetch(worklist, worklist_index(worklist, n_front, n_work - 1ull - nidx));
             }
 #endif
-            for (int jb = 0; jb < tb.Fs; jb += SP1_SEG) sp1_emit(M, s_wk, jb, min(jb + SP1_SEG, tb.Fs), stage, dst, lane);
+            for (int jb = 0; jb < tb.Fs; jb += SP1_SEG) sp1_emit(M, s_wk, s_exp2, jb, min(jb + SP1_SEG, tb.Fs), stage, dst, lane);
         }
         g = g_next;
     }
@@ -2385,6 +2439,7 @@ static int launch_chunk(nrmc_rt_s *h, Lane &ln, int lane_id, cudaStream_t st, co
         else
             K_roots<false><<<h->grid_roots, ROOTS_THREADS, 0, st>>>(h->ice, kin, to, af, rootq, d_roots, wl, d_count);
         *n_launches += 3;
+        if (wl.beta) { K_unpack_work<<<1, 1, 0, st>>>(cnt); ++*n_launches; }
     } else {
         // bottom reflections: the same pipeline over (pair, mode) work items
         CK(ln.modes.reserve((size_t)kin.n_pairs * M));
