@@ -515,6 +515,12 @@ NRMC_HD Root solve_bracket(const Curve &cv, const Bracket &b)
 #endif
         }
     }
+    // a bracket made by the hump search ends at a point next to the curve's maximum (g > 0 there, dg ~ 0): vertex parabola there
+    if (!whole) {
+        const bool b_pos = b.gb > 0.0;
+        const double xp = b_pos ? b.b : b.a, xn = b_pos ? b.a : b.b, gp = b_pos ? b.gb : b.ga, gn = b_pos ? b.ga : b.gb;
+        if (gp > 0.0 && gn < 0.0) x0 = xp - (xp - xn) * NRMC_SQRT(gp * NRMC_RCP(gp - gn));
+    }
 #endif
     r.v = solve_piece(cv, b.piece, b.a, b.ga, b.b, b.gb, x0);
     const double q = NRMC_RCP(1.0 + r.v * r.v);

@@ -665,7 +665,10 @@ K_slots_m(KInput in, TraceOutputs out, AttFill af, int M, int S, int K1, int8_t 
     }
 }
 
-__global__ void __launch_bounds__(ROOTS_THREADS)
+#ifndef ROOTS_M_MIN_BLOCKS
+#define ROOTS_M_MIN_BLOCKS 8    // 64 registers (151 unconstrained: 3 blocks); cfg4 on the B200: 3 blocks 7.39, 4: 6.42, 5: 5.90, 6: 5.81, 8: 5.59 ms
+#endif
+__global__ void __launch_bounds__(ROOTS_THREADS, ROOTS_M_MIN_BLOCKS)
 K_roots_m(IceParams ice, KInput in, TraceOutputs out, AttFill af, int M, int S, int K1, const int8_t *slot_base, RootQ rootq,
           const unsigned long long *root_count, WorkList worklist, unsigned long long *work_count)
 {
@@ -1114,8 +1117,11 @@ __device__ __forceinline__ void att_generic_body(const IceParams &ice, const Att
     }
 }
 
+#ifndef ATT_MIN_BLOCKS
+#define ATT_MIN_BLOCKS 6         // 80 registers (106 unconstrained); cfg4 + MB1 on the B200: 4 blocks 86.0, 5: 81.8, 6: 77.1, 8: 77.2 ms
+#endif
 template <bool GL3>
-__global__ void __launch_bounds__(ATT_THREADS)
+__global__ void __launch_bounds__(ATT_THREADS, ATT_MIN_BLOCKS)
 K_att(IceParams ice, KInput in, AttTables tb, WorkList worklist, const unsigned long long *work_count, unsigned long long *ticket, int nseg_max,
       double *att_sparse, double *att_dense)
 {
