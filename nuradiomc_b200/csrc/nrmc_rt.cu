@@ -319,20 +319,34 @@ K_classify(IceParams ice, KInput in, TraceOutputs out, AttFill af, RmaxTable rma
         Frame2D f;
         make_frame(x1, y1, z1, x2, y2, z2, f);
         const int status = pair_status(ice, f);
-        if (status == 0) {
+        // shadow zone: no ray of the pair reaches further than R_max at the deeper grid corner (monotone in both depths, range_max).
+        // Tested FIRST: a pair beyond the bound needs no geometry and no junction values (47 % of the cfg5 pairs have no
+        // solution, and a fifth of the warps consist of such pairs only: vertices far from every station of the warp).
+        bool beyond = false;
+#ifndef CLASSIFY_LATE_RMAX
+        if (status == 0 && rmax.t) {
+            const int i1 = (int)ceil(-f.z1 / rmax.dz), i2 = (int)ceil(-f.z2 / rmax.dz);
+            if (i1 < rmax.n && i2 < rmax.n && i1 >= 0 && i2 >= 0) {
+                const double bound = __ldg(rmax.t + i1 * rmax.n + i2);
+                beyond = f.rho > bound * (1.0 + 1e-9) + 1e-6;
+            }
+        }
+#endif
+        if (status == 0 && !beyond) {
             make_pair_geom(ice, f.z1, f.z2, fmax(f.rho, 1e-12), g);
             Curve cv;
             cv.ice = &ice; cv.g = &g; cv.k = 0; cv.rcase = 1;
             bool need_hump;
             nb = classify_mode(cv, J1, J2, J3, br, need_hump);
+#ifdef CLASSIFY_LATE_RMAX
             if (need_hump && rmax.t) {
-                // shadow zone: the range cannot exceed R_max at the deeper grid corner (monotone in both depths, range_max)
                 const int i1 = (int)ceil(-f.z1 / rmax.dz), i2 = (int)ceil(-f.z2 / rmax.dz);
                 if (i1 < rmax.n && i2 < rmax.n && i1 >= 0 && i2 >= 0) {
                     const double bound = __ldg(rmax.t + i1 * rmax.n + i2);
                     if (f.rho > bound * (1.0 + 1e-9) + 1e-6) need_hump = false;
                 }
             }
+#endif
             kind = nb > 0 ? 1 : (need_hump ? 2 : 0);
         }
         if (kind == 0) write_no_solution(out, p, status);
@@ -373,7 +387,10 @@ K_classify(IceParams ice, KInput in, TraceOutputs out, AttFill af, RmaxTable rma
 }
 
 #define HUMP_THREADS 128
-__global__ void __launch_bounds__(HUMP_THREADS, 4)
+#ifndef HUMP_MIN_BLOCKS
+#define HUMP_MIN_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(HUMP_THREADS, HUMP_MIN_BLOCKS)
 K_hump(IceParams ice, KInput in, TraceOutputs out, AttFill af, HumpQ humpq, const unsigned long long *hump_count, RootQ rootq,
        unsigned long long *root_count)
 {
@@ -615,7 +632,7 @@ K_classify_m(IceParams ice, KInput in, TraceOutputs out, RmaxTable rmax, int M, 
     push_hump(kind == 2, p, g, J1, J2, J3, mode_bits(k, rcase, md), humpq, hump_count, lane);
 }
 
-__global__ void __launch_bounds__(HUMP_THREADS, 4)
+__global__ void __launch_bounds__(HUMP_THREADS, HUMP_MIN_BLOCKS)
 K_hump_m(IceParams ice, KInput in, int M, int8_t *mode_count, HumpQ humpq, const unsigned long long *hump_count, RootQ rootq,
          unsigned long long *root_count)
 {
