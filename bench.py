@@ -501,6 +501,12 @@ def main():
             e["frac"] = e["achieved"] / fp64_peak
             e["traffic"] = units * h["dram_bytes_per_unit"]
             e["counts_from"] = h.get("report")
+            # pipe utilisation of the same capture: FP64 instructions of any kind (a DADD or DMUL occupies the pipe like a DFMA but
+            # counts one FLOP) / the pipe's issue rate, lanes active per warp instruction, resident warps
+            for k_src, k_dst in (("fp64_pipe_active_pct", "ncu_fp64_pipe_active_pct"), ("threads_per_warp_instruction", "ncu_threads_per_warp_instruction"),
+                                 ("achieved_occupancy_pct", "ncu_achieved_occupancy_pct"), ("registers", "registers")):
+                if k_src in h:
+                    e[k_dst] = h[k_src]
         return e
     kernels = {"classify": kernel_entry("classify", n_pairs_rank, "pairs"), "hump": kernel_entry("hump", n_pairs_rank, "pairs"),
                "roots": kernel_entry("roots", n_sol_launch, "solutions")}
