@@ -101,6 +101,27 @@ __device__ __forceinline__ double nrmc_log(double x)
 }
 #define NRMC_RCP(x) nrmc_rcp(x)
 #define NRMC_RSQRT(x) nrmc_rsqrt(x)
+// the same for arguments KNOWN to be positive normal numbers (1 + t^2, n_ice^2 - beta^2, radicands clamped from below): no selects
+__device__ __forceinline__ double nrmc_rcp_pn(double x)
+{
+    double y0;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(x));
+    double e = fma(-x, y0, 1.0);
+    double y = fma(y0, e, y0);
+    e = fma(-x, y, 1.0);
+    return fma(y, e, y);
+}
+__device__ __forceinline__ double nrmc_rsqrt_pn(double x)
+{
+    double y0;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(x));
+    double e = fma(-(x * y0), y0, 1.0);
+    double y = fma(fma(0.375, e, 0.5) * e, y0, y0);
+    e = fma(-(x * y), y, 1.0);
+    return fma(0.5 * e, y, y);
+}
+#define NRMC_RCP_PN(x) nrmc_rcp_pn(x)
+#define NRMC_RSQRT_PN(x) nrmc_rsqrt_pn(x)
 #define NRMC_LOG(x) nrmc_log(x)
 // sqrt(x) for x >= 0 (0 -> 0) through the fast reciprocal square root
 __device__ __forceinline__ double nrmc_sqrt_pos(double x) { const double r = x * nrmc_rsqrt(x); return x > 0.0 ? r : 0.0; }
@@ -108,11 +129,15 @@ __device__ __forceinline__ double nrmc_sqrt_pos(double x) { const double r = x *
 #elif defined(__CUDA_ARCH__)
 #define NRMC_RCP(x) (1.0 / (x))
 #define NRMC_RSQRT(x) rsqrt(x)
+#define NRMC_RCP_PN(x) (1.0 / (x))
+#define NRMC_RSQRT_PN(x) rsqrt(x)
 #define NRMC_LOG(x) log(x)
 #define NRMC_SQRT(x) sqrt(x)
 #else
 #define NRMC_RCP(x) (1.0 / (x))
 #define NRMC_RSQRT(x) (1.0 / sqrt(x))
+#define NRMC_RCP_PN(x) (1.0 / (x))
+#define NRMC_RSQRT_PN(x) (1.0 / sqrt(x))
 #define NRMC_LOG(x) log(x)
 #define NRMC_SQRT(x) sqrt(x)
 #endif
@@ -246,14 +271,14 @@ NRMC_HD double curve_eval(const Curve &cv, int p, double t, double &dg)
     const PairGeom &g = *cv.g;
     const bool band = (p == 1 || p == 2), turned = (p >= 2);
     const PieceConsts pc = piece_consts(ice, g, band);
-    const double q = NRMC_RCP(1.0 + t * t);
+    const double q = NRMC_RCP_PN(1.0 + t * t);
     const double beta = pc.nX * (2.0 * t) * q;
     const double sig = pc.nX * ((1.0 - t) * (1.0 + t)) * q;
     const double sg2 = sig * sig;
-    const double c = pc.c0 + sg2;
-    const double irc = NRMC_RSQRT(c), rc = c * irc;
+    const double c = pc.c0 + sg2;                       // n_ice^2 - beta^2 >= n_ice^2 - n(z2)^2 > 0
+    const double irc = NRMC_RSQRT_PN(c), rc = c * irc;
     const double x1 = pc.O1 + sg2, x2 = pc.O2 + sg2;
-    const double is1 = NRMC_RSQRT(NRMC_MAX(x1, 1e-300)), is2 = NRMC_RSQRT(NRMC_MAX(x2, 1e-300));
+    const double is1 = NRMC_RSQRT_PN(NRMC_MAX(x1, 1e-300)), is2 = NRMC_RSQRT_PN(NRMC_MAX(x2, 1e-300));
     const double s1 = x1 * is1, s2 = band ? sig : x2 * is2;
     const double k1 = rc * s1 + (c - ice.n_ice * g.g1), k2 = rc * s2 + (c - ice.n_ice * g.g2);
     const double KT = band ? ice.dn * beta : rc * sig + (c - ice.n_ice * ice.dn);
