@@ -1584,6 +1584,120 @@ K_att_gl1(IceParams ice, AttTables tb, Gl1Tables gt, WorkList worklist, const un
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Separable models (MB1, GL2: L(z, f) = fa(f) p0(z), attenuation.py:198-204, :229-244), any number of bottom reflections, sparse
+// output.  Away from the 1 m floor of :252-255 the exponent of every frequency and every path segment is ONE depth integral per
+// panel, G_p = int ds / p0, over fa(f); where fa p0 <= 1 on the whole path (GL2 above 1.58 GHz: negative length, floored) it is the
+// path length S_p = int ds.  The product of the segments' factors is exp(-sum_p m_p H_p) with m_p the number of times the path runs
+// through panel p (plan_total_mult) -- the per-segment factors themselves are only needed for a DENSE output of a bottom-reflected
+// path (np.interp per segment, py:1077-1086): that case stays with the generic kernel.  One THREAD per solution: the panels of the
+// plan as 16-node slots exactly as the generic warp-per-solution kernel cuts them (same nodes, same floor decisions), no shuffle
+// reductions, no shared-memory round trips per solution; a solution with a frequency whose floor is crossed ON the path goes to
+// the generic kernel through the fall-back list.  cfg4 + MB1 (3.4e7 solutions): 77 ms in the generic kernel.
+// ---------------------------------------------------------------------------------------------------------------
+#ifndef SEP_MIN_BLOCKS
+#define SEP_MIN_BLOCKS 8        // 64 registers; cfg4 + MB1 on the B200: 4 blocks 20.5, 5: 19.4, 6: 18.9, 8: 18.6 ms (generic kernel: 77.0)
+#endif
+// depth factor p0(z) of the separable models as att_node, MB1 in power form: 1250 * 0.08886 * exp(-0.048827 * (225.6746 - 86.517596 *
+// log10(x))) / 231.21 = A x^kappa, x = 848.870 - d (attenuation.py:239-244), with the solver's log and the table-free exponential
+// instead of the library's exp and log10 (two slow-path branches per node); differs from att_node by 1e-15 relative
+__device__ __forceinline__ double sep_p0(int model, double z)
+{
+    if (model == NRMC_ATT_MB1) {
+        const double x = NRMC_MAX(fma(z, 420.0 / 576.0, 848.870), 1e-3);   // 848.870 - d, d = -z 420 / 576 (> 428 above the 576 m shelf bottom)
+        return 7.872503543690096e-06 * exp_c_bounded(1.8346312901726596 * NRMC_LOG(x));
+    }
+    return ((((-4.58987344e-17 * z - 2.89124473e-13) * z - 5.16435542e-10) * z - 2.58901767e-07) * z + 1.58815679e-05) * z + 1.20547286e+00;   // GL2
+}
+__global__ void __launch_bounds__(SP1_THREADS, SEP_MIN_BLOCKS)
+K_att_sep(IceParams ice, AttTables tb, WorkList worklist, const unsigned long long *work_count, int sparse_is_tmp, double *att_sparse,
+          WorkList fallback, unsigned long long *fallback_count)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *s_fa = reinterpret_cast<double *>(smem_raw);
+    double *stage = s_fa + tb.Fs_pad + (threadIdx.x >> 5) * (32 * GL1_ROW);
+    for (int j = threadIdx.x; j < tb.Fs_pad; j += SP1_THREADS) s_fa[j] = tb.fa[j];
+    __syncthreads();
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned long long n_front = work_count[0], n_work = n_front + work_count[WL_BACK];
+    unsigned long long *ticket = const_cast<unsigned long long *>(work_count) + (CNT_TICKET_ATT - CNT_WORK);
+    unsigned long long g_next = warp_ticket(ticket, 32ull, lane);
+    while (g_next < n_work) {
+        const unsigned long long idx = g_next + lane;
+        g_next = warp_ticket(ticket, 32ull, lane);
+        const unsigned long long w = idx < n_work ? n_work - 1ull - idx : n_work;
+        double GG = 0.0, SS = 0.0, pmin = INFINITY, pmax = -INFINITY;
+        double *dst = nullptr;
+        SolRec rec;
+        bool active = false, to_generic = false;
+        if (w < n_work) {
+            const unsigned long long wi = worklist_index(worklist, n_front, w);
+            rec = worklist_load(worklist, wi);
+            if (sparse_is_tmp) rec.row = (int64_t)wi;               // scratch rows: work-list position
+            AttPlan plan;
+            att_plan_rec(ice, rec, plan);
+            active = true;
+            double G0 = 0, G1 = 0, G2 = 0, S0 = 0, S1 = 0, S2 = 0;
+#pragma unroll 1
+            for (int slot = 0; slot < plan.n_slots; ++slot) {
+                double lo, hi;
+                int panel;
+                plan_slot(plan, slot, lo, hi, panel);
+                double ga = 0.0, gb = 0.0, sa = 0.0, sb = 0.0;
+#pragma unroll 1
+                for (int q = 0; q < NRMC_NQ / 2; ++q) {          // two nodes per trip: independent chains
+                    double za, wa, zb, wb;
+                    node_geometry_fast(ice, plan, lo, hi, c_glx[q], c_glw[q], za, wa);
+                    node_geometry_fast(ice, plan, lo, hi, c_glx[NRMC_NQ - 1 - q], c_glw[NRMC_NQ - 1 - q], zb, wb);
+#ifdef SEP_STOCK_NODE
+                    AttNode na, nb;
+                    att_node(ice.att_model, za, tb.gl3, na);
+                    att_node(ice.att_model, zb, tb.gl3, nb);
+                    const double pa = na.p0, pb = nb.p0;
+#else
+                    const double pa = sep_p0(ice.att_model, za), pb = sep_p0(ice.att_model, zb);
+#endif
+                    ga = fma(wa, NRMC_RCP(pa), ga); gb = fma(wb, NRMC_RCP(pb), gb);
+                    sa += wa; sb += wb;
+                    pmin = NRMC_MIN(pmin, NRMC_MIN(pa, pb)); pmax = NRMC_MAX(pmax, NRMC_MAX(pa, pb));
+                }
+                ga += gb; sa += sb;
+                if (panel == 0) { G0 += ga; S0 += sa; } else if (panel == 1) { G1 += ga; S1 += sa; } else { G2 += ga; S2 += sa; }
+            }
+            const double m0 = (double)plan_total_mult(plan, 0), m1 = (double)plan_total_mult(plan, 1), m2 = (double)plan_total_mult(plan, 2);
+            GG = m0 * G0 + m1 * G1 + m2 * G2;
+            SS = m0 * S0 + m1 * S1 + m2 * S2;
+            dst = att_sparse + rec.row * (int64_t)tb.Fs;
+        }
+        if (g_next + lane < n_work) worklist_prefetch(worklist, worklist_index(worklist, n_front, n_work - 1ull - (g_next + lane)));
+        // factors, GL1_SEG frequencies at a time through the warp's staging rows (coalesced row stores, as K_att_sp1)
+        for (int jb = 0; jb < tb.Fs; jb += GL1_SEG) {
+            const int je = min(jb + GL1_SEG, tb.Fs);
+            double *mine = stage + lane * GL1_ROW;
+            for (int j = jb; j < je; ++j) {
+                const double fa = s_fa[j];
+                double v = NAN;                                       // floor crossed on the path: the generic kernel redoes the row
+                if (active) {
+                    const double a = fa * pmin, b = fa * pmax;
+                    if (a >= 1.0 && b >= 1.0) v = exp_c_neg8(-GG * NRMC_RCP(fa));
+                    else if (a <= 1.0 && b <= 1.0) v = exp_c_neg8(-SS);
+                    else to_generic = true;
+                }
+                mine[j - jb] = v;
+            }
+            __syncwarp();
+            const int len = je - jb;
+#pragma unroll 4
+            for (int r = 0; r < 32; ++r) {
+                double *row = reinterpret_cast<double *>(__shfl_sync(FULL_MASK, reinterpret_cast<unsigned long long>(dst), r));
+                if (row != nullptr && (int)lane < len) __stcs(row + jb + lane, stage[r * GL1_ROW + lane]);
+            }
+            __syncwarp();
+        }
+        if (active && to_generic) worklist_store(fallback, atomicAdd(fallback_count, 1ull), rec);
+    }
+}
+
 // one hard (solution, frequency) item per thread: direct quadrature of ds / max(A - s_f, 1) on sub-panels graded towards the deep
 // end of the path (widths w, 0.4 w, 0.16 w on the up-going leg; the leg after the turning point is one panel), 16 nodes each
 __global__ void __launch_bounds__(128)
@@ -2035,8 +2149,8 @@ struct nrmc_rt_s {
     std::vector<double> freq_out, freq_sparse;
     AttTables tb;
     Sp1Tables sp1;
-    bool have_sp1 = false, have_gl1 = false;
-    int grid_att = 0, grid_sp1 = 0, grid_gl1 = 0;      // resident blocks (occupancy x SMs) of the persistent attenuation kernels
+    bool have_sp1 = false, have_gl1 = false, have_sep = false;
+    int grid_att = 0, grid_sp1 = 0, grid_gl1 = 0, grid_sep = 0;      // resident blocks (occupancy x SMs) of the persistent attenuation kernels
     int grid_gl1_item = 0, grid_gl1_fine = 0;
     Gl1Tables gl1;
     int grid_small = 0, grid_small_noatt = 0;          // the same for the cooperative small-batch kernel (with / without the attenuation tables)
@@ -2263,6 +2377,14 @@ int nrmc_rt_set_frequencies(nrmc_rt_t h, const double *frequency, int32_t n, dou
         else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, K_small<false>, ATT_THREADS, h->smem_att));
         h->grid_small = std::max(1, nb) * h->n_sm;
     }
+    h->have_sep = false;
+    if ((h->ice.att_model == NRMC_ATT_MB1 || h->ice.att_model == NRMC_ATT_GL2) && !getenv("NRMC_SEP_GENERIC")) {     // (the variable: A/B and tests)
+        h->smem_gl1 = (size_t)Fs_pad * 8 + (size_t)(SP1_THREADS / 32) * 32 * GL1_ROW * sizeof(double);
+        int nb = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, K_att_sep, SP1_THREADS, h->smem_gl1));
+        h->grid_sep = std::max(1, nb) * h->n_sm;
+        h->have_sep = true;
+    }
     h->have_gl1 = false;
     if (h->ice.att_model == NRMC_ATT_GL1 && h->ice.n_refl == 0 && !getenv("NRMC_GL1_GENERIC")) {     // (the variable: A/B and tests)
         h->smem_gl1 = (size_t)Fs_pad * 8 + (size_t)(SP1_THREADS / 32) * 32 * GL1_ROW * sizeof(double);
@@ -2482,7 +2604,10 @@ static int launch_chunk(nrmc_rt_s *h, Lane &ln, int lane_id, cudaStream_t st, co
     if (want_att) {
         const AttTables &tb = h->tb;
         const int nseg_max = h->ice.n_refl + 1;
-        if (h->have_sp1 || h->have_gl1) {
+        // separable models: the thread-per-solution kernel forms the PRODUCT of the segments' factors, which is all a sparse output
+        // needs; a dense output of a bottom-reflected path interpolates every segment on its own (generic kernel)
+        const bool use_sep = h->have_sep && (h->ice.n_refl == 0 || att_dense == nullptr);
+        if (h->have_sp1 || h->have_gl1 || use_sep) {
             // thread-per-solution kernel (SP1 moments / GL1) -> sparse factors; the solutions it hands back -> generic kernel;
             // dense = interp(sparse)
             unsigned long long *d_fb = cnt + CNT_FALLBACK;
@@ -2504,7 +2629,9 @@ static int launch_chunk(nrmc_rt_s *h, Lane &ln, int lane_id, cudaStream_t st, co
                 K_gl1_item<<<h->grid_gl1_item, 128, 0, st>>>(h->ice, tb, wl, sparse_is_tmp, sparse, items, cnt + CNT_ITEMS, item_cap, fine, cnt + CNT_FINE);
                 K_gl1_fine<<<h->grid_gl1_fine, 128, 0, st>>>(h->ice, tb, wl, sparse_is_tmp, sparse, fine, cnt + CNT_FINE);
                 *n_launches += 2;
-            } else
+            } else if (use_sep)
+                K_att_sep<<<h->grid_sep, SP1_THREADS, h->smem_gl1, st>>>(h->ice, tb, wl, d_count, sparse_is_tmp, sparse, fb, d_fb);
+            else
                 K_att_sp1<<<h->grid_sp1, SP1_THREADS, h->smem_sp1, st>>>(h->ice, kin, tb, h->sp1, wl, d_count, sparse_is_tmp, sparse, fb, d_fb);
             if (ln.timed) cudaEventRecord(ln.kev[2], st);
             K_att<false><<<h->grid_att, ATT_THREADS, h->smem_att, st>>>(h->ice, kin, tb, fb, d_fb, cnt + CNT_TICKET_KATT, nseg_max, sparse, nullptr);

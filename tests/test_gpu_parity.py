@@ -1110,3 +1110,41 @@ def test_small_batch_path_scalar_api(make, oracle_mod, monkeypatch):
         rt.find_solutions()
         o = oracle_mod.Oracle("southpole_2015").trace(np.array([x1]), np.array([xb]))
         assert rt.get_number_of_solutions() == o["n_sol"][0]
+
+
+@pytest.mark.parametrize("ice,model,n_refl,rmax,zmin,ant,fmax", [
+    ("mooresbay_simple", "MB1", 1, 1000, -500, [[3, 3, -5.], [-3, 0, -1.]], None),          # cfg4 + MB1
+    ("mooresbay_simple", "MB1", 2, 800, -570, [[0, 0, -5.]], 0.6),
+    ("greenland_simple", "GL2", 0, 3000, -2500, [[0, 0, -100.], [10, 0, -2.]], None),       # bins above 1.58 GHz: negative length -> 1 m floor
+])
+def test_separable_models_thread_per_solution_kernel(make, oracle_mod, monkeypatch, ice, model, n_refl, rmax, zmin, ant, fmax):
+    """K_att_sep (MB1 / GL2, sparse output, any number of bottom reflections) against the generic warp-per-solution kernel on
+    the same solutions (same nodes and floor decisions: 1e-8) and against the tight oracle (1e-4); with a dense output of a
+    bottom-reflected path the generic kernel must have been used (per-segment interpolation, py:1077-1086)"""
+    ff = np.fft.rfftfreq(256, 0.25)          # 0 ... 2 GHz
+    V, A = cylinder(700 + n_refl, 1500, rmax, zmin), np.array(ant, float)
+    kw = dict(outer=True, frequency=ff, max_detector_freq=fmax, attenuation="sparse", compact=True)
+    fast = make(ice, attenuation_model=model, n_reflections=n_refl, n_frequencies_integration=20).trace_batch(V, A, **kw)
+    monkeypatch.setenv("NRMC_SEP_GENERIC", "1")
+    rt_g = make(ice, attenuation_model=model, n_reflections=n_refl, n_frequencies_integration=20)
+    gen = rt_g.trace_batch(V, A, **kw)
+    monkeypatch.delenv("NRMC_SEP_GENERIC")
+    n = int(fast["sol_offset"][-1])
+    assert n == int(gen["sol_offset"][-1]) and n > 1000
+    np.testing.assert_array_equal(fast["n_sol"], gen["n_sol"])
+    a, b = fast["attenuation_sparse"][:n], gen["attenuation_sparse"][:n]
+    assert np.isfinite(a).all() and np.isfinite(b).all()
+    big = b > 1e-3
+    assert big.sum() > 1000 and np.max(np.abs(a[big] / b[big] - 1)) < 1e-8
+    assert np.max(np.abs(a - b)[~big]) < 1e-10 if (~big).any() else True
+    if model == "GL2":
+        assert (fast.frequencies_sparse > 1.6).any()      # floored bins on the whole path: exp(-path length)
+    # tight oracle on the padded layout of a subset (pair mode)
+    sel = np.arange(0, len(V), 5)
+    X1 = np.repeat(V[sel], len(A), axis=0)
+    X2 = np.tile(A, (len(sel), 1))
+    pad = make(ice, attenuation_model=model, n_reflections=n_refl, n_frequencies_integration=20).trace_batch(
+        X1, X2, frequency=ff, max_detector_freq=fmax, attenuation="sparse")
+    ora = oracle_mod.Oracle(ice, attenuation_model=model, n_reflections=n_refl, n_freq=20, tight=True).trace(X1, X2, ff, fmax)
+    np.testing.assert_array_equal(pad["n_sol"], ora["n_sol"])
+    assert_attenuation_parity(pad["attenuation_sparse"], ora["attenuation_sparse"])
