@@ -486,7 +486,12 @@ def main():
     mk = meas["ms_kernel"]
     w_pair, w_props, w_att = reference_model_flops(cfg, Fs)
     refl = cfg["n_refl"] > 0
-    att_kernel = {"SP1": "K_att_sp1", "GL1": "K_att_gl1"}.get(cfg["att"], "K_att") if (with_att and not refl) else ("K_att" if with_att else None)
+    if not with_att:
+        att_kernel = None
+    elif cfg["att"] in ("MB1", "GL2") and (not refl or cfg["att_out"] == "sparse"):
+        att_kernel = "K_att_sep"
+    else:
+        att_kernel = {"SP1": "K_att_sp1", "GL1": "K_att_gl1"}.get(cfg["att"], "K_att") if not refl else "K_att"
     names = {"classify": "K_classify_m" if refl else "K_classify", "hump": "K_hump_m" if refl else "K_hump",
              "roots": "K_roots_m" if refl else "K_roots", "attenuation_main": att_kernel}
 

@@ -1,13 +1,20 @@
 // nrmc_rt.cu -- sm_100a kernels and the C ABI (include/nrmc_rt.h) of the batched analytic ray tracer.
 //
 //   K_classify / K_hump / K_roots (+ _m variants for media with a reflective bottom)
-//                  binned solver: junction values of the range curve per (pair, mode) -> bracket / hump items in HBM queues
-//                  (warp-aggregated appends) -> maximum search -> safeguarded Newton per bracket, closed-form properties,
-//                  SoA stores, 64-byte solution records for the attenuation kernels.
-//   K_att_sp1      SP1: thread per solution, 12-node panels, frequency-independent moments, tables staged by TMA bulk copies
-//                  (cp.async.bulk + mbarrier), staged coalesced row stores.
-//   K_att          other models and multi-segment paths: warp per solution, half-warp per 16-node slot, shuffle reductions;
-//                  separable fast path for MB1 / GL2; GL3: the reference's 10 m discretisation cell for cell.
+//                  binned solver: junction values of the range curve per (pair, mode) -> bracket / hump items in SoA queues in HBM
+//                  (block- / warp-aggregated appends) -> maximum search -> safeguarded Newton per bracket, closed-form properties,
+//                  SoA stores, solution records for the attenuation kernels (two-ended SoA work list).
+//   K_att_sp1      SP1: thread per solution, 12-node panels, 12 frequency-independent Chebyshev moments in the ice temperature,
+//                  coefficient table staged by TMA bulk copies (cp.async.bulk + mbarrier), table exponentials, staged coalesced
+//                  row stores.
+//   K_att_gl1 / K_gl1_item / K_gl1_fine
+//                  GL1: thread per solution, closed-form Chebyshev series per frequency; hard (solution, frequency) items per
+//                  thread / per warp.
+//   K_att_sep      MB1 / GL2 (separable), sparse output: thread per solution, one depth integral per panel.
+//   K_att          everything else (GL3: the reference's 10 m discretisation cell for cell; dense output of bottom-reflected
+//                  paths; fall-back lists of the kernels above): warp per solution, half-warp per 16-node slot.
+//   K_small        N <= 2048 pairs: one cooperative launch (thread-per-pair trace, grid barrier, generic attenuation).
+//   Persistent kernels draw their work from ticket counters (warp_ticket), not from a static stride.
 //   K_apply_effects, K_pack_*, K_att_expand, K_rmax_table, K_att_length, K_fp64_peak: see the comments at each kernel.
 //
 // No tensor cores: nothing here is a contraction.  There is no CPU fallback: every entry point
