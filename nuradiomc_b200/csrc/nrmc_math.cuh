@@ -301,18 +301,19 @@ NRMC_HD double curve_eval(const Curve &cv, int p, double t, double &dg)
         if (WITH_D) dlnP = ((turned ? 2.0 * dKT * k1 * k2 - dk2 * k1 * KT : dk2 * k1) - dk1 * k2 * Kx) * iv;
     } else {
         const ModeCoeffs m = mode_coeffs(cv.k, cv.rcase, turned);
-        const double xr = pc.Or + sg2, isr = NRMC_RSQRT(NRMC_MAX(xr, 1e-300)), sr = xr * isr;
+        const double xr = pc.Or + sg2, isr = NRMC_RSQRT_PN(NRMC_MAX(xr, 1e-300)), sr = xr * isr;
         const double kr = rc * sr + (c - ice.n_ice * ice.gr);
         double num = 1.0, den = 1.0;
         if (m.a1 > 0) num *= k1; else den *= k1;            // |a1| == 1
         if (m.a2 > 0) num *= k2; else den *= k2;            // |a2| == 1
         num *= ipow(KT, m.aT);
         den *= ipow(kr, -m.ar);
-        P = num / den;
+        P = num * NRMC_RCP(den);
         lin = m.a1 * g.z1 + m.a2 * g.z2 + m.ar * ice.zr;
         if (WITH_D) {
+            // (fast-path reciprocals: every true division costs a slow-path branch in the kernel; 5 of them per evaluation here)
             const double dkr = drc * sr + rc * (sp * (sig * isr)) + dc;
-            dlnP = m.a1 * dk1 / k1 + m.a2 * dk2 / k2 + m.ar * dkr / kr + (m.aT ? m.aT * dKT / KT : 0.0);
+            dlnP = m.a1 * dk1 * NRMC_RCP(k1) + m.a2 * dk2 * NRMC_RCP(k2) + m.ar * dkr * NRMC_RCP(kr) + (m.aT ? m.aT * dKT * NRMC_RCP(KT) : 0.0);
         }
     }
     const double Bk = lin - ice.z0 * NRMC_LOG(P);

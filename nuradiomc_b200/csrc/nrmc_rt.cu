@@ -605,9 +605,23 @@ K_classify_m(IceParams ice, KInput in, TraceOutputs out, RmaxTable rmax, int M, 
 {
     const int64_t t = (int64_t)blockIdx.x * CLASSIFY_THREADS + threadIdx.x;
     const unsigned lane = threadIdx.x & 31u;
+#ifdef CLASSIFY_M_PAIR_MAJOR
     const bool in_range = t < in.n_pairs * M;
     const int64_t p = in_range ? t / M : 0;
     const int md = in_range ? (int)(t - p * M) : 0;
+#else
+    // a WARP works on one mode of 32 consecutive pairs (tiles of 32 pairs x M modes): the k = 0 and k > 0 branches of the range
+    // curve, the launch cases and the bounce counts do not diverge inside a warp, and the queue entries a warp appends -- hence
+    // the entries a warp of K_roots_m reads -- are of one mode too.  (Pair-major items, t = pair M + mode, put all modes of a
+    // pair into neighbouring lanes: every warp ran both branches.)
+    const int64_t tile = t / (32 * M);
+    const int r = (int)(t - tile * (32 * M));
+    const int md_raw = r >> 5;
+    const int64_t p_raw = tile * 32 + (r & 31);
+    const bool in_range = p_raw < in.n_pairs;
+    const int64_t p = in_range ? p_raw : 0;
+    const int md = in_range ? md_raw : 0;
+#endif
     int k, rcase;
     mode_of(md, k, rcase);
     int kind = 0, nb = 0;
@@ -633,7 +647,7 @@ K_classify_m(IceParams ice, KInput in, TraceOutputs out, RmaxTable rmax, int M, 
             }
             kind = nb > 0 ? 1 : (need_hump ? 2 : 0);
         }
-        if (kind != 2) mode_count[t] = (int8_t)(kind == 1 ? nb : 0);
+        if (kind != 2) mode_count[p * M + md] = (int8_t)(kind == 1 ? nb : 0);
     }
     push_brackets(kind == 1, p, g, br, nb, rootq, root_count, lane, mode_bits(k, rcase, md));
     push_hump(kind == 2, p, g, J1, J2, J3, mode_bits(k, rcase, md), humpq, hump_count, lane);
@@ -2596,7 +2610,11 @@ static int launch_chunk(nrmc_rt_s *h, Lane &ln, int lane_id, cudaStream_t st, co
         // bottom reflections: the same pipeline over (pair, mode) work items
         CK(ln.modes.reserve((size_t)kin.n_pairs * M));
         int8_t *modes = (int8_t *)ln.modes.p;
+#ifdef CLASSIFY_M_PAIR_MAJOR
         const int64_t items = kin.n_pairs * M;
+#else
+        const int64_t items = ((kin.n_pairs + 31) / 32) * 32 * M;       // tiles of 32 pairs x M modes
+#endif
         K_classify_m<<<(unsigned)((items + CLASSIFY_THREADS - 1) / CLASSIFY_THREADS), CLASSIFY_THREADS, 0, st>>>(
             h->ice, kin, to, h->rmax, M, modes, rootq, d_roots, humpq, d_humps);
         if (ln.timed) cudaEventRecord(ln.kev[0], st);
