@@ -309,7 +309,10 @@ __device__ __forceinline__ void write_no_solution(const TraceOutputs &out, int64
 }
 
 #define CLASSIFY_THREADS 256
-__global__ void __launch_bounds__(CLASSIFY_THREADS)
+#ifndef CLASSIFY_MIN_BLOCKS
+#define CLASSIFY_MIN_BLOCKS 6   // 40 registers + spills; A/B on the B200: 4 blocks 3.30, 5: 3.13, 6: 3.04, 8: 3.39 ms per 1e8 pairs
+#endif
+__global__ void __launch_bounds__(CLASSIFY_THREADS, CLASSIFY_MIN_BLOCKS)
 K_classify(IceParams ice, KInput in, TraceOutputs out, AttFill af, RmaxTable rmax, RootQ rootq, unsigned long long *root_count,
            HumpQ humpq, unsigned long long *hump_count)
 {
@@ -599,7 +602,7 @@ K_roots(IceParams ice, KInput in, TraceOutputs out, AttFill af, RootQ rootq, con
 // the counts of a pair into slot offsets (the reference's result order: mode first, then C0 ascending, py:2122-2125) and
 // fills the unused slots, K_roots_m writes every solution to its slot.
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(CLASSIFY_THREADS)
+__global__ void __launch_bounds__(CLASSIFY_THREADS, 4)      // (5 blocks the same, 6 and 8 slower: A/B on cfg4)
 K_classify_m(IceParams ice, KInput in, TraceOutputs out, RmaxTable rmax, int M, int8_t *mode_count, RootQ rootq,
              unsigned long long *root_count, HumpQ humpq, unsigned long long *hump_count)
 {
