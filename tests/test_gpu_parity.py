@@ -1148,3 +1148,30 @@ def test_separable_models_thread_per_solution_kernel(make, oracle_mod, monkeypat
     ora = oracle_mod.Oracle(ice, attenuation_model=model, n_reflections=n_refl, n_freq=20, tight=True).trace(X1, X2, ff, fmax)
     np.testing.assert_array_equal(pad["n_sol"], ora["n_sol"])
     assert_attenuation_parity(pad["attenuation_sparse"], ora["attenuation_sparse"])
+
+
+def test_separable_kernel_floor_crossed_on_the_path(make, oracle_mod, monkeypatch):
+    """GL2 at 1.5762 GHz: the length (852 m - 540 m/GHz f) p0(z) crosses the 1 m floor of attenuation.py:252-255 ON the paths
+    (p0 varies between 1.0 and 1.3 with depth).  K_att_sep hands such solutions to the generic kernel through its fall-back
+    list; the other frequency of the same solutions stays on its fast path."""
+    ff = np.array([0.0, 0.3, 1.5762])
+    V, A = cylinder(911, 4000, 3000, -2500), np.array([[0, 0, -100.], [10, 0, -2.]])
+    kw = dict(outer=True, frequency=ff, attenuation="sparse", compact=True)
+    fast = make("greenland_simple", attenuation_model="GL2").trace_batch(V, A, **kw)
+    monkeypatch.setenv("NRMC_SEP_GENERIC", "1")
+    gen = make("greenland_simple", attenuation_model="GL2").trace_batch(V, A, **kw)
+    monkeypatch.delenv("NRMC_SEP_GENERIC")
+    n = int(fast["sol_offset"][-1])
+    assert n == int(gen["sol_offset"][-1]) and n > 3000
+    a, b = fast["attenuation_sparse"][:n], gen["attenuation_sparse"][:n]
+    assert np.isfinite(a).all()
+    np.testing.assert_allclose(a, b, rtol=1e-8, atol=1e-300)      # fast path or fall-back (then the generic kernel wrote the row in both runs)
+    # the floor really is crossed on some paths: the factor is neither exp(-path length) nor exp(-G / fa) there
+    S = fast["path_length"][:n]
+    assert (np.abs(a[:, 1] - np.exp(-S)) > 1e-6 * np.exp(-S)).sum() > 100
+    sel = np.arange(0, len(V), 20)
+    X1, X2 = np.repeat(V[sel], len(A), axis=0), np.tile(A, (len(sel), 1))
+    pad = make("greenland_simple", attenuation_model="GL2").trace_batch(X1, X2, frequency=ff, attenuation="sparse")
+    ora = oracle_mod.Oracle("greenland_simple", attenuation_model="GL2", tight=True).trace(X1, X2, ff, None)
+    np.testing.assert_array_equal(pad["n_sol"], ora["n_sol"])
+    assert_attenuation_parity(pad["attenuation_sparse"], ora["attenuation_sparse"])
