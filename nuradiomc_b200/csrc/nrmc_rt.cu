@@ -1857,7 +1857,10 @@ K_att_expand(AttTables tb, WorkList worklist, const unsigned long long *work_cou
     __syncthreads();
     const int lane = threadIdx.x & 31;
     // (A/B on the B200, 105 GB of rows per cfg3 step: 4 bins in flight per lane 21.4 ms = 4.9 TB/s; 8 or 16 in flight, write-through /
-    //  streaming stores, 16-byte stores: 28 - 31 ms; walking the rows in output order through an inverse map: 23.3 ms)
+    //  streaming stores, 16-byte stores: 28 - 31 ms; walking the rows in output order through an inverse map: 23.3 ms; rows staged in
+    //  shared memory and handed to the copy engine as 4 KB TMA bulk stores (cp.async.bulk.global.shared::cta, 2 - 4 buffers per warp,
+    //  4 - 8 warps per block): 43.3 ms for every variant -- one bulk store per 4 KB does not keep the engine busy;
+    //  profiles/r2_ab_runs.log)
     const unsigned long long n_front = work_count[0], n_work = n_front + work_count[WL_BACK];
     for (unsigned long long w = (unsigned long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w < n_work;
          w += (unsigned long long)gridDim.x * (blockDim.x >> 5)) {
