@@ -14,7 +14,8 @@ for small in (False, True):
         os.environ.pop("NRMC_NO_SMALL_PATH", None)
     else:
         os.environ["NRMC_NO_SMALL_PATH"] = "1"
-    for ice, att, nr in (("southpole_2015", "SP1", 0), ("greenland_simple", "GL1", 0), ("greenland_simple", "GL3", 0), ("mooresbay_simple", "MB1", 1)):
+    for ice, att, nr in (("southpole_2015", "SP1", 0), ("greenland_simple", "GL1", 0), ("greenland_simple", "GL3", 0), ("mooresbay_simple", "MB1", 1),
+                         ("greenland_simple", "GL2", 0)):
         rt = prop(medium.get_ice_model(ice), attenuation_model=att, n_reflections=nr, n_frequencies_integration=8)
         V, A = cylinder(1, N, 3000 if nr == 0 else 800, -2700 if nr == 0 else -500), np.array([[0, 0, -5.], [300, 0, -150.]])
         axes = np.random.default_rng(2).normal(size=(len(V), 3))
@@ -24,6 +25,8 @@ for small in (False, True):
             r2 = rt.trace_batch(V, A, outer=True, frequency=ff, max_detector_freq=1.0, attenuation="both", compact=True, pinned=True)
             r3 = rt.trace_batch(V, A, outer=True, frequency=ff, attenuation="dense", shower_axis=axes, delta_C_cut=0.7)
             r6 = rt.trace_batch(V, A, outer=True, frequency=np.array([0.3]), attenuation="both")          # a single frequency
+            if att in ("MB1", "GL2"):      # K_att_sep (sparse output), incl. a GL2 frequency whose 1 m floor is crossed on the path (fall-back list)
+                r7 = rt.trace_batch(V, A, outer=True, frequency=np.array([0.0, 0.3, 1.5762, 1.9]), attenuation="sparse", compact=True)
             dv = torch.tensor(np.ascontiguousarray(V.T), device="cuda:0"); da = torch.tensor(np.ascontiguousarray(A.T), device="cuda:0")
             r4 = rt.trace_batch_device(dv, da, outer=True, frequency=ff, max_detector_freq=1.0, attenuation="both", sync_stats=True)
             foc = rt.focusing_batch(dv, da, r4, outer=True)
