@@ -87,6 +87,7 @@ __device__ __forceinline__ void load_pair(const KInput &in, int64_t p, double &x
 #define CNT_TICKET_FINE 13
 #define CNT_WORK_PACKED 14       // K_roots: front | back << 32 (one atomic per warp), split into CNT_WORK / CNT_WORK + WL_BACK afterwards
 #define CNT_STRIDE 16
+static_assert(CNT_WORK_PACKED < CNT_STRIDE && CNT_TICKET_FINE < CNT_STRIDE, "ticket / packed counters must lie inside the lane's counter block (zeroed per chunk)");
 #define N_LANES 3               // two pipeline lanes of the host-memory calls + the lane of device-resident calls
 #define DEV_LANE 2
 #define CNT_ROWBASE (N_LANES * CNT_STRIDE)   // running row base of a compact device-resident call (not reset per chunk)
