@@ -80,3 +80,49 @@ def test_moment_form_reproduces_the_direct_sum():
                 worst = max(worst, abs(series / direct - 1.0))
         assert 0 < worst < 3e-7, (name, worst)
         print(name, "worst relative truncation", worst)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# table exponentials of K_att_sp1 (sp1_emit / one_minus_exp_neg_tab in nrmc_rt.cu), restated in numpy
+# ---------------------------------------------------------------------------------------------------------------
+MAGIC = 6755399441055744.0          # 1.5 * 2^52: adding it rounds to the nearest integer, which sits in the low word
+TAB = np.exp2(np.arange(256) / 256.0)
+
+
+def _reduce(x):
+    """n = round(x 256 / ln 2), r = x - n ln 2 / 256  (|r| <= ln 2 / 512), as the two FMAs of the kernel"""
+    t = x * 369.3299304675746 + MAGIC
+    n = (t - MAGIC).astype(np.int64)
+    r = x - n * 0.0027076061740622863
+    return n, r
+
+
+def exp_table(x):
+    """emit: exp(x) = 2^k 2^(i/256) (1 + r + r^2/2), x <= 0 clamped at -700"""
+    x = np.where(x > -700.0, x, -700.0)
+    n, r = _reduce(x)
+    return np.ldexp(TAB[n & 255] * (1.0 + r * (1.0 + 0.5 * r)), (n >> 8).astype(np.int64))
+
+
+def one_minus_exp_neg_table(y):
+    """node geometry: 1 - exp(-y) = (1 - A) - A q, A = 2^k 2^(i/256), q = r + r^2/2 + r^3/6"""
+    n, r = _reduce(-y)
+    A = np.ldexp(TAB[n & 255], (n >> 8).astype(np.int64))
+    q = r + r * r * (0.5 + r / 6.0)
+    return (1.0 - A) - A * q
+
+
+def test_table_exponential_of_the_emit():
+    """truncation r^3/6 <= 4.1e-10 relative on the attenuation factor (tolerance 1e-4), over the whole exponent range"""
+    x = -np.concatenate([np.linspace(0, 40, 400001), np.logspace(-12, 2.8, 20001), [0.0, 699.9, 700.0, 1e4]])
+    ref = np.exp(np.where(x > -700.0, x, -700.0))
+    assert np.max(np.abs(exp_table(x) / ref - 1.0)) < 4.2e-10
+    assert exp_table(np.array([0.0]))[0] == 1.0
+
+
+def test_table_one_minus_exp_of_the_node_geometry():
+    """relative accuracy 1e-10 of 1 - exp(-u^2/z0) including u -> 0, where it IS -q (the quadrature weights need 1e-7)"""
+    y = np.concatenate([np.logspace(-14, 1.7, 200001), np.linspace(0, 45, 100001)[1:]])
+    ref = -np.expm1(-y)
+    assert np.max(np.abs(one_minus_exp_neg_table(y) / ref - 1.0)) < 1.2e-10
+    assert one_minus_exp_neg_table(np.array([0.0]))[0] == 0.0
