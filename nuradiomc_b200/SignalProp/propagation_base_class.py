@@ -15,67 +15,47 @@ logger = logging.getLogger('NuRadioMC.SignalProp.ray_tracing_base')
 
 class ray_tracing_base:
 
+    # (keyword argument, key in config['propagation'], default) of the three settings a configuration file may override (:86-133)
+    _SETTINGS = (("n_frequencies_integration", "n_freq", 100), ("n_reflections", "n_reflections", 0), ("attenuation_model", "attenuation_model", "SP1"))
+
     def __init__(self, medium, attenuation_model=None, log_level=logging.NOTSET,
                  n_frequencies_integration=None, n_reflections=None, config=None,
                  detector=None, ray_tracing_2D_kwards={}, use_cpp=None):
         self.__logger = logging.getLogger('NuRadioMC.SignalProp.ray_tracing_base')
         self.__logger.setLevel(log_level)
-        self._medium = medium
-        self._config = config
+        self._medium, self._config, self._detector = medium, config, detector
         self._set_arguments(n_frequencies_integration, n_reflections, attenuation_model)
+        self._max_detector_frequency = self._nyquist_of(detector)
+        self.reset_solutions()
 
-        self._detector = detector
-        self._max_detector_frequency = None
-        if self._detector is not None:
-            # largest Nyquist frequency over the stations, taken from each station's first channel (:64-80)
-            for station_id in self._detector.get_station_ids():
-                channel_ids = self._detector.get_channel_ids(station_id)
-                sampling_frequency = self._detector.get_sampling_frequency(station_id, channel_ids[0])
-                for channel_id in channel_ids:
-                    if self._detector.get_sampling_frequency(station_id, channel_id) != sampling_frequency:
-                        self.__logger.warning(
-                            f"Channels of station {station_id} have different sampling frequencies; using the one of "
-                            f"channel {channel_ids[0]} ({sampling_frequency / units.GHz:.1f} GHz) for the attenuation grid.")
-                if self._max_detector_frequency is None or sampling_frequency * .5 > self._max_detector_frequency:
-                    self._max_detector_frequency = sampling_frequency * .5
-
-        self._X1 = None
-        self._X2 = None
-        self._results = None
+    def _nyquist_of(self, detector):
+        """largest Nyquist frequency over the stations, each station represented by its first channel (:64-80); None without detector"""
+        if detector is None:
+            return None
+        best = None
+        for sid in detector.get_station_ids():
+            channels = detector.get_channel_ids(sid)
+            rate = detector.get_sampling_frequency(sid, channels[0])
+            if any(detector.get_sampling_frequency(sid, c) != rate for c in channels):
+                self.__logger.warning(f"station {sid}: channels differ in sampling rate, the attenuation grid follows channel "
+                                      f"{channels[0]} ({rate / units.GHz:.1f} GHz)")
+            best = 0.5 * rate if best is None else max(best, 0.5 * rate)
+        return best
 
     def _set_arguments(self, n_frequencies_integration, n_reflections, attenuation_model):
-        """config wins over keyword arguments (with a warning), defaults are 100 / 0 / 'SP1' (:86-133)"""
-        self._n_frequencies_integration = None
-        self._n_reflections = None
-        self._attenuation_model = None
-        if self._config is not None:
-            prop = self._config['propagation']
-            if 'n_freq' in prop:
-                if n_frequencies_integration is not None:
-                    self.__logger.warning(f"Overriding n_frequencies_integration from config file from "
-                                          f"{n_frequencies_integration} to {prop['n_freq']}")
-                self._n_frequencies_integration = prop['n_freq']
-            if 'n_reflections' in prop:
-                if n_reflections is not None:
-                    self.__logger.warning(f"Overriding n_reflections from config file from {n_reflections} to "
-                                          f"{prop['n_reflections']}")
-                self._n_reflections = prop['n_reflections']
-            if 'attenuation_model' in prop:
-                if attenuation_model is not None:
-                    self.__logger.warning(f"Overriding attenuation_model from config file from {attenuation_model} to "
-                                          f"{prop['attenuation_model']}")
-                self._attenuation_model = prop['attenuation_model']
-        if self._n_frequencies_integration is None:
-            self._n_frequencies_integration = n_frequencies_integration or 100
-        if self._n_reflections is None:
-            self._n_reflections = n_reflections or 0
-        if self._attenuation_model is None:
-            self._attenuation_model = attenuation_model or 'SP1'
-        if self._n_reflections:
-            if not hasattr(self._medium, "reflection") or self._medium.reflection is None:
-                self.__logger.warning("Ray paths with bottom reflections requested but medium does not have any "
-                                      "reflective layer, setting number of reflections to zero.")
-                self._n_reflections = 0
+        """a value in config['propagation'] wins over the keyword argument (with a warning); defaults 100 / 0 / 'SP1' (:86-133)"""
+        given = {"n_frequencies_integration": n_frequencies_integration, "n_reflections": n_reflections, "attenuation_model": attenuation_model}
+        from_file = self._config['propagation'] if self._config is not None else {}
+        for name, key, default in self._SETTINGS:
+            value = given[name]
+            if key in from_file:
+                if value is not None:
+                    self.__logger.warning(f"{name}: the configuration file ({from_file[key]}) overrides the argument ({value})")
+                value = from_file[key]
+            setattr(self, "_" + name, value or default)
+        if self._n_reflections and getattr(self._medium, "reflection", None) is None:
+            self.__logger.warning("bottom reflections requested for a medium without reflective layer: n_reflections set to 0")
+            self._n_reflections = 0
 
     def reset_solutions(self):
         self._X1 = None
