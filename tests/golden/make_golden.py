@@ -96,6 +96,14 @@ def cases():
     V, A = pairs(cylinder(55, 50, 6000., -2700.), g5)
     c["sp2015_cfg5_large"] = dict(ice="southpole_2015", att="SP1", n_refl=0, n_freq=25, X1=V, X2=A,
                                   freqs=np.fft.rfftfreq(1022, 0.2), fmax=1.2)
+    # round 2: the separable models through K_att_sep (n_reflections = 0: sparse factors from the thread-per-solution kernel, dense by
+    # interpolation), pinned to the reference directly
+    V, A = pairs(cylinder(66, 150, 3000., -2500.), np.array([[0, 0, -100.], [10, 0, -2.]]))
+    c["greenland_GL2_large"] = dict(ice="greenland_simple", att="GL2", n_refl=0, n_freq=20, X1=V, X2=A,
+                                    freqs=np.fft.rfftfreq(256, 0.25), fmax=None)
+    V, A = pairs(cylinder(67, 110, 1000., -550.), np.array([[3, 3, -5.], [-3, 0, -1.]]))
+    c["mooresbay_MB1_direct"] = dict(ice="mooresbay_simple", att="MB1", n_refl=0, n_freq=25, X1=V, X2=A,
+                                     freqs=np.fft.rfftfreq(256, 0.5), fmax=0.6)
     V, A = pairs(cylinder(8, 10, 800., -550.), np.array([[3, 3, -5.]]))
     c["mooresbay_GL3"] = dict(ice="mooresbay_simple", att="GL3", n_refl=1, n_freq=10, X1=V, X2=A,
                               freqs=np.fft.rfftfreq(128, 0.5), fmax=None)

@@ -54,7 +54,8 @@ def test_T06_golden_through_kernel(make):
 
 @pytest.mark.parametrize("name", ["sp_simple_T05", "sp2015_cfg2", "mooresbay_cfg4", "mooresbay_T06", "sp1_cfg1",
                                   "greenland_cfg3", "mooresbay_cfg4_MB1", "sp2015_cfg5_SP1", "greenland_GL2", "greenland_GL3",
-                                  "mooresbay_GL3", "greenland_cfg3_large", "sp2015_cfg5_large"])
+                                  "mooresbay_GL3", "greenland_cfg3_large", "sp2015_cfg5_large", "greenland_GL2_large",
+                                  "mooresbay_MB1_direct"])
 def test_python_reference_fixtures(make, name):
     """fixtures produced by the reference's own Python path (tests/golden/make_golden.py)"""
     g = load_golden(name)
