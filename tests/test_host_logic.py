@@ -189,3 +189,27 @@ def test_pair_lookup_of_prepare_batch():
     ref = {X1[i].tobytes() + Y2[i].tobytes(): i for i in range(len(X1))}
     got = _pair_lookup(X1, Y2, False)
     assert got == ref and all(isinstance(k, bytes) and len(k) == 48 for k in got)
+
+
+def test_bench_workloads_and_roofline_inputs():
+    """bench.py without a GPU: the BASELINE workloads have the sizes SURVEY.md 8(d) states, the reference-algorithm FLOP model
+    gives the figures DESIGN.md quotes, and profiles/hw_counts.json holds executed-FLOP counts for every kernel the bench looks up"""
+    import json
+    import bench
+    sizes = {"cfg1": (1000, 1), "cfg2": (1_000_000, 4), "cfg3": (1_000_000, 24), "cfg4": (1_000_000, 8), "cfg5": (1_000_000, 100)}
+    for name, (nv, na) in sizes.items():
+        cfg = bench.CONFIGS[name]
+        assert cfg["n_vertices"] == nv and cfg["antennas"].shape == (na, 3), name
+        V, A, _ = bench.workload(1000, name)
+        assert V.shape == (3, 1000) and A.shape == (3, na) and (V[2] <= 0).all() and (A[2] < 0).all()
+        assert np.array_equal(V, bench.workload(1000, name)[0])                       # seeded: the same vertices every time
+    r = np.hypot(*bench.workload(20000, "cfg5")[0][:2])
+    assert r.max() < 6000.0 and abs(np.mean(r ** 2) / 6000.0 ** 2 - 0.5) < 0.02       # uniform in the cylinder's cross section
+    assert bench.reference_model_flops(bench.CONFIGS["cfg5"], 37) == (3050, 600, 31272)   # SURVEY.md 8(d): W_att(SP1, F = 37)
+    assert bench.reference_model_flops(bench.CONFIGS["cfg2"], 0) == (3050, 600, 0)
+    assert bench.reference_model_flops(bench.CONFIGS["cfg4"], 0)[0] == 50 + 3 * 30 * 100 * 2
+    hw = json.load(open(os.path.join(ROOT, "profiles", "hw_counts.json")))
+    for key in ("K_classify", "K_hump", "K_roots", "K_att_sp1", "cfg3:K_att_gl1", "cfg4:K_roots_m", "cfg4:K_classify_m", "cfg4mb1:K_att_sep"):
+        assert hw[key]["fp64_flops_per_unit"] > 0 and hw[key]["dram_bytes_per_unit"] > 0, key
+    X1, X2 = bench.pairs_of(*bench.workload(10, "cfg3")[:2], 50)
+    assert X1.shape == X2.shape == (50, 3) and np.array_equal(X2[:24], bench.RNOG) and np.array_equal(X1[0], X1[23])
